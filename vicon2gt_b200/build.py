@@ -1,0 +1,111 @@
+"""In-tree native builds (no JIT cache): the CUDA solver library for sm_100a and the host
+simulator library.  The oracle (test infrastructure) has its own recipe in oracle/Makefile.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG_DIR)
+CSRC = os.path.join(PKG_DIR, "csrc")
+HOST = os.path.join(PKG_DIR, "host")
+
+_LIBS = {
+    "cuda": os.path.join(PKG_DIR, "libvicon2gt_b200.so"),
+    "sim": os.path.join(HOST, "libv2gt_sim.so"),
+    "oracle": os.path.join(ROOT, "oracle", "liboracle.so"),
+}
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--expt-relaxed-constexpr",
+]
+
+
+def lib_path(name):
+    return _LIBS[name]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _run(cmd, cwd=None):
+    r = subprocess.run(cmd, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("build failed: " + " ".join(cmd))
+    return r.stdout
+
+
+def _find(exe, fallbacks):
+    p = shutil.which(exe)
+    if p:
+        return p
+    for f in fallbacks:
+        if os.path.exists(f):
+            return f
+    raise RuntimeError(f"{exe} not found")
+
+
+def cuda_sources():
+    srcs = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+    hdrs = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
+    hdrs.append(os.path.join(ROOT, "include", "vicon2gt_b200.h"))
+    return srcs, hdrs
+
+
+def build_cuda(force=False, verbose=False, extra=()):
+    """nvcc -> vicon2gt_b200/libvicon2gt_b200.so (sm_100a only; cross-compiles without a GPU)."""
+    srcs, hdrs = cuda_sources()
+    out = _LIBS["cuda"]
+    if not force and not _newer(out, srcs + hdrs):
+        return out
+    nvcc = _find("nvcc", ["/usr/local/cuda/bin/nvcc"])
+    nccl_inc = []
+    for cand in ("/usr/include/nccl.h",):
+        if os.path.exists(cand):
+            nccl_inc = ["-DV2GT_HAVE_NCCL=1"]
+    cmd = [nvcc] + NVCC_FLAGS + list(extra) + nccl_inc + ["-I", os.path.join(ROOT, "include"), "-shared", "-o", out] + srcs
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+    log = _run(cmd)
+    if verbose:
+        print(log)
+    return out
+
+
+def build_sim(force=False):
+    src = os.path.join(HOST, "sim.cpp")
+    deps = [src, os.path.join(HOST, "v2gt_sim.h"), os.path.join(CSRC, "v2gt_math.cuh")]
+    out = _LIBS["sim"]
+    if not force and not _newer(out, deps):
+        return out
+    gxx = _find("g++", ["/usr/bin/g++"])
+    _run([gxx, "-O2", "-std=c++17", "-fPIC", "-Wall", "-Wno-unknown-pragmas", "-shared", "-o", out, src])
+    return out
+
+
+def build_oracle(force=False):
+    """Test infrastructure: compiles oracle/'s C++ restatement (building the checker is not using it)."""
+    odir = os.path.join(ROOT, "oracle")
+    if force and os.path.exists(_LIBS["oracle"]):
+        os.remove(_LIBS["oracle"])
+    _run(["make", "-s", "-C", odir])
+    return _LIBS["oracle"]
+
+
+def build_all(force=False, verbose=False):
+    build_sim(force)
+    build_cuda(force, verbose)
+    build_oracle(force)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print("built:", ", ".join(_LIBS.values()))

@@ -1,0 +1,180 @@
+"""Synthetic input generator (host C++ library libv2gt_sim.so, see host/sim.cpp).
+
+Produces the IMU / vicon streams and state-time grid of the reference's `run_simulation`
+(src/run_simulation.cpp:108-158) for the BASELINE.json configurations.  The reference's
+trajectory text files are not shipped with this repo; `make_trajectory` synthesises a smooth
+trajectory of the same shape (start time, row count, spacing).
+"""
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from ._cdefs import SimParams, c_double_p, c_int32_p, dptr
+from .build import lib_path
+
+_lib = None
+
+
+def _load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path("sim")
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} missing: run `python -c 'import __graft_entry__ as g; g.build()'` first")
+    lib = C.CDLL(path)
+    lib.v2gt_sim_create.restype = C.c_void_p
+    lib.v2gt_sim_create.argtypes = [C.POINTER(SimParams)]
+    lib.v2gt_sim_destroy.argtypes = [C.c_void_p]
+    lib.v2gt_sim_error.restype = C.c_char_p
+    lib.v2gt_sim_error.argtypes = [C.c_void_p]
+    lib.v2gt_sim_params_default.argtypes = [C.POINTER(SimParams)]
+    lib.v2gt_sim_load_trajectory_file.argtypes = [C.c_void_p, C.c_char_p]
+    lib.v2gt_sim_set_trajectory.argtypes = [C.c_void_p, C.c_int64, c_double_p]
+    lib.v2gt_sim_make_trajectory.argtypes = [C.c_double, C.c_int64, C.c_double, C.c_double, c_double_p]
+    lib.v2gt_sim_run.argtypes = [C.c_void_p]
+    for n in ("v2gt_sim_n_imu", "v2gt_sim_n_vicon", "v2gt_sim_n_states"):
+        getattr(lib, n).restype = C.c_int64
+        getattr(lib, n).argtypes = [C.c_void_p]
+    lib.v2gt_sim_get.argtypes = [C.c_void_p] + [c_double_p] * 7
+    lib.v2gt_sim_get_truth.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p]
+    lib.v2gt_sim_get_state_in_vicon.argtypes = [C.c_void_p, C.c_int64, c_double_p, c_double_p, c_int32_p]
+    _lib = lib
+    return lib
+
+
+@dataclass
+class Dataset:
+    """One trial's inputs, as fed to Propagator::feed_imu / Interpolator::feed_pose / the solver ctor."""
+
+    imu_t: np.ndarray
+    imu_w: np.ndarray
+    imu_a: np.ndarray
+    vic_t: np.ndarray
+    vic_q: np.ndarray
+    vic_p: np.ndarray
+    vic_R_const: np.ndarray  # 18 doubles: R_q (3x3), R_p (3x3) for every pose (run_simulation.cpp:84-96)
+    state_t: np.ndarray
+    truth: dict = field(default_factory=dict)
+    seed: int = 0
+
+    @property
+    def n_imu(self):
+        return len(self.imu_t)
+
+    @property
+    def n_vicon(self):
+        return len(self.vic_t)
+
+    @property
+    def n_times(self):
+        return len(self.state_t)
+
+    def nbytes(self):
+        return sum(a.nbytes for a in (self.imu_t, self.imu_w, self.imu_a, self.vic_t, self.vic_q, self.vic_p, self.state_t))
+
+
+def default_sim_params(**kw):
+    p = SimParams()
+    _load().v2gt_sim_params_default(C.byref(p))
+    for k, v in kw.items():
+        if k == "sigma_vicon_pose":
+            for i in range(6):
+                p.sigma_vicon_pose[i] = float(v[i])
+        else:
+            setattr(p, k, v)
+    return p
+
+
+def make_trajectory(t_start, n_rows, dt=0.05, extent_m=20.0):
+    """Synthesised trajectory rows `t x y z qx qy qz qw` (JPL q_GtoI)."""
+    rows = np.zeros((n_rows, 8))
+    _load().v2gt_sim_make_trajectory(float(t_start), int(n_rows), float(dt), float(extent_m), dptr(rows))
+    return rows
+
+
+# Shapes of the reference's trajectory files (start time, rows, mean spacing) used by BASELINE.json's
+# configs; the files themselves are not shipped (data/tum_corridor1_512_16_okvis.txt, data/euroc_V1_01_easy.txt).
+TRAJ_SHAPES = {
+    "tum_corridor1": dict(t_start=1520531829.301144123, n_rows=5986, dt=0.05, extent_m=20.0),
+    "euroc_V1_01": dict(t_start=1403715273.26214, n_rows=2895, dt=0.05, extent_m=2.5),
+}
+
+
+def simulate(traj_rows=None, traj_path=None, seed=0, vicon_sigmas=(0.0174, 0.0174, 0.0174, 0.05, 0.05, 0.05),
+             freq_imu=400.0, freq_cam=20.0, freq_vicon=100.0, state_freq=100, max_imu=0, fixed_truth=None, **noise):
+    """Run the simulator once and return a Dataset (defaults = launch/sim.launch of the reference)."""
+    lib = _load()
+    p = default_sim_params(seed=int(seed), sim_freq_imu=float(freq_imu), sim_freq_cam=float(freq_cam),
+                           sim_freq_vicon=float(freq_vicon), state_freq=int(state_freq), max_imu=int(max_imu),
+                           sigma_vicon_pose=vicon_sigmas, **noise)
+    if fixed_truth is not None:
+        p.use_fixed_truth = 1
+        for i in range(9):
+            p.fixed_R_BtoI[i] = float(np.asarray(fixed_truth["R_BtoI"]).reshape(-1)[i])
+            p.fixed_R_GtoV[i] = float(np.asarray(fixed_truth["R_GtoV"]).reshape(-1)[i])
+        for i in range(3):
+            p.fixed_p_BinI[i] = float(fixed_truth["p_BinI"][i])
+        p.fixed_viconimu_dt = float(fixed_truth["viconimu_dt"])
+    h = lib.v2gt_sim_create(C.byref(p))
+    try:
+        if traj_path is not None:
+            if lib.v2gt_sim_load_trajectory_file(h, traj_path.encode()) != 0:
+                raise RuntimeError(lib.v2gt_sim_error(h).decode())
+        else:
+            rows = np.ascontiguousarray(traj_rows, dtype=np.float64)
+            if lib.v2gt_sim_set_trajectory(h, rows.shape[0], dptr(rows)) != 0:
+                raise RuntimeError("trajectory too short")
+        if lib.v2gt_sim_run(h) != 0:
+            raise RuntimeError(lib.v2gt_sim_error(h).decode())
+        M, V, N = lib.v2gt_sim_n_imu(h), lib.v2gt_sim_n_vicon(h), lib.v2gt_sim_n_states(h)
+        imu_t, imu_w, imu_a = np.zeros(M), np.zeros((M, 3)), np.zeros((M, 3))
+        vic_t, vic_q, vic_p = np.zeros(V), np.zeros((V, 4)), np.zeros((V, 3))
+        state_t = np.zeros(N)
+        lib.v2gt_sim_get(h, dptr(imu_t), dptr(imu_w), dptr(imu_a), dptr(vic_t), dptr(vic_q), dptr(vic_p), dptr(state_t))
+        R_BtoI, p_BinI, R_GtoV = np.zeros((3, 3)), np.zeros(3), np.zeros((3, 3))
+        dt = C.c_double()
+        lib.v2gt_sim_get_truth(h, dptr(R_BtoI), dptr(p_BinI), C.byref(dt), dptr(R_GtoV))
+        truth = dict(R_BtoI=R_BtoI, p_BinI=p_BinI, viconimu_dt=dt.value, R_GtoV=R_GtoV)
+        # truth states at the state times (Simulator::get_state_in_vicon), for accuracy checks
+        st = np.zeros((N, 17))
+        ok = np.zeros(N, dtype=np.int32)
+        if N:
+            lib.v2gt_sim_get_state_in_vicon(h, N, dptr(state_t), dptr(st), ok.ctypes.data_as(c_int32_p))
+        truth["states"] = st
+        truth["states_ok"] = ok
+    finally:
+        lib.v2gt_sim_destroy(h)
+    s = np.asarray(vicon_sigmas, dtype=np.float64)
+    R_const = np.zeros(18)
+    R_const[[0, 4, 8]] = s[:3] ** 2  # R_q diag (run_simulation.cpp:89-91)
+    R_const[[9, 13, 17]] = s[3:] ** 2  # R_p diag
+    return Dataset(imu_t, imu_w, imu_a, vic_t, vic_q, vic_p, R_const, state_t, truth, int(seed))
+
+
+def make_config(name, seed=0, duration_s=None, **kw):
+    """Datasets shaped like BASELINE.json's configs, on synthesised trajectories.
+
+    name: "C1" sim.launch defaults (400 Hz IMU, 100 Hz vicon, 100 Hz states, corridor1 shape)
+          "C2" EuRoC V1_01 shape: states at the trajectory timestamps (20 Hz), 200 Hz IMU, 100 Hz vicon
+          "C3" TUM corridor1 shape: states at the trajectory timestamps (20 Hz), 200 Hz IMU, 100 Hz vicon
+    duration_s truncates the trajectory (smaller problems for tests).
+    """
+    if name == "C1":
+        shape = dict(TRAJ_SHAPES["tum_corridor1"])
+        sim_kw = dict(freq_imu=400.0, freq_cam=20.0, freq_vicon=100.0, state_freq=100)
+    elif name == "C2":
+        shape = dict(TRAJ_SHAPES["euroc_V1_01"])
+        sim_kw = dict(freq_imu=200.0, freq_cam=20.0, freq_vicon=100.0, state_freq=0)
+    elif name == "C3":
+        shape = dict(TRAJ_SHAPES["tum_corridor1"])
+        sim_kw = dict(freq_imu=200.0, freq_cam=20.0, freq_vicon=100.0, state_freq=0)
+    else:
+        raise ValueError(name)
+    if duration_s is not None:
+        shape["n_rows"] = max(8, min(shape["n_rows"], int(round(duration_s / shape["dt"])) + 1))
+    rows = make_trajectory(**shape)
+    sim_kw.update(kw)
+    return simulate(traj_rows=rows, seed=seed, **sim_kw)
