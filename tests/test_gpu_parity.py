@@ -1,0 +1,275 @@
+"""GPU parity tests (-m gpu): every stage of the CUDA path against the CPU oracle, through the C ABI.
+
+Tolerances (BASELINE.json north_star): bracket indices bit-exact; states / extrinsics / time offset within
+1e-6 (m, rad, s) after matched iterations; final chi2 within 1e-8 relative.  Intermediate quantities are
+held to tighter, stage-specific bounds written next to each assert.
+"""
+import numpy as np
+import pytest
+
+from conftest import default_params
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(ds, params=None, **opts):
+    from oracle import binding as ob
+    from vicon2gt_b200 import api
+
+    p = params if params is not None else default_params()
+    orc = ob.OracleSolver.from_dataset(p, ds)
+    bs = api.BatchSolver(1, keep_cov=1, **opts)
+    bs.set_trial_dataset(0, p, ds)
+    return orc, bs
+
+
+def _rel(a, b, floor=0.0):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.max(np.abs(a - b) / (np.abs(b) + floor)) if a.size else 0.0
+
+
+def _relmax(a, b):
+    """max |a-b| / max |b| (matrix-level relative error)."""
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+# --------------------------------------------------------------------------------------------------
+def test_interp_brackets_bitexact_and_values(ds_c1_small):
+    ds = ds_c1_small
+    orc, bs = _pair(ds)
+    bs.upload()
+    rng = np.random.default_rng(0)
+    vt = ds.vic_t
+    q = np.concatenate([
+        vt[::7],                                        # exact hits (bracket k-1, k+1 quirk)
+        vt[:3], vt[-3:],                                # first / last samples
+        [vt[0] - 1.0, vt[-1] + 1.0, vt[0], vt[-1]],     # out of range / boundaries
+        rng.uniform(vt[0] - 0.05, vt[-1] + 0.05, 4000), # random
+        np.nextafter(vt[100:110], np.inf), np.nextafter(vt[100:110], -np.inf),
+    ])
+    for gap in (0.1, 5.0, 0.004):
+        a = orc.eval_interp(q, gap)
+        b = bs.eval_interp(0, q, gap)
+        assert np.array_equal(a["idx0"], b["idx0"])  # bit-exact
+        assert np.array_equal(a["idx1"], b["idx1"])
+        assert np.array_equal(a["ok"], b["ok"])
+        ok = a["ok"] == 1
+        assert ok.sum() > 100
+        assert np.max(np.abs(a["q"][ok] - b["q"][ok])) < 1e-13
+        assert np.max(np.abs(a["p"][ok] - b["p"][ok])) < 1e-12
+        assert _relmax(b["R"][ok], a["R"][ok]) < 1e-12
+        assert _relmax(b["H_toff"][ok], a["H_toff"][ok]) < 1e-11
+
+
+@pytest.mark.parametrize("dsname", ["ds_c1_small", "ds_c3_small"])
+def test_build_parity(dsname, request):
+    """Initial guess (states) and continuous preintegration of every interval."""
+    ds = request.getfixturevalue(dsname)
+    orc, bs = _pair(ds)
+    assert orc.clean() == 0 and orc.build(True) == 0
+    bs.upload()
+    bs.build(True)
+    inf = bs.info(0)
+    assert inf.status == 0
+    to, xo = orc.states()
+    tg, xg = bs.states(0)
+    assert inf.n_states == len(to)
+    assert np.array_equal(to, tg)  # same surviving timestamps
+    assert np.max(np.abs(xo - xg)) < 1e-12
+    po, Po = orc.preint()
+    pg, Pg = bs.preint(0, cov=True)
+    assert po.shape == pg.shape
+    assert np.array_equal(po[:, 0], pg[:, 0])  # DT exact (preint.DT == time1 - time0 check)
+    assert np.max(np.abs(po[:, 1:11] - pg[:, 1:11])) < 1e-13  # alpha beta q
+    assert _relmax(pg[:, 17:62], po[:, 17:62]) < 1e-12  # J_q J_b J_a H_b H_a
+    # covariance: RK4 in block form vs dense form, <= 1e-10 relative to each matrix's scale
+    scale = np.sqrt(np.abs(np.einsum("nii->ni", Po.reshape(-1, 15, 15))))
+    rel = np.abs(Pg - Po).reshape(-1, 15, 15) / (scale[:, :, None] * scale[:, None, :])
+    assert rel.max() < 1e-10
+    # information matrix
+    sc = np.sqrt(np.abs(np.einsum("nii->ni", po[:, 63:].reshape(-1, 15, 15))))
+    reli = np.abs(pg[:, 63:] - po[:, 63:]).reshape(-1, 15, 15) / (sc[:, :, None] * sc[:, None, :])
+    assert reli.max() < 1e-8
+
+
+@pytest.mark.parametrize("dsname", ["ds_c1_small", "ds_c3_small"])
+def test_linearize_parity(dsname, request):
+    ds = request.getfixturevalue(dsname)
+    orc, bs = _pair(ds)
+    assert orc.clean() == 0 and orc.build(True) == 0
+    bs.upload()
+    bs.build(True)
+    rng = np.random.default_rng(1)
+    for it in range(2):
+        if it == 1:
+            # move both to the same perturbed estimate (outliers for Huber, non-zero biases, moved globals)
+            t, x = orc.states()
+            x = x.copy()
+            x[:, 4:7] += 1e-3 * rng.standard_normal((len(t), 3))
+            x[:, 10:13] += 1e-2 * rng.standard_normal((len(t), 3))
+            x[:, 13:16] += 0.05 * rng.standard_normal((len(t), 3))
+            g = orc.globals10()
+            g[4:7] += 0.05
+            g[7] += 0.0123
+            g[8:10] += 0.02
+            assert orc.set_estimate(x, g) == 0
+            bs.set_estimate(0, x, g)
+        a = orc.linearize()
+        b = bs.linearize(0)
+        assert abs(a["cost"] - b["cost"]) / a["cost"] < 1e-11
+        assert abs(a["lin_error0"] - b["lin_error0"]) / a["lin_error0"] < 1e-11
+        for k in ("D", "O", "B"):
+            # per-state blocks relative to the block's own scale
+            sc = np.max(np.abs(a[k]), axis=1, keepdims=True) + 1e-300
+            assert np.max(np.abs(a[k] - b[k]) / sc) < 1e-10, k
+        assert _relmax(b["g"], a["g"]) < 1e-10
+        assert _relmax(b["Gamma"], a["Gamma"]) < 1e-11
+        assert _relmax(b["g_gamma"], a["g_gamma"]) < 1e-9
+
+
+@pytest.mark.parametrize("segments", [1, 2, 7, 32, 0])
+def test_solve_parity(ds_c3_small, segments):
+    """(H + lambda I) delta = g : partitioned GPU solve vs the oracle's sequential block Cholesky."""
+    ds = ds_c3_small
+    orc, bs = _pair(ds, segments=segments)
+    assert orc.clean() == 0 and orc.build(True) == 0
+    bs.upload()
+    bs.build(True)
+    orc.linearize()
+    bs.linearize(0)
+    for lam in (1e-5, 1e-2, 1e3, 1e10):
+        do, oko = orc.solve(lam)
+        dg, okg = bs.solve(0, lam)
+        assert oko and okg
+        n = (len(do) - 9) // 15
+        so = do[: 15 * n].reshape(n, 15)
+        sg = dg[: 15 * n].reshape(n, 15)
+        # per-component-type scale (theta, bg, v, ba, p have very different magnitudes)
+        sc = np.max(np.abs(so), axis=0) + 1e-300
+        assert np.max(np.abs(so - sg) / sc) < 1e-7, lam
+        assert np.max(np.abs(do[15 * n:] - dg[15 * n:]) / (np.abs(do[15 * n:]) + 1e-12)) < 1e-6, lam
+
+
+def _compare_solution(orc, bs, tol_state=1e-6, tol_chi2=1e-8):
+    from vicon2gt_b200._cdefs import TrialInfo
+
+    io, ig = orc.info(TrialInfo), bs.info(0)
+    assert io.status == 0 and ig.status == 0
+    to, xo = orc.states()
+    tg, xg = bs.states(0)
+    assert np.array_equal(to, tg)
+    # quaternions: compare the rotation angle between the two estimates
+    dq = np.abs(np.sum(xo[:, :4] * xg[:, :4], axis=1))
+    ang = 2 * np.arccos(np.clip(dq, 0, 1))
+    assert ang.max() < tol_state
+    assert np.max(np.abs(xo[:, 4:] - xg[:, 4:])) < tol_state
+    qo, po, toffo, tho = orc.calibration()
+    qg, pg, toffg, thg = bs.calibration(0)
+    assert 2 * np.arccos(min(1.0, abs(float(qo @ qg)))) < tol_state
+    assert np.max(np.abs(po - pg)) < tol_state
+    assert abs(toffo - toffg) < tol_state
+    assert np.max(np.abs(tho - thg)) < tol_state
+    assert abs(io.final_error - ig.final_error) / io.final_error < tol_chi2
+    return io, ig
+
+
+@pytest.mark.parametrize("dsname", ["ds_c1_small", "ds_c2_small", "ds_c3_small"])
+def test_end_to_end_parity(dsname, request):
+    """Full build_and_solve: matched LM policy, 30 iterations."""
+    ds = request.getfixturevalue(dsname)
+    orc, bs = _pair(ds)
+    assert orc.build_and_solve() == 0
+    bs.build_and_solve()
+    io, ig = _compare_solution(orc, bs)
+    assert io.iterations == ig.iterations
+    assert ig.tries > 0 and ig.linearizations > 0
+
+
+def test_end_to_end_fixed_calibration(ds_c3_small):
+    """estimate_* flags false: calibration columns are zeroed, the damping keeps the system solvable."""
+    ds = ds_c3_small
+    p = default_params(estimate_toff_vicon_to_imu=0, estimate_ori_vicon_to_imu=0, estimate_pos_vicon_to_imu=0,
+                       toff_imu_to_vicon=float(ds.truth["viconimu_dt"]), R_BtoI=ds.truth["R_BtoI"], p_BinI=ds.truth["p_BinI"])
+    orc, bs = _pair(ds, p)
+    assert orc.build_and_solve() == 0
+    bs.build_and_solve()
+    _compare_solution(orc, bs)
+    q0, p0, t0, _ = bs.calibration(0)
+    assert abs(t0 - ds.truth["viconimu_dt"]) < 1e-15
+    assert np.max(np.abs(p0 - ds.truth["p_BinI"])) < 1e-15
+
+
+def test_relinearization_loop(ds_c2_small):
+    """num_loop_relin = 1: preintegration is rebuilt at the estimated biases and the solve repeated."""
+    p = default_params(num_loop_relin=1, lm_max_iterations=8)
+    orc, bs = _pair(ds_c2_small, p)
+    assert orc.build_and_solve() == 0
+    bs.build_and_solve()
+    _compare_solution(orc, bs)
+
+
+def test_batch_of_trials_matches_single(ds_c1_small, ds_c2_small, ds_c3_small):
+    """Independent trials of different shapes in one batch give the single-trial answers."""
+    from vicon2gt_b200 import api
+
+    p = default_params(lm_max_iterations=6)
+    dss = [ds_c2_small, ds_c1_small, ds_c3_small, ds_c2_small]
+    bs = api.BatchSolver(len(dss))
+    for i, ds in enumerate(dss):
+        bs.set_trial_dataset(i, p, ds)
+    bs.build_and_solve()
+    for i, ds in enumerate(dss):
+        single = api.BatchSolver(1)
+        single.set_trial_dataset(0, p, ds)
+        single.build_and_solve()
+        tb, xb = bs.states(i)
+        ts, xs = single.states(0)
+        assert np.array_equal(tb, ts)
+        assert np.max(np.abs(xb - xs)) < 1e-7
+        assert abs(bs.info(i).final_error - single.info(0).final_error) / single.info(0).final_error < 1e-9
+        single.close()
+    # trials 0 and 3 are the same problem: bitwise identical (deterministic reductions)
+    assert np.array_equal(bs.states(0)[1], bs.states(3)[1])
+    bs.close()
+
+
+def test_error_codes_do_not_kill_the_batch(ds_c2_small):
+    """A failing trial reports a status code; the other trials of the batch still solve."""
+    from vicon2gt_b200 import api
+
+    ds = ds_c2_small
+    p = default_params(lm_max_iterations=3)
+    bs = api.BatchSolver(3)
+    bs.set_trial_dataset(0, p, ds)
+    # trial 1: all state times outside the vicon window -> ALL_OUT_OF_RANGE (reference: exit)
+    bs.set_trial(1, p, ds.imu_t, ds.imu_w, ds.imu_a, ds.vic_t, ds.vic_q, ds.vic_p, ds.state_t + 1e4, vic_R_const=ds.vic_R_const)
+    # trial 2: a single vicon pose -> NO_VICON
+    bs.set_trial(2, p, ds.imu_t, ds.imu_w, ds.imu_a, ds.vic_t[:1], ds.vic_q[:1], ds.vic_p[:1], ds.state_t,
+                 vic_R_const=ds.vic_R_const)
+    bs.build_and_solve()
+    assert bs.info(0).status == 0 and bs.info(0).iterations == 3
+    assert bs.info(1).status == 5
+    assert bs.info(2).status == 4
+    bs.close()
+
+
+def test_write_to_file_matches_oracle(ds_c2_small, tmp_path):
+    p = default_params(lm_max_iterations=4)
+    orc, bs = _pair(ds_c2_small, p)
+    assert orc.build_and_solve() == 0
+    bs.build_and_solve()
+    orc.write_to_file(str(tmp_path / "o.csv"), str(tmp_path / "o.txt"))
+    bs.write_to_file(0, str(tmp_path / "g" / "g.csv"), str(tmp_path / "g" / "g.txt"))
+    lo = (tmp_path / "o.csv").read_text().splitlines()
+    lg = (tmp_path / "g" / "g.csv").read_text().splitlines()
+    assert lo[0] == lg[0] == "#time(ns),px,py,pz,qw,qx,qy,qz,vx,vy,vz,bwx,bwy,bwz,bax,bay,baz"
+    assert len(lo) == len(lg)
+    for a, b in zip(lo[1:], lg[1:]):
+        fa, fb = a.split(","), b.split(",")
+        assert fa[0] == fb[0]  # nanosecond stamp, printed with 20 significant digits
+        assert np.allclose([float(v) for v in fa[1:]], [float(v) for v in fb[1:]], rtol=0, atol=2e-5)
+    io = (tmp_path / "o.txt").read_text().split("\n")
+    ig = (tmp_path / "g" / "g.txt").read_text().split("\n")
+    assert [l for l in io if l.endswith(": ")] == [l for l in ig if l.endswith(": ")]  # same section headers
+    assert len(io) == len(ig)

@@ -1,0 +1,333 @@
+"""Python mirror of the reference's solver interface over the C ABI (ctypes, no torch types).
+
+`ViconGraphSolver` follows src/solver/ViconGraphSolver.h:61-168 of the reference: it is built from a
+parameter struct, a `Propagator` (feed_imu) and an `Interpolator` (feed_pose) store and the state
+timestamps, and offers build_and_solve / write_to_file / get_imu_poses / get_calibration.
+`BatchSolver` is the batch form (many independent trials per GPU) the Monte-Carlo configs use.
+Everything numeric happens in vicon2gt_b200/libvicon2gt_b200.so (CUDA, sm_100a); there is no CPU path.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from ._cdefs import PREINT_DIM, STATUS_NAMES, Params, TrialInfo, c_double_p, c_int32_p, c_int64_p, dptr, i32ptr
+from .build import lib_path
+
+_lib = None
+
+
+class V2gtError(RuntimeError):
+    def __init__(self, code, where=""):
+        self.code = code
+        super().__init__(f"vicon2gt_b200: {where} failed with status {code} ({STATUS_NAMES.get(code, '?')})")
+
+
+def load_library():
+    """Load the CUDA library; raises if it has not been built (there is no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path("cuda")
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: build it with `python -m vicon2gt_b200.build` (nvcc, sm_100a). "
+                           "vicon2gt_b200 has no CPU implementation.")
+    L = C.CDLL(path)
+    vp = C.c_void_p
+    L.v2gt_version.restype = C.c_char_p
+    L.v2gt_params_default.argtypes = [C.POINTER(Params)]
+    L.v2gt_device_count.argtypes = [c_int32_p]
+    L.v2gt_batch_create.argtypes = [C.c_int32, C.c_int32, C.POINTER(vp)]
+    L.v2gt_batch_destroy.argtypes = [vp]
+    L.v2gt_batch_set_option.argtypes = [vp, C.c_char_p, C.c_double]
+    L.v2gt_batch_set_trial.argtypes = [vp, C.c_int32, C.POINTER(Params), C.c_int64, c_double_p, c_double_p, c_double_p, C.c_int64,
+                                       c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, C.c_int64, c_double_p]
+    for n in ("v2gt_batch_upload", "v2gt_batch_optimize", "v2gt_batch_build_and_solve", "v2gt_batch_sync"):
+        getattr(L, n).argtypes = [vp]
+    L.v2gt_batch_build.argtypes = [vp, C.c_int32]
+    L.v2gt_batch_get_info.argtypes = [vp, C.c_int32, C.POINTER(TrialInfo)]
+    L.v2gt_batch_get_states.argtypes = [vp, C.c_int32, C.c_int64, c_double_p, c_double_p, c_int64_p]
+    L.v2gt_batch_get_calibration.argtypes = [vp, C.c_int32, c_double_p, c_double_p, c_double_p, c_double_p]
+    L.v2gt_batch_write_to_file.argtypes = [vp, C.c_int32, C.c_char_p, C.c_char_p]
+    L.v2gt_eval_interp.argtypes = [vp, C.c_int32, C.c_int64, c_double_p, C.c_double, c_int32_p, c_int32_p, c_int32_p, c_double_p,
+                                   c_double_p, c_double_p, c_double_p]
+    L.v2gt_batch_get_preint.argtypes = [vp, C.c_int32, C.c_int64, c_double_p, c_int64_p]
+    L.v2gt_batch_get_preint_cov.argtypes = [vp, C.c_int32, C.c_int64, c_double_p, c_int64_p]
+    L.v2gt_batch_set_estimate.argtypes = [vp, C.c_int32, C.c_int64, c_double_p, c_double_p]
+    L.v2gt_eval_linearize.argtypes = [vp, C.c_int32, C.c_int64] + [c_double_p] * 8
+    L.v2gt_eval_solve.argtypes = [vp, C.c_int32, C.c_double, C.c_int64, c_double_p, c_int32_p]
+    L.v2gt_eval_cost.argtypes = [vp, C.c_int32, c_double_p]
+    L.v2gt_batch_get_lm_trace.argtypes = [vp, C.c_int32, C.c_int64, c_double_p, c_int64_p]
+    L.v2gt_batch_get_timing.argtypes = [vp, c_double_p, c_int64_p]
+    _lib = L
+    return L
+
+
+def default_params(**kw):
+    """ViconGraphSolverParams with the reference defaults (ViconGraphSolver.cpp:34-75, sim.launch)."""
+    p = Params()
+    load_library().v2gt_params_default(C.byref(p))
+    for k, v in kw.items():
+        if k in ("R_GtoV", "R_BtoI", "p_BinI"):
+            arr = np.asarray(v, dtype=np.float64).reshape(-1)
+            for i, x in enumerate(arr):
+                getattr(p, k)[i] = float(x)
+        else:
+            setattr(p, k, v)
+    return p
+
+
+def device_count():
+    n = C.c_int32(0)
+    load_library().v2gt_device_count(C.byref(n))
+    return n.value
+
+
+def _c(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _check(code, where):
+    if code != 0:
+        raise V2gtError(code, where)
+
+
+class BatchSolver:
+    """A batch of independent build-and-solve problems resident on one GPU."""
+
+    def __init__(self, n_trials, device=0, **options):
+        self._L = load_library()
+        self.n_trials = int(n_trials)
+        self.h = C.c_void_p()
+        _check(self._L.v2gt_batch_create(int(device), self.n_trials, C.byref(self.h)), "v2gt_batch_create")
+        for k, v in options.items():
+            self.set_option(k, v)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.v2gt_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_option(self, name, value):
+        _check(self._L.v2gt_batch_set_option(self.h, name.encode(), float(value)), f"set_option({name})")
+
+    def set_trial(self, trial, params, imu_t, imu_w, imu_a, vic_t, vic_q, vic_p, state_t, vic_Rq=None, vic_Rp=None, vic_R_const=None):
+        a = [_c(x) for x in (imu_t, imu_w, imu_a, vic_t, vic_q, vic_p, vic_Rq, vic_Rp, vic_R_const, state_t)]
+        _check(self._L.v2gt_batch_set_trial(self.h, int(trial), C.byref(params), len(a[0]), dptr(a[0]), dptr(a[1]), dptr(a[2]),
+                                            len(a[3]), dptr(a[3]), dptr(a[4]), dptr(a[5]), dptr(a[6]), dptr(a[7]), dptr(a[8]),
+                                            len(a[9]), dptr(a[9])), "v2gt_batch_set_trial")
+
+    def set_trial_dataset(self, trial, params, ds):
+        self.set_trial(trial, params, ds.imu_t, ds.imu_w, ds.imu_a, ds.vic_t, ds.vic_q, ds.vic_p, ds.state_t,
+                       vic_R_const=ds.vic_R_const)
+
+    def upload(self):
+        _check(self._L.v2gt_batch_upload(self.h), "v2gt_batch_upload")
+
+    def build(self, init_states=True):
+        _check(self._L.v2gt_batch_build(self.h, 1 if init_states else 0), "v2gt_batch_build")
+
+    def optimize(self):
+        _check(self._L.v2gt_batch_optimize(self.h), "v2gt_batch_optimize")
+
+    def build_and_solve(self):
+        _check(self._L.v2gt_batch_build_and_solve(self.h), "v2gt_batch_build_and_solve")
+
+    def sync(self):
+        _check(self._L.v2gt_batch_sync(self.h), "v2gt_batch_sync")
+
+    def info(self, trial=0):
+        inf = TrialInfo()
+        _check(self._L.v2gt_batch_get_info(self.h, int(trial), C.byref(inf)), "v2gt_batch_get_info")
+        return inf
+
+    def states(self, trial=0):
+        n = C.c_int64()
+        _check(self._L.v2gt_batch_get_states(self.h, int(trial), 0, None, None, C.byref(n)), "v2gt_batch_get_states")
+        t, x = np.zeros(n.value), np.zeros((n.value, 16))
+        _check(self._L.v2gt_batch_get_states(self.h, int(trial), n.value, dptr(t), dptr(x), C.byref(n)), "v2gt_batch_get_states")
+        return t, x
+
+    def calibration(self, trial=0):
+        q, p, th = np.zeros(4), np.zeros(3), np.zeros(2)
+        toff = C.c_double()
+        _check(self._L.v2gt_batch_get_calibration(self.h, int(trial), dptr(q), dptr(p), C.byref(toff), dptr(th)),
+               "v2gt_batch_get_calibration")
+        return q, p, toff.value, th
+
+    def globals10(self, trial=0):
+        q, p, toff, th = self.calibration(trial)
+        return np.concatenate([q, p, [toff], th])
+
+    def write_to_file(self, trial, csv_path, info_path):
+        _check(self._L.v2gt_batch_write_to_file(self.h, int(trial), csv_path.encode(), info_path.encode()),
+               "v2gt_batch_write_to_file")
+
+    # ---- evaluation-only entry points (parity tests)
+    def eval_interp(self, trial, t_query, gap_thresh):
+        t = _c(t_query)
+        n = len(t)
+        i0, i1, ok = (np.zeros(n, dtype=np.int32) for _ in range(3))
+        q, p, R, H = np.zeros((n, 4)), np.zeros((n, 3)), np.zeros((n, 36)), np.zeros((n, 6))
+        _check(self._L.v2gt_eval_interp(self.h, int(trial), n, dptr(t), float(gap_thresh), i32ptr(i0), i32ptr(i1), i32ptr(ok),
+                                        dptr(q), dptr(p), dptr(R), dptr(H)), "v2gt_eval_interp")
+        return dict(idx0=i0, idx1=i1, ok=ok, q=q, p=p, R=R, H_toff=H)
+
+    def preint(self, trial=0, cov=False):
+        n = C.c_int64()
+        _check(self._L.v2gt_batch_get_preint(self.h, int(trial), 0, None, C.byref(n)), "v2gt_batch_get_preint")
+        out = np.zeros((n.value, PREINT_DIM))
+        _check(self._L.v2gt_batch_get_preint(self.h, int(trial), n.value, dptr(out), C.byref(n)), "v2gt_batch_get_preint")
+        if not cov:
+            return out
+        P = np.zeros((n.value, 225))
+        _check(self._L.v2gt_batch_get_preint_cov(self.h, int(trial), n.value, dptr(P), C.byref(n)), "v2gt_batch_get_preint_cov")
+        return out, P
+
+    def set_estimate(self, trial, states=None, globals10=None):
+        s, g = _c(states), _c(globals10)
+        n = 0 if s is None else s.shape[0]
+        _check(self._L.v2gt_batch_set_estimate(self.h, int(trial), n, dptr(s), dptr(g)), "v2gt_batch_set_estimate")
+
+    def linearize(self, trial=0):
+        n = self.info(trial).n_states
+        D, O, B, g = np.zeros((n, 225)), np.zeros((n, 225)), np.zeros((n, 135)), np.zeros((n, 15))
+        G, gG = np.zeros(81), np.zeros(9)
+        cost, lin0 = C.c_double(), C.c_double()
+        _check(self._L.v2gt_eval_linearize(self.h, int(trial), n, dptr(D), dptr(O), dptr(B), dptr(g), dptr(G), dptr(gG),
+                                           C.byref(cost), C.byref(lin0)), "v2gt_eval_linearize")
+        return dict(D=D, O=O, B=B, g=g, Gamma=G, g_gamma=gG, cost=cost.value, lin_error0=lin0.value)
+
+    def solve(self, trial, lam):
+        n = self.info(trial).n_states
+        delta = np.zeros(15 * n + 9)
+        ok = C.c_int32()
+        _check(self._L.v2gt_eval_solve(self.h, int(trial), float(lam), len(delta), dptr(delta), C.byref(ok)), "v2gt_eval_solve")
+        return delta, bool(ok.value)
+
+    def cost(self, trial=0):
+        c = C.c_double()
+        _check(self._L.v2gt_eval_cost(self.h, int(trial), C.byref(c)), "v2gt_eval_cost")
+        return c.value
+
+    def lm_trace(self, trial=0):
+        n = C.c_int64()
+        _check(self._L.v2gt_batch_get_lm_trace(self.h, int(trial), 0, None, C.byref(n)), "v2gt_batch_get_lm_trace")
+        rows = np.zeros((n.value, 5))
+        if n.value:
+            _check(self._L.v2gt_batch_get_lm_trace(self.h, int(trial), n.value, dptr(rows), C.byref(n)), "v2gt_batch_get_lm_trace")
+        return rows
+
+    def timing(self):
+        ms = np.zeros(8)
+        launches = np.zeros(8, dtype=np.int64)
+        self._L.v2gt_batch_get_timing(self.h, dptr(ms), launches.ctypes.data_as(c_int64_p))
+        return ms, launches
+
+
+class Propagator:
+    """IMU store of the reference (src/meas/Propagator.h:41-55): holds the noise densities, appends samples."""
+
+    def __init__(self, sigma_w, sigma_wb, sigma_a, sigma_ab):
+        self.sigmas = (float(sigma_w), float(sigma_wb), float(sigma_a), float(sigma_ab))
+        self._t, self._w, self._a = [], [], []
+
+    def feed_imu(self, timestamp, wm, am):
+        self._t.append(float(timestamp))
+        self._w.append(np.asarray(wm, dtype=np.float64).reshape(3))
+        self._a.append(np.asarray(am, dtype=np.float64).reshape(3))
+
+    def feed_imu_array(self, t, w, a):
+        self._t.extend(np.asarray(t, dtype=np.float64).tolist())
+        self._w.extend(np.asarray(w, dtype=np.float64).reshape(-1, 3))
+        self._a.extend(np.asarray(a, dtype=np.float64).reshape(-1, 3))
+
+    def arrays(self):
+        n = len(self._t)
+        return (np.asarray(self._t, dtype=np.float64), np.asarray(self._w, dtype=np.float64).reshape(n, 3),
+                np.asarray(self._a, dtype=np.float64).reshape(n, 3))
+
+
+class Interpolator:
+    """Vicon pose store of the reference (src/meas/Interpolator.h:55-81); sorting / de-duplication with
+    std::set semantics is done by the library when the trial is staged."""
+
+    def __init__(self):
+        self._t, self._q, self._p, self._Rq, self._Rp = [], [], [], [], []
+
+    def feed_pose(self, timestamp, q, p, R_q, R_p):
+        self._t.append(float(timestamp))
+        self._q.append(np.asarray(q, dtype=np.float64).reshape(4))
+        self._p.append(np.asarray(p, dtype=np.float64).reshape(3))
+        self._Rq.append(np.asarray(R_q, dtype=np.float64).reshape(9))
+        self._Rp.append(np.asarray(R_p, dtype=np.float64).reshape(9))
+
+    def arrays(self):
+        n = len(self._t)
+        return (np.asarray(self._t), np.asarray(self._q).reshape(n, 4), np.asarray(self._p).reshape(n, 3),
+                np.asarray(self._Rq).reshape(n, 9), np.asarray(self._Rp).reshape(n, 9))
+
+    def get_time_min(self):
+        return min(self._t) if self._t else float("inf")
+
+    def get_time_max(self):
+        return max(self._t) if self._t else float("-inf")
+
+
+class ViconGraphSolver:
+    """Single-trajectory solver with the reference's method names (minus the ROS-only `visualize`)."""
+
+    def __init__(self, params, propagator, interpolator, timestamp_cameras, device=0, **options):
+        self.params = params
+        sw, swb, sa, sab = propagator.sigmas
+        params.sigma_w, params.sigma_wb, params.sigma_a, params.sigma_ab = sw, swb, sa, sab
+        self._batch = BatchSolver(1, device=device, **options)
+        it, iw, ia = propagator.arrays()
+        vt, vq, vp, vRq, vRp = interpolator.arrays()
+        self._batch.set_trial(0, params, it, iw, ia, vt, vq, vp, np.asarray(timestamp_cameras, dtype=np.float64), vic_Rq=vRq,
+                              vic_Rp=vRp)
+
+    def build_and_solve(self):
+        self._batch.build_and_solve()
+        inf = self._batch.info(0)
+        if inf.status != 0:
+            # the reference calls std::exit(EXIT_FAILURE) here (ViconGraphSolver.cpp:99-150, 508-524)
+            raise V2gtError(inf.status, "build_and_solve")
+        return inf
+
+    def write_to_file(self, csvfilepath, infofilepath):
+        self._batch.write_to_file(0, csvfilepath, infofilepath)
+
+    def get_imu_poses(self):
+        """times, poses[n][10] = [q(4) p(3) v(3)] as the reference's get_imu_poses (.cpp:357-375)."""
+        t, x = self._batch.states(0)
+        poses = np.concatenate([x[:, 0:4], x[:, 13:16], x[:, 7:10]], axis=1)
+        return t, poses
+
+    def get_calibration(self):
+        """toff, R_BtoI, p_BinI, R_GtoV as the reference's get_calibration (.cpp:377-388)."""
+        q, p, toff, th = self._batch.calibration(0)
+        x, y, z, w = q
+        # quat_2_Rot (JPL): (2w^2-1) I - 2w [v]x + 2 v v^T
+        v = np.array([x, y, z])
+        vx = np.array([[0, -z, y], [z, 0, -x], [-y, x, 0]])
+        R_BtoI = (2 * w * w - 1) * np.eye(3) - 2 * w * vx + 2 * np.outer(v, v)
+        cx, sx, cy, sy = np.cos(th[0]), np.sin(th[0]), np.cos(th[1]), np.sin(th[1])
+        R_GtoV = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]]) @ np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+        return toff, R_BtoI, p, R_GtoV
+
+    @property
+    def batch(self):
+        return self._batch

@@ -1,0 +1,844 @@
+// vicon2gt_b200: batch handle, host staging, device memory, the C ABI of include/vicon2gt_b200.h.
+//
+// Host-side counterpart of the reference's ViconGraphSolver / Propagator / Interpolator stores:
+//   * v2gt_batch_set_trial   = Propagator::feed_imu x M, Interpolator::feed_pose x V (std::set
+//                              semantics: sorted by time, duplicate keys dropped, first wins),
+//                              timestamp_cameras
+//   * v2gt_batch_upload      = timestamp cleaning of ViconGraphSolver::build_and_solve
+//                              (.cpp:114-159; has_bounding_imu is t_imu[0] <= t <= t_imu[M-1] for the
+//                              time-ordered store) + one H2D copy per array from pinned memory
+//   * build / optimize       = kernel launches on the handle's stream; nothing here computes
+// There is no CPU fallback: every entry point that needs the GPU fails with V2GT_ERR_NO_DEVICE /
+// V2GT_ERR_CUDA when CUDA is unavailable.
+#include "v2gt_common.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <limits>
+#include <numeric>
+#include <sstream>
+#include <string>
+#include <sys/stat.h>
+#include <vector>
+
+namespace v2 {
+int launch_init_states(const DevPtrs &d, int n_max, int init_states, cudaStream_t st);
+int launch_preintegrate(const DevPtrs &d, int n_max, int keep_cov, cudaStream_t st);
+int launch_linearize(const DevPtrs &d, int n_max, int force_all, cudaStream_t st);
+int launch_cost(const DevPtrs &d, int n_max, int which, int force_all, cudaStream_t st);
+int launch_solve(const DevPtrs &d, int force_all, cudaStream_t st);
+int launch_lm_begin(const DevPtrs &d, cudaStream_t st);
+int launch_lm_pre_try(const DevPtrs &d, cudaStream_t st);
+int launch_lm_decide(const DevPtrs &d, int count_active, cudaStream_t st);
+int asm_chunks(int n_max);
+} // namespace v2
+
+using namespace v2;
+
+struct HostTrial {
+  v2gt_params prm;
+  std::vector<double> imu_t, imu_s;        // imu_s: [M][8]
+  std::vector<double> vic_t, vic_s, vic_c; // vic_s: [V][8]; vic_c: [V][18] or empty
+  double vic_Rconst[18];
+  bool cov_const = true;
+  std::vector<double> state_t_raw, state_t; // before / after cleaning
+  double vic_tmin = std::numeric_limits<double>::infinity(), vic_tmax = -std::numeric_limits<double>::infinity();
+  v2gt_trial_info info{};
+  bool set = false;
+};
+
+struct v2gt_batch {
+  int device = 0;
+  int T = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<HostTrial> trials;
+  DevPtrs d{};
+  std::vector<void *> dev_allocs;
+  std::vector<void *> pinned_allocs;
+  int n_max = 0; // max raw states over trials
+  bool uploaded = false, built = false, values_init = false;
+  // options
+  int opt_segments = 0;       // 0 = auto
+  int opt_keep_cov = 0;
+  int opt_tries_per_sync = 8;
+  // pinned readback
+  int *h_active = nullptr;
+  // timing
+  cudaEvent_t ev[16];
+  bool ev_ok = false;
+  double ms[8] = {0};
+  int64_t launches[8] = {0};
+  std::vector<LmState> h_lm;
+  std::vector<int> h_nstates, h_removed;
+  bool results_cached = false;
+};
+
+namespace {
+
+template <typename Tp> int dev_alloc(v2gt_batch *b, Tp **p, size_t count) {
+  *p = nullptr;
+  if (count == 0)
+    count = 1;
+  void *q = nullptr;
+  cudaError_t e = cudaMalloc(&q, count * sizeof(Tp));
+  if (e != cudaSuccess) {
+    fprintf(stderr, "[vicon2gt_b200] cudaMalloc of %zu bytes failed: %s\n", count * sizeof(Tp), cudaGetErrorString(e));
+    return V2GT_ERR_CUDA;
+  }
+  b->dev_allocs.push_back(q);
+  *p = (Tp *)q;
+  return V2GT_OK;
+}
+template <typename Tp> int pin_alloc(v2gt_batch *b, Tp **p, size_t count) {
+  if (count == 0)
+    count = 1;
+  void *q = nullptr;
+  if (cudaMallocHost(&q, count * sizeof(Tp)) != cudaSuccess)
+    return V2GT_ERR_CUDA;
+  b->pinned_allocs.push_back(q);
+  *p = (Tp *)q;
+  return V2GT_OK;
+}
+void free_device(v2gt_batch *b) {
+  for (void *p : b->dev_allocs)
+    cudaFree(p);
+  b->dev_allocs.clear();
+  for (void *p : b->pinned_allocs)
+    cudaFreeHost(p);
+  b->pinned_allocs.clear();
+  b->h_active = nullptr;
+  b->uploaded = false;
+  b->built = false;
+}
+
+#define V2_TRY(expr)                                                                                                             \
+  do {                                                                                                                           \
+    int _s = (expr);                                                                                                             \
+    if (_s != V2GT_OK)                                                                                                           \
+      return _s;                                                                                                                 \
+  } while (0)
+
+int fetch_results(v2gt_batch *b) {
+  if (b->results_cached)
+    return V2GT_OK;
+  V2_CUDA_CHECK(cudaStreamSynchronize(b->stream));
+  b->h_lm.resize(b->T);
+  b->h_nstates.resize(b->T);
+  b->h_removed.resize(b->T);
+  V2_CUDA_CHECK(cudaMemcpy(b->h_lm.data(), b->d.lm, sizeof(LmState) * b->T, cudaMemcpyDeviceToHost));
+  V2_CUDA_CHECK(cudaMemcpy(b->h_nstates.data(), b->d.n_states, sizeof(int) * b->T, cudaMemcpyDeviceToHost));
+  V2_CUDA_CHECK(cudaMemcpy(b->h_removed.data(), b->d.removed_no_vicon, sizeof(int) * b->T, cudaMemcpyDeviceToHost));
+  b->results_cached = true;
+  return V2GT_OK;
+}
+
+// Eigen-style dense print with the stream's precision and aligned columns (info file)
+std::string eigen_print(const double *m, int R, int C, int precision = 6) {
+  std::vector<std::string> cells(R * C);
+  size_t width = 0;
+  for (int i = 0; i < R * C; i++) {
+    std::ostringstream o;
+    o << std::setprecision(precision) << m[i];
+    cells[i] = o.str();
+    width = std::max(width, cells[i].size());
+  }
+  std::ostringstream out;
+  for (int r = 0; r < R; r++) {
+    if (r)
+      out << "\n";
+    for (int c = 0; c < C; c++) {
+      if (c)
+        out << " ";
+      out << std::setw((int)width) << cells[r * C + c];
+    }
+  }
+  return out.str();
+}
+
+void make_dirs_for(const std::string &path) {
+  for (size_t i = 1; i < path.size(); i++)
+    if (path[i] == '/') {
+      std::string sub = path.substr(0, i);
+      mkdir(sub.c_str(), 0755);
+    }
+}
+
+} // namespace
+
+namespace v2 {
+// accessors used by eval.cu (the handle layout is private to this file)
+const DevPtrs *batch_devptrs(v2gt_batch *b) { return &b->d; }
+cudaStream_t batch_stream(v2gt_batch *b) { return b->stream; }
+int batch_device(v2gt_batch *b) { return b->device; }
+int batch_nmax(v2gt_batch *b) { return b->n_max; }
+bool batch_built(v2gt_batch *b) { return b->built; }
+bool batch_uploaded(v2gt_batch *b) { return b->uploaded; }
+void batch_invalidate(v2gt_batch *b) { b->results_cached = false; }
+} // namespace v2
+
+extern "C" {
+
+const char *v2gt_version(void) { return "vicon2gt_b200 0.1 (sm_100a, fp64)"; }
+
+void v2gt_params_default(v2gt_params *p) {
+  std::memset(p, 0, sizeof(*p));
+  const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  std::memcpy(p->R_GtoV, I, sizeof(I));
+  std::memcpy(p->R_BtoI, I, sizeof(I));
+  p->gravity_magnitude = 9.81;
+  p->estimate_toff_vicon_to_imu = 1;
+  p->estimate_ori_vicon_to_imu = 1;
+  p->estimate_pos_vicon_to_imu = 1;
+  p->num_loop_relin = 0;
+  p->sigma_w = 1.6968e-04;
+  p->sigma_wb = 1.9393e-05;
+  p->sigma_a = 2.0000e-3;
+  p->sigma_ab = 3.0000e-03;
+  p->lm_max_iterations = 30;
+  p->lm_max_tries = 0;
+  p->lm_lambda_initial = 1e-5;
+  p->lm_lambda_factor = 10.0;
+  p->lm_lambda_upper_bound = 1e20;
+  p->lm_lambda_lower_bound = 0.0;
+  p->lm_min_model_fidelity = 1e-3;
+  p->lm_relative_error_tol = 1e-30;
+  p->lm_absolute_error_tol = 1e-30;
+  p->huber_k = 1.345;
+  p->time_offset_window = 0.25;
+  p->interp_gap_init = 5.0;
+  p->interp_gap_factor = 0.1;
+}
+
+int v2gt_device_count(int32_t *count) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *count = 0;
+    cudaGetLastError();
+    return V2GT_ERR_NO_DEVICE;
+  }
+  *count = n;
+  return V2GT_OK;
+}
+
+int v2gt_batch_create(int32_t device, int32_t n_trials, v2gt_batch **out) {
+  if (!out || n_trials <= 0)
+    return V2GT_ERR_INVALID_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    fprintf(stderr, "[vicon2gt_b200] no CUDA device: this library has no CPU path\n");
+    return V2GT_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= n)
+    return V2GT_ERR_INVALID_ARG;
+  V2_CUDA_CHECK(cudaSetDevice(device));
+  v2gt_batch *b = new v2gt_batch();
+  b->device = device;
+  b->T = n_trials;
+  b->trials.resize(n_trials);
+  V2_CUDA_CHECK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 16; i++)
+    V2_CUDA_CHECK(cudaEventCreate(&b->ev[i]));
+  b->ev_ok = true;
+  *out = b;
+  return V2GT_OK;
+}
+
+int v2gt_batch_destroy(v2gt_batch *b) {
+  if (!b)
+    return V2GT_OK;
+  cudaSetDevice(b->device);
+  if (b->stream)
+    cudaStreamSynchronize(b->stream);
+  free_device(b);
+  if (b->ev_ok)
+    for (int i = 0; i < 16; i++)
+      cudaEventDestroy(b->ev[i]);
+  if (b->stream)
+    cudaStreamDestroy(b->stream);
+  delete b;
+  return V2GT_OK;
+}
+
+int v2gt_batch_set_option(v2gt_batch *b, const char *name, double value) {
+  if (!b || !name)
+    return V2GT_ERR_INVALID_ARG;
+  const std::string n(name);
+  if (n == "segments")
+    b->opt_segments = (int)value;
+  else if (n == "keep_cov")
+    b->opt_keep_cov = (int)value;
+  else if (n == "tries_per_sync")
+    b->opt_tries_per_sync = std::max(1, (int)value);
+  else
+    return V2GT_ERR_INVALID_ARG;
+  return V2GT_OK;
+}
+
+int v2gt_batch_set_trial(v2gt_batch *b, int32_t trial, const v2gt_params *params, int64_t n_imu, const double *imu_t,
+                         const double *imu_w, const double *imu_a, int64_t n_vicon, const double *vic_t, const double *vic_q,
+                         const double *vic_p, const double *vic_Rq, const double *vic_Rp, const double *vic_R_const,
+                         int64_t n_times, const double *state_t) {
+  if (!b || trial < 0 || trial >= b->T || !params || n_imu < 0 || n_vicon < 0 || n_times < 0)
+    return V2GT_ERR_INVALID_ARG;
+  if ((n_imu && (!imu_t || !imu_w || !imu_a)) || (n_vicon && (!vic_t || !vic_q || !vic_p)) || (n_times && !state_t))
+    return V2GT_ERR_INVALID_ARG;
+  if (n_vicon && !(vic_Rq && vic_Rp) && !vic_R_const)
+    return V2GT_ERR_INVALID_ARG;
+  HostTrial &h = b->trials[trial];
+  h = HostTrial();
+  h.prm = *params;
+  // ---- IMU: kept in feed order (Propagator::feed_imu appends)
+  h.imu_t.assign(imu_t, imu_t + n_imu);
+  h.imu_s.resize((size_t)n_imu * 8);
+  for (int64_t i = 0; i < n_imu; i++) {
+    double *o = &h.imu_s[(size_t)i * 8];
+    o[0] = imu_t[i];
+    o[1] = imu_w[3 * i];
+    o[2] = imu_w[3 * i + 1];
+    o[3] = imu_w[3 * i + 2];
+    o[4] = imu_a[3 * i];
+    o[5] = imu_a[3 * i + 1];
+    o[6] = imu_a[3 * i + 2];
+    o[7] = 0.0;
+  }
+  // ---- vicon: std::set<POSEDATA> keyed by timestamp -> stable sort + keep the first of equal keys
+  std::vector<int64_t> order((size_t)n_vicon);
+  std::iota(order.begin(), order.end(), (int64_t)0);
+  bool sorted = true;
+  for (int64_t i = 0; i + 1 < n_vicon; i++)
+    if (!(vic_t[i] < vic_t[i + 1])) {
+      sorted = false;
+      break;
+    }
+  if (!sorted)
+    std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return vic_t[x] < vic_t[y]; });
+  h.cov_const = !(vic_Rq && vic_Rp);
+  if (h.cov_const)
+    std::memcpy(h.vic_Rconst, vic_R_const, sizeof(h.vic_Rconst));
+  h.vic_t.reserve((size_t)n_vicon);
+  h.vic_s.reserve((size_t)n_vicon * 8);
+  if (!h.cov_const)
+    h.vic_c.reserve((size_t)n_vicon * 18);
+  for (int64_t k = 0; k < n_vicon; k++) {
+    const int64_t i = order[(size_t)k];
+    // time_min / time_max are updated for every fed pose, duplicates included (Interpolator.cpp:35-37)
+    h.vic_tmin = std::min(h.vic_tmin, vic_t[i]);
+    h.vic_tmax = std::max(h.vic_tmax, vic_t[i]);
+    if (!h.vic_t.empty() && h.vic_t.back() == vic_t[i])
+      continue;
+    h.vic_t.push_back(vic_t[i]);
+    const double row[8] = {vic_q[4 * i], vic_q[4 * i + 1], vic_q[4 * i + 2], vic_q[4 * i + 3],
+                           vic_p[3 * i], vic_p[3 * i + 1], vic_p[3 * i + 2], 0.0};
+    h.vic_s.insert(h.vic_s.end(), row, row + 8);
+    if (!h.cov_const) {
+      h.vic_c.insert(h.vic_c.end(), vic_Rq + 9 * i, vic_Rq + 9 * i + 9);
+      h.vic_c.insert(h.vic_c.end(), vic_Rp + 9 * i, vic_Rp + 9 * i + 9);
+    }
+  }
+  h.state_t_raw.assign(state_t, state_t + n_times);
+  h.set = true;
+  b->uploaded = false;
+  b->built = false;
+  b->results_cached = false;
+  return V2GT_OK;
+}
+
+int v2gt_batch_upload(v2gt_batch *b) {
+  if (!b)
+    return V2GT_ERR_INVALID_ARG;
+  V2_CUDA_CHECK(cudaSetDevice(b->device));
+  free_device(b);
+  b->results_cached = false;
+  const int T = b->T;
+  // ---- per-trial guards and timestamp cleaning (ViconGraphSolver.cpp:99-150)
+  std::vector<TrialDev> td(T);
+  std::vector<LmState> lm(T);
+  long long S = 0, M = 0, V = 0, C = 0;
+  b->n_max = 0;
+  for (int t = 0; t < T; t++) {
+    HostTrial &h = b->trials[t];
+    if (!h.set)
+      return V2GT_ERR_INVALID_ARG;
+    h.info = v2gt_trial_info{};
+    std::memset(&lm[t], 0, sizeof(LmState));
+    h.state_t.clear();
+    int status = V2GT_OK;
+    if (h.state_t_raw.empty())
+      status = V2GT_ERR_NO_TIMESTAMPS;
+    else if (h.vic_t.size() < 2)
+      status = V2GT_ERR_NO_VICON;
+    else {
+      const double first = h.vic_tmin + h.prm.toff_imu_to_vicon + 2 * h.prm.time_offset_window;
+      const double last = h.vic_tmax + h.prm.toff_imu_to_vicon - 2 * h.prm.time_offset_window;
+      // has_bounding_imu (Propagator.cpp:165-193): some sample <= t and some sample >= t seen before the
+      // scan breaks; for the time-ordered store this is t_imu[0] <= t <= t_imu[M-1].  The general
+      // (unordered) case is reproduced with running prefix extrema.
+      const size_t Mi = h.imu_t.size();
+      bool imu_sorted = true;
+      for (size_t i = 0; i + 1 < Mi; i++)
+        if (h.imu_t[i + 1] < h.imu_t[i]) {
+          imu_sorted = false;
+          break;
+        }
+      for (double ts : h.state_t_raw) {
+        bool bounded = false;
+        if (Mi > 0) {
+          if (imu_sorted) {
+            bounded = (h.imu_t.front() <= ts) && (h.imu_t.back() >= ts);
+          } else {
+            bool lo = false, hi = false;
+            for (size_t i = 0; i < Mi; i++) {
+              if (h.imu_t[i] <= ts)
+                lo = true;
+              if (h.imu_t[i] >= ts)
+                hi = true;
+              if (lo && hi)
+                break;
+            }
+            bounded = lo && hi;
+          }
+        }
+        if (!bounded)
+          h.info.removed_no_imu++;
+        else if (ts < first)
+          h.info.removed_before++;
+        else if (ts > last)
+          h.info.removed_after++;
+        else
+          h.state_t.push_back(ts);
+      }
+      if (h.state_t.empty())
+        status = V2GT_ERR_ALL_OUT_OF_RANGE;
+    }
+    h.info.status = status;
+    lm[t].status = status;
+    TrialDev &d = td[t];
+    std::memset(&d, 0, sizeof(d));
+    d.imu_off = M;
+    d.n_imu = (long long)h.imu_t.size();
+    d.vic_off = V;
+    d.n_vic = (long long)h.vic_t.size();
+    d.st_off = S;
+    d.n_raw = (status == V2GT_OK) ? (long long)h.state_t.size() : 0;
+    d.vic_cov_const = h.cov_const ? 1 : 0;
+    std::memcpy(d.vic_Rconst, h.vic_Rconst, sizeof(d.vic_Rconst));
+    d.prm = h.prm;
+    M += d.n_imu;
+    V += d.n_vic;
+    S += d.n_raw;
+    if (!h.cov_const)
+      C += d.n_vic;
+    b->n_max = std::max<int>(b->n_max, (int)d.n_raw);
+  }
+  // ---- segments per trial: enough warps to fill the GPU, never more than ~sqrt(n) per chain
+  int P = b->opt_segments;
+  if (P <= 0) {
+    const int target_warps = 148 * 24;
+    P = (target_warps + T - 1) / T;
+    const int cap = std::max(1, (int)std::ceil(std::sqrt((double)std::max(1, b->n_max)) * 1.0));
+    P = std::min(P, cap);
+  }
+  P = std::max(1, std::min(P, std::max(1, b->n_max / 2)));
+  DevPtrs &d = b->d;
+  std::memset(&d, 0, sizeof(d));
+  d.T = T;
+  d.S = S;
+  d.M = M;
+  d.V = V;
+  d.P = P;
+  d.nchunk = std::max(1, (b->n_max + V2GT_CHUNK - 1) / V2GT_CHUNK);
+  const int nasm = std::max(1, asm_chunks(b->n_max));
+
+  // ---- pinned staging + device arrays
+  double *h_imu_t, *h_imu_s, *h_vic_t, *h_vic_s, *h_vic_c, *h_st_t;
+  int *h_trial_of, *h_nst;
+  long long *h_coff;
+  V2_TRY(pin_alloc(b, &h_imu_t, (size_t)M));
+  V2_TRY(pin_alloc(b, &h_imu_s, (size_t)M * 8));
+  V2_TRY(pin_alloc(b, &h_vic_t, (size_t)V));
+  V2_TRY(pin_alloc(b, &h_vic_s, (size_t)V * 8));
+  V2_TRY(pin_alloc(b, &h_vic_c, (size_t)C * 18));
+  V2_TRY(pin_alloc(b, &h_st_t, (size_t)S));
+  V2_TRY(pin_alloc(b, &h_trial_of, (size_t)S));
+  V2_TRY(pin_alloc(b, &h_nst, (size_t)T));
+  V2_TRY(pin_alloc(b, &h_coff, (size_t)T));
+  V2_TRY(pin_alloc(b, &b->h_active, 1));
+  long long coff = 0;
+  for (int t = 0; t < T; t++) {
+    const HostTrial &h = b->trials[t];
+    const TrialDev &q = td[t];
+    if (q.n_imu) {
+      std::memcpy(h_imu_t + q.imu_off, h.imu_t.data(), sizeof(double) * q.n_imu);
+      std::memcpy(h_imu_s + 8 * q.imu_off, h.imu_s.data(), sizeof(double) * 8 * q.n_imu);
+    }
+    if (q.n_vic) {
+      std::memcpy(h_vic_t + q.vic_off, h.vic_t.data(), sizeof(double) * q.n_vic);
+      std::memcpy(h_vic_s + 8 * q.vic_off, h.vic_s.data(), sizeof(double) * 8 * q.n_vic);
+    }
+    if (!h.cov_const) {
+      h_coff[t] = coff * 18;
+      std::memcpy(h_vic_c + 18 * coff, h.vic_c.data(), sizeof(double) * 18 * q.n_vic);
+      coff += q.n_vic;
+    } else {
+      h_coff[t] = -1;
+    }
+    for (long long i = 0; i < q.n_raw; i++) {
+      h_st_t[q.st_off + i] = h.state_t[(size_t)i];
+      h_trial_of[q.st_off + i] = t;
+    }
+    h_nst[t] = (int)q.n_raw;
+  }
+  double *p_imu_t, *p_imu_s, *p_vic_t, *p_vic_s, *p_vic_c;
+  long long *p_coff;
+  TrialDev *p_trials;
+  V2_TRY(dev_alloc(b, &p_imu_t, (size_t)M));
+  V2_TRY(dev_alloc(b, &p_imu_s, (size_t)M * 8));
+  V2_TRY(dev_alloc(b, &p_vic_t, (size_t)V));
+  V2_TRY(dev_alloc(b, &p_vic_s, (size_t)V * 8));
+  V2_TRY(dev_alloc(b, &p_vic_c, (size_t)C * 18));
+  V2_TRY(dev_alloc(b, &p_coff, (size_t)T));
+  V2_TRY(dev_alloc(b, &p_trials, (size_t)T));
+  V2_TRY(dev_alloc(b, &d.n_states, (size_t)T));
+  V2_TRY(dev_alloc(b, &d.trial_of, (size_t)S));
+  V2_TRY(dev_alloc(b, &d.st_t, (size_t)S));
+  V2_TRY(dev_alloc(b, &d.st_t_tmp, (size_t)S));
+  V2_TRY(dev_alloc(b, &d.x, (size_t)2 * S * X_STRIDE));
+  V2_TRY(dev_alloc(b, &d.glob, (size_t)2 * T * GLOB_STRIDE));
+  V2_TRY(dev_alloc(b, &d.valid, (size_t)S));
+  V2_TRY(dev_alloc(b, &d.pre, (size_t)S * PRE_STRIDE));
+  V2_TRY(dev_alloc(b, &d.info, (size_t)S * INFO_STRIDE));
+  if (b->opt_keep_cov)
+    V2_TRY(dev_alloc(b, &d.cov, (size_t)S * 225));
+  V2_TRY(dev_alloc(b, &d.fpi, (size_t)S * FPI_STRIDE));
+  V2_TRY(dev_alloc(b, &d.fpv, (size_t)S * FPV_STRIDE));
+  V2_TRY(dev_alloc(b, &d.HD, (size_t)S * HD_STRIDE));
+  V2_TRY(dev_alloc(b, &d.HO, (size_t)S * HO_STRIDE));
+  V2_TRY(dev_alloc(b, &d.HB, (size_t)S * HB_STRIDE));
+  V2_TRY(dev_alloc(b, &d.Hg, (size_t)S * HG_STRIDE));
+  V2_TRY(dev_alloc(b, &d.fac, (size_t)S * FAC_STRIDE));
+  V2_TRY(dev_alloc(b, &d.seg, (size_t)T * P * SEG_STRIDE));
+  V2_TRY(dev_alloc(b, &d.red, (size_t)T * P * RED_STRIDE));
+  V2_TRY(dev_alloc(b, &d.xsep, (size_t)T * P * 16));
+  V2_TRY(dev_alloc(b, &d.delta, (size_t)S * 16));
+  V2_TRY(dev_alloc(b, &d.part_asm, (size_t)T * nasm * PART_STRIDE));
+  V2_TRY(dev_alloc(b, &d.part_cost, (size_t)T * d.nchunk * 2));
+  V2_TRY(dev_alloc(b, &d.gamma, (size_t)T * 96));
+  V2_TRY(dev_alloc(b, &d.xg, (size_t)T * 16));
+  V2_TRY(dev_alloc(b, &d.lm, (size_t)T));
+  V2_TRY(dev_alloc(b, &d.trace, (size_t)T * TRACE_MAX * 5));
+  V2_TRY(dev_alloc(b, &d.n_active, 1));
+  V2_TRY(dev_alloc(b, &d.removed_no_vicon, (size_t)T));
+  d.trials = p_trials;
+  d.imu_t = p_imu_t;
+  d.imu_s = p_imu_s;
+  d.vic_t = p_vic_t;
+  d.vic_s = p_vic_s;
+  d.vic_c = p_vic_c;
+  d.vic_c_off = p_coff;
+  cudaStream_t st = b->stream;
+  V2_CUDA_CHECK(cudaMemcpyAsync(p_imu_t, h_imu_t, sizeof(double) * M, cudaMemcpyHostToDevice, st));
+  V2_CUDA_CHECK(cudaMemcpyAsync(p_imu_s, h_imu_s, sizeof(double) * 8 * M, cudaMemcpyHostToDevice, st));
+  V2_CUDA_CHECK(cudaMemcpyAsync(p_vic_t, h_vic_t, sizeof(double) * V, cudaMemcpyHostToDevice, st));
+  V2_CUDA_CHECK(cudaMemcpyAsync(p_vic_s, h_vic_s, sizeof(double) * 8 * V, cudaMemcpyHostToDevice, st));
+  if (C)
+    V2_CUDA_CHECK(cudaMemcpyAsync(p_vic_c, h_vic_c, sizeof(double) * 18 * C, cudaMemcpyHostToDevice, st));
+  V2_CUDA_CHECK(cudaMemcpyAsync(p_coff, h_coff, sizeof(long long) * T, cudaMemcpyHostToDevice, st));
+  V2_CUDA_CHECK(cudaMemcpyAsync(d.st_t, h_st_t, sizeof(double) * S, cudaMemcpyHostToDevice, st));
+  V2_CUDA_CHECK(cudaMemcpyAsync(d.trial_of, h_trial_of, sizeof(int) * S, cudaMemcpyHostToDevice, st));
+  V2_CUDA_CHECK(cudaMemcpyAsync(d.n_states, h_nst, sizeof(int) * T, cudaMemcpyHostToDevice, st));
+  V2_CUDA_CHECK(cudaMemcpyAsync(p_trials, td.data(), sizeof(TrialDev) * T, cudaMemcpyHostToDevice, st));
+  V2_CUDA_CHECK(cudaMemcpyAsync(d.lm, lm.data(), sizeof(LmState) * T, cudaMemcpyHostToDevice, st));
+  V2_CUDA_CHECK(cudaMemsetAsync(d.removed_no_vicon, 0, sizeof(int) * T, st));
+  V2_CUDA_CHECK(cudaMemsetAsync(d.x, 0, sizeof(double) * 2 * S * X_STRIDE, st));
+  V2_CUDA_CHECK(cudaMemsetAsync(d.HO, 0, sizeof(double) * S * HO_STRIDE, st));
+  V2_CUDA_CHECK(cudaMemsetAsync(d.trace, 0, sizeof(double) * T * TRACE_MAX * 5, st));
+  V2_CUDA_CHECK(cudaMemsetAsync(d.xg, 0, sizeof(double) * T * 16, st));
+  V2_CUDA_CHECK(cudaStreamSynchronize(st)); // td / lm are stack-owned host vectors
+  b->uploaded = true;
+  b->built = false;
+  b->values_init = false;
+  for (int k = 0; k < 8; k++) {
+    b->ms[k] = 0;
+    b->launches[k] = 0;
+  }
+  return V2GT_OK;
+}
+
+// initial values of the four global nodes (ViconGraphSolver.cpp:400-413)
+static int init_globals(v2gt_batch *b) {
+  const int T = b->T;
+  std::vector<double> g((size_t)2 * T * GLOB_STRIDE, 0.0);
+  for (int t = 0; t < T; t++) {
+    const v2gt_params &p = b->trials[t].prm;
+    double q[4], rpy[3];
+    v2::rot_2_quat(p.R_BtoI, q);
+    v2::rot2rpy(p.R_GtoV, rpy);
+    for (int half = 0; half < 2; half++) {
+      double *o = &g[((size_t)half * T + t) * GLOB_STRIDE];
+      o[GL_Q] = q[0];
+      o[GL_Q + 1] = q[1];
+      o[GL_Q + 2] = q[2];
+      o[GL_Q + 3] = q[3];
+      o[GL_P] = p.p_BinI[0];
+      o[GL_P + 1] = p.p_BinI[1];
+      o[GL_P + 2] = p.p_BinI[2];
+      o[GL_TOFF] = p.toff_imu_to_vicon;
+      o[GL_THX] = rpy[0];
+      o[GL_THY] = rpy[1];
+    }
+  }
+  V2_CUDA_CHECK(cudaMemcpyAsync(b->d.glob, g.data(), sizeof(double) * g.size(), cudaMemcpyHostToDevice, b->stream));
+  V2_CUDA_CHECK(cudaStreamSynchronize(b->stream));
+  return V2GT_OK;
+}
+
+int v2gt_batch_build(v2gt_batch *b, int32_t init_states) {
+  if (!b)
+    return V2GT_ERR_INVALID_ARG;
+  V2_CUDA_CHECK(cudaSetDevice(b->device));
+  if (!b->uploaded)
+    V2_TRY(v2gt_batch_upload(b));
+  b->results_cached = false;
+  if (init_states) {
+    V2_TRY(init_globals(b));
+    b->values_init = true;
+  } else if (!b->values_init) {
+    return V2GT_ERR_NOT_BUILT;
+  }
+  V2_CUDA_CHECK(cudaEventRecord(b->ev[0], b->stream));
+  V2_TRY(launch_init_states(b->d, b->n_max, init_states ? 1 : 0, b->stream));
+  std::swap(b->d.st_t, b->d.st_t_tmp); // k_compact wrote the surviving times into st_t_tmp
+  V2_TRY(launch_preintegrate(b->d, b->n_max, b->opt_keep_cov, b->stream));
+  V2_CUDA_CHECK(cudaEventRecord(b->ev[1], b->stream));
+  b->launches[0] += 3;
+  b->built = true;
+  return V2GT_OK;
+}
+
+int v2gt_batch_optimize(v2gt_batch *b) {
+  if (!b)
+    return V2GT_ERR_INVALID_ARG;
+  if (!b->built)
+    return V2GT_ERR_NOT_BUILT;
+  V2_CUDA_CHECK(cudaSetDevice(b->device));
+  b->results_cached = false;
+  cudaStream_t st = b->stream;
+  const DevPtrs &d = b->d;
+  V2_CUDA_CHECK(cudaEventRecord(b->ev[2], st));
+  V2_TRY(launch_cost(d, b->n_max, 0, 1, st));
+  V2_TRY(launch_lm_begin(d, st));
+  b->launches[5] += 1;
+  b->launches[6] += 1;
+  // worst case number of tries: every outer iteration may walk lambda from its floor to the upper bound
+  int max_rounds = 0;
+  for (int t = 0; t < b->T; t++) {
+    const v2gt_params &p = b->trials[t].prm;
+    const double span = std::log(std::max(p.lm_lambda_upper_bound, 1.0) / std::max(1e-300, std::min(p.lm_lambda_initial, 1e-30))) /
+                        std::log(std::max(p.lm_lambda_factor, 1.0001));
+    int r = (int)((p.lm_max_iterations + 1) * (span + 2));
+    if (p.lm_max_tries > 0)
+      r = std::min(r, p.lm_max_tries + 1);
+    max_rounds = std::max(max_rounds, r);
+  }
+  int rounds = 0;
+  while (rounds < max_rounds) {
+    const int chunk = b->opt_tries_per_sync;
+    V2_CUDA_CHECK(cudaMemsetAsync(d.n_active, 0, sizeof(int), st));
+    for (int k = 0; k < chunk; k++) {
+      V2_TRY(launch_lm_pre_try(d, st));
+      V2_TRY(launch_linearize(d, b->n_max, 0, st));
+      V2_TRY(launch_solve(d, 0, st));
+      V2_TRY(launch_cost(d, b->n_max, 1, 0, st));
+      V2_TRY(launch_lm_decide(d, k == chunk - 1 ? 1 : 0, st));
+      b->launches[1] += 3;
+      b->launches[2] += 1;
+      b->launches[3] += 1;
+      b->launches[4] += 1;
+      b->launches[5] += 1;
+      b->launches[6] += 2;
+    }
+    rounds += chunk;
+    V2_CUDA_CHECK(cudaMemcpyAsync(b->h_active, d.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+    V2_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (*b->h_active == 0)
+      break;
+  }
+  V2_CUDA_CHECK(cudaEventRecord(b->ev[3], st));
+  V2_CUDA_CHECK(cudaStreamSynchronize(st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, b->ev[0], b->ev[1]);
+  b->ms[0] = ms;
+  cudaEventElapsedTime(&ms, b->ev[2], b->ev[3]);
+  b->ms[7] = ms;
+  return V2GT_OK;
+}
+
+int v2gt_batch_build_and_solve(v2gt_batch *b) {
+  if (!b)
+    return V2GT_ERR_INVALID_ARG;
+  if (!b->uploaded)
+    V2_TRY(v2gt_batch_upload(b));
+  int loops = 0;
+  for (int t = 0; t < b->T; t++)
+    loops = std::max(loops, (int)b->trials[t].prm.num_loop_relin);
+  for (int i = 0; i <= loops; i++) {
+    V2_TRY(v2gt_batch_build(b, i == 0 ? 1 : 0));
+    V2_TRY(v2gt_batch_optimize(b));
+  }
+  return V2GT_OK;
+}
+
+int v2gt_batch_sync(v2gt_batch *b) {
+  if (!b)
+    return V2GT_ERR_INVALID_ARG;
+  V2_CUDA_CHECK(cudaSetDevice(b->device));
+  V2_CUDA_CHECK(cudaStreamSynchronize(b->stream));
+  return V2GT_OK;
+}
+
+int v2gt_batch_get_info(v2gt_batch *b, int32_t trial, v2gt_trial_info *info) {
+  if (!b || !info || trial < 0 || trial >= b->T)
+    return V2GT_ERR_INVALID_ARG;
+  *info = b->trials[trial].info;
+  if (!b->uploaded)
+    return V2GT_OK;
+  V2_CUDA_CHECK(cudaSetDevice(b->device));
+  V2_TRY(fetch_results(b));
+  const LmState &lm = b->h_lm[trial];
+  info->status = lm.status;
+  info->n_states = b->h_nstates[trial];
+  info->removed_no_vicon = b->h_removed[trial];
+  info->iterations = lm.iterations;
+  info->tries = lm.tries;
+  info->linearizations = lm.linearizations;
+  info->lm_state = lm.lm_state;
+  info->initial_error = lm.initial_error;
+  info->final_error = lm.error;
+  info->lambda = lm.lambda;
+  return V2GT_OK;
+}
+
+int v2gt_batch_get_states(v2gt_batch *b, int32_t trial, int64_t capacity, double *times, double *states, int64_t *n_out) {
+  if (!b || trial < 0 || trial >= b->T || !b->built)
+    return b && !b->built ? V2GT_ERR_NOT_BUILT : V2GT_ERR_INVALID_ARG;
+  V2_CUDA_CHECK(cudaSetDevice(b->device));
+  V2_TRY(fetch_results(b));
+  const int n = b->h_nstates[trial];
+  if (n_out)
+    *n_out = n;
+  if (capacity < n)
+    return (times || states) ? V2GT_ERR_INVALID_ARG : V2GT_OK;
+  std::vector<TrialDev> td(1);
+  V2_CUDA_CHECK(cudaMemcpy(td.data(), b->d.trials + trial, sizeof(TrialDev), cudaMemcpyDeviceToHost));
+  const long long off = td[0].st_off;
+  const int cur = b->h_lm[trial].cur;
+  if (times && n)
+    V2_CUDA_CHECK(cudaMemcpy(times, b->d.st_t + off, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  if (states && n)
+    V2_CUDA_CHECK(cudaMemcpy(states, b->d.x + ((long long)cur * b->d.S + off) * X_STRIDE, sizeof(double) * n * X_STRIDE,
+                             cudaMemcpyDeviceToHost));
+  return V2GT_OK;
+}
+
+int v2gt_batch_get_calibration(v2gt_batch *b, int32_t trial, double *q_BtoI, double *p_BinI, double *t_off, double *theta_xy) {
+  if (!b || trial < 0 || trial >= b->T || !b->values_init)
+    return b && !b->values_init ? V2GT_ERR_NOT_BUILT : V2GT_ERR_INVALID_ARG;
+  V2_CUDA_CHECK(cudaSetDevice(b->device));
+  V2_TRY(fetch_results(b));
+  const int cur = b->h_lm[trial].cur;
+  double g[GLOB_STRIDE];
+  V2_CUDA_CHECK(cudaMemcpy(g, b->d.glob + ((long long)cur * b->T + trial) * GLOB_STRIDE, sizeof(g), cudaMemcpyDeviceToHost));
+  if (q_BtoI)
+    std::memcpy(q_BtoI, g + GL_Q, 4 * sizeof(double));
+  if (p_BinI)
+    std::memcpy(p_BinI, g + GL_P, 3 * sizeof(double));
+  if (t_off)
+    *t_off = g[GL_TOFF];
+  if (theta_xy) {
+    theta_xy[0] = g[GL_THX];
+    theta_xy[1] = g[GL_THY];
+  }
+  return V2GT_OK;
+}
+
+int v2gt_batch_write_to_file(v2gt_batch *b, int32_t trial, const char *csv_path, const char *info_path) {
+  if (!b || !csv_path || !info_path)
+    return V2GT_ERR_INVALID_ARG;
+  int64_t n = 0;
+  V2_TRY(v2gt_batch_get_states(b, trial, 0, nullptr, nullptr, &n));
+  std::vector<double> times((size_t)n), X((size_t)n * 16);
+  V2_TRY(v2gt_batch_get_states(b, trial, n, times.data(), X.data(), &n));
+  double q_BtoI[4], p_BinI[3], toff, th[2];
+  V2_TRY(v2gt_batch_get_calibration(b, trial, q_BtoI, p_BinI, &toff, th));
+  std::remove(csv_path);
+  std::remove(info_path);
+  make_dirs_for(csv_path);
+  make_dirs_for(info_path);
+  std::ofstream of_state(csv_path, std::ofstream::out | std::ofstream::app);
+  if (!of_state)
+    return V2GT_ERR_INVALID_ARG;
+  of_state << "#time(ns),px,py,pz,qw,qx,qy,qz,vx,vy,vz,bwx,bwy,bwz,bax,bay,baz" << std::endl;
+  double R_GtoV[9], q_GtoV[4];
+  v2::rot_xy(th[0], th[1], R_GtoV);
+  v2::rot_2_quat(R_GtoV, q_GtoV);
+  for (int64_t i = 0; i < n; i++) {
+    const double *x = &X[(size_t)i * 16];
+    double q[4], p[3], v[3];
+    v2::quat_mul(x, q_GtoV, q);
+    v2::mv3_t(R_GtoV, x + 13, p);
+    v2::mv3_t(R_GtoV, x + 7, v);
+    of_state << std::setprecision(20) << std::floor(1e9 * times[(size_t)i]) << "," << std::setprecision(6) << p[0] << "," << p[1]
+             << "," << p[2] << "," << q[3] << "," << q[0] << "," << q[1] << "," << q[2] << "," << v[0] << "," << v[1] << "," << v[2]
+             << "," << x[4] << "," << x[5] << "," << x[6] << "," << x[10] << "," << x[11] << "," << x[12] << std::endl;
+  }
+  of_state.close();
+  std::ofstream of_info(info_path, std::ofstream::out | std::ofstream::app);
+  if (!of_info)
+    return V2GT_ERR_INVALID_ARG;
+  double R_BtoI[9];
+  v2::quat_2_Rot(q_BtoI, R_BtoI);
+  of_info << "R_BtoI: " << std::endl << eigen_print(R_BtoI, 3, 3) << std::endl << std::endl;
+  of_info << "q_BtoI: " << std::endl << eigen_print(q_BtoI, 4, 1) << std::endl << std::endl;
+  of_info << "p_BinI: " << std::endl << eigen_print(p_BinI, 3, 1) << std::endl << std::endl;
+  of_info << "R_GtoV: " << std::endl << eigen_print(R_GtoV, 3, 3) << std::endl << std::endl;
+  of_info << "R_GtoV (thetax, thetay): " << std::endl;
+  of_info << th[0] << " " << th[0] << std::endl << std::endl; // thetax printed twice, as the reference does (.cpp:244)
+  of_info << "gravity norm: " << std::endl << b->trials[trial].prm.gravity_magnitude << std::endl << std::endl;
+  of_info << "t_off_vicon_to_imu: " << std::endl << eigen_print(&toff, 1, 1) << std::endl << std::endl;
+  of_info.close();
+  return V2GT_OK;
+}
+
+int v2gt_batch_get_timing(v2gt_batch *b, double *ms, int64_t *launches) {
+  if (!b)
+    return V2GT_ERR_INVALID_ARG;
+  for (int k = 0; k < 8; k++) {
+    if (ms)
+      ms[k] = b->ms[k];
+    if (launches)
+      launches[k] = b->launches[k];
+  }
+  return V2GT_OK;
+}
+
+int v2gt_batch_get_lm_trace(v2gt_batch *b, int32_t trial, int64_t capacity, double *rows, int64_t *n_out) {
+  if (!b || trial < 0 || trial >= b->T || !b->built)
+    return V2GT_ERR_INVALID_ARG;
+  V2_CUDA_CHECK(cudaSetDevice(b->device));
+  V2_TRY(fetch_results(b));
+  const int n = b->h_lm[trial].n_trace;
+  if (n_out)
+    *n_out = n;
+  const int m = (int)std::min<int64_t>(n, capacity);
+  if (rows && m > 0)
+    V2_CUDA_CHECK(cudaMemcpy(rows, b->d.trace + (long long)trial * TRACE_MAX * 5, sizeof(double) * 5 * m, cudaMemcpyDeviceToHost));
+  return V2GT_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,622 @@
+// vicon2gt_b200 kernels (3) and (4a): factor evaluation and normal-equation assembly.
+//
+//   k_factor_eval<JAC>  one thread per state: vicon factor of the state + IMU factor to the next
+//                       state; cost partials (always) and Jacobian pieces (JAC)
+//   k_assemble          five threads per state (one per 3-column block of the state): the
+//                       state's 15x15 diagonal block, its 15x15 coupling to the next state, its
+//                       15x9 border and gradient, straight from the 3x3 block structure of the
+//                       Jacobians (H1 has 13 non-zero 3x3 blocks, H2 five) and the information
+//                       matrix; each state owns its blocks, no atomics
+//   k_reduce_gamma      fixed-order reduction of the 9x9 global block / gradient / linear error
+// Replaces GTSAM's NonlinearFactorGraph::linearize + error for the graph built in
+// ViconGraphSolver::build_problem (SURVEY Appendix B gives the block structure).
+#include "v2gt_factors.cuh"
+#include <stdio.h>
+
+namespace v2 {
+
+// ------------------------------------------------------------------------------------------------
+// grid (nchunk, T), V2GT_CHUNK threads.  which = 0: evaluate the current estimate, 1: the trial point.
+template <bool JAC>
+__global__ void __launch_bounds__(V2GT_CHUNK) k_factor_eval(DevPtrs d, int which, int force_all) {
+  const int t = blockIdx.y;
+  const LmState &lm = d.lm[t];
+  __shared__ double s_red[2][V2GT_CHUNK / 32];
+  // trial-level predicates are uniform across the CTA
+  if (!force_all) {
+    if (lm.lm_state != 0 || lm.status != V2GT_OK)
+      return;
+    if (JAC && !lm.need_lin)
+      return;
+    if (!JAC && lm.solve_failed)
+      return;
+  }
+  const TrialDev &tr = d.trials[t];
+  const int n = d.n_states[t];
+  const int i = blockIdx.x * V2GT_CHUNK + threadIdx.x;
+  const int buf = which ? (1 - lm.cur) : lm.cur;
+  double cost = 0.0, lin0 = 0.0;
+  if (i < n) {
+    const long long s = tr.st_off + i;
+    const double *gl = d.glob + ((long long)buf * d.T + t) * GLOB_STRIDE;
+    const double *xb = d.x + (long long)buf * d.S * X_STRIDE;
+    double xi[16];
+    {
+      const double4 *p4 = reinterpret_cast<const double4 *>(xb + s * X_STRIDE);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const double4 v = p4[k];
+        xi[4 * k] = v.x; xi[4 * k + 1] = v.y; xi[4 * k + 2] = v.z; xi[4 * k + 3] = v.w;
+      }
+    }
+    // ---- vicon factor
+    {
+      ViconPieces vp;
+      const bool cc = tr.vic_cov_const != 0;
+      const double *vc = cc ? tr.vic_Rconst : d.vic_c + d.vic_c_off[t];
+      vicon_factor<JAC>(tr, d.vic_t + tr.vic_off, d.vic_s + 8 * tr.vic_off, vc, cc, d.st_t[s], xi, gl, vp);
+      cost += huber_loss(tr.prm.huber_k, vp.dist);
+      double r2 = 0;
+#pragma unroll
+      for (int k = 0; k < 6; k++)
+        r2 += vp.r[k] * vp.r[k];
+      lin0 += 0.5 * r2;
+      if (JAC) {
+        double *o = d.fpv + s * FPV_STRIDE;
+#pragma unroll
+        for (int k = 0; k < 6; k++)
+          o[FPV_R + k] = vp.r[k];
+#pragma unroll
+        for (int k = 0; k < 36; k++)
+          o[FPV_A + k] = vp.A[k];
+#pragma unroll
+        for (int k = 0; k < 42; k++)
+          o[FPV_G + k] = vp.G[k];
+        o[FPV_HAS] = vp.has;
+        o[FPV_IDX0] = vp.idx0;
+        o[FPV_IDX1] = vp.idx1;
+        o[FPV_W] = vp.w;
+      }
+    }
+    // ---- IMU factor i -> i+1
+    if (i < n - 1) {
+      double xj[16];
+      {
+        const double4 *p4 = reinterpret_cast<const double4 *>(xb + (s + 1) * X_STRIDE);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const double4 v = p4[k];
+          xj[4 * k] = v.x; xj[4 * k + 1] = v.y; xj[4 * k + 2] = v.z; xj[4 * k + 3] = v.w;
+        }
+      }
+      GravTerms G;
+      grav_terms(gl[GL_THX], gl[GL_THY], tr.prm.gravity_magnitude, G);
+      ImuPieces ip;
+      imu_factor<JAC>(d.pre + s * PRE_STRIDE, xi, xj, G, ip);
+      const double q = 0.5 * quad_form15(d.info + s * INFO_STRIDE, ip.e);
+      cost += q;
+      lin0 += q;
+      if (JAC) {
+        double *o = d.fpi + s * FPI_STRIDE;
+#pragma unroll
+        for (int k = 0; k < 15; k++)
+          o[FPI_E + k] = ip.e[k];
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+          o[FPI_TTH + k] = ip.Tth[k];
+          o[FPI_TB + k] = ip.Tb[k];
+          o[FPI_RK + k] = ip.Rk[k];
+          o[FPI_JTH2 + k] = ip.Jth2[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          o[FPI_SV + k] = ip.sv[k];
+          o[FPI_SP + k] = ip.sp[k];
+        }
+      }
+    }
+  }
+  // ---- fixed-order CTA reduction of (cost, lin0)
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cost += __shfl_down_sync(0xffffffffu, cost, o);
+    lin0 += __shfl_down_sync(0xffffffffu, lin0, o);
+  }
+  if (lane == 0) {
+    s_red[0][wid] = cost;
+    s_red[1][wid] = lin0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double c = 0, l = 0;
+    for (int w = 0; w < V2GT_CHUNK / 32; w++) {
+      c += s_red[0][w];
+      l += s_red[1][w];
+    }
+    double *pc = d.part_cost + ((long long)t * d.nchunk + blockIdx.x) * 2;
+    pc[0] = c;
+    pc[1] = l;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+constexpr int ASM_STATES = 64;            // states per CTA
+constexpr int ASM_THREADS = ASM_STATES * 5;
+
+// 3x3 helpers on registers:  C += A B, C += A^T B, C -= ...
+__device__ __forceinline__ void mm3_acc(const double *A, const double *B, double *C) {
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+      C[3 * r + c] += A[3 * r] * B[c] + A[3 * r + 1] * B[3 + c] + A[3 * r + 2] * B[6 + c];
+}
+__device__ __forceinline__ void mm3_tn_acc(const double *A, const double *B, double *C) {
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+      C[3 * r + c] += A[r] * B[c] + A[3 + r] * B[3 + c] + A[6 + r] * B[6 + c];
+}
+__device__ __forceinline__ void zero9(double *A) {
+#pragma unroll
+  for (int e = 0; e < 9; e++)
+    A[e] = 0.0;
+}
+__device__ __forceinline__ void ld9(const double *__restrict__ p, double *o) {
+#pragma unroll
+  for (int e = 0; e < 9; e++)
+    o[e] = __ldg(p + e);
+}
+
+// H1 block (row-block a, column-block dcol) of the IMU factor; returns false when the block is zero.
+// kind: 0 dense in M, 1 = -I, (others dense).   fpi: pieces row, pre: preintegration row.
+__device__ __forceinline__ bool h1_block(const double *__restrict__ fpi, const double *__restrict__ pre, int a, int dcol,
+                                         double *M) {
+  // rows a: 0 th, 1 bg, 2 v, 3 ba, 4 p
+  if (dcol == 0) {
+    if (a == 0) { ld9(fpi + FPI_TTH, M); return true; }
+    if (a == 2) { double s[3] = {__ldg(fpi + FPI_SV), __ldg(fpi + FPI_SV + 1), __ldg(fpi + FPI_SV + 2)}; skew(s, M); return true; }
+    if (a == 4) { double s[3] = {__ldg(fpi + FPI_SP), __ldg(fpi + FPI_SP + 1), __ldg(fpi + FPI_SP + 2)}; skew(s, M); return true; }
+    return false;
+  }
+  if (dcol == 1) {
+    if (a == 0) { ld9(fpi + FPI_TB, M); return true; }
+    if (a == 1) { eye3(M); for (int e = 0; e < 9; e++) M[e] = -M[e]; return true; }
+    if (a == 2) { ld9(pre + PRE_JB, M); for (int e = 0; e < 9; e++) M[e] = -M[e]; return true; }
+    if (a == 4) { ld9(pre + PRE_JA, M); for (int e = 0; e < 9; e++) M[e] = -M[e]; return true; }
+    return false;
+  }
+  if (dcol == 2) {
+    if (a == 2) { ld9(fpi + FPI_RK, M); for (int e = 0; e < 9; e++) M[e] = -M[e]; return true; }
+    if (a == 4) { const double dt = __ldg(pre + PRE_DT); ld9(fpi + FPI_RK, M); for (int e = 0; e < 9; e++) M[e] = -dt * M[e]; return true; }
+    return false;
+  }
+  if (dcol == 3) {
+    if (a == 2) { ld9(pre + PRE_HB, M); for (int e = 0; e < 9; e++) M[e] = -M[e]; return true; }
+    if (a == 3) { eye3(M); for (int e = 0; e < 9; e++) M[e] = -M[e]; return true; }
+    if (a == 4) { ld9(pre + PRE_HA, M); for (int e = 0; e < 9; e++) M[e] = -M[e]; return true; }
+    return false;
+  }
+  // dcol == 4
+  if (a == 4) { ld9(fpi + FPI_RK, M); for (int e = 0; e < 9; e++) M[e] = -M[e]; return true; }
+  return false;
+}
+// H2 diagonal block c of the IMU factor
+__device__ __forceinline__ void h2_block(const double *__restrict__ fpi, int c, double *M) {
+  if (c == 0)
+    ld9(fpi + FPI_JTH2, M);
+  else if (c == 2 || c == 4)
+    ld9(fpi + FPI_RK, M);
+  else
+    eye3(M);
+}
+// H3 row blocks (v and p rows), 3x2 each:  R dt g Hxy  and  1/2 R dt^2 g Hxy   (ImuFactorCPIv1.cpp:199-201)
+__device__ __forceinline__ void h3_blocks(const double *__restrict__ fpi, const double *__restrict__ pre, const GravTerms &G,
+                                          double *H3v, double *H3p) {
+  double Rk[9];
+  ld9(fpi + FPI_RK, Rk);
+  const double dt = __ldg(pre + PRE_DT);
+  const double dt2 = dt * dt;
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      const double a = ((Rk[3 * r] * dt) * G.gmag) * G.Hxy[c] + ((Rk[3 * r + 1] * dt) * G.gmag) * G.Hxy[2 + c] +
+                       ((Rk[3 * r + 2] * dt) * G.gmag) * G.Hxy[4 + c];
+      const double b = (((0.5 * Rk[3 * r]) * dt2) * G.gmag) * G.Hxy[c] + (((0.5 * Rk[3 * r + 1]) * dt2) * G.gmag) * G.Hxy[2 + c] +
+                       (((0.5 * Rk[3 * r + 2]) * dt2) * G.gmag) * G.Hxy[4 + c];
+      H3v[2 * r + c] = a;
+      H3p[2 * r + c] = b;
+    }
+}
+
+// grid (ceil(n_max / ASM_STATES), T), ASM_THREADS threads
+__global__ void __launch_bounds__(ASM_THREADS) k_assemble(DevPtrs d, int force_all) {
+  const int t = blockIdx.y;
+  const LmState &lm = d.lm[t];
+  if (!force_all && (lm.lm_state != 0 || lm.status != V2GT_OK || !lm.need_lin))
+    return;
+  const TrialDev &tr = d.trials[t];
+  const int n = d.n_states[t];
+  const int li = threadIdx.x / 5, dcol = threadIdx.x % 5;
+  const int i = blockIdx.x * ASM_STATES + li;
+  __shared__ double s_part[ASM_STATES][PART_STRIDE + 1];
+  for (int k = threadIdx.x; k < ASM_STATES * (PART_STRIDE + 1); k += ASM_THREADS)
+    (&s_part[0][0])[k] = 0.0;
+  __syncthreads();
+  if (i < n) {
+    const long long s = tr.st_off + i;
+    const double *gl = d.glob + ((long long)lm.cur * d.T + t) * GLOB_STRIDE;
+    GravTerms G;
+    grav_terms(gl[GL_THX], gl[GL_THY], tr.prm.gravity_magnitude, G);
+    double Dcol[5][9]; // D[c][dcol], c = 0..4
+    double Bg[6];      // B[dcol][7:9]  3x2
+    double gv[3];      // g[dcol]
+#pragma unroll
+    for (int c = 0; c < 5; c++)
+      zero9(Dcol[c]);
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+      Bg[k] = 0.0;
+    gv[0] = gv[1] = gv[2] = 0.0;
+    double *HO = d.HO + s * HO_STRIDE;
+
+    // ================= H1-type contributions of factor i (i -> i+1)
+    if (i < n - 1) {
+      const double *fpi = d.fpi + s * FPI_STRIDE;
+      const double *pre = d.pre + s * PRE_STRIDE;
+      const double *inf = d.info + s * INFO_STRIDE;
+      double Y[5][9]; // Y[a] = sum_b Lambda_ab H1[b][dcol]
+#pragma unroll
+      for (int a = 0; a < 5; a++)
+        zero9(Y[a]);
+#pragma unroll
+      for (int b = 0; b < 5; b++) {
+        double Hb[9];
+        if (!h1_block(fpi, pre, b, dcol, Hb))
+          continue;
+#pragma unroll
+        for (int a = 0; a < 5; a++) {
+          double L[9];
+          ld_sym_blk(inf, a, b, L);
+          mm3_acc(L, Hb, Y[a]);
+        }
+      }
+      // D1[c][dcol] = sum_a H1[a][c]^T Y[a]
+#pragma unroll
+      for (int c = 0; c < 5; c++) {
+#pragma unroll
+        for (int a = 0; a < 5; a++) {
+          double Hc[9];
+          if (!h1_block(fpi, pre, a, c, Hc))
+            continue;
+          mm3_tn_acc(Hc, Y[a], Dcol[c]);
+        }
+      }
+      // O[dcol][e] = Y[e]^T H2[e][e]
+#pragma unroll
+      for (int e = 0; e < 5; e++) {
+        double H2e[9], Ob[9];
+        h2_block(fpi, e, H2e);
+        zero9(Ob);
+        mm3_tn_acc(Y[e], H2e, Ob);
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+          for (int c = 0; c < 3; c++)
+            HO[(3 * dcol + r) * 15 + 3 * e + c] = Ob[3 * r + c];
+      }
+      // B1[dcol] = Y[v]^T H3v + Y[p]^T H3p ; g1[dcol] = -sum_a Y[a]^T e[a]
+      double H3v[6], H3p[6];
+      h3_blocks(fpi, pre, G, H3v, H3p);
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          double sacc = 0;
+#pragma unroll
+          for (int k = 0; k < 3; k++)
+            sacc += Y[2][3 * k + r] * H3v[2 * k + c] + Y[4][3 * k + r] * H3p[2 * k + c];
+          Bg[2 * r + c] += sacc;
+        }
+#pragma unroll
+      for (int a = 0; a < 5; a++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+          double sacc = 0;
+#pragma unroll
+          for (int k = 0; k < 3; k++)
+            sacc += Y[a][3 * k + r] * __ldg(fpi + FPI_E + 3 * a + k);
+          gv[r] -= sacc;
+        }
+      // gravity 2x2 block and gradient of this factor (thread dcol == 3 owns it)
+      if (dcol == 3) {
+        // Lambda rows v and p applied to H3 and e
+        double LH[2][6]; // (Lambda H3)[a] for a = v, p  (3x2)
+        double Le[2][3];
+#pragma unroll
+        for (int ai = 0; ai < 2; ai++) {
+          const int a = (ai == 0) ? 2 : 4;
+          double Lv[9], Lp[9];
+          ld_sym_blk(inf, a, 2, Lv);
+          ld_sym_blk(inf, a, 4, Lp);
+#pragma unroll
+          for (int r = 0; r < 3; r++) {
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+              double sacc = 0;
+#pragma unroll
+              for (int k = 0; k < 3; k++)
+                sacc += Lv[3 * r + k] * H3v[2 * k + c] + Lp[3 * r + k] * H3p[2 * k + c];
+              LH[ai][2 * r + c] = sacc;
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < 3; r++) {
+            double sacc = 0;
+#pragma unroll
+            for (int bb = 0; bb < 5; bb++) {
+              double Lb[9];
+              ld_sym_blk(inf, a, bb, Lb);
+#pragma unroll
+              for (int k = 0; k < 3; k++)
+                sacc += Lb[3 * r + k] * __ldg(fpi + FPI_E + 3 * bb + k);
+            }
+            Le[ai][r] = sacc;
+          }
+        }
+        double *sp = s_part[li];
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+#pragma unroll
+          for (int c = 0; c < 2; c++) {
+            double sacc = 0;
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+              sacc += H3v[2 * k + r] * LH[0][2 * k + c] + H3p[2 * k + r] * LH[1][2 * k + c];
+            sp[56 + 2 * r + c] = sacc;
+          }
+          double sg = 0;
+#pragma unroll
+          for (int k = 0; k < 3; k++)
+            sg += H3v[2 * k + r] * Le[0][k] + H3p[2 * k + r] * Le[1][k];
+          sp[60 + r] = -sg;
+        }
+      }
+    } else {
+      // last state: no coupling block
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 15; c++)
+          HO[(3 * dcol + r) * 15 + c] = 0.0;
+    }
+
+    // ================= H2-type contributions of factor i-1 (i-1 -> i)
+    if (i > 0) {
+      const double *fpi = d.fpi + (s - 1) * FPI_STRIDE;
+      const double *pre = d.pre + (s - 1) * PRE_STRIDE;
+      const double *inf = d.info + (s - 1) * INFO_STRIDE;
+      double H2d[9];
+      h2_block(fpi, dcol, H2d);
+      // D2[c][dcol] = H2[c]^T Lambda_{c,dcol} H2[dcol]
+#pragma unroll
+      for (int c = 0; c < 5; c++) {
+        double L[9], T[9], H2c[9];
+        ld_sym_blk(inf, c, dcol, L);
+        zero9(T);
+        mm3_acc(L, H2d, T);
+        h2_block(fpi, c, H2c);
+        mm3_tn_acc(H2c, T, Dcol[c]);
+      }
+      // B2[dcol] = H2[dcol]^T (Lambda_{d,v} H3v + Lambda_{d,p} H3p) ; g2[dcol] = -H2[dcol]^T sum_a Lambda_{d,a} e_a
+      double H3v[6], H3p[6];
+      h3_blocks(fpi, pre, G, H3v, H3p);
+      double Lv[9], Lp[9], U[6], le[3] = {0, 0, 0};
+      ld_sym_blk(inf, dcol, 2, Lv);
+      ld_sym_blk(inf, dcol, 4, Lp);
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          double sacc = 0;
+#pragma unroll
+          for (int k = 0; k < 3; k++)
+            sacc += Lv[3 * r + k] * H3v[2 * k + c] + Lp[3 * r + k] * H3p[2 * k + c];
+          U[2 * r + c] = sacc;
+        }
+#pragma unroll
+      for (int a = 0; a < 5; a++) {
+        double L[9];
+        ld_sym_blk(inf, dcol, a, L);
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+          for (int k = 0; k < 3; k++)
+            le[r] += L[3 * r + k] * __ldg(fpi + FPI_E + 3 * a + k);
+      }
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          double sacc = 0;
+#pragma unroll
+          for (int k = 0; k < 3; k++)
+            sacc += H2d[3 * k + r] * U[2 * k + c];
+          Bg[2 * r + c] += sacc;
+        }
+        double sg = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+          sg += H2d[3 * k + r] * le[k];
+        gv[r] -= sg;
+      }
+    }
+
+    // ================= vicon factor of state i
+    const double *fpv = d.fpv + s * FPV_STRIDE;
+    double Bv[21]; // B[dcol][0:7]  3x7
+#pragma unroll
+    for (int k = 0; k < 21; k++)
+      Bv[k] = 0.0;
+    if (dcol == 0 || dcol == 4) {
+      const int co = (dcol == 0) ? 0 : 3; // my columns inside A
+      double Ad[18];                      // A(:, co:co+3)  6x3
+#pragma unroll
+      for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+          Ad[3 * r + c] = __ldg(fpv + FPV_A + 6 * r + co + c);
+      // D[c][dcol] += A_c^T A_d for c in {theta (0), p (4)}
+#pragma unroll
+      for (int ci = 0; ci < 2; ci++) {
+        const int c = ci ? 4 : 0, cco = ci ? 3 : 0;
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+          for (int cc = 0; cc < 3; cc++) {
+            double sacc = 0;
+#pragma unroll
+            for (int k = 0; k < 6; k++)
+              sacc += __ldg(fpv + FPV_A + 6 * k + cco + r) * Ad[3 * k + cc];
+            Dcol[c][3 * r + cc] += sacc;
+          }
+      }
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+#pragma unroll
+        for (int c = 0; c < 7; c++) {
+          double sacc = 0;
+#pragma unroll
+          for (int k = 0; k < 6; k++)
+            sacc += Ad[3 * k + r] * __ldg(fpv + FPV_G + 7 * k + c);
+          Bv[7 * r + c] = sacc;
+        }
+        double sg = 0;
+#pragma unroll
+        for (int k = 0; k < 6; k++)
+          sg += Ad[3 * k + r] * __ldg(fpv + FPV_R + k);
+        gv[r] -= sg;
+      }
+    }
+    if (dcol == 1) {
+      // global 7x7 block and gradient of the vicon factor: G^T G, -G^T r
+      double *sp = s_part[li];
+#pragma unroll
+      for (int r = 0; r < 7; r++) {
+#pragma unroll
+        for (int c = 0; c < 7; c++) {
+          double sacc = 0;
+#pragma unroll
+          for (int k = 0; k < 6; k++)
+            sacc += __ldg(fpv + FPV_G + 7 * k + r) * __ldg(fpv + FPV_G + 7 * k + c);
+          sp[7 * r + c] = sacc;
+        }
+        double sg = 0;
+#pragma unroll
+        for (int k = 0; k < 6; k++)
+          sg += __ldg(fpv + FPV_G + 7 * k + r) * __ldg(fpv + FPV_R + k);
+        sp[49 + r] = -sg;
+      }
+    }
+
+    // ================= store this thread's strips
+    double *HD = d.HD + s * HD_STRIDE;
+#pragma unroll
+    for (int c = 0; c < 5; c++)
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int cc = 0; cc < 3; cc++)
+          HD[(3 * c + r) * 15 + 3 * dcol + cc] = Dcol[c][3 * r + cc];
+    double *HB = d.HB + s * HB_STRIDE;
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+#pragma unroll
+      for (int c = 0; c < 7; c++)
+        HB[(3 * dcol + r) * 9 + c] = Bv[7 * r + c];
+      HB[(3 * dcol + r) * 9 + 7] = Bg[2 * r];
+      HB[(3 * dcol + r) * 9 + 8] = Bg[2 * r + 1];
+      d.Hg[s * HG_STRIDE + 3 * dcol + r] = gv[r];
+    }
+  }
+  __syncthreads();
+  // fixed-order reduction over the CTA's states
+  if (threadIdx.x < 62) {
+    double sacc = 0;
+    for (int k = 0; k < ASM_STATES; k++)
+      sacc += s_part[k][threadIdx.x];
+    d.part_asm[((long long)t * gridDim.x + blockIdx.x) * PART_STRIDE + threadIdx.x] = sacc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// grid T, 64 threads: gamma[t] = [Gamma 9x9 | g 9], lm.lin_error0, from the per-CTA partials (fixed order).
+__global__ void __launch_bounds__(64) k_reduce_gamma(DevPtrs d, int n_asm_chunks, int force_all) {
+  const int t = blockIdx.x;
+  LmState &lm = d.lm[t];
+  if (!force_all && (lm.lm_state != 0 || lm.status != V2GT_OK || !lm.need_lin))
+    return;
+  const int n = d.n_states[t];
+  const int used = (n + ASM_STATES - 1) / ASM_STATES;
+  __shared__ double s_v[64];
+  double sacc = 0;
+  if (threadIdx.x < 62)
+    for (int k = 0; k < used && k < n_asm_chunks; k++)
+      sacc += d.part_asm[((long long)t * n_asm_chunks + k) * PART_STRIDE + threadIdx.x];
+  s_v[threadIdx.x] = sacc;
+  __syncthreads();
+  double *gm = d.gamma + (long long)t * 96;
+  if (threadIdx.x < 81) {
+    // handled below by a strided loop (64 threads, 81+9 outputs)
+  }
+  for (int k = threadIdx.x; k < 90; k += 64) {
+    double v = 0.0;
+    if (k < 81) {
+      const int r = k / 9, c = k % 9;
+      if (r < 7 && c < 7)
+        v = s_v[7 * r + c];
+      else if (r >= 7 && c >= 7)
+        v = s_v[56 + 2 * (r - 7) + (c - 7)];
+    } else {
+      const int r = k - 81;
+      v = (r < 7) ? s_v[49 + r] : s_v[60 + (r - 7)];
+    }
+    gm[k] = v;
+  }
+  if (threadIdx.x == 0) {
+    const int usedc = (n + V2GT_CHUNK - 1) / V2GT_CHUNK;
+    double l0 = 0;
+    for (int k = 0; k < usedc; k++)
+      l0 += d.part_cost[((long long)t * d.nchunk + k) * 2 + 1];
+    lm.lin_error0 = l0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+int launch_linearize(const DevPtrs &d, int n_max, int force_all, cudaStream_t st) {
+  if (n_max <= 0)
+    return V2GT_OK;
+  dim3 g1((n_max + V2GT_CHUNK - 1) / V2GT_CHUNK, d.T);
+  k_factor_eval<true><<<g1, V2GT_CHUNK, 0, st>>>(d, 0, force_all);
+  const int nasm = (n_max + ASM_STATES - 1) / ASM_STATES;
+  dim3 g2(nasm, d.T);
+  k_assemble<<<g2, ASM_THREADS, 0, st>>>(d, force_all);
+  k_reduce_gamma<<<d.T, 64, 0, st>>>(d, nasm, force_all);
+  V2_CUDA_CHECK(cudaGetLastError());
+  return V2GT_OK;
+}
+
+int launch_cost(const DevPtrs &d, int n_max, int which, int force_all, cudaStream_t st) {
+  if (n_max <= 0)
+    return V2GT_OK;
+  dim3 g1((n_max + V2GT_CHUNK - 1) / V2GT_CHUNK, d.T);
+  k_factor_eval<false><<<g1, V2GT_CHUNK, 0, st>>>(d, which, force_all);
+  V2_CUDA_CHECK(cudaGetLastError());
+  return V2GT_OK;
+}
+
+int asm_chunks(int n_max) { return (n_max + ASM_STATES - 1) / ASM_STATES; }
+
+} // namespace v2

@@ -1,0 +1,181 @@
+// vicon2gt_b200 kernel (5): device-resident Levenberg-Marquardt bookkeeping.
+//
+// Restates the GTSAM 4.2a5 policy the reference configures in ViconGraphSolver.cpp:547-567
+// (LevenbergMarquardtOptimizer::iterate / tryLambda, NonlinearOptimizer::defaultOptimize,
+// checkConvergence) as a per-trial state machine that lives in device memory.  Every trial of
+// the batch advances by one damped solve ("try") per round; all decisions (accept / reject,
+// lambda update, relinearise, stop) are taken on the device, the host only enqueues rounds.
+#include "v2gt_common.cuh"
+#include <float.h>
+#include <stdio.h>
+
+namespace v2 {
+
+struct SegGeomLm {
+  int stride, nseg, nsep;
+};
+__device__ inline SegGeomLm seg_geom_lm(int n, int P) {
+  SegGeomLm g;
+  int st = (n + 1 + P - 1) / P;
+  g.stride = st < 2 ? 2 : st;
+  g.nseg = (n + g.stride - 1) / g.stride;
+  g.nsep = n / g.stride;
+  return g;
+}
+
+__device__ inline double sum_cost(const DevPtrs &d, int t, int which) {
+  const int n = d.n_states[t];
+  const int used = (n + V2GT_CHUNK - 1) / V2GT_CHUNK;
+  double s = 0;
+  for (int k = 0; k < used; k++)
+    s += d.part_cost[((long long)t * d.nchunk + k) * 2 + which];
+  return s;
+}
+
+// one thread per trial; the cost partials of the CURRENT estimate must be in part_cost
+__global__ void k_lm_begin(DevPtrs d) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= d.T)
+    return;
+  LmState &lm = d.lm[t];
+  const v2gt_params &p = d.trials[t].prm;
+  lm.lambda = p.lm_lambda_initial;
+  lm.iterations = 0;
+  lm.tries = 0;
+  lm.linearizations = 0;
+  lm.need_lin = 1;
+  lm.solve_failed = 0;
+  lm.n_trace = 0;
+  lm.lm_state = 0;
+  if (lm.status != V2GT_OK) {
+    lm.lm_state = 2;
+    return;
+  }
+  lm.error = sum_cost(d, t, 0);
+  lm.initial_error = lm.error;
+  lm.current_error = lm.error;
+  if (lm.iterations >= p.lm_max_iterations) // defaultOptimize's early return
+    lm.lm_state = 1;
+}
+
+// before each try
+__global__ void k_lm_pre_try(DevPtrs d) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= d.T)
+    return;
+  LmState &lm = d.lm[t];
+  if (lm.lm_state != 0)
+    return;
+  const v2gt_params &p = d.trials[t].prm;
+  if (p.lm_max_tries > 0 && lm.tries >= p.lm_max_tries) {
+    lm.lm_state = 4;
+    return;
+  }
+  if (lm.need_lin) {
+    lm.current_error = lm.error; // currentError = error() at the top of defaultOptimize's loop
+    lm.linearizations++;
+  }
+  lm.tries++;
+  lm.solve_failed = 0;
+}
+
+// after each try: tryLambda's decision + the loop condition of defaultOptimize
+__global__ void k_lm_decide(DevPtrs d, int count_active) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= d.T)
+    return;
+  LmState &lm = d.lm[t];
+  if (lm.lm_state != 0)
+    return;
+  const v2gt_params &p = d.trials[t].prm;
+  const int n = d.n_states[t];
+  bool step_ok = false, stop_search = false;
+  double new_error = INFINITY, lin_change = 0.0, cost_change = 0.0;
+  if (!lm.solve_failed) {
+    const SegGeomLm sg = seg_geom_lm(n, d.P);
+    const double *xg = d.xg + (long long)t * 16;
+    double gd = xg[10] + xg[12], dd = xg[11] + xg[13];
+    for (int j = 0; j < sg.nseg; j++) {
+      const double *so = d.seg + ((long long)t * d.P + j) * SEG_STRIDE;
+      gd += so[SEG_DOT];
+      dd += so[SEG_DOT + 1];
+    }
+    // linear.error(0) - linear.error(delta) = g.delta - 1/2 delta' H delta = 1/2 (g.delta + lambda |delta|^2)
+    lin_change = 0.5 * (gd + lm.lambda * dd);
+    if (lin_change >= 0.0) {
+      new_error = sum_cost(d, t, 0); // partials of the trial point
+      cost_change = lm.error - new_error;
+      if (lin_change > DBL_EPSILON * lm.lin_error0) {
+        const double fidelity = cost_change / lin_change;
+        step_ok = fidelity > p.lm_min_model_fidelity;
+      }
+      const double min_abs_tol = p.lm_relative_error_tol * lm.error;
+      if (fabs(cost_change) < min_abs_tol)
+        stop_search = true;
+    }
+  }
+  if (lm.n_trace < TRACE_MAX) {
+    double *tr = d.trace + ((long long)t * TRACE_MAX + lm.n_trace) * 5;
+    tr[0] = lm.lambda;
+    tr[1] = lm.error;
+    tr[2] = new_error;
+    tr[3] = lin_change;
+    tr[4] = step_ok ? 1.0 : 0.0;
+    lm.n_trace++;
+  }
+  bool end_iterate = false, gave_up = false;
+  if (step_ok) {
+    lm.cur = 1 - lm.cur; // the trial point becomes the estimate
+    lm.error = new_error;
+    lm.lambda = fmax(p.lm_lambda_lower_bound, lm.lambda / p.lm_lambda_factor);
+    lm.iterations++;
+    end_iterate = true;
+  } else if (!stop_search) {
+    lm.lambda *= p.lm_lambda_factor;
+    if (lm.lambda >= p.lm_lambda_upper_bound) {
+      gave_up = true;
+      end_iterate = true;
+    }
+  } else {
+    end_iterate = true;
+  }
+  lm.need_lin = 0;
+  if (end_iterate) {
+    lm.need_lin = 1;
+    const double cur_err = lm.current_error, new_err = lm.error;
+    if (lm.iterations >= p.lm_max_iterations) {
+      lm.lm_state = 1;
+    } else if (new_err <= 0.0) {
+      lm.lm_state = 2;
+    } else {
+      const double abs_dec = cur_err - new_err;
+      const double rel_dec = abs_dec / cur_err;
+      const bool converged = (p.lm_relative_error_tol != 0.0 && rel_dec <= p.lm_relative_error_tol) ||
+                             (abs_dec <= p.lm_absolute_error_tol);
+      if (converged)
+        lm.lm_state = gave_up ? 3 : 2;
+      else if (!isfinite(cur_err))
+        lm.lm_state = 2;
+    }
+  }
+  if (count_active && lm.lm_state == 0)
+    atomicAdd(d.n_active, 1);
+}
+
+int launch_lm_begin(const DevPtrs &d, cudaStream_t st) {
+  k_lm_begin<<<(d.T + 127) / 128, 128, 0, st>>>(d);
+  V2_CUDA_CHECK(cudaGetLastError());
+  return V2GT_OK;
+}
+int launch_lm_pre_try(const DevPtrs &d, cudaStream_t st) {
+  k_lm_pre_try<<<(d.T + 127) / 128, 128, 0, st>>>(d);
+  V2_CUDA_CHECK(cudaGetLastError());
+  return V2GT_OK;
+}
+int launch_lm_decide(const DevPtrs &d, int count_active, cudaStream_t st) {
+  k_lm_decide<<<(d.T + 127) / 128, 128, 0, st>>>(d, count_active);
+  V2_CUDA_CHECK(cudaGetLastError());
+  return V2GT_OK;
+}
+
+} // namespace v2

@@ -1,0 +1,143 @@
+// vicon2gt_b200: shared host/device definitions for the batch solver (sm_100a, fp64).
+//
+// Data layout in HBM (all arrays are concatenated over the trials of a batch; a trial
+// owns the slot range [st_off, st_off + n_raw) of every per-state array, of which the first
+// n_states[t] slots are live after compaction):
+//   imu_t   [M]        sample times (dense, for the batched binary search)
+//   imu_s   [M][8]     (t, w3, a3, pad)            one 64-byte line per sample
+//   vic_t   [V]        pose times (sorted, unique)
+//   vic_s   [V][8]     (q4, p3, pad)               one 64-byte line per pose
+//   vic_c   [V][18]    (R_q 3x3, R_p 3x3) or absent when the trial has one constant covariance
+//   st_t    [S]        state times
+//   x       [2][S][16] JPLNavState rows (q4 bg3 v3 ba3 p3), double buffered (current / trial point)
+//   glob    [2][T][16] q_BtoI4 p_BinI3 t_off theta_x theta_y (+pad), double buffered
+//   pre     [S][64]    preintegration constants of interval slot s -> s+1 (PRE_* offsets below)
+//   info    [S][120]   P^-1 of that interval, packed lower triangle (row-major: r*(r+1)/2 + c)
+//   fpi     [S][64]    per-factor linearisation pieces of the IMU factor (FPI_* offsets)
+//   fpv     [S][88]    per-factor pieces of the vicon factor (FPV_* offsets)
+//   HD HO HB Hg        normal-equation blocks per state: D 15x15, O 15x15 (k,k+1), B 15x9, g 15
+//   fac     [S][720]   elimination factors per state: L (120 packed), W_O 225, W_F 225, W_B 135, w_g 15
+//   delta   [S][16]    LM step per state
+#pragma once
+#include "../../include/vicon2gt_b200.h"
+#include "v2gt_math.cuh"
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace v2 {
+
+// ---- preintegration constants row (64 doubles)
+constexpr int PRE_DT = 0, PRE_ALPHA = 1, PRE_BETA = 4, PRE_Q = 7, PRE_BGLIN = 11, PRE_BALIN = 14, PRE_JQ = 17, PRE_JB = 26,
+              PRE_JA = 35, PRE_HB = 44, PRE_HA = 53, PRE_NSTEPS = 62, PRE_STRIDE = 64;
+constexpr int INFO_STRIDE = 120;
+constexpr int X_STRIDE = 16, GLOB_STRIDE = 16;
+// globals row
+constexpr int GL_Q = 0, GL_P = 4, GL_TOFF = 7, GL_THX = 8, GL_THY = 9;
+
+// ---- IMU factor pieces (64 doubles): residual + the non-trivial Jacobian blocks
+//  e[15]; Tth[9] = H1(0:3,0:3); Tb[9] = H1(0:3,3:6); sv[3], sp[3] (H1(6:9,0:3) = [sv]x, H1(12:15,0:3) = [sp]x);
+//  Rk[9] = quat_2_Rot(q_k); Jth2[9] = H2(0:3,0:3); valid flag
+constexpr int FPI_E = 0, FPI_TTH = 15, FPI_TB = 24, FPI_SV = 33, FPI_SP = 36, FPI_RK = 39, FPI_JTH2 = 48, FPI_VALID = 57,
+              FPI_STRIDE = 64;
+// ---- vicon factor pieces (88 doubles): Huber-reweighted whitened system
+//  r[6] = sqrt(w) W e ; A[6][6] = sqrt(w) W H1(:, [0:3, 12:15]) ; G[6][7] = sqrt(w) W [H2 H3 H4] ; has_vicon ; idx0 ; idx1 ; w
+constexpr int FPV_R = 0, FPV_A = 6, FPV_G = 42, FPV_HAS = 84, FPV_IDX0 = 85, FPV_IDX1 = 86, FPV_W = 87, FPV_STRIDE = 88;
+
+// ---- normal-equation blocks
+constexpr int HD_STRIDE = 225, HO_STRIDE = 225, HB_STRIDE = 135, HG_STRIDE = 16;
+// ---- elimination factor row
+constexpr int FAC_L = 0, FAC_WO = 120, FAC_WF = 345, FAC_WB = 570, FAC_WG = 705, FAC_STRIDE = 720;
+// ---- per-segment outputs (contributions to the separators and the globals)
+//  SL 225, BL 135, gL 15 (to the left separator); DR 225, C 225 (H[R][L]), BR 135, gR 15 (to the right
+//  separator); GS 81, gS 9 (to the globals); dot partials: g.delta, |delta|^2 (written by back-substitution)
+constexpr int SEG_SL = 0, SEG_BL = 225, SEG_GL = 360, SEG_DR = 375, SEG_C = 600, SEG_BR = 825, SEG_GR = 960, SEG_GS = 975,
+              SEG_GG = 1056, SEG_DOT = 1065, SEG_STRIDE = 1072;
+// ---- per-separator factor rows of the reduced chain: L 120, W_O 225, W_B 135, w_g 15 (+pad)
+constexpr int RED_L = 0, RED_WO = 120, RED_WB = 345, RED_WG = 480, RED_STRIDE = 496;
+// ---- per-CTA partial sums of the assembly / cost kernels
+//  assembly: Gamma vicon 7x7 (49) + g (7) + gravity 2x2 (4) + g (2) + lin_error0 (1) -> 63 (+pad)
+constexpr int PART_STRIDE = 64;
+
+__host__ __device__ inline int tri(int r, int c) { return r * (r + 1) / 2 + c; } // packed lower, r >= c
+
+// Per-trial description (device copy of the host staging result)
+struct TrialDev {
+  long long imu_off, n_imu;
+  long long vic_off, n_vic;
+  long long st_off, n_raw;
+  int vic_cov_const; // 1: vic_Rconst applies to every pose
+  int pad0;
+  double vic_Rconst[18];
+  v2gt_params prm;
+};
+
+// Device-resident Levenberg-Marquardt state of one trial
+struct LmState {
+  double lambda;
+  double error;          // cost at the current estimate
+  double current_error;  // cost at the start of the current outer iteration (defaultOptimize's currentError)
+  double lin_error0;     // 1/2 |b|^2 of the current linearisation
+  double new_error;      // scratch: cost at the trial point
+  double lin_change;     // scratch
+  double initial_error;
+  int iterations, tries, linearizations;
+  int lm_state;          // 0 running, 1 max iterations, 2 converged, 3 lambda gave up, 4 try cap
+  int need_lin;          // 1: the next try starts a new outer iteration (relinearise)
+  int solve_failed;      // set by the elimination kernels (non-positive pivot)
+  int cur;               // which half of x/glob holds the current estimate
+  int status;            // V2GT_OK or error code of the build stage
+  int n_trace;
+  int pad;
+};
+constexpr int TRACE_MAX = 1024; // rows of [lambda, cost_before, cost_after, lin_change, accepted] kept per trial
+
+struct DevPtrs {
+  int T;
+  long long S, M, V; // totals
+  int P;             // max segments per trial
+  const TrialDev *trials;
+  int *n_states;     // [T] live states per trial
+  int *trial_of;     // [S] trial index of a state slot
+  const double *imu_t, *imu_s, *vic_t, *vic_s, *vic_c;
+  const long long *vic_c_off; // [T] offset into vic_c (or -1)
+  double *st_t, *st_t_tmp;
+  double *x, *glob;  // double buffered
+  int *valid;        // [S] scratch flags of the build stage
+  double *pre, *info, *cov;
+  double *fpi, *fpv;
+  double *HD, *HO, *HB, *Hg;
+  double *fac, *seg, *red, *xsep;
+  double *delta;
+  double *part_asm;  // [T][nchunk][PART_STRIDE]
+  double *part_cost; // [T][nchunk][2]
+  double *gamma;     // [T][96]: Gamma 81 + g 9 (assembled, undamped)
+  double *xg;        // [T][16]: global step
+  LmState *lm;
+  double *trace;     // [T][TRACE_MAX][5]
+  int *n_active;     // device counter of running trials
+  int *removed_no_vicon; // [T]
+  int nchunk;        // chunks (CTAs) per trial of the per-state kernels
+};
+
+#if defined(__CUDACC__)
+// 32-byte read-only load as two 16-byte __ldg (there is no __ldg overload for double4)
+__device__ __forceinline__ double4 ldg4(const double *p) {
+  const double2 a = __ldg(reinterpret_cast<const double2 *>(p));
+  const double2 b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+#endif
+
+#define V2GT_CHUNK 128 // states per CTA chunk in the per-state kernels (trial aligned)
+
+} // namespace v2
+
+#define V2_CUDA_CHECK(expr)                                                                                                      \
+  do {                                                                                                                           \
+    cudaError_t _e = (expr);                                                                                                     \
+    if (_e != cudaSuccess) {                                                                                                     \
+      fprintf(stderr, "[vicon2gt_b200] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(_e), __FILE__, __LINE__,                  \
+              cudaGetErrorString(_e));                                                                                           \
+      return V2GT_ERR_CUDA;                                                                                                      \
+    }                                                                                                                            \
+  } while (0)
