@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- solved trajectories / second of the vicon2gt build-and-solve hot path on B200.
+
+Workload (BASELINE.json configs[3], the one the metric is quoted on): a Monte-Carlo batch of independent
+simulated trials of the `launch/sim.launch` shape (400 Hz IMU, 100 Hz vicon, 100 Hz states, ~29.8 k states,
+~119.6 k IMU samples, ~29.9 k vicon poses per trial), sharded one batch per GPU with no communication
+(weak scaling: --trials trials per GPU).  One "step" = the full build-and-solve of the rank's batch
+(state initialisation, continuous preintegration, 30-iteration Levenberg-Marquardt).
+
+  value  trajectories/s with the inputs already resident in HBM (CUDA events around build + optimise)
+  e2e    the same through the public API with HOST buffers: staging + pinned H2D copy of every input array,
+         build + optimise, D2H read of states + calibration, wall clock around the call
+  roofline  dominant kernel (k_seg_eliminate): algorithmic bytes / summed launch durations (CUDA events on the
+         handle's stream, inside the timed steps) against MEASURED_PEAKS.json's HBM number; FP64 fraction
+         against a DFMA peak measured in the same process
+  cpu_baseline  the oracle (CPU restatement of the reference; the reference itself cannot be built here:
+         no Eigen / Boost / GTSAM / ROS) on a bounded sample of the same workload
+
+`--impl reference` times that CPU restatement on all host threads instead (kind "port").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "solved_trajectories_per_second"
+UNIT = "trajectories/s"
+# algorithmic work per state and damped solve (stated in DESIGN.md)
+ELIM_ALG_BYTES_PER_STATE = 2 * (120 + 225 + 135 + 15) * 8  # read D,O,B,g once + write L,W_O,W_B,w_g once = 7920 B
+ELIM_ALG_FLOPS_PER_STATE = 19.4e3                           # block-tridiagonal-arrow Cholesky, Thomas-equivalent
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--trials", type=int, default=int(os.environ.get("V2GT_BENCH_TRIALS", "16")),
+                    help="trials per GPU (weak scaling; 128 per GPU = the 1024-trial batch on 8 GPUs)")
+    ap.add_argument("--duration", type=float, default=0.0, help="truncate the trajectory to this many seconds (0 = full)")
+    ap.add_argument("--segments", type=int, default=0)
+    ap.add_argument("--cpu-sample-s", type=float, default=40.0, help="length of the CPU baseline sample trajectory")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
+    return ap.parse_args()
+
+
+def dist_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def make_trials(n, seed0, duration):
+    """n distinct simulated trials (seeds seed0..), generated on host threads (the C++ simulator releases the GIL)."""
+    from vicon2gt_b200 import sim
+
+    out = [None] * n
+    kw = {} if duration <= 0 else dict(duration_s=duration)
+
+    def work(i):
+        out[i] = sim.make_config("C1", seed=seed0 + i, **kw)
+
+    nthr = max(1, min(n, os.cpu_count() or 1))
+    idx = list(range(n))
+    threads = []
+    for k in range(nthr):
+        th = threading.Thread(target=lambda k=k: [work(i) for i in idx[k::nthr]])
+        th.start()
+        threads.append(th)
+    for th in threads:
+        th.join()
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline(sample_s, threads):
+    """Oracle (CPU restatement of the reference) on a bounded sample: one sim.launch-shaped trial truncated to
+    `sample_s` seconds per thread.  Returns equivalent full-size trajectories / s."""
+    from oracle import binding as ob
+    from vicon2gt_b200 import sim
+    from vicon2gt_b200._cdefs import TrialInfo
+
+    full_states = 29798.0  # states of a full sim.launch trial after cleaning
+    dss = [sim.make_config("C1", seed=1000 + i, duration_s=sample_s) for i in range(threads)]
+    p = ob.default_params()
+    solvers = [ob.OracleSolver.from_dataset(p, ds) for ds in dss]
+    res = [None] * threads
+
+    def work(i):
+        st = solvers[i].build_and_solve()
+        inf = solvers[i].info(TrialInfo)
+        res[i] = (st, inf.n_states, inf.tries, inf.iterations)
+
+    t0 = time.perf_counter()
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    dt = time.perf_counter() - t0
+    n_states = sum(r[1] for r in res)
+    value = (n_states / full_states) / dt
+    sample = (f"{threads} x sim.launch-shaped trial truncated to {sample_s:.0f} s ({res[0][1]} states, {res[0][2]} damped solves, "
+              f"{res[0][3]} LM iterations each), full build_and_solve, {dt:.1f} s wall; scaled by states to the "
+              f"{int(full_states)}-state trial")
+    return value, sample, dt
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    vals, dts = [], []
+    sample = ""
+    for k in range(args.warmup + args.steps):
+        # keep the whole run within a few minutes: shrink the sample when many steps are requested
+        sample_s = max(8.0, min(args.cpu_sample_s, 160.0 / max(1, args.warmup + args.steps)))
+        v, sample, dt = cpu_baseline(sample_s, threads)
+        if k >= args.warmup:
+            vals.append(v)
+            dts.append(dt)
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(dts)), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "MC batch of sim.launch-shaped trials (BASELINE.json configs[3]); CPU restatement of the reference "
+                               "(GTSAM/Eigen/ROS are not installable here), bounded sample per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    rank, local_rank, world = dist_env()
+    from vicon2gt_b200 import api, build
+
+    if not os.path.exists(build.lib_path("cuda")) or not os.path.exists(build.lib_path("sim")):
+        build.build_sim()
+        build.build_cuda()
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    device = local_rank if world > 1 else 0
+    T = args.trials
+    p = api.default_params()
+    trials = make_trials(T, seed0=rank * T, duration=args.duration)
+    h2d = int(sum(ds.nbytes() for ds in trials))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    opts = {}
+    if args.segments > 0:
+        opts["segments"] = args.segments
+    bs = api.BatchSolver(T, device=device, **opts)
+
+    def stage_and_upload():
+        for i, ds in enumerate(trials):
+            bs.set_trial_dataset(i, p, ds)
+        bs.upload()
+
+    def read_back():
+        nbytes = 0
+        for i in range(T):
+            t, x = bs.states(i)
+            g = bs.globals10(i)
+            nbytes += t.nbytes + x.nbytes + g.nbytes
+        return nbytes
+
+    # ---------------- device-resident steps: inputs already in HBM
+    stage_and_upload()
+    for _ in range(args.warmup):
+        bs.build(True)
+        bs.optimize()
+    sampler = ClockSampler(device)
+    barrier()
+    bs.sync()
+    sampler.start()
+    ms0, l0 = bs.timing()
+    dev_ms = build_ms = opt_ms = 0.0
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        bs.build(True)
+        bs.optimize()
+        m_after, _ = bs.timing()
+        build_ms += m_after[0]  # CUDA events on the handle's stream
+        opt_ms += m_after[7]
+    dev_ms = build_ms + opt_ms
+    bs.sync()
+    barrier()
+    wall_s = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    ms1, l1 = bs.timing()
+    dev_s = max_over_ranks(dev_ms * 1e-3)
+    value = world * T * args.steps / dev_s
+
+    # per-trial work counters (for the roofline accounting)
+    infos = [bs.info(i) for i in range(T)]
+    ok = sum(1 for inf in infos if inf.status == 0)
+    solve_units = float(sum(inf.tries * inf.n_states for inf in infos))  # state-blocks eliminated per step
+    phase_ms = (ms1 - ms0)
+    phase_ms[0], phase_ms[7] = build_ms, opt_ms  # these two slots hold the last call only
+    launches = int((l1 - l0).sum())
+    elim_ms = float(phase_ms[2])
+    hbm_peak, peak_src = measured_peaks()
+    fp64_peak = api.measure_fp64_peak(device)
+    elim_bytes = solve_units * args.steps * ELIM_ALG_BYTES_PER_STATE
+    elim_flops = solve_units * args.steps * ELIM_ALG_FLOPS_PER_STATE
+    achieved_gbs = elim_bytes / (elim_ms * 1e-3) / 1e9 if elim_ms > 0 else 0.0
+    achieved_tf = elim_flops / (elim_ms * 1e-3) / 1e12 if elim_ms > 0 else 0.0
+
+    # ---------------- end to end through the public API with host buffers
+    e2e_s = 0.0
+    d2h = 0
+    barrier()
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        stage_and_upload()
+        bs.build_and_solve()
+        d2h = read_back()
+        e2e_s += time.perf_counter() - t0
+    e2e_s = max_over_ranks(e2e_s)
+    e2e_value = world * T * args.steps / e2e_s
+
+    # ---------------- LM iteration latency on a single trajectory (second half of the metric)
+    latency = None
+    if not args.no_latency and rank == 0:
+        one = api.BatchSolver(1, device=device)
+        one.set_trial_dataset(0, p, trials[0])
+        one.upload()
+        one.build(True)
+        one.optimize()  # warm
+        one.build(True)
+        one.optimize()
+        m, _ = one.timing()
+        inf = one.info(0)
+        latency = {"config": "single sim.launch-shaped trajectory", "n_states": inf.n_states, "lm_iterations": inf.iterations,
+                   "damped_solves": inf.tries, "build_ms": float(m[0]), "optimize_ms": float(m[7]),
+                   "ms_per_lm_iteration": float(m[7]) / max(1, inf.iterations), "ms_per_damped_solve": float(m[7]) / max(1, inf.tries)}
+        one.close()
+
+    cpu = None
+    if not args.no_cpu_baseline and rank == 0:
+        v, sample, _ = cpu_baseline(args.cpu_sample_s if args.duration <= 0 else min(args.cpu_sample_s, args.duration), 1)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample}
+
+    total_states = sum_over_ranks(float(sum(inf.n_states for inf in infos)))
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": ("MC batch of independent sim.launch-shaped trials (BASELINE.json configs[3]): 400 Hz IMU, 100 Hz vicon, "
+                             "100 Hz states, 30-iteration LM; %d trials per GPU, %d GPU(s), no communication" % (T, world)),
+                "trials_per_gpu": T, "states_total": int(total_states), "trials_ok": ok,
+                "trajectory": "synthesised, tum_corridor1 shape" + ("" if args.duration <= 0 else f", truncated to {args.duration:.0f} s"),
+                "l2": "working set per step (%.1f GB factors + blocks per GPU) exceeds the 126 MB L2" % (total_states / world * 12.5e3 / 1e9),
+                "timing": "CUDA events on the solver stream (build + optimise), max over ranks",
+                "wall_s_timed_region": wall_s,
+            },
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {
+                "kernel": "k_seg_eliminate", "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "share_of_step": elim_ms / max(1e-9, dev_ms),
+                "fp64": {"achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / max(fp64_peak, 1e-9),
+                         "peak_source": "measured DFMA loop (v2gt_measure_fp64_peak)"},
+                "algorithmic_bytes_per_state_block": ELIM_ALG_BYTES_PER_STATE, "algorithmic_flops_per_state_block": ELIM_ALG_FLOPS_PER_STATE,
+            },
+            "phases_ms_per_step": {k: float(phase_ms[i]) / args.steps for i, k in
+                                   enumerate(["build", "linearize", "eliminate", "reduced", "backsub", "cost", "lm", "optimize_total"])},
+            "lm_iteration_latency": latency,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    bs.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

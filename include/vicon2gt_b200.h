@@ -180,6 +180,9 @@ int v2gt_batch_get_lm_trace(v2gt_batch *b, int32_t trial, int64_t capacity, doub
  * [4] back-substitute+retract [5] cost evaluation [6] LM bookkeeping; launches[7] kernel launch counts. */
 int v2gt_batch_get_timing(v2gt_batch *b, double *ms, int64_t *launches);
 int v2gt_batch_set_option(v2gt_batch *b, const char *name, double value);
+/* Measured FP64 FMA peak of `device` in TFLOP/s (dependent-chain-free DFMA loop, best of 4): the FP64
+ * roofline denominator (MEASURED_PEAKS.json only carries HBM and bf16 tensor numbers). */
+int v2gt_measure_fp64_peak(int32_t device, double *tflops);
 
 #ifdef __cplusplus
 }

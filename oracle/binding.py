@@ -89,6 +89,22 @@ def _c(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
 
 
+def default_params(**kw):
+    """v2gt_params with the reference defaults, filled by the oracle's own copy of the defaults."""
+    from vicon2gt_b200._cdefs import Params
+
+    p = Params()
+    lib().orc_params_default(C.byref(p))
+    for k, v in kw.items():
+        if k in ("R_GtoV", "R_BtoI", "p_BinI"):
+            arr = np.asarray(v, dtype=np.float64).reshape(-1)
+            for i, x in enumerate(arr):
+                getattr(p, k)[i] = float(x)
+        else:
+            setattr(p, k, v)
+    return p
+
+
 class OracleSolver:
     """CPU restatement of ViconGraphSolver over one trial's inputs."""
 

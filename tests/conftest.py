@@ -49,18 +49,8 @@ def default_params(**kw):
     """v2gt_params with the reference defaults, filled by the ORACLE's copy of the defaults so that CPU-only
     tests do not depend on the CUDA library."""
     from oracle import binding as ob
-    from vicon2gt_b200._cdefs import Params
 
-    p = Params()
-    ob.lib().orc_params_default(C.byref(p))
-    for k, v in kw.items():
-        if k in ("R_GtoV", "R_BtoI", "p_BinI"):
-            arr = np.asarray(v, dtype=np.float64).reshape(-1)
-            for i, x in enumerate(arr):
-                getattr(p, k)[i] = float(x)
-        else:
-            setattr(p, k, v)
-    return p
+    return ob.default_params(**kw)
 
 
 @pytest.fixture(scope="session")

@@ -59,6 +59,7 @@ def load_library():
     L.v2gt_eval_cost.argtypes = [vp, C.c_int32, c_double_p]
     L.v2gt_batch_get_lm_trace.argtypes = [vp, C.c_int32, C.c_int64, c_double_p, c_int64_p]
     L.v2gt_batch_get_timing.argtypes = [vp, c_double_p, c_int64_p]
+    L.v2gt_measure_fp64_peak.argtypes = [C.c_int32, c_double_p]
     _lib = L
     return L
 
@@ -81,6 +82,13 @@ def device_count():
     n = C.c_int32(0)
     load_library().v2gt_device_count(C.byref(n))
     return n.value
+
+
+def measure_fp64_peak(device=0):
+    """Measured FP64 FMA peak (TFLOP/s) of a device."""
+    v = C.c_double()
+    _check(load_library().v2gt_measure_fp64_peak(int(device), C.byref(v)), "v2gt_measure_fp64_peak")
+    return v.value
 
 
 def _c(a):

@@ -30,6 +30,10 @@ int launch_preintegrate(const DevPtrs &d, int n_max, int keep_cov, cudaStream_t 
 int launch_linearize(const DevPtrs &d, int n_max, int force_all, cudaStream_t st);
 int launch_cost(const DevPtrs &d, int n_max, int which, int force_all, cudaStream_t st);
 int launch_solve(const DevPtrs &d, int force_all, cudaStream_t st);
+int solve_configure();
+int launch_eliminate(const DevPtrs &d, int force_all, cudaStream_t st);
+int launch_reduced(const DevPtrs &d, int force_all, cudaStream_t st);
+int launch_backsub(const DevPtrs &d, int force_all, cudaStream_t st);
 int launch_lm_begin(const DevPtrs &d, cudaStream_t st);
 int launch_lm_pre_try(const DevPtrs &d, cudaStream_t st);
 int launch_lm_decide(const DevPtrs &d, int count_active, cudaStream_t st);
@@ -68,6 +72,8 @@ struct v2gt_batch {
   int *h_active = nullptr;
   // timing
   cudaEvent_t ev[16];
+  std::vector<cudaEvent_t> ev_pool;
+  int64_t tries_enqueued = 0;
   bool ev_ok = false;
   double ms[8] = {0};
   int64_t launches[8] = {0};
@@ -259,6 +265,8 @@ int v2gt_batch_destroy(v2gt_batch *b) {
   if (b->ev_ok)
     for (int i = 0; i < 16; i++)
       cudaEventDestroy(b->ev[i]);
+  for (cudaEvent_t e : b->ev_pool)
+    cudaEventDestroy(e);
   if (b->stream)
     cudaStreamDestroy(b->stream);
   delete b;
@@ -646,16 +654,33 @@ int v2gt_batch_optimize(v2gt_batch *b) {
       r = std::min(r, p.lm_max_tries + 1);
     max_rounds = std::max(max_rounds, r);
   }
+  V2_TRY(solve_configure());
+  // per-phase device timing: 7 events per try, re-used every chunk (the host synchronises once per chunk)
+  const int chunk = b->opt_tries_per_sync;
+  while ((int)b->ev_pool.size() < 7 * chunk) {
+    cudaEvent_t e;
+    V2_CUDA_CHECK(cudaEventCreate(&e));
+    b->ev_pool.push_back(e);
+  }
   int rounds = 0;
   while (rounds < max_rounds) {
-    const int chunk = b->opt_tries_per_sync;
     V2_CUDA_CHECK(cudaMemsetAsync(d.n_active, 0, sizeof(int), st));
     for (int k = 0; k < chunk; k++) {
+      cudaEvent_t *e = &b->ev_pool[7 * k];
       V2_TRY(launch_lm_pre_try(d, st));
+      V2_CUDA_CHECK(cudaEventRecord(e[0], st));
       V2_TRY(launch_linearize(d, b->n_max, 0, st));
-      V2_TRY(launch_solve(d, 0, st));
+      V2_CUDA_CHECK(cudaEventRecord(e[1], st));
+      V2_TRY(launch_eliminate(d, 0, st));
+      V2_CUDA_CHECK(cudaEventRecord(e[2], st));
+      V2_TRY(launch_reduced(d, 0, st));
+      V2_CUDA_CHECK(cudaEventRecord(e[3], st));
+      V2_TRY(launch_backsub(d, 0, st));
+      V2_CUDA_CHECK(cudaEventRecord(e[4], st));
       V2_TRY(launch_cost(d, b->n_max, 1, 0, st));
+      V2_CUDA_CHECK(cudaEventRecord(e[5], st));
       V2_TRY(launch_lm_decide(d, k == chunk - 1 ? 1 : 0, st));
+      V2_CUDA_CHECK(cudaEventRecord(e[6], st));
       b->launches[1] += 3;
       b->launches[2] += 1;
       b->launches[3] += 1;
@@ -666,6 +691,15 @@ int v2gt_batch_optimize(v2gt_batch *b) {
     rounds += chunk;
     V2_CUDA_CHECK(cudaMemcpyAsync(b->h_active, d.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
     V2_CUDA_CHECK(cudaStreamSynchronize(st));
+    for (int k = 0; k < chunk; k++) {
+      cudaEvent_t *e = &b->ev_pool[7 * k];
+      for (int ph = 0; ph < 6; ph++) {
+        float m = 0;
+        cudaEventElapsedTime(&m, e[ph], e[ph + 1]);
+        b->ms[1 + ph] += m;
+      }
+    }
+    b->tries_enqueued += chunk;
     if (*b->h_active == 0)
       break;
   }

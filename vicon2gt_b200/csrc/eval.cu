@@ -344,3 +344,55 @@ int v2gt_eval_solve(v2gt_batch *b, int32_t trial, double lambda, int64_t capacit
 }
 
 } // extern "C"
+
+// ---- FP64 FMA peak microbenchmark (the roofline denominator MEASURED_PEAKS.json does not carry)
+namespace v2 {
+__global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-9, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+} // namespace v2
+
+extern "C" int v2gt_measure_fp64_peak(int32_t device, double *tflops) {
+  if (!tflops)
+    return V2GT_ERR_INVALID_ARG;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return V2GT_ERR_NO_DEVICE;
+  }
+  V2_CUDA_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  V2_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  double *d_out = nullptr;
+  V2_CUDA_CHECK(cudaMalloc(&d_out, sizeof(double) * blocks * threads));
+  cudaEvent_t e0, e1;
+  V2_CUDA_CHECK(cudaEventCreate(&e0));
+  V2_CUDA_CHECK(cudaEventCreate(&e1));
+  double best = 0;
+  for (int rep = 0; rep < 5; rep++) {
+    V2_CUDA_CHECK(cudaEventRecord(e0));
+    v2::k_dfma_peak<<<blocks, threads>>>(d_out, iters, 0.999999, 1e-7);
+    V2_CUDA_CHECK(cudaEventRecord(e1));
+    V2_CUDA_CHECK(cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 64.0 * iters * (double)blocks * threads;
+    const double tf = flops / (ms * 1e-3) * 1e-12;
+    if (rep > 0 && tf > best)
+      best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
+  *tflops = best;
+  return V2GT_OK;
+}

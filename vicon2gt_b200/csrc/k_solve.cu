@@ -599,20 +599,44 @@ __global__ void __launch_bounds__(BS_WARPS * 32) k_seg_backsub(DevPtrs d, int fo
 }
 
 // ------------------------------------------------------------------------------------------------
-int launch_solve(const DevPtrs &d, int force_all, cudaStream_t st) {
+int solve_configure() {
   const size_t sm1 = sizeof(double) * W_TOTAL * ELIM_WARPS;
   const size_t sm2 = sizeof(double) * (RED_SMEM + 128);
   const size_t sm3 = sizeof(double) * BS_SMEM_PER_WARP * BS_WARPS;
   V2_CUDA_CHECK(cudaFuncSetAttribute(k_seg_eliminate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
   V2_CUDA_CHECK(cudaFuncSetAttribute(k_reduced, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
   V2_CUDA_CHECK(cudaFuncSetAttribute(k_seg_backsub, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
+  return V2GT_OK;
+}
+int launch_eliminate(const DevPtrs &d, int force_all, cudaStream_t st) {
+  const size_t sm1 = sizeof(double) * W_TOTAL * ELIM_WARPS;
   dim3 g1((d.P + ELIM_WARPS - 1) / ELIM_WARPS, d.T);
   k_seg_eliminate<<<g1, ELIM_WARPS * 32, sm1, st>>>(d, force_all);
+  V2_CUDA_CHECK(cudaGetLastError());
+  return V2GT_OK;
+}
+int launch_reduced(const DevPtrs &d, int force_all, cudaStream_t st) {
+  const size_t sm2 = sizeof(double) * (RED_SMEM + 128);
   k_reduced<<<d.T, 32, sm2, st>>>(d, force_all);
+  V2_CUDA_CHECK(cudaGetLastError());
+  return V2GT_OK;
+}
+int launch_backsub(const DevPtrs &d, int force_all, cudaStream_t st) {
+  const size_t sm3 = sizeof(double) * BS_SMEM_PER_WARP * BS_WARPS;
   dim3 g3((d.P + BS_WARPS - 1) / BS_WARPS, d.T);
   k_seg_backsub<<<g3, BS_WARPS * 32, sm3, st>>>(d, force_all);
   V2_CUDA_CHECK(cudaGetLastError());
   return V2GT_OK;
+}
+int launch_solve(const DevPtrs &d, int force_all, cudaStream_t st) {
+  int s = solve_configure();
+  if (s != V2GT_OK)
+    return s;
+  if ((s = launch_eliminate(d, force_all, st)) != V2GT_OK)
+    return s;
+  if ((s = launch_reduced(d, force_all, st)) != V2GT_OK)
+    return s;
+  return launch_backsub(d, force_all, st);
 }
 
 } // namespace v2
