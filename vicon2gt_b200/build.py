@@ -70,13 +70,26 @@ def build_cuda(force=False, verbose=False, extra=()):
     for cand in ("/usr/include/nccl.h",):
         if os.path.exists(cand):
             nccl_inc = ["-DV2GT_HAVE_NCCL=1"]
-    cmd = [nvcc] + NVCC_FLAGS + list(extra) + nccl_inc + ["-I", os.path.join(ROOT, "include"), "-shared", "-o", out] + srcs
+    # one nvcc per translation unit, in parallel, then one link step (objects live in _obj/, git-ignored)
+    from concurrent.futures import ThreadPoolExecutor
+
+    objdir = os.path.join(PKG_DIR, "_obj")
+    os.makedirs(objdir, exist_ok=True)
+    common = [nvcc] + NVCC_FLAGS + list(extra) + nccl_inc + ["-I", os.path.join(ROOT, "include")]
     if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-    log = _run(cmd)
-    if verbose:
-        print(log)
+        common += ["-Xptxas", "-v"]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        if force or _newer(obj, [src] + hdrs):
+            log = _run(common + ["-c", src, "-o", obj])
+            if verbose:
+                print(log)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        objs = list(ex.map(compile_one, srcs))
+    _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs)
     return out
 
 

@@ -525,17 +525,16 @@ int v2gt_batch_upload(v2gt_batch *b) {
     V2_TRY(dev_alloc(b, &d.cov, (size_t)S * 225));
   V2_TRY(dev_alloc(b, &d.fpi, (size_t)S * FPI_STRIDE));
   V2_TRY(dev_alloc(b, &d.fpv, (size_t)S * FPV_STRIDE));
-  V2_TRY(dev_alloc(b, &d.HD, (size_t)S * HD_STRIDE));
-  V2_TRY(dev_alloc(b, &d.HO, (size_t)S * HO_STRIDE));
-  V2_TRY(dev_alloc(b, &d.HB, (size_t)S * HB_STRIDE));
-  V2_TRY(dev_alloc(b, &d.Hg, (size_t)S * HG_STRIDE));
+  V2_TRY(dev_alloc(b, &d.ne, (size_t)S * NE_STRIDE));
   V2_TRY(dev_alloc(b, &d.fac, (size_t)S * FAC_STRIDE));
   V2_TRY(dev_alloc(b, &d.seg, (size_t)T * P * SEG_STRIDE));
-  V2_TRY(dev_alloc(b, &d.red, (size_t)T * P * RED_STRIDE));
-  V2_TRY(dev_alloc(b, &d.xsep, (size_t)T * P * 16));
+  V2_TRY(dev_alloc(b, &d.red_ne, ((size_t)T * P + 2) * NE_STRIDE));
+  V2_TRY(dev_alloc(b, &d.red_fac, ((size_t)T * P + 2) * FAC_STRIDE));
+  V2_TRY(dev_alloc(b, &d.red_fb, (size_t)T * 640));
+  V2_TRY(dev_alloc(b, &d.xsep, (size_t)T * (P + 1) * 16));
   V2_TRY(dev_alloc(b, &d.delta, (size_t)S * 16));
   V2_TRY(dev_alloc(b, &d.part_asm, (size_t)T * nasm * PART_STRIDE));
-  V2_TRY(dev_alloc(b, &d.part_cost, (size_t)T * d.nchunk * 2));
+  V2_TRY(dev_alloc(b, &d.part_cost, (size_t)T * d.nchunk * 4));
   V2_TRY(dev_alloc(b, &d.gamma, (size_t)T * 96));
   V2_TRY(dev_alloc(b, &d.xg, (size_t)T * 16));
   V2_TRY(dev_alloc(b, &d.lm, (size_t)T));
@@ -564,7 +563,7 @@ int v2gt_batch_upload(v2gt_batch *b) {
   V2_CUDA_CHECK(cudaMemcpyAsync(d.lm, lm.data(), sizeof(LmState) * T, cudaMemcpyHostToDevice, st));
   V2_CUDA_CHECK(cudaMemsetAsync(d.removed_no_vicon, 0, sizeof(int) * T, st));
   V2_CUDA_CHECK(cudaMemsetAsync(d.x, 0, sizeof(double) * 2 * S * X_STRIDE, st));
-  V2_CUDA_CHECK(cudaMemsetAsync(d.HO, 0, sizeof(double) * S * HO_STRIDE, st));
+  V2_CUDA_CHECK(cudaMemsetAsync(d.delta, 0, sizeof(double) * S * 16, st));
   V2_CUDA_CHECK(cudaMemsetAsync(d.trace, 0, sizeof(double) * T * TRACE_MAX * 5, st));
   V2_CUDA_CHECK(cudaMemsetAsync(d.xg, 0, sizeof(double) * T * 16, st));
   V2_CUDA_CHECK(cudaStreamSynchronize(st)); // td / lm are stack-owned host vectors
@@ -683,7 +682,7 @@ int v2gt_batch_optimize(v2gt_batch *b) {
       V2_CUDA_CHECK(cudaEventRecord(e[6], st));
       b->launches[1] += 3;
       b->launches[2] += 1;
-      b->launches[3] += 1;
+      b->launches[3] += 2;
       b->launches[4] += 1;
       b->launches[5] += 1;
       b->launches[6] += 2;

@@ -214,13 +214,13 @@ int v2gt_batch_set_estimate(v2gt_batch *b, int32_t trial, int64_t n_in, const do
 static int host_cost(v2gt_batch *b, int trial, int n, double *cost) {
   const DevPtrs &d = *batch_devptrs(b);
   const int used = (n + V2GT_CHUNK - 1) / V2GT_CHUNK;
-  std::vector<double> pc((size_t)used * 2);
+  std::vector<double> pc((size_t)used * 4);
   if (used)
-    V2_CUDA_CHECK(cudaMemcpy(pc.data(), d.part_cost + (long long)trial * d.nchunk * 2, sizeof(double) * 2 * used,
+    V2_CUDA_CHECK(cudaMemcpy(pc.data(), d.part_cost + (long long)trial * d.nchunk * 4, sizeof(double) * 4 * used,
                              cudaMemcpyDeviceToHost));
   double c = 0;
   for (int k = 0; k < used; k++)
-    c += pc[2 * k];
+    c += pc[4 * k];
   *cost = c;
   return V2GT_OK;
 }
@@ -276,18 +276,23 @@ int v2gt_eval_linearize(v2gt_batch *b, int32_t trial, int64_t capacity, double *
     return s;
   if ((D || O || B || g) && capacity < n)
     return V2GT_ERR_INVALID_ARG;
-  if (n) {
-    if (D)
-      V2_CUDA_CHECK(cudaMemcpy(D, d.HD + td.st_off * HD_STRIDE, sizeof(double) * 225 * n, cudaMemcpyDeviceToHost));
-    if (O)
-      V2_CUDA_CHECK(cudaMemcpy(O, d.HO + td.st_off * HO_STRIDE, sizeof(double) * 225 * n, cudaMemcpyDeviceToHost));
-    if (B)
-      V2_CUDA_CHECK(cudaMemcpy(B, d.HB + td.st_off * HB_STRIDE, sizeof(double) * 135 * n, cudaMemcpyDeviceToHost));
-    if (g) {
-      std::vector<double> tmp((size_t)n * HG_STRIDE);
-      V2_CUDA_CHECK(cudaMemcpy(tmp.data(), d.Hg + td.st_off * HG_STRIDE, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost));
-      for (int i = 0; i < n; i++)
-        std::memcpy(g + 15 * (size_t)i, &tmp[(size_t)i * HG_STRIDE], sizeof(double) * 15);
+  if (n && (D || O || B || g)) {
+    // unpack the per-state records [D 15x15 | M 15x25 = O 15, B 9, g 1]
+    std::vector<double> rec((size_t)n * NE_STRIDE);
+    V2_CUDA_CHECK(cudaMemcpy(rec.data(), d.ne + td.st_off * NE_STRIDE, sizeof(double) * rec.size(), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++) {
+      const double *r = &rec[(size_t)i * NE_STRIDE];
+      if (D)
+        std::memcpy(D + 225 * (size_t)i, r + NE_D, sizeof(double) * 225);
+      for (int a = 0; a < 15; a++) {
+        const double *mr = r + NE_M + NE_MW * a;
+        if (O)
+          std::memcpy(O + 225 * (size_t)i + 15 * a, mr, sizeof(double) * 15);
+        if (B)
+          std::memcpy(B + 135 * (size_t)i + 9 * a, mr + NE_MB, sizeof(double) * 9);
+        if (g)
+          g[15 * (size_t)i + a] = mr[NE_MG];
+      }
     }
   }
   double gm[96];

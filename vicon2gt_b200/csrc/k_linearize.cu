@@ -15,13 +15,35 @@
 
 namespace v2 {
 
+// JPLNavState::retract (src/gtsam/JPLNavState.cpp:25-54) of one state row: q <- dq(dtheta) (x) q, the rest adds
+__device__ __forceinline__ void retract_state(const double *x0, const double *dx, double *x1) {
+  double dq[4], q[4];
+  small_quat(dx, dq);
+  quat_mul(dq, x0, q);
+  x1[0] = q[0]; x1[1] = q[1]; x1[2] = q[2]; x1[3] = q[3];
+#pragma unroll
+  for (int k = 0; k < 12; k++)
+    x1[4 + k] = x0[4 + k] + dx[3 + k];
+}
+__device__ __forceinline__ void ld16(const double *p, double *o) {
+  const double4 *p4 = reinterpret_cast<const double4 *>(p);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const double4 v = p4[k];
+    o[4 * k] = v.x; o[4 * k + 1] = v.y; o[4 * k + 2] = v.z; o[4 * k + 3] = v.w;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
-// grid (nchunk, T), V2GT_CHUNK threads.  which = 0: evaluate the current estimate, 1: the trial point.
+// grid (nchunk, T), V2GT_CHUNK threads.  which = 0: evaluate the current estimate; 1: the trial point
+// x (+) delta, which this kernel forms itself (Values::retract fused into the error evaluation: the state
+// rows of the trial point are written to the other half of the double buffer) together with the two dot
+// products g.delta and |delta|^2 of the LM model-fidelity test.
 template <bool JAC>
 __global__ void __launch_bounds__(V2GT_CHUNK) k_factor_eval(DevPtrs d, int which, int force_all) {
   const int t = blockIdx.y;
   const LmState &lm = d.lm[t];
-  __shared__ double s_red[2][V2GT_CHUNK / 32];
+  __shared__ double s_red[4][V2GT_CHUNK / 32];
   // trial-level predicates are uniform across the CTA
   if (!force_all) {
     if (lm.lm_state != 0 || lm.status != V2GT_OK)
@@ -35,19 +57,30 @@ __global__ void __launch_bounds__(V2GT_CHUNK) k_factor_eval(DevPtrs d, int which
   const int n = d.n_states[t];
   const int i = blockIdx.x * V2GT_CHUNK + threadIdx.x;
   const int buf = which ? (1 - lm.cur) : lm.cur;
-  double cost = 0.0, lin0 = 0.0;
+  double cost = 0.0, lin0 = 0.0, gd = 0.0, dd = 0.0;
   if (i < n) {
     const long long s = tr.st_off + i;
     const double *gl = d.glob + ((long long)buf * d.T + t) * GLOB_STRIDE;
     const double *xb = d.x + (long long)buf * d.S * X_STRIDE;
+    const double *xcur = d.x + (long long)lm.cur * d.S * X_STRIDE;
     double xi[16];
-    {
-      const double4 *p4 = reinterpret_cast<const double4 *>(xb + s * X_STRIDE);
+    if (!JAC && which) {
+      double x0[16], dl[16];
+      ld16(xcur + s * X_STRIDE, x0);
+      ld16(d.delta + s * 16, dl);
+      retract_state(x0, dl, xi);
+      double4 *o4 = reinterpret_cast<double4 *>(d.x + ((long long)buf * d.S + s) * X_STRIDE);
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const double4 v = p4[k];
-        xi[4 * k] = v.x; xi[4 * k + 1] = v.y; xi[4 * k + 2] = v.z; xi[4 * k + 3] = v.w;
+      for (int k = 0; k < 4; k++)
+        o4[k] = make_double4(xi[4 * k], xi[4 * k + 1], xi[4 * k + 2], xi[4 * k + 3]);
+      const double *gk = d.ne + s * NE_STRIDE + NE_M + NE_MG;
+#pragma unroll
+      for (int k = 0; k < 15; k++) {
+        gd += __ldg(gk + NE_MW * k) * dl[k];
+        dd += dl[k] * dl[k];
       }
+    } else {
+      ld16(xb + s * X_STRIDE, xi);
     }
     // ---- vicon factor
     {
@@ -81,13 +114,13 @@ __global__ void __launch_bounds__(V2GT_CHUNK) k_factor_eval(DevPtrs d, int which
     // ---- IMU factor i -> i+1
     if (i < n - 1) {
       double xj[16];
-      {
-        const double4 *p4 = reinterpret_cast<const double4 *>(xb + (s + 1) * X_STRIDE);
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const double4 v = p4[k];
-          xj[4 * k] = v.x; xj[4 * k + 1] = v.y; xj[4 * k + 2] = v.z; xj[4 * k + 3] = v.w;
-        }
+      if (!JAC && which) {
+        double x0[16], dl[16];
+        ld16(xcur + (s + 1) * X_STRIDE, x0);
+        ld16(d.delta + (s + 1) * 16, dl);
+        retract_state(x0, dl, xj);
+      } else {
+        ld16(xb + (s + 1) * X_STRIDE, xj);
       }
       GravTerms G;
       grav_terms(gl[GL_THX], gl[GL_THY], tr.prm.gravity_magnitude, G);
@@ -116,27 +149,27 @@ __global__ void __launch_bounds__(V2GT_CHUNK) k_factor_eval(DevPtrs d, int which
       }
     }
   }
-  // ---- fixed-order CTA reduction of (cost, lin0)
+  // ---- fixed-order CTA reduction of (cost, lin0, g.delta, |delta|^2)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     cost += __shfl_down_sync(0xffffffffu, cost, o);
     lin0 += __shfl_down_sync(0xffffffffu, lin0, o);
+    gd += __shfl_down_sync(0xffffffffu, gd, o);
+    dd += __shfl_down_sync(0xffffffffu, dd, o);
   }
   if (lane == 0) {
     s_red[0][wid] = cost;
     s_red[1][wid] = lin0;
+    s_red[2][wid] = gd;
+    s_red[3][wid] = dd;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    double c = 0, l = 0;
-    for (int w = 0; w < V2GT_CHUNK / 32; w++) {
-      c += s_red[0][w];
-      l += s_red[1][w];
-    }
-    double *pc = d.part_cost + ((long long)t * d.nchunk + blockIdx.x) * 2;
-    pc[0] = c;
-    pc[1] = l;
+  if (threadIdx.x < 4) {
+    double c = 0;
+    for (int w = 0; w < V2GT_CHUNK / 32; w++)
+      c += s_red[threadIdx.x][w];
+    d.part_cost[((long long)t * d.nchunk + blockIdx.x) * 4 + threadIdx.x] = c;
   }
 }
 
@@ -261,7 +294,8 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(DevPtrs d, int force_a
     for (int k = 0; k < 6; k++)
       Bg[k] = 0.0;
     gv[0] = gv[1] = gv[2] = 0.0;
-    double *HO = d.HO + s * HO_STRIDE;
+    double *ne = d.ne + s * NE_STRIDE;
+    double *HO = ne + NE_M; // O block: row stride NE_MW
 
     // ================= H1-type contributions of factor i (i -> i+1)
     if (i < n - 1) {
@@ -306,7 +340,7 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(DevPtrs d, int force_a
         for (int r = 0; r < 3; r++)
 #pragma unroll
           for (int c = 0; c < 3; c++)
-            HO[(3 * dcol + r) * 15 + 3 * e + c] = Ob[3 * r + c];
+            HO[(3 * dcol + r) * NE_MW + 3 * e + c] = Ob[3 * r + c];
       }
       // B1[dcol] = Y[v]^T H3v + Y[p]^T H3p ; g1[dcol] = -sum_a Y[a]^T e[a]
       double H3v[6], H3p[6];
@@ -390,7 +424,7 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(DevPtrs d, int force_a
 #pragma unroll
       for (int r = 0; r < 3; r++)
         for (int c = 0; c < 15; c++)
-          HO[(3 * dcol + r) * 15 + c] = 0.0;
+          HO[(3 * dcol + r) * NE_MW + c] = 0.0;
     }
 
     // ================= H2-type contributions of factor i-1 (i-1 -> i)
@@ -522,7 +556,7 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(DevPtrs d, int force_a
     }
 
     // ================= store this thread's strips
-    double *HD = d.HD + s * HD_STRIDE;
+    double *HD = ne + NE_D;
 #pragma unroll
     for (int c = 0; c < 5; c++)
 #pragma unroll
@@ -530,15 +564,15 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(DevPtrs d, int force_a
 #pragma unroll
         for (int cc = 0; cc < 3; cc++)
           HD[(3 * c + r) * 15 + 3 * dcol + cc] = Dcol[c][3 * r + cc];
-    double *HB = d.HB + s * HB_STRIDE;
+    double *HB = ne + NE_M + NE_MB;
 #pragma unroll
     for (int r = 0; r < 3; r++) {
 #pragma unroll
       for (int c = 0; c < 7; c++)
-        HB[(3 * dcol + r) * 9 + c] = Bv[7 * r + c];
-      HB[(3 * dcol + r) * 9 + 7] = Bg[2 * r];
-      HB[(3 * dcol + r) * 9 + 8] = Bg[2 * r + 1];
-      d.Hg[s * HG_STRIDE + 3 * dcol + r] = gv[r];
+        HB[(3 * dcol + r) * NE_MW + c] = Bv[7 * r + c];
+      HB[(3 * dcol + r) * NE_MW + 7] = Bg[2 * r];
+      HB[(3 * dcol + r) * NE_MW + 8] = Bg[2 * r + 1];
+      ne[NE_M + (3 * dcol + r) * NE_MW + NE_MG] = gv[r];
     }
   }
   __syncthreads();
@@ -589,7 +623,7 @@ __global__ void __launch_bounds__(64) k_reduce_gamma(DevPtrs d, int n_asm_chunks
     const int usedc = (n + V2GT_CHUNK - 1) / V2GT_CHUNK;
     double l0 = 0;
     for (int k = 0; k < usedc; k++)
-      l0 += d.part_cost[((long long)t * d.nchunk + k) * 2 + 1];
+      l0 += d.part_cost[((long long)t * d.nchunk + k) * 4 + 1];
     lm.lin_error0 = l0;
   }
 }

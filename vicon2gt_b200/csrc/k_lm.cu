@@ -11,24 +11,12 @@
 
 namespace v2 {
 
-struct SegGeomLm {
-  int stride, nseg, nsep;
-};
-__device__ inline SegGeomLm seg_geom_lm(int n, int P) {
-  SegGeomLm g;
-  int st = (n + 1 + P - 1) / P;
-  g.stride = st < 2 ? 2 : st;
-  g.nseg = (n + g.stride - 1) / g.stride;
-  g.nsep = n / g.stride;
-  return g;
-}
-
 __device__ inline double sum_cost(const DevPtrs &d, int t, int which) {
   const int n = d.n_states[t];
   const int used = (n + V2GT_CHUNK - 1) / V2GT_CHUNK;
   double s = 0;
   for (int k = 0; k < used; k++)
-    s += d.part_cost[((long long)t * d.nchunk + k) * 2 + which];
+    s += d.part_cost[((long long)t * d.nchunk + k) * 4 + which];
   return s;
 }
 
@@ -88,18 +76,12 @@ __global__ void k_lm_decide(DevPtrs d, int count_active) {
   if (lm.lm_state != 0)
     return;
   const v2gt_params &p = d.trials[t].prm;
-  const int n = d.n_states[t];
   bool step_ok = false, stop_search = false;
   double new_error = INFINITY, lin_change = 0.0, cost_change = 0.0;
   if (!lm.solve_failed) {
-    const SegGeomLm sg = seg_geom_lm(n, d.P);
+    // g.delta and |delta|^2: the states' parts come from the trial-point evaluation, the globals' from the reduced solve
     const double *xg = d.xg + (long long)t * 16;
-    double gd = xg[10] + xg[12], dd = xg[11] + xg[13];
-    for (int j = 0; j < sg.nseg; j++) {
-      const double *so = d.seg + ((long long)t * d.P + j) * SEG_STRIDE;
-      gd += so[SEG_DOT];
-      dd += so[SEG_DOT + 1];
-    }
+    const double gd = xg[10] + sum_cost(d, t, 2), dd = xg[11] + sum_cost(d, t, 3);
     // linear.error(0) - linear.error(delta) = g.delta - 1/2 delta' H delta = 1/2 (g.delta + lambda |delta|^2)
     lin_change = 0.5 * (gd + lm.lambda * dd);
     if (lin_change >= 0.0) {

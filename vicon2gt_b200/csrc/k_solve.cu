@@ -3,16 +3,19 @@
 // LevenbergMarquardtOptimizer::tryLambda for the graph of ViconGraphSolver.cpp:390-536).
 //
 // The chain of n 15x15 blocks of one trial is cut into segments separated by single "separator"
-// states.  One warp owns one segment:
-//   k_seg_eliminate  block Cholesky through the segment's interior, left to right, carrying the
-//                    fill-in towards the segment's left separator (F columns), its border to the 9
-//                    globals (B columns) and the right-hand side; Schur contributions to the two
-//                    separators and to the global 9x9 block are left in registers/shared memory and
-//                    written once per segment
-//   k_reduced        one warp per trial: block Cholesky over the separator chain, Schur complement
-//                    onto the 9 globals, 9x9 solve, back-substitution of the separators, retract of
-//                    the globals
-//   k_seg_backsub    back-substitution through the segment interiors + retract of the states
+// states.  One warp owns one segment and walks it state by state:
+//   k_seg_eliminate     per state: D = L L^T as an LDL^T factorisation carried out together with the
+//                       Gauss-Jordan inverse L^-1 (both live in registers, distributed in the 8x8 tile
+//                       order of the FP64 mma fragments); W = L^-1 [O | F | B | g] and the Schur update
+//                       S = W^T W are chains of mma.sync.m8n8k4.f64 on register fragments (no shared
+//                       memory traffic in the inner products); the state's normal-equation record is
+//                       streamed HBM -> shared memory with cp.async one state ahead.  F is the fill-in
+//                       towards the segment's left separator, B the border to the 9 globals, g the rhs.
+//   k_reduced_assemble  normal-equation records of the separator chain from the segment outputs
+//   k_reduced           one warp per trial: the same elimination over the separator chain, the Schur
+//                       complement onto the 9 globals, the 9x9 solve, back-substitution of the separators,
+//                       retract of the globals
+//   k_seg_backsub       back-substitution through the segment interiors (writes the step delta)
 // Every trial and every segment takes the same arithmetic path in the same order: results are
 // deterministic run to run.
 #include "v2gt_common.cuh"
@@ -32,151 +35,281 @@ __host__ __device__ inline SegGeom seg_geom(int n, int P) {
   return g;
 }
 
-// per-warp shared memory working set of the elimination (doubles)
-constexpr int W_D = 0;              // 15x15 current diagonal block -> L (lower)
-constexpr int W_M = 225;            // 15x40 [O | F | B | g] -> W = L^-1 [.]
-constexpr int W_CD = W_M + 600;     // carry to the next node: D 225, F 225, B 135, g 15
-constexpr int W_CF = W_CD + 225;
-constexpr int W_CB = W_CF + 225;
-constexpr int W_CG = W_CB + 135;
-constexpr int W_SL = W_CG + 15;     // accumulators for the left separator: 225, 135, 15
-constexpr int W_BL = W_SL + 225;
-constexpr int W_GL = W_BL + 135;
-constexpr int W_GS = W_GL + 15;     // accumulators for the globals: 81, 9
-constexpr int W_GG = W_GS + 81;
-constexpr int W_TOTAL = W_GG + 9 + 1; // 1891 -> even
+// ---- per-warp shared memory (doubles): two staged normal-equation records + the broadcast buffers of the
+// factorisation (column of D [16] + row of X [16], double buffered)
+constexpr int SW_STAGE = 0, SW_CB = 2 * NE_STRIDE, SW_TOTAL = 2 * NE_STRIDE + 64;
 constexpr int ELIM_WARPS = 4;
 
-// In-place Cholesky of the 15x15 block at w[W_D] (lower triangle used) followed by the forward
-// substitution of the 40 columns of w[W_M].  Returns false on a non-positive pivot.
-__device__ __forceinline__ bool chol_trsm(double *w, int lane, int ncols_active_from) {
-  double *D = w + W_D;
-  double *M = w + W_M;
+// D[8x8] += A[8x4] B[4x8] on the FP64 tensor path; fragments (lane = 4 gid + tid):
+//   a = A[gid][tid], b = B[tid][gid], (c0, c1) = C[gid][2 tid + {0,1}]
+__device__ __forceinline__ void dmma(double &c0, double &c1, const double a, const double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(double *smem, const double *gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// stream one 600-double record into shared memory (300 16-byte chunks over the warp)
+__device__ __forceinline__ void stage_record(double *dst, const double *src, int lane) {
+#pragma unroll
+  for (int k = 0; k < 10; k++) {
+    const int ch = lane + 32 * k;
+    if (ch < NE_STRIDE / 2)
+      cp_async16(dst + 2 * ch, src + 2 * ch);
+  }
+}
+
+// Running Schur state of a chain elimination (all "+S" = sums of W^T W products).
+//   cy[t][u][e] = S[8t+gid][8u+2tid+e] of the last eliminated state (u = O-row tile; tile (0,1) is unused)
+//   p15[t]      = sum over the chain of S[15][8t+gid]   (held by lanes tid == 3; F column 0 against F, B, g)
+//   pt[i][e]    = sum over the chain of tiles (2,2)(2,3)(2,4)(3,3)(3,4)(4,4): S[8ta+gid][8tb+2tid+e]
+struct ElimAcc {
+  double cy[5][2][2];
+  double p15[5];
+  double pt[6][2];
+};
+__device__ __forceinline__ void acc_zero(ElimAcc &A) {
+#pragma unroll
+  for (int t = 0; t < 5; t++) {
+    A.p15[t] = 0.0;
+#pragma unroll
+    for (int u = 0; u < 2; u++)
+      A.cy[t][u][0] = A.cy[t][u][1] = 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++)
+    A.pt[i][0] = A.pt[i][1] = 0.0;
+}
+
+// LDL^T of the 15x15 block held as the tiles d00 = D[gid][2tid+e], d10 = D[8+gid][2tid+e],
+// d11 = D[8+gid][8+2tid+e] together with the Gauss-Jordan inverse of its unit-lower factor; returns
+// L^-1 = D^-1/2 L'^-1 (L = Cholesky factor) in the same tile order.  cb: 64 doubles of shared memory.
+__device__ __forceinline__ bool ldl_inverse(double (&d00)[2], double (&d10)[2], double (&d11)[2], double (&li00)[2],
+                                            double (&li10)[2], double (&li11)[2], double *cb, const int gid, const int tid) {
+  double x00[2], x10[2], x11[2];
+  x00[0] = (gid == 2 * tid) ? 1.0 : 0.0;
+  x00[1] = (gid == 2 * tid + 1) ? 1.0 : 0.0;
+  x10[0] = x10[1] = 0.0;
+  x11[0] = x00[0];
+  x11[1] = x00[1];
+  double p0 = 1.0, p1 = 1.0;
   bool ok = true;
+#pragma unroll
   for (int j = 0; j < 15; j++) {
-    const double djj = D[16 * j];
-    if (!(djj > 0.0))
-      ok = false;
-    const double ljj = sqrt(djj);
-    const double inv = 1.0 / ljj;
-    __syncwarp();
-    if (lane == 0)
-      D[16 * j] = ljj;
-    const int r = j + 1 + lane;
-    if (r < 15)
-      D[15 * r + j] *= inv;
-    __syncwarp();
-    // trailing update of the lower triangle: rows r > j, columns j < c <= r
-    if (r < 15) {
-      const double lrj = D[15 * r + j];
-      for (int c = j + 1; c <= r; c++)
-        D[15 * r + c] -= lrj * D[15 * c + j];
+    double *buf = cb + 32 * (j & 1);
+    // the holders publish column j of D (rows 0..15) and row j of X (columns 0..15)
+    if (j < 8) {
+      if (tid == (j >> 1)) {
+        buf[gid] = d00[j & 1];
+        buf[8 + gid] = d10[j & 1];
+      }
+      if (gid == j)
+        *reinterpret_cast<double2 *>(buf + 16 + 2 * tid) = make_double2(x00[0], x00[1]);
+    } else {
+      if (tid == ((j - 8) >> 1))
+        buf[8 + gid] = d11[j & 1];
+      if (gid == j - 8) {
+        *reinterpret_cast<double2 *>(buf + 16 + 2 * tid) = make_double2(x10[0], x10[1]);
+        *reinterpret_cast<double2 *>(buf + 24 + 2 * tid) = make_double2(x11[0], x11[1]);
+      }
     }
     __syncwarp();
-  }
-  // forward substitution, one column per lane (two passes over the 40 columns)
-  for (int c = lane + ncols_active_from; c < 40; c += 32) {
-    double x[15];
-#pragma unroll
-    for (int r = 0; r < 15; r++)
-      x[r] = M[40 * r + c];
-#pragma unroll
-    for (int r = 0; r < 15; r++) {
-      double s = x[r];
-#pragma unroll
-      for (int k = 0; k < r; k++)
-        s -= D[15 * r + k] * x[k];
-      x[r] = s / D[16 * r];
+    const double piv = buf[j];
+    ok = ok && (piv > 0.0);
+    const double rinv = 1.0 / piv;
+    if (j < 8) {
+      p0 = (gid == j) ? piv : p0;
+      const double mr0 = (gid > j) ? buf[gid] * rinv : 0.0;
+      const double mr1 = buf[8 + gid] * rinv;
+      const double2 c0 = *reinterpret_cast<const double2 *>(buf + 2 * tid);
+      const double2 c1 = *reinterpret_cast<const double2 *>(buf + 8 + 2 * tid);
+      const double2 xr = *reinterpret_cast<const double2 *>(buf + 16 + 2 * tid);
+      d00[0] = fma(-mr0, c0.x, d00[0]);
+      d00[1] = fma(-mr0, c0.y, d00[1]);
+      d10[0] = fma(-mr1, c0.x, d10[0]);
+      d10[1] = fma(-mr1, c0.y, d10[1]);
+      d11[0] = fma(-mr1, c1.x, d11[0]);
+      d11[1] = fma(-mr1, c1.y, d11[1]);
+      x00[0] = fma(-mr0, xr.x, x00[0]);
+      x00[1] = fma(-mr0, xr.y, x00[1]);
+      x10[0] = fma(-mr1, xr.x, x10[0]);
+      x10[1] = fma(-mr1, xr.y, x10[1]);
+    } else {
+      p1 = (8 + gid == j) ? piv : p1;
+      const double mr1 = (8 + gid > j) ? buf[8 + gid] * rinv : 0.0;
+      const double2 c1 = *reinterpret_cast<const double2 *>(buf + 8 + 2 * tid);
+      const double2 xr0 = *reinterpret_cast<const double2 *>(buf + 16 + 2 * tid);
+      const double2 xr1 = *reinterpret_cast<const double2 *>(buf + 24 + 2 * tid);
+      d11[0] = fma(-mr1, c1.x, d11[0]);
+      d11[1] = fma(-mr1, c1.y, d11[1]);
+      x10[0] = fma(-mr1, xr0.x, x10[0]);
+      x10[1] = fma(-mr1, xr0.y, x10[1]);
+      x11[0] = fma(-mr1, xr1.x, x11[0]);
+      x11[1] = fma(-mr1, xr1.y, x11[1]);
     }
-#pragma unroll
-    for (int r = 0; r < 15; r++)
-      M[40 * r + c] = x[r];
   }
-  __syncwarp();
+  const double s0 = rsqrt(p0);
+  const double s1 = (gid < 7) ? rsqrt(p1) : 0.0; // row 15 is padding
+  li00[0] = s0 * x00[0];
+  li00[1] = s0 * x00[1];
+  li10[0] = s1 * x10[0];
+  li10[1] = s1 * x10[1];
+  li11[0] = s1 * x11[0];
+  li11[1] = s1 * x11[1];
   return ok;
 }
 
-// Schur updates from W (15x40 at w[W_M]): carry (next node) = -W_O^T [W_O W_F W_B w_g];
-// left-separator accumulators -= W_F^T [W_F W_B w_g]; global accumulators -= W_B^T [W_B w_g].
+// Eliminate one state.  st: its staged normal-equation record (shared memory); Finit: for the first state of a
+// segment with a left separator, the record of that separator (global; F = O_sep^T), else nullptr.
+// On return A.cy holds this state's Schur tiles and the persistent sums are updated; the factor record is stored.
 template <bool HAS_F>
-__device__ __forceinline__ void schur_update(double *w, int lane) {
-  const double *M = w + W_M;
-  const int total = HAS_F ? 1065 : 1065; // index space is shared; F pairs are skipped when !HAS_F
-  for (int idx = lane; idx < total; idx += 32) {
-    int a, b;
-    if (idx < 600) {
-      a = idx / 40;
-      b = idx - 40 * a;
-    } else if (idx < 975) {
-      const int i2 = idx - 600;
-      a = 15 + i2 / 25;
-      b = 15 + (i2 - 25 * (i2 / 25));
-    } else {
-      const int i3 = idx - 975;
-      a = 30 + i3 / 10;
-      b = 30 + (i3 - 10 * (i3 / 10));
-    }
-    if (!HAS_F && ((a >= 15 && a < 30) || (b >= 15 && b < 30)))
-      continue;
-    double s = 0;
+__device__ __forceinline__ bool elim_node(const double *st, const double *__restrict__ Finit, const double lambda, ElimAcc &A,
+                                          double *cb, double *__restrict__ fac, const int lane) {
+  const int gid = lane >> 2, tid = lane & 3;
+  // ---- D = record + lambda I - carry, as tiles
+  double d00[2], d10[2], d11[2];
 #pragma unroll
-    for (int k = 0; k < 15; k++)
-      s += M[40 * k + a] * M[40 * k + b];
-    if (a < 15) {
-      if (b < 15)
-        w[W_CD + 15 * a + b] = -s;
-      else if (b < 30)
-        w[W_CF + 15 * a + (b - 15)] = -s;
-      else if (b < 39)
-        w[W_CB + 9 * a + (b - 30)] = -s;
-      else
-        w[W_CG + a] = -s;
-    } else if (a < 30) {
-      if (b < 30)
-        w[W_SL + 15 * (a - 15) + (b - 15)] -= s;
-      else if (b < 39)
-        w[W_BL + 9 * (a - 15) + (b - 30)] -= s;
-      else
-        w[W_GL + (a - 15)] -= s;
-    } else {
-      if (b < 39)
-        w[W_GS + 9 * (a - 30) + (b - 30)] -= s;
-      else
-        w[W_GG + (a - 30)] -= s;
-    }
+  for (int e = 0; e < 2; e++) {
+    const int c = 2 * tid + e;
+    d00[e] = st[NE_D + 15 * gid + c] - A.cy[0][0][e] + ((gid == c) ? lambda : 0.0);
+    d10[e] = (gid < 7) ? st[NE_D + 15 * (8 + gid) + c] - A.cy[1][0][e] : 0.0;
+    const int c1 = 8 + c;
+    if (gid < 7 && c1 < 15)
+      d11[e] = st[NE_D + 15 * (8 + gid) + c1] - A.cy[1][1][e] + ((gid == c) ? lambda : 0.0);
+    else
+      d11[e] = (gid == 7 && c1 == 15) ? 1.0 : 0.0;
   }
-  __syncwarp();
+  // ---- M = [O | F | B | g] (16x40, row 15 zero) in fragment order m[kk][t] = M[8u+2tid+e][8t+gid], kk = 2u+e
+  double m[4][5];
+#pragma unroll
+  for (int kk = 0; kk < 4; kk++) {
+    const int u = kk >> 1, e = kk & 1;
+    const int r = 8 * u + 2 * tid + e;
+    const bool rv = r < 15;
+    const double *mrow = st + NE_M + NE_MW * (rv ? r : 0);
+    m[kk][0] = rv ? mrow[gid] : 0.0;
+    double v1, v2, v3;
+    if (HAS_F) {
+      if (Finit) {
+        const double *fi = Finit + NE_M + (rv ? r : 0);
+        v1 = __ldg(fi);                        // F[r][0]     = O_sep[0][r]
+        v2 = __ldg(fi + NE_MW * (1 + gid));    // F[r][1+gid]
+        v3 = (gid < 6) ? __ldg(fi + NE_MW * (9 + gid)) : 0.0;
+      } else {
+        v1 = -A.cy[1][u][e];
+        v2 = -A.cy[2][u][e];
+        v3 = -A.cy[3][u][e];
+      }
+    } else {
+      v1 = v2 = v3 = 0.0;
+    }
+    m[kk][1] = rv ? ((gid < 7) ? mrow[8 + gid] : v1) : 0.0;
+    m[kk][2] = rv ? v2 : 0.0;
+    m[kk][3] = rv ? ((gid < 6) ? v3 : mrow[NE_MB + gid - 6] - A.cy[3][u][e]) : 0.0;
+    m[kk][4] = rv ? mrow[17 + gid] - A.cy[4][u][e] : 0.0;
+  }
+  __syncwarp(); // every lane has consumed the staged record and the carry
+  // ---- factorisation + inverse
+  double li00[2], li10[2], li11[2];
+  const bool ok = ldl_inverse(d00, d10, d11, li00, li10, li11, cb, gid, tid);
+  // ---- W^T = M^T L^-T  (row tile u of W from the kk-steps its triangle reaches)
+  double w[4][5];
+#pragma unroll
+  for (int t = 0; t < 5; t++) {
+    if (!HAS_F && t == 2) {
+      w[0][t] = w[1][t] = w[2][t] = w[3][t] = 0.0;
+      continue;
+    }
+    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+    dmma(a0, a1, m[0][t], li00[0]);
+    dmma(b0, b1, m[0][t], li10[0]);
+    dmma(a0, a1, m[1][t], li00[1]);
+    dmma(b0, b1, m[1][t], li10[1]);
+    dmma(b0, b1, m[2][t], li11[0]);
+    dmma(b0, b1, m[3][t], li11[1]);
+    w[0][t] = a0;
+    w[1][t] = a1;
+    w[2][t] = b0;
+    w[3][t] = b1;
+  }
+  // ---- factor record (fragment order, fully coalesced 16-byte stores)
+  {
+    double2 *f2 = reinterpret_cast<double2 *>(fac);
+    f2[lane] = make_double2(li00[0], li00[1]);
+    f2[32 + lane] = make_double2(li10[0], li10[1]);
+    f2[64 + lane] = make_double2(li11[0], li11[1]);
+#pragma unroll
+    for (int u = 0; u < 2; u++)
+#pragma unroll
+      for (int t = 0; t < 5; t++)
+        f2[FAC_W / 2 + (u * 5 + t) * 32 + lane] = make_double2(w[2 * u][t], w[2 * u + 1][t]);
+  }
+  // ---- Schur tiles S = W^T W
+#pragma unroll
+  for (int t = 0; t < 5; t++)
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      double c0 = 0.0, c1 = 0.0;
+      if (!(t == 0 && u == 1) && (HAS_F || t != 2)) {
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++)
+          dmma(c0, c1, w[kk][t], w[kk][u]);
+      }
+      A.cy[t][u][0] = c0;
+      A.cy[t][u][1] = c1;
+    }
+  if (HAS_F) {
+#pragma unroll
+    for (int t = 1; t < 5; t++)
+      A.p15[t] += A.cy[t][1][1];
+  }
+  {
+    int i = 0;
+#pragma unroll
+    for (int ta = 2; ta < 5; ta++)
+#pragma unroll
+      for (int tb = ta; tb < 5; tb++) {
+        if (HAS_F || ta != 2) {
+#pragma unroll
+          for (int kk = 0; kk < 4; kk++)
+            dmma(A.pt[i][0], A.pt[i][1], w[kk][ta], w[kk][tb]);
+        }
+        i++;
+      }
+  }
+  return ok;
 }
 
-// store L (packed lower) and W to the factor row of a node
-__device__ __forceinline__ void store_factor(const double *w, double *__restrict__ fac, int lane, bool has_f) {
-  for (int idx = lane; idx < 120; idx += 32) {
-    // idx -> (r, c) of the packed lower triangle
-    int r = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
-    while (tri(r + 1, 0) <= idx)
-      r++;
-    while (tri(r, 0) > idx)
-      r--;
-    const int c = idx - tri(r, 0);
-    fac[FAC_L + idx] = w[W_D + 15 * r + c];
+// Eliminate `count` consecutive states whose records start at ne0 (stride NE_STRIDE); factor records to fac0.
+template <bool HAS_F>
+__device__ __forceinline__ bool elim_chain(const double *__restrict__ ne0, const int count, const double *__restrict__ left_sep_ne,
+                                           const double lambda, double *__restrict__ fac0, ElimAcc &A, double *w, const int lane) {
+  double *stage = w + SW_STAGE;
+  double *cb = w + SW_CB;
+  bool ok = true;
+  if (count > 0)
+    stage_record(stage, ne0, lane);
+  cp_async_commit();
+  for (int k = 0; k < count; k++) {
+    if (k + 1 < count)
+      stage_record(stage + NE_STRIDE * ((k + 1) & 1), ne0 + (long long)(k + 1) * NE_STRIDE, lane);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
+    ok = elim_node<HAS_F>(stage + NE_STRIDE * (k & 1), (HAS_F && k == 0) ? left_sep_ne : nullptr, lambda, A, cb,
+                          fac0 + (long long)k * FAC_STRIDE, lane) && ok;
   }
-  for (int idx = lane; idx < 225; idx += 32) {
-    const int r = idx / 15, c = idx - 15 * r;
-    fac[FAC_WO + idx] = w[W_M + 40 * r + c];
-    fac[FAC_WF + idx] = has_f ? w[W_M + 40 * r + 15 + c] : 0.0;
-  }
-  for (int idx = lane; idx < 135; idx += 32) {
-    const int r = idx / 9, c = idx - 9 * r;
-    fac[FAC_WB + idx] = w[W_M + 40 * r + 30 + c];
-  }
-  if (lane < 15)
-    fac[FAC_WG + lane] = w[W_M + 40 * lane + 39];
+  cp_async_wait<0>();
+  return ok;
 }
 
 // ------------------------------------------------------------------------------------------------
 // grid: (ceil(P / ELIM_WARPS), T); block: ELIM_WARPS warps; warp -> segment j of trial t
 __global__ void __launch_bounds__(ELIM_WARPS * 32) k_seg_eliminate(DevPtrs d, int force_all) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   const int t = blockIdx.y;
   LmState &lm = d.lm[t];
   if (!force_all && (lm.lm_state != 0 || lm.status != V2GT_OK))
@@ -187,68 +320,110 @@ __global__ void __launch_bounds__(ELIM_WARPS * 32) k_seg_eliminate(DevPtrs d, in
   const SegGeom sg = seg_geom(n, d.P);
   if (j >= sg.nseg)
     return;
-  double *w = smem + (size_t)wid * W_TOTAL;
+  double *w = smem + (size_t)wid * SW_TOTAL;
   const TrialDev &tr = d.trials[t];
   const double lambda = lm.lambda;
   const int a0 = j * sg.stride;
   const int b1 = min(n, (j + 1) * sg.stride - 1); // exclusive end of the interior
   const bool has_left = (j >= 1);
-  const bool has_right = ((j + 1) * sg.stride - 1 < n);
-  for (int k = lane; k < W_TOTAL; k += 32)
-    w[k] = 0.0;
-  __syncwarp();
-  bool ok = true;
-  for (int k = a0; k < b1; k++) {
-    const long long s = tr.st_off + k;
-    const double *HD = d.HD + s * HD_STRIDE;
-    const double *HO = d.HO + s * HO_STRIDE;
-    const double *HB = d.HB + s * HB_STRIDE;
-    const double *Hg = d.Hg + s * HG_STRIDE;
-    // current blocks = assembled blocks + carry (+ lambda I)
-    for (int idx = lane; idx < 225; idx += 32) {
-      const int r = idx / 15, c = idx - 15 * r;
-      w[W_D + idx] = HD[idx] + w[W_CD + idx] + ((r == c) ? lambda : 0.0);
-      w[W_M + 40 * r + c] = HO[idx];
-      double f = w[W_CF + idx];
-      if (k == a0 && has_left)
-        f = d.HO[(s - 1) * HO_STRIDE + 15 * c + r]; // H[a0][L] = O_L^T
-      w[W_M + 40 * r + 15 + c] = f;
-    }
-    for (int idx = lane; idx < 135; idx += 32) {
-      const int r = idx / 9, c = idx - 9 * r;
-      w[W_M + 40 * r + 30 + c] = HB[idx] + w[W_CB + idx];
-    }
-    if (lane < 15)
-      w[W_M + 40 * lane + 39] = Hg[lane] + w[W_CG + lane];
-    __syncwarp();
-    ok = chol_trsm(w, lane, 0) && ok;
-    store_factor(w, d.fac + s * FAC_STRIDE, lane, has_left);
-    if (has_left)
-      schur_update<true>(w, lane);
-    else
-      schur_update<false>(w, lane);
-  }
-  // segment outputs
+  const long long s0 = tr.st_off + a0;
+  ElimAcc A;
+  acc_zero(A);
+  bool ok;
+  if (has_left)
+    ok = elim_chain<true>(d.ne + s0 * NE_STRIDE, b1 - a0, d.ne + (s0 - 1) * NE_STRIDE, lambda, d.fac + s0 * FAC_STRIDE, A, w, lane);
+  else
+    ok = elim_chain<false>(d.ne + s0 * NE_STRIDE, b1 - a0, nullptr, lambda, d.fac + s0 * FAC_STRIDE, A, w, lane);
+  // ---- segment outputs
+  const int gid = lane >> 2, tid = lane & 3;
   double *so = d.seg + ((long long)t * d.P + j) * SEG_STRIDE;
-  for (int idx = lane; idx < 225; idx += 32) {
-    so[SEG_SL + idx] = has_left ? w[W_SL + idx] : 0.0;
-    so[SEG_DR + idx] = has_right ? w[W_CD + idx] : 0.0;
-    so[SEG_C + idx] = (has_right && has_left) ? w[W_CF + idx] : 0.0;
+  double *cyo = so + SEG_CY, *fbo = so + SEG_FB;
+#pragma unroll
+  for (int tt = 0; tt < 5; tt++)
+#pragma unroll
+    for (int u = 0; u < 2; u++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        if (tt == 0 && u == 1)
+          continue;
+        const int r = 8 * u + 2 * tid + e, c = 8 * tt + gid;
+        if (r < 15) {
+          cyo[40 * r + c] = A.cy[tt][u][e];
+          if (tt == 1 && u == 0 && c < 15)
+            cyo[40 * c + r] = A.cy[tt][u][e]; // mirror of the D part
+        }
+      }
+  if (tid == 3) {
+#pragma unroll
+    for (int tt = 1; tt < 5; tt++) {
+      const int b = 8 * tt + gid - 15;
+      if (b >= 0) {
+        fbo[b] = A.p15[tt];
+        fbo[25 * b] = A.p15[tt];
+      }
+    }
   }
-  for (int idx = lane; idx < 135; idx += 32) {
-    so[SEG_BL + idx] = has_left ? w[W_BL + idx] : 0.0;
-    so[SEG_BR + idx] = has_right ? w[W_CB + idx] : 0.0;
+  {
+    int i = 0;
+#pragma unroll
+    for (int ta = 2; ta < 5; ta++)
+#pragma unroll
+      for (int tb = ta; tb < 5; tb++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int a = 8 * ta + gid - 15, b = 8 * tb + 2 * tid + e - 15;
+          fbo[25 * a + b] = A.pt[i][e];
+          fbo[25 * b + a] = A.pt[i][e];
+        }
+        i++;
+      }
   }
-  if (lane < 15) {
-    so[SEG_GL + lane] = has_left ? w[W_GL + lane] : 0.0;
-    so[SEG_GR + lane] = has_right ? w[W_CG + lane] : 0.0;
-  }
-  for (int idx = lane; idx < 81; idx += 32)
-    so[SEG_GS + idx] = w[W_GS + idx];
-  if (lane < 9)
-    so[SEG_GG + lane] = w[W_GG + lane];
   if (!ok && lane == 0)
     atomicExch(&lm.solve_failed, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Normal-equation records of the separator chain.  grid (P, T), 128 threads; CTA -> separator m = blockIdx.x + 1.
+__global__ void __launch_bounds__(128) k_reduced_assemble(DevPtrs d, int force_all) {
+  const int t = blockIdx.y;
+  const LmState &lm = d.lm[t];
+  if (!force_all && (lm.lm_state != 0 || lm.status != V2GT_OK))
+    return;
+  const int n = d.n_states[t];
+  const SegGeom sg = seg_geom(n, d.P);
+  const int m = blockIdx.x + 1;
+  if (m > sg.nsep)
+    return;
+  const TrialDev &tr = d.trials[t];
+  const long long s = tr.st_off + (long long)m * sg.stride - 1;
+  const double *ne = d.ne + s * NE_STRIDE;
+  const double *segl = d.seg + ((long long)t * d.P + (m - 1)) * SEG_STRIDE; // this separator closes segment m-1
+  const bool has_r = (m < sg.nseg);                                         // ... and opens segment m
+  const double *segr = d.seg + ((long long)t * d.P + m) * SEG_STRIDE;
+  const bool has_next = has_r && (m + 1 <= sg.nsep);
+  double *out = d.red_ne + ((long long)t * d.P + m) * NE_STRIDE;
+  for (int idx = threadIdx.x; idx < NE_STRIDE; idx += blockDim.x) {
+    double v;
+    if (idx < NE_M) {
+      const int i = idx / 15, jn = idx - 15 * i;
+      v = ne[idx] - segl[SEG_CY + 40 * i + jn];
+      if (has_r)
+        v -= segr[SEG_FB + 25 * i + jn];
+    } else {
+      const int q = idx - NE_M;
+      const int i = q / NE_MW, c = q - NE_MW * i;
+      if (c < 15) {
+        // coupling separator m -> m+1 through segment m:  H[m][m+1](i, c) = -S(rows: O index c, column F index i)
+        v = has_next ? -segr[SEG_CY + 40 * c + XC_F + i] : 0.0;
+      } else {
+        const int k = c - 15; // border columns 0..8, rhs 9
+        v = ne[idx] - segl[SEG_CY + 40 * i + XC_B + k];
+        if (has_r)
+          v -= segr[SEG_FB + 25 * i + 15 + k];
+      }
+    }
+    out[idx] = v;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -268,181 +443,180 @@ __device__ inline void retract_globals(const double *g0, const double *dx, doubl
     g1[k] = 0.0;
 }
 
-// back-substitution of one node held in shared memory:  x = L^-T (w_g - W_O x_next - W_F x_left - W_B x_glob)
-// f: factor row (720 doubles, shared or global), lanes 0..14 return x[lane].
-__device__ __forceinline__ double backsub_node(const double *f, int lane, const double *x_next, const double *x_left,
-                                               const double *x_glob, bool has_next, bool has_left) {
-  double rhs = 0.0;
-  if (lane < 15) {
-    rhs = f[FAC_WG + lane];
-    if (has_next) {
+// Back-substitution state of one chain: the lane's slice xv[8t+gid] of the extended vector
+// [x_next (15) | x_left (15) | x_glob (9) | -1]; slices 0 and 1 follow the chain, the rest is fixed.
+struct BackVec {
+  double xv[5];
+};
+__device__ __forceinline__ void backvec_init(BackVec &V, const double *x_next, const double *x_left, const double *x_glob,
+                                             const int gid) {
+  V.xv[0] = x_next[gid];
+  V.xv[1] = (gid < 7) ? x_next[8 + gid] : x_left[0];
+  V.xv[2] = x_left[1 + gid];
+  V.xv[3] = (gid < 6) ? x_left[9 + gid] : x_glob[gid - 6];
+  V.xv[4] = (gid < 7) ? x_glob[2 + gid] : -1.0;
+}
+struct FacRegs {
+  double2 li[3];
+  double2 w[10];
+};
+__device__ __forceinline__ void fac_load(FacRegs &F, const double *__restrict__ fac, const int lane) {
+  const double2 *f2 = reinterpret_cast<const double2 *>(fac);
 #pragma unroll
-      for (int a = 0; a < 15; a++)
-        rhs -= f[FAC_WO + 15 * lane + a] * x_next[a];
+  for (int i = 0; i < 3; i++)
+    F.li[i] = __ldcs(f2 + 32 * i + lane);
+#pragma unroll
+  for (int i = 0; i < 10; i++)
+    F.w[i] = __ldcs(f2 + FAC_W / 2 + 32 * i + lane);
+}
+// x = L^-T (w_g - W_O x_next - W_F x_left - W_B x_glob); on return every lane holds x[2tid+e] in y0[e] and
+// x[8+2tid+e] in y1[e], and V follows the chain.
+__device__ __forceinline__ void backsub_node(const FacRegs &F, BackVec &V, double (&y0)[2], double (&y1)[2], const double x_left0,
+                                             const int gid, const int tid) {
+  double p[4];
+#pragma unroll
+  for (int u = 0; u < 2; u++) {
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int t = 0; t < 5; t++) {
+      a = fma(F.w[u * 5 + t].x, V.xv[t], a);
+      b = fma(F.w[u * 5 + t].y, V.xv[t], b);
     }
-    if (has_left) {
-#pragma unroll
-      for (int a = 0; a < 15; a++)
-        rhs -= f[FAC_WF + 15 * lane + a] * x_left[a];
-    }
-#pragma unroll
-    for (int a = 0; a < 9; a++)
-      rhs -= f[FAC_WB + 9 * lane + a] * x_glob[a];
+    p[2 * u] = a;
+    p[2 * u + 1] = b;
   }
-  // L^T x = rhs, backward; lane c finalises x_c, everyone below subtracts
-  double x = 0.0;
-  for (int c = 14; c >= 0; c--) {
-    double xc = 0.0;
-    if (lane == c) {
-      xc = rhs / f[FAC_L + tri(c, c)];
-      x = xc;
-    }
-    xc = __shfl_sync(0xffffffffu, xc, c);
-    if (lane < c)
-      rhs -= f[FAC_L + tri(c, lane)] * xc;
+#pragma unroll
+  for (int o = 4; o < 32; o <<= 1)
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      p[k] += __shfl_xor_sync(0xffffffffu, p[k], o);
+  // rhs[gid], rhs[8+gid] live on the lanes with tid' = gid / 2, register kk = (gid & 1) (+2)
+  const int src = gid >> 1;
+  const double s0 = __shfl_sync(0xffffffffu, p[0], src), s1 = __shfl_sync(0xffffffffu, p[1], src);
+  const double s2 = __shfl_sync(0xffffffffu, p[2], src), s3 = __shfl_sync(0xffffffffu, p[3], src);
+  const double r_lo = -((gid & 1) ? s1 : s0), r_hi = -((gid & 1) ? s3 : s2);
+  y0[0] = fma(F.li[0].x, r_lo, F.li[1].x * r_hi);
+  y0[1] = fma(F.li[0].y, r_lo, F.li[1].y * r_hi);
+  y1[0] = F.li[2].x * r_hi;
+  y1[1] = F.li[2].y * r_hi;
+#pragma unroll
+  for (int o = 4; o < 32; o <<= 1) {
+    y0[0] += __shfl_xor_sync(0xffffffffu, y0[0], o);
+    y0[1] += __shfl_xor_sync(0xffffffffu, y0[1], o);
+    y1[0] += __shfl_xor_sync(0xffffffffu, y1[0], o);
+    y1[1] += __shfl_xor_sync(0xffffffffu, y1[1], o);
   }
-  return x;
+  const double t0 = __shfl_sync(0xffffffffu, y0[0], src), t1 = __shfl_sync(0xffffffffu, y0[1], src);
+  const double t2 = __shfl_sync(0xffffffffu, y1[0], src), t3 = __shfl_sync(0xffffffffu, y1[1], src);
+  V.xv[0] = (gid & 1) ? t1 : t0;
+  V.xv[1] = (gid < 7) ? ((gid & 1) ? t3 : t2) : x_left0;
+}
+// store x (15 values) of a state: lanes gid == 0 hold all of it between them
+__device__ __forceinline__ void store_x(double *__restrict__ dst, const double (&y0)[2], const double (&y1)[2], const int gid,
+                                        const int tid) {
+  if (gid == 0) {
+    *reinterpret_cast<double2 *>(dst + 2 * tid) = make_double2(y0[0], y0[1]);
+    *reinterpret_cast<double2 *>(dst + 8 + 2 * tid) = make_double2(y1[0], (tid == 3) ? 0.0 : y1[1]);
+  }
 }
 
-constexpr int RED_SMEM = W_TOTAL + 32; // + x_next (15) + x_glob (9) scratch
+constexpr int RED_SMEM = SW_TOTAL + 160; // + 9x9 system (90) + x_glob (16) + x scratch (32)
 
 // grid: T CTAs of one warp.
 __global__ void __launch_bounds__(32) k_reduced(DevPtrs d, int force_all) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   const int t = blockIdx.x;
   LmState &lm = d.lm[t];
   if (!force_all && (lm.lm_state != 0 || lm.status != V2GT_OK))
     return;
   const int lane = threadIdx.x;
+  const int gid = lane >> 2, tid = lane & 3;
   const int n = d.n_states[t];
   const SegGeom sg = seg_geom(n, d.P);
   const TrialDev &tr = d.trials[t];
   const double lambda = lm.lambda;
   double *w = smem;
-  double *xs = smem + W_TOTAL; // [0:15) x_next, [16:25) x_glob
-  for (int k = lane; k < RED_SMEM; k += 32)
-    w[k] = 0.0;
-  __syncwarp();
-  bool ok = true;
-  const double *segs = d.seg + (long long)t * d.P * SEG_STRIDE;
-  // ---- forward elimination over the separators m = 1..nsep (node m*stride-1)
-  for (int m = 1; m <= sg.nsep; m++) {
-    const long long s = tr.st_off + (long long)m * sg.stride - 1;
-    const double *HD = d.HD + s * HD_STRIDE;
-    const double *HB = d.HB + s * HB_STRIDE;
-    const double *Hg = d.Hg + s * HG_STRIDE;
-    const double *sl = segs + (long long)(m - 1) * SEG_STRIDE; // segment on the left  (this node is its right separator)
-    const bool has_rseg = (m < sg.nseg);                        // segment on the right (this node is its left separator)
-    const double *sr = segs + (long long)m * SEG_STRIDE;
-    const bool has_next = (m + 1 <= sg.nsep);
-    for (int idx = lane; idx < 225; idx += 32) {
-      const int r = idx / 15, c = idx - 15 * r;
-      double v = HD[idx] + w[W_CD + idx] + sl[SEG_DR + idx] + ((r == c) ? lambda : 0.0);
-      if (has_rseg)
-        v += sr[SEG_SL + idx];
-      w[W_D + idx] = v;
-      // coupling to the next separator: H[s_m][s_m+1] = C^T of the right segment
-      w[W_M + 40 * r + c] = (has_next && has_rseg) ? sr[SEG_C + 15 * c + r] : 0.0;
-      w[W_M + 40 * r + 15 + c] = 0.0;
-    }
-    for (int idx = lane; idx < 135; idx += 32) {
-      const int r = idx / 9, c = idx - 9 * r;
-      double v = HB[idx] + w[W_CB + idx] + sl[SEG_BR + idx];
-      if (has_rseg)
-        v += sr[SEG_BL + idx];
-      w[W_M + 40 * r + 30 + c] = v;
-    }
-    if (lane < 15) {
-      double v = Hg[lane] + w[W_CG + lane] + sl[SEG_GR + lane];
-      if (has_rseg)
-        v += sr[SEG_GL + lane];
-      w[W_M + 40 * lane + 39] = v;
-    }
-    __syncwarp();
-    ok = chol_trsm(w, lane, 0) && ok;
-    // factor row of the reduced chain
-    double *rf = d.red + ((long long)t * d.P + m) * RED_STRIDE;
-    for (int idx = lane; idx < 120; idx += 32) {
-      int r = 0;
-      while (tri(r + 1, 0) <= idx)
-        r++;
-      rf[RED_L + idx] = w[W_D + 15 * r + (idx - tri(r, 0))];
-    }
-    for (int idx = lane; idx < 225; idx += 32) {
-      const int r = idx / 15, c = idx - 15 * r;
-      rf[RED_WO + idx] = w[W_M + 40 * r + c];
-    }
-    for (int idx = lane; idx < 135; idx += 32) {
-      const int r = idx / 9, c = idx - 9 * r;
-      rf[RED_WB + idx] = w[W_M + 40 * r + 30 + c];
-    }
-    if (lane < 15)
-      rf[RED_WG + lane] = w[W_M + 40 * lane + 39];
-    schur_update<false>(w, lane);
+  double *G9 = smem + SW_TOTAL;       // 9x9 + rhs 9
+  double *xgs = smem + SW_TOTAL + 96; // x_glob (16)
+  double *xz = smem + SW_TOTAL + 112; // zeros / x_next scratch (32)
+  // ---- forward elimination over the separators m = 1..nsep
+  ElimAcc A;
+  acc_zero(A);
+  const long long r0 = (long long)t * d.P + 1;
+  bool ok = elim_chain<false>(d.red_ne + r0 * NE_STRIDE, sg.nsep, nullptr, lambda, d.red_fac + r0 * FAC_STRIDE, A, w, lane);
+  // ---- global 9x9: Gamma + lambda I - sum_seg S_BB - S_BB(separator chain); rhs likewise
+  double *fbr = d.red_fb + (long long)t * 640; // 25x25 scratch in global (only the B,g rows/columns are meaningful)
+  {
+    int i = 0;
+#pragma unroll
+    for (int ta = 2; ta < 5; ta++)
+#pragma unroll
+      for (int tb = ta; tb < 5; tb++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int a = 8 * ta + gid - 15, b = 8 * tb + 2 * tid + e - 15;
+          fbr[25 * a + b] = A.pt[i][e];
+          fbr[25 * b + a] = A.pt[i][e];
+        }
+        i++;
+      }
   }
-  // ---- global 9x9: Gamma + lambda I + segment contributions (fixed order) + separator contributions
   __syncwarp();
+  const double *segs = d.seg + (long long)t * d.P * SEG_STRIDE;
   const double *gm = d.gamma + (long long)t * 96;
   for (int idx = lane; idx < 90; idx += 32) {
-    double v = gm[idx];
-    if (idx < 81) {
-      v += w[W_GS + idx];
-      for (int jj = 0; jj < sg.nseg; jj++)
-        v += segs[(long long)jj * SEG_STRIDE + SEG_GS + idx];
-      if (idx / 9 == idx % 9)
-        v += lambda;
-    } else {
-      v += w[W_GG + idx - 81];
-      for (int jj = 0; jj < sg.nseg; jj++)
-        v += segs[(long long)jj * SEG_STRIDE + SEG_GG + idx - 81];
-    }
-    xs[32 + idx] = v; // staged, then copied to G9 (W_GS/W_GG live inside w, W_D is free now)
+    const int r = (idx < 81) ? idx / 9 : idx - 81;
+    const int c = (idx < 81) ? idx - 9 * r : 9;
+    double v = gm[idx] - fbr[25 * (15 + r) + 15 + c];
+    for (int jj = 0; jj < sg.nseg; jj++)
+      v -= segs[(long long)jj * SEG_STRIDE + SEG_FB + 25 * (15 + r) + 15 + c];
+    if (idx < 81 && r == c)
+      v += lambda;
+    G9[idx] = v;
   }
+  for (int idx = lane; idx < 48; idx += 32)
+    xgs[idx] = 0.0; // x_glob + scratch zeros
   __syncwarp();
-  // (RED_SMEM is W_TOTAL + 32; stage area overlaps nothing we still need: use the M region instead)
-  for (int idx = lane; idx < 90; idx += 32)
-    w[W_M + idx] = xs[32 + idx];
-  __syncwarp();
-  double *A = w + W_M; // 9x9 + rhs(9)
+  double *Am = G9;
   if (lane == 0) {
     // symmetrise, Cholesky, solve (tiny, sequential)
     for (int r = 0; r < 9; r++)
       for (int c = 0; c < r; c++) {
-        const double v = 0.5 * (A[9 * r + c] + A[9 * c + r]);
-        A[9 * r + c] = v;
-        A[9 * c + r] = v;
+        const double v = 0.5 * (Am[9 * r + c] + Am[9 * c + r]);
+        Am[9 * r + c] = v;
+        Am[9 * c + r] = v;
       }
     for (int jj = 0; jj < 9; jj++) {
-      double dd = A[10 * jj];
+      double dd = Am[10 * jj];
       for (int k = 0; k < jj; k++)
-        dd -= A[9 * jj + k] * A[9 * jj + k];
+        dd -= Am[9 * jj + k] * Am[9 * jj + k];
       if (!(dd > 0.0))
         ok = false;
       const double l = sqrt(dd);
-      A[10 * jj] = l;
+      Am[10 * jj] = l;
       for (int r = jj + 1; r < 9; r++) {
-        double sacc = A[9 * r + jj];
+        double sacc = Am[9 * r + jj];
         for (int k = 0; k < jj; k++)
-          sacc -= A[9 * r + k] * A[9 * jj + k];
-        A[9 * r + jj] = sacc / l;
+          sacc -= Am[9 * r + k] * Am[9 * jj + k];
+        Am[9 * r + jj] = sacc / l;
       }
     }
     double y[9], x[9];
     for (int r = 0; r < 9; r++) {
-      double sacc = A[81 + r];
+      double sacc = Am[81 + r];
       for (int k = 0; k < r; k++)
-        sacc -= A[9 * r + k] * y[k];
-      y[r] = sacc / A[10 * r];
+        sacc -= Am[9 * r + k] * y[k];
+      y[r] = sacc / Am[10 * r];
     }
     for (int r = 8; r >= 0; r--) {
       double sacc = y[r];
       for (int k = r + 1; k < 9; k++)
-        sacc -= A[9 * k + r] * x[k];
-      x[r] = sacc / A[10 * r];
+        sacc -= Am[9 * k + r] * x[k];
+      x[r] = sacc / Am[10 * r];
     }
     double gd = 0, dd2 = 0;
     for (int r = 0; r < 9; r++) {
-      xs[16 + r] = x[r];
+      xgs[r] = x[r];
       gd += gm[81 + r] * x[r];
       dd2 += x[r] * x[r];
     }
@@ -452,7 +626,6 @@ __global__ void __launch_bounds__(32) k_reduced(DevPtrs d, int force_all) {
     xg[10] = gd;
     xg[11] = dd2;
   }
-  ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) && ok;
   __syncwarp();
   if (!__all_sync(0xffffffffu, ok)) {
     if (lane == 0)
@@ -460,41 +633,20 @@ __global__ void __launch_bounds__(32) k_reduced(DevPtrs d, int force_all) {
     return;
   }
   // ---- back-substitution of the separators (right to left)
-  double gd = 0, dd2 = 0;
+  BackVec V;
+  backvec_init(V, xz, xz, xgs, gid);
   for (int m = sg.nsep; m >= 1; m--) {
-    const double *rf = d.red + ((long long)t * d.P + m) * RED_STRIDE;
-    // gather into the FAC layout expected by backsub_node (W_F absent)
-    double *f = w; // W_TOTAL >= 720
-    for (int idx = lane; idx < 120; idx += 32)
-      f[FAC_L + idx] = rf[RED_L + idx];
-    for (int idx = lane; idx < 225; idx += 32)
-      f[FAC_WO + idx] = rf[RED_WO + idx];
-    for (int idx = lane; idx < 135; idx += 32)
-      f[FAC_WB + idx] = rf[RED_WB + idx];
-    if (lane < 15)
-      f[FAC_WG + lane] = rf[RED_WG + lane];
-    __syncwarp();
-    const double x = backsub_node(f, lane, xs, xs, xs + 16, m < sg.nsep, false);
-    __syncwarp();
+    FacRegs F;
+    fac_load(F, d.red_fac + ((long long)t * d.P + m) * FAC_STRIDE, lane);
+    double y0[2], y1[2];
+    backsub_node(F, V, y0, y1, 0.0, gid, tid);
     const long long s = tr.st_off + (long long)m * sg.stride - 1;
-    if (lane < 15) {
-      xs[lane] = x;
-      d.xsep[((long long)t * d.P + m) * 16 + lane] = x;
-      gd += d.Hg[s * HG_STRIDE + lane] * x;
-      dd2 += x * x;
-    }
-    __syncwarp();
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    gd += __shfl_down_sync(0xffffffffu, gd, o);
-    dd2 += __shfl_down_sync(0xffffffffu, dd2, o);
+    store_x(d.xsep + ((long long)t * (d.P + 1) + m) * 16, y0, y1, gid, tid);
+    store_x(d.delta + s * 16, y0, y1, gid, tid);
   }
   if (lane == 0) {
-    double *xg = d.xg + (long long)t * 16;
-    xg[12] = gd;
-    xg[13] = dd2;
     // trial point of the globals
+    const double *xg = d.xg + (long long)t * 16;
     const double *g0 = d.glob + ((long long)lm.cur * d.T + t) * GLOB_STRIDE;
     double *g1 = d.glob + ((long long)(1 - lm.cur) * d.T + t) * GLOB_STRIDE;
     retract_globals(g0, xg, g1);
@@ -502,129 +654,80 @@ __global__ void __launch_bounds__(32) k_reduced(DevPtrs d, int force_all) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// JPLNavState::retract (src/gtsam/JPLNavState.cpp:25-54) of one state row
-__device__ inline void retract_state(const double *x0, const double *dx, double *x1) {
-  double dq[4], q[4];
-  small_quat(dx, dq);
-  quat_mul(dq, x0, q);
-  x1[0] = q[0]; x1[1] = q[1]; x1[2] = q[2]; x1[3] = q[3];
-#pragma unroll
-  for (int k = 0; k < 12; k++)
-    x1[4 + k] = x0[4 + k] + dx[3 + k];
-}
-
 constexpr int BS_WARPS = 4;
-constexpr int BS_SMEM_PER_WARP = 720 + 64; // factor row + x_next(16) x_left(16) x_glob(16) delta(16)
 
 // grid: (ceil(P / BS_WARPS), T); warp -> segment j of trial t
 __global__ void __launch_bounds__(BS_WARPS * 32) k_seg_backsub(DevPtrs d, int force_all) {
-  extern __shared__ double smem[];
+  __shared__ double s_x[BS_WARPS][48];
   const int t = blockIdx.y;
   LmState &lm = d.lm[t];
   if (!force_all && (lm.lm_state != 0 || lm.status != V2GT_OK || lm.solve_failed))
     return;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int gid = lane >> 2, tid = lane & 3;
   const int j = blockIdx.x * BS_WARPS + wid;
   const int n = d.n_states[t];
   const SegGeom sg = seg_geom(n, d.P);
   if (j >= sg.nseg)
     return;
   const TrialDev &tr = d.trials[t];
-  double *f = smem + (size_t)wid * BS_SMEM_PER_WARP;
-  double *x_next = f + 720, *x_left = f + 736, *x_glob = f + 752, *dl = f + 768;
   const int a0 = j * sg.stride;
   const int b1 = min(n, (j + 1) * sg.stride - 1);
   const bool has_left = (j >= 1);
   const bool has_right = ((j + 1) * sg.stride - 1 < n);
+  double *xs = s_x[wid]; // [0,16) x_next, [16,32) x_left, [32,48) x_glob
   if (lane < 16) {
-    x_next[lane] = (has_right && lane < 15) ? d.xsep[((long long)t * d.P + (j + 1)) * 16 + lane] : 0.0;
-    x_left[lane] = (has_left && lane < 15) ? d.xsep[((long long)t * d.P + j) * 16 + lane] : 0.0;
-    x_glob[lane] = (lane < 9) ? d.xg[(long long)t * 16 + lane] : 0.0;
+    xs[lane] = (has_right && lane < 15) ? d.xsep[((long long)t * (d.P + 1) + (j + 1)) * 16 + lane] : 0.0;
+    xs[16 + lane] = (has_left && lane < 15) ? d.xsep[((long long)t * (d.P + 1) + j) * 16 + lane] : 0.0;
+    xs[32 + lane] = (lane < 9) ? d.xg[(long long)t * 16 + lane] : 0.0;
   }
   __syncwarp();
-  const int cur = lm.cur;
-  const double *xc = d.x + (long long)cur * d.S * X_STRIDE;
-  double *xo = d.x + (long long)(1 - cur) * d.S * X_STRIDE;
-  double gd = 0, dd2 = 0;
-  // the separators themselves are retracted by the segment on their right (or by segment nseg-1 for a trailing one)
+  BackVec V;
+  backvec_init(V, xs, xs + 16, xs + 32, gid);
+  const double x_left0 = xs[16];
+  if (b1 <= a0)
+    return;
+  FacRegs F, Fn;
+  fac_load(F, d.fac + (tr.st_off + b1 - 1) * FAC_STRIDE, lane);
   for (int k = b1 - 1; k >= a0; k--) {
     const long long s = tr.st_off + k;
-    const double *fg = d.fac + s * FAC_STRIDE;
-    for (int idx = lane; idx < 720; idx += 32)
-      f[idx] = fg[idx];
-    __syncwarp();
-    const bool has_next = (k < b1 - 1) || has_right;
-    const double x = backsub_node(f, lane, x_next, x_left, x_glob, has_next, has_left);
-    __syncwarp();
-    if (lane < 15) {
-      x_next[lane] = x;
-      dl[lane] = x;
-      d.delta[s * 16 + lane] = x;
-      gd += d.Hg[s * HG_STRIDE + lane] * x;
-      dd2 += x * x;
-    }
-    __syncwarp();
-    if (lane == 0)
-      retract_state(xc + s * X_STRIDE, dl, xo + s * X_STRIDE);
-    __syncwarp();
-  }
-  // retract the separator states: left separator of this segment; a trailing separator (no right segment) by its left segment
-  if (lane == 0) {
-    if (has_left) {
-      const long long s = tr.st_off + a0 - 1;
-      for (int k = 0; k < 15; k++)
-        d.delta[s * 16 + k] = x_left[k];
-      retract_state(xc + s * X_STRIDE, x_left, xo + s * X_STRIDE);
-    }
-    if (has_right && j == sg.nseg - 1) {
-      const long long s = tr.st_off + b1;
-      double xr[15];
-      for (int k = 0; k < 15; k++) {
-        xr[k] = d.xsep[((long long)t * d.P + (j + 1)) * 16 + k];
-        d.delta[s * 16 + k] = xr[k];
-      }
-      retract_state(xc + s * X_STRIDE, xr, xo + s * X_STRIDE);
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    gd += __shfl_down_sync(0xffffffffu, gd, o);
-    dd2 += __shfl_down_sync(0xffffffffu, dd2, o);
-  }
-  if (lane == 0) {
-    double *so = d.seg + ((long long)t * d.P + j) * SEG_STRIDE;
-    so[SEG_DOT] = gd;
-    so[SEG_DOT + 1] = dd2;
+    if (k > a0)
+      fac_load(Fn, d.fac + (s - 1) * FAC_STRIDE, lane);
+    double y0[2], y1[2];
+    backsub_node(F, V, y0, y1, x_left0, gid, tid);
+    store_x(d.delta + s * 16, y0, y1, gid, tid);
+    F = Fn;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 int solve_configure() {
-  const size_t sm1 = sizeof(double) * W_TOTAL * ELIM_WARPS;
-  const size_t sm2 = sizeof(double) * (RED_SMEM + 128);
-  const size_t sm3 = sizeof(double) * BS_SMEM_PER_WARP * BS_WARPS;
+  const size_t sm1 = sizeof(double) * SW_TOTAL * ELIM_WARPS;
+  const size_t sm2 = sizeof(double) * RED_SMEM;
   V2_CUDA_CHECK(cudaFuncSetAttribute(k_seg_eliminate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
   V2_CUDA_CHECK(cudaFuncSetAttribute(k_reduced, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
-  V2_CUDA_CHECK(cudaFuncSetAttribute(k_seg_backsub, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
   return V2GT_OK;
 }
 int launch_eliminate(const DevPtrs &d, int force_all, cudaStream_t st) {
-  const size_t sm1 = sizeof(double) * W_TOTAL * ELIM_WARPS;
+  const size_t sm1 = sizeof(double) * SW_TOTAL * ELIM_WARPS;
   dim3 g1((d.P + ELIM_WARPS - 1) / ELIM_WARPS, d.T);
   k_seg_eliminate<<<g1, ELIM_WARPS * 32, sm1, st>>>(d, force_all);
   V2_CUDA_CHECK(cudaGetLastError());
   return V2GT_OK;
 }
 int launch_reduced(const DevPtrs &d, int force_all, cudaStream_t st) {
-  const size_t sm2 = sizeof(double) * (RED_SMEM + 128);
+  const size_t sm2 = sizeof(double) * RED_SMEM;
+  if (d.P > 1) {
+    dim3 g0(d.P - 1, d.T);
+    k_reduced_assemble<<<g0, 128, 0, st>>>(d, force_all);
+  }
   k_reduced<<<d.T, 32, sm2, st>>>(d, force_all);
   V2_CUDA_CHECK(cudaGetLastError());
   return V2GT_OK;
 }
 int launch_backsub(const DevPtrs &d, int force_all, cudaStream_t st) {
-  const size_t sm3 = sizeof(double) * BS_SMEM_PER_WARP * BS_WARPS;
   dim3 g3((d.P + BS_WARPS - 1) / BS_WARPS, d.T);
-  k_seg_backsub<<<g3, BS_WARPS * 32, sm3, st>>>(d, force_all);
+  k_seg_backsub<<<g3, BS_WARPS * 32, 0, st>>>(d, force_all);
   V2_CUDA_CHECK(cudaGetLastError());
   return V2GT_OK;
 }

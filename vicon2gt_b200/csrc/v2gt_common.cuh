@@ -15,8 +15,9 @@
 //   info    [S][120]   P^-1 of that interval, packed lower triangle (row-major: r*(r+1)/2 + c)
 //   fpi     [S][64]    per-factor linearisation pieces of the IMU factor (FPI_* offsets)
 //   fpv     [S][88]    per-factor pieces of the vicon factor (FPV_* offsets)
-//   HD HO HB Hg        normal-equation blocks per state: D 15x15, O 15x15 (k,k+1), B 15x9, g 15
-//   fac     [S][720]   elimination factors per state: L (120 packed), W_O 225, W_F 225, W_B 135, w_g 15
+//   ne      [S][600]   normal-equation record per state: D 15x15 (225) | M 15x25 = [O 15 (k,k+1) | B 9 | g 1]
+//                      (one contiguous, 16-byte aligned record: streamed with cp.async by the elimination)
+//   fac     [S][832]   elimination factors per state in mma-fragment order: L^-1 (3 8x8 tiles) | W (16x40)
 //   delta   [S][16]    LM step per state
 #pragma once
 #include "../../include/vicon2gt_b200.h"
@@ -43,17 +44,21 @@ constexpr int FPI_E = 0, FPI_TTH = 15, FPI_TB = 24, FPI_SV = 33, FPI_SP = 36, FP
 //  r[6] = sqrt(w) W e ; A[6][6] = sqrt(w) W H1(:, [0:3, 12:15]) ; G[6][7] = sqrt(w) W [H2 H3 H4] ; has_vicon ; idx0 ; idx1 ; w
 constexpr int FPV_R = 0, FPV_A = 6, FPV_G = 42, FPV_HAS = 84, FPV_IDX0 = 85, FPV_IDX1 = 86, FPV_W = 87, FPV_STRIDE = 88;
 
-// ---- normal-equation blocks
-constexpr int HD_STRIDE = 225, HO_STRIDE = 225, HB_STRIDE = 135, HG_STRIDE = 16;
-// ---- elimination factor row
-constexpr int FAC_L = 0, FAC_WO = 120, FAC_WF = 345, FAC_WB = 570, FAC_WG = 705, FAC_STRIDE = 720;
-// ---- per-segment outputs (contributions to the separators and the globals)
-//  SL 225, BL 135, gL 15 (to the left separator); DR 225, C 225 (H[R][L]), BR 135, gR 15 (to the right
-//  separator); GS 81, gS 9 (to the globals); dot partials: g.delta, |delta|^2 (written by back-substitution)
-constexpr int SEG_SL = 0, SEG_BL = 225, SEG_GL = 360, SEG_DR = 375, SEG_C = 600, SEG_BR = 825, SEG_GR = 960, SEG_GS = 975,
-              SEG_GG = 1056, SEG_DOT = 1065, SEG_STRIDE = 1072;
-// ---- per-separator factor rows of the reduced chain: L 120, W_O 225, W_B 135, w_g 15 (+pad)
-constexpr int RED_L = 0, RED_WO = 120, RED_WB = 345, RED_WG = 480, RED_STRIDE = 496;
+// ---- normal-equation record of one state (row-major pieces)
+//  D  15x15 at [0, 225);  M 15x25 at [225, 600): columns [0,15) = O (coupling to the next state),
+//  [15,24) = B (border to the 9 globals), 24 = g (right-hand side)
+constexpr int NE_D = 0, NE_M = 225, NE_MW = 25, NE_MB = 15, NE_MG = 24, NE_STRIDE = 600;
+// ---- elimination factor record of one state, in the register order of the mma.m8n8k4 fragments
+//  (lane = 4 gid + tid):  L^-1 tiles (0,0) (1,0) (1,1): [tile][lane][e] = Linv[8u+gid][8v+2tid+e]   (192)
+//  W = L^-1 [O F B g] (16x40, row 15 is padding): [u][t][lane][e] = W[8u+2tid+e][8t+gid]            (640)
+constexpr int FAC_LI = 0, FAC_W = 192, FAC_STRIDE = 832;
+// ---- extended column order of one elimination step: [O 0..14 | F 15..29 | B 30..38 | g 39]
+constexpr int XC_F = 15, XC_B = 30, XC_G = 39, XC_N = 40;
+// ---- per-segment outputs, all "+S" (the consumer subtracts):
+//  CY 15x40: S[r][c] = sum W_O^T [W_O W_F W_B w_g] after the last interior state (Schur terms of the right
+//  separator: D, coupling to the left separator, border, rhs);  FB 25x25 (symmetric): sum over the segment
+//  of [W_F W_B w_g]^T [W_F W_B w_g] (Schur terms of the left separator and the globals)
+constexpr int SEG_CY = 0, SEG_FB = 600, SEG_STRIDE = 1232;
 // ---- per-CTA partial sums of the assembly / cost kernels
 //  assembly: Gamma vicon 7x7 (49) + g (7) + gravity 2x2 (4) + g (2) + lin_error0 (1) -> 63 (+pad)
 constexpr int PART_STRIDE = 64;
@@ -105,11 +110,13 @@ struct DevPtrs {
   int *valid;        // [S] scratch flags of the build stage
   double *pre, *info, *cov;
   double *fpi, *fpv;
-  double *HD, *HO, *HB, *Hg;
-  double *fac, *seg, *red, *xsep;
+  double *ne;        // [S][NE_STRIDE]
+  double *fac, *seg; // [S][FAC_STRIDE], [T][P][SEG_STRIDE]
+  double *red_ne, *red_fac, *red_fb; // reduced (separator) chain: [T][P][NE_STRIDE], [T][P][FAC_STRIDE], [T][640]
+  double *xsep;      // [T][P+1][16] separator steps (slot m = separator m, 1-based)
   double *delta;
   double *part_asm;  // [T][nchunk][PART_STRIDE]
-  double *part_cost; // [T][nchunk][2]
+  double *part_cost; // [T][nchunk][4]: cost, lin_error0, g.delta, |delta|^2
   double *gamma;     // [T][96]: Gamma 81 + g 9 (assembled, undamped)
   double *xg;        // [T][16]: global step
   LmState *lm;
