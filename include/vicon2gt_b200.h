@@ -104,6 +104,8 @@ typedef struct v2gt_batch v2gt_batch; /* opaque; owns all device memory; one hos
 /* Library / device queries. */
 const char *v2gt_version(void);
 int v2gt_device_count(int32_t *count);
+/* sizeof(v2gt_params), sizeof(v2gt_trial_info) as compiled: lets a binding check its struct mirrors. */
+int v2gt_abi_struct_sizes(int32_t *params_bytes, int32_t *trial_info_bytes);
 
 /* Create a batch of `n_trials` independent problems on CUDA device `device`. */
 int v2gt_batch_create(int32_t device, int32_t n_trials, v2gt_batch **out);

@@ -75,3 +75,8 @@ def ds_c2_small():
     from vicon2gt_b200 import sim
 
     return sim.make_config("C2", seed=7, duration_s=25.0, vicon_sigmas=(1e-3, 1e-3, 1e-3, 1e-2, 1e-2, 1e-2))
+
+
+def load_golden(name):
+    """tests/golden/<name>.npz: fixed inputs + the oracle's outputs on them (tools/make_golden.py)."""
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", name + ".npz")))

@@ -292,3 +292,49 @@ def test_write_to_file_matches_oracle(ds_c2_small, tmp_path):
     ig = (tmp_path / "g" / "g.txt").read_text().split("\n")
     assert [l for l in io if l.endswith(": ")] == [l for l in ig if l.endswith(": ")]  # same section headers
     assert len(io) == len(ig)
+
+
+@pytest.mark.parametrize("name", ["c2_8s", "c1_3s"])
+def test_cuda_path_matches_golden_fixture(name):
+    """CUDA path against the committed golden vectors (inputs + oracle outputs, tools/make_golden.py): bracket
+    indices bit-exact, states / calibration within 1e-6, chi2 within 1e-8 relative -- no oracle call in this test."""
+    from conftest import load_golden
+    from vicon2gt_b200 import api
+
+    g = load_golden(name)
+    p = default_params(lm_max_iterations=int(g["lm_max_iterations"]))
+    bs = api.BatchSolver(1, keep_cov=1)
+    bs.set_trial(0, p, g["imu_t"], g["imu_w"], g["imu_a"], g["vic_t"], g["vic_q"], g["vic_p"], g["state_t"],
+                 vic_R_const=g["vic_R_const"])
+    bs.upload()
+    it = bs.eval_interp(0, g["interp_t"], 0.1)
+    for k in ("idx0", "idx1", "ok"):
+        assert np.array_equal(it[k], g["interp_" + k])
+    ok = g["interp_ok"] == 1
+    assert np.max(np.abs(it["p"][ok] - g["interp_p"][ok])) < 1e-12
+    bs.build(True)
+    t0, x0 = bs.states(0)
+    assert np.array_equal(t0, g["init_times"]) and np.max(np.abs(x0 - g["init_states"])) < 1e-12
+    pre, cov = bs.preint(0, cov=True)
+    assert np.array_equal(pre[:, 0], g["preint"][:, 0])
+    assert np.max(np.abs(pre[:, 1:11] - g["preint"][:, 1:11])) < 1e-13
+    lin = bs.linearize(0)
+    assert abs(lin["cost"] - g["lin_cost"]) / g["lin_cost"] < 1e-11
+    assert _relmax(lin["g"], g["lin_g"]) < 1e-10
+    assert _relmax(lin["D"][::25], g["lin_D"]) < 1e-10 and _relmax(lin["O"][::25], g["lin_O"]) < 1e-10
+    delta, okd = bs.solve(0, 1e-5)
+    n = len(t0)
+    assert okd
+    sc = np.max(np.abs(g["solve_delta"][: 15 * n].reshape(n, 15)), axis=0)
+    assert np.max(np.abs(delta[: 15 * n] - g["solve_delta"][: 15 * n]).reshape(n, 15) / sc) < 1e-7
+    bs.build_and_solve()
+    inf = bs.info(0)
+    assert inf.status == 0
+    _, x1 = bs.states(0)
+    dq = np.abs(np.sum(x1[:, :4] * g["final_states"][:, :4], axis=1))
+    assert (2 * np.arccos(np.clip(dq, 0, 1))).max() < 1e-6
+    assert np.max(np.abs(x1[:, 4:] - g["final_states"][:, 4:])) < 1e-6
+    gl = bs.globals10(0)
+    assert np.max(np.abs(gl[4:] - g["final_globals"][4:])) < 1e-6
+    assert abs(inf.final_error - g["final_error"]) / g["final_error"] < 1e-8
+    bs.close()

@@ -218,6 +218,14 @@ void v2gt_params_default(v2gt_params *p) {
   p->interp_gap_factor = 0.1;
 }
 
+int v2gt_abi_struct_sizes(int32_t *params_bytes, int32_t *trial_info_bytes) {
+  if (params_bytes)
+    *params_bytes = (int32_t)sizeof(v2gt_params);
+  if (trial_info_bytes)
+    *trial_info_bytes = (int32_t)sizeof(v2gt_trial_info);
+  return V2GT_OK;
+}
+
 int v2gt_device_count(int32_t *count) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
