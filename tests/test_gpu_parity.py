@@ -325,8 +325,20 @@ def test_cuda_path_matches_golden_fixture(name):
     delta, okd = bs.solve(0, 1e-5)
     n = len(t0)
     assert okd
+    # the step satisfies the damped normal equations to round-off (backward stable) ...
+    D, O, B = lin["D"].reshape(n, 15, 15), lin["O"].reshape(n, 15, 15), lin["B"].reshape(n, 15, 9)
+    x, xg = delta[: 15 * n].reshape(n, 15), delta[15 * n:]
+    r = np.einsum("nij,nj->ni", D, x) + 1e-5 * x + np.einsum("nij,j->ni", B, xg) - lin["g"]
+    r[:-1] += np.einsum("nij,nj->ni", O[:-1], x[1:])
+    r[1:] += np.einsum("nji,nj->ni", O[:-1], x[:-1])
+    rg = lin["Gamma"].reshape(9, 9) @ xg + 1e-5 * xg + np.einsum("nij,ni->j", B, x) - lin["g_gamma"]
+    gn = np.sqrt(np.sum(lin["g"] ** 2) + np.sum(lin["g_gamma"] ** 2))
+    assert np.sqrt(np.sum(r ** 2) + np.sum(rg ** 2)) / gn < 1e-12
+    # ... and agrees with the oracle's step as far as the conditioning allows: c2_8s has cond(H) ~ 2e9; c1_3s
+    # (3 s of data from the far initial guess) has cond(H) ~ 2e15, where two backward-stable solvers (the oracle,
+    # SuperLU, this one) differ by ~1e-4 in the step itself
     sc = np.max(np.abs(g["solve_delta"][: 15 * n].reshape(n, 15)), axis=0)
-    assert np.max(np.abs(delta[: 15 * n] - g["solve_delta"][: 15 * n]).reshape(n, 15) / sc) < 1e-7
+    assert np.max(np.abs(delta[: 15 * n] - g["solve_delta"][: 15 * n]).reshape(n, 15) / sc) < (1e-7 if name == "c2_8s" else 5e-3)
     bs.build_and_solve()
     inf = bs.info(0)
     assert inf.status == 0

@@ -140,19 +140,21 @@ int v2gt_batch_get_preint(v2gt_batch *b, int32_t trial, int64_t capacity, double
     return V2GT_OK;
   if (capacity < m)
     return V2GT_ERR_INVALID_ARG;
+  // device layout is struct-of-arrays ([element][slot]): copy the trial's columns of every plane, then transpose
   std::vector<double> pre((size_t)m * PRE_STRIDE), inf((size_t)m * INFO_STRIDE);
   if (m) {
-    V2_CUDA_CHECK(cudaMemcpy(pre.data(), d.pre + td.st_off * PRE_STRIDE, sizeof(double) * pre.size(), cudaMemcpyDeviceToHost));
-    V2_CUDA_CHECK(cudaMemcpy(inf.data(), d.info + td.st_off * INFO_STRIDE, sizeof(double) * inf.size(), cudaMemcpyDeviceToHost));
+    V2_CUDA_CHECK(cudaMemcpy2D(pre.data(), sizeof(double) * m, d.pre + td.st_off, sizeof(double) * d.S, sizeof(double) * m, PRE_STRIDE,
+                               cudaMemcpyDeviceToHost));
+    V2_CUDA_CHECK(cudaMemcpy2D(inf.data(), sizeof(double) * m, d.info + td.st_off, sizeof(double) * d.S, sizeof(double) * m,
+                               INFO_STRIDE, cudaMemcpyDeviceToHost));
   }
   for (int i = 0; i < m; i++) {
     double *o = out + (size_t)i * V2GT_PREINT_DIM;
-    const double *p = &pre[(size_t)i * PRE_STRIDE];
-    std::memcpy(o, p, sizeof(double) * 63); // identical layout for [0, 63)
-    const double *L = &inf[(size_t)i * INFO_STRIDE];
+    for (int e = 0; e < 63; e++)
+      o[e] = pre[(size_t)e * m + i]; // identical order for [0, 63)
     for (int r = 0; r < 15; r++)
       for (int c = 0; c < 15; c++)
-        o[63 + 15 * r + c] = (r >= c) ? L[tri(r, c)] : L[tri(c, r)];
+        o[63 + 15 * r + c] = inf[(size_t)((r >= c) ? tri(r, c) : tri(c, r)) * m + i];
   }
   return V2GT_OK;
 }

@@ -737,7 +737,7 @@ __global__ void __launch_bounds__(PRE_NT) k_preintegrate(DevPtrs d, int keep_cov
   }
 
   // ---- outputs
-  double *pr = d.pre + s * PRE_STRIDE;
+  const SoaW pr{d.pre + s, d.S};
   double q[4];
   rot_2_quat(c.R, q);
   pr[PRE_DT] = c.DT;
@@ -801,7 +801,7 @@ __global__ void __launch_bounds__(PRE_NT) k_preintegrate(DevPtrs d, int keep_cov
       Li[tri(r, cc) * PRE_NT] = sacc / Lm[tri(r, r) * PRE_NT];
     }
   }
-  double *inf = d.info + s * INFO_STRIDE;
+  const SoaW inf{d.info + s, d.S};
   bool nan_found = false;
   for (int r = 0; r < 15; r++)
     for (int cc = 0; cc <= r; cc++) {

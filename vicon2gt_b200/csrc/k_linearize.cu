@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(V2GT_CHUNK) k_factor_eval(DevPtrs d, int which
         r2 += vp.r[k] * vp.r[k];
       lin0 += 0.5 * r2;
       if (JAC) {
-        double *o = d.fpv + s * FPV_STRIDE;
+        const SoaW o{d.fpv + s, d.S};
 #pragma unroll
         for (int k = 0; k < 6; k++)
           o[FPV_R + k] = vp.r[k];
@@ -125,12 +125,12 @@ __global__ void __launch_bounds__(V2GT_CHUNK) k_factor_eval(DevPtrs d, int which
       GravTerms G;
       grav_terms(gl[GL_THX], gl[GL_THY], tr.prm.gravity_magnitude, G);
       ImuPieces ip;
-      imu_factor<JAC>(d.pre + s * PRE_STRIDE, xi, xj, G, ip);
-      const double q = 0.5 * quad_form15(d.info + s * INFO_STRIDE, ip.e);
+      imu_factor<JAC>(SoaR{d.pre + s, d.S}, xi, xj, G, ip);
+      const double q = 0.5 * quad_form15(SoaR{d.info + s, d.S}, ip.e);
       cost += q;
       lin0 += q;
       if (JAC) {
-        double *o = d.fpi + s * FPI_STRIDE;
+        const SoaW o{d.fpi + s, d.S};
 #pragma unroll
         for (int k = 0; k < 15; k++)
           o[FPI_E + k] = ip.e[k];
@@ -197,21 +197,21 @@ __device__ __forceinline__ void zero9(double *A) {
   for (int e = 0; e < 9; e++)
     A[e] = 0.0;
 }
-__device__ __forceinline__ void ld9(const double *__restrict__ p, double *o) {
+__device__ __forceinline__ void ld9(const SoaR p, double *o) {
 #pragma unroll
   for (int e = 0; e < 9; e++)
-    o[e] = __ldg(p + e);
+    o[e] = p[e];
 }
 
 // H1 block (row-block a, column-block dcol) of the IMU factor; returns false when the block is zero.
 // kind: 0 dense in M, 1 = -I, (others dense).   fpi: pieces row, pre: preintegration row.
-__device__ __forceinline__ bool h1_block(const double *__restrict__ fpi, const double *__restrict__ pre, int a, int dcol,
+__device__ __forceinline__ bool h1_block(const SoaR fpi, const SoaR pre, int a, int dcol,
                                          double *M) {
   // rows a: 0 th, 1 bg, 2 v, 3 ba, 4 p
   if (dcol == 0) {
     if (a == 0) { ld9(fpi + FPI_TTH, M); return true; }
-    if (a == 2) { double s[3] = {__ldg(fpi + FPI_SV), __ldg(fpi + FPI_SV + 1), __ldg(fpi + FPI_SV + 2)}; skew(s, M); return true; }
-    if (a == 4) { double s[3] = {__ldg(fpi + FPI_SP), __ldg(fpi + FPI_SP + 1), __ldg(fpi + FPI_SP + 2)}; skew(s, M); return true; }
+    if (a == 2) { double s[3] = {fpi[FPI_SV], fpi[FPI_SV + 1], fpi[FPI_SV + 2]}; skew(s, M); return true; }
+    if (a == 4) { double s[3] = {fpi[FPI_SP], fpi[FPI_SP + 1], fpi[FPI_SP + 2]}; skew(s, M); return true; }
     return false;
   }
   if (dcol == 1) {
@@ -223,7 +223,7 @@ __device__ __forceinline__ bool h1_block(const double *__restrict__ fpi, const d
   }
   if (dcol == 2) {
     if (a == 2) { ld9(fpi + FPI_RK, M); for (int e = 0; e < 9; e++) M[e] = -M[e]; return true; }
-    if (a == 4) { const double dt = __ldg(pre + PRE_DT); ld9(fpi + FPI_RK, M); for (int e = 0; e < 9; e++) M[e] = -dt * M[e]; return true; }
+    if (a == 4) { const double dt = pre[PRE_DT]; ld9(fpi + FPI_RK, M); for (int e = 0; e < 9; e++) M[e] = -dt * M[e]; return true; }
     return false;
   }
   if (dcol == 3) {
@@ -237,7 +237,7 @@ __device__ __forceinline__ bool h1_block(const double *__restrict__ fpi, const d
   return false;
 }
 // H2 diagonal block c of the IMU factor
-__device__ __forceinline__ void h2_block(const double *__restrict__ fpi, int c, double *M) {
+__device__ __forceinline__ void h2_block(const SoaR fpi, int c, double *M) {
   if (c == 0)
     ld9(fpi + FPI_JTH2, M);
   else if (c == 2 || c == 4)
@@ -246,11 +246,11 @@ __device__ __forceinline__ void h2_block(const double *__restrict__ fpi, int c, 
     eye3(M);
 }
 // H3 row blocks (v and p rows), 3x2 each:  R dt g Hxy  and  1/2 R dt^2 g Hxy   (ImuFactorCPIv1.cpp:199-201)
-__device__ __forceinline__ void h3_blocks(const double *__restrict__ fpi, const double *__restrict__ pre, const GravTerms &G,
+__device__ __forceinline__ void h3_blocks(const SoaR fpi, const SoaR pre, const GravTerms &G,
                                           double *H3v, double *H3p) {
   double Rk[9];
   ld9(fpi + FPI_RK, Rk);
-  const double dt = __ldg(pre + PRE_DT);
+  const double dt = pre[PRE_DT];
   const double dt2 = dt * dt;
 #pragma unroll
   for (int r = 0; r < 3; r++)
@@ -273,7 +273,9 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(DevPtrs d, int force_a
     return;
   const TrialDev &tr = d.trials[t];
   const int n = d.n_states[t];
-  const int li = threadIdx.x / 5, dcol = threadIdx.x % 5;
+  // thread = (column block dcol, state li) with dcol uniform per warp: no divergence on the block structure, and
+  // lane <-> state makes every struct-of-arrays read coalesced
+  const int li = threadIdx.x % ASM_STATES, dcol = threadIdx.x / ASM_STATES;
   const int i = blockIdx.x * ASM_STATES + li;
   __shared__ double s_part[ASM_STATES][PART_STRIDE + 1];
   for (int k = threadIdx.x; k < ASM_STATES * (PART_STRIDE + 1); k += ASM_THREADS)
@@ -299,9 +301,9 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(DevPtrs d, int force_a
 
     // ================= H1-type contributions of factor i (i -> i+1)
     if (i < n - 1) {
-      const double *fpi = d.fpi + s * FPI_STRIDE;
-      const double *pre = d.pre + s * PRE_STRIDE;
-      const double *inf = d.info + s * INFO_STRIDE;
+      const SoaR fpi{d.fpi + s, d.S};
+      const SoaR pre{d.pre + s, d.S};
+      const SoaR inf{d.info + s, d.S};
       double Y[5][9]; // Y[a] = sum_b Lambda_ab H1[b][dcol]
 #pragma unroll
       for (int a = 0; a < 5; a++)
@@ -362,7 +364,7 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(DevPtrs d, int force_a
           double sacc = 0;
 #pragma unroll
           for (int k = 0; k < 3; k++)
-            sacc += Y[a][3 * k + r] * __ldg(fpi + FPI_E + 3 * a + k);
+            sacc += Y[a][3 * k + r] * fpi[FPI_E + 3 * a + k];
           gv[r] -= sacc;
         }
       // gravity 2x2 block and gradient of this factor (thread dcol == 3 owns it)
@@ -396,7 +398,7 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(DevPtrs d, int force_a
               ld_sym_blk(inf, a, bb, Lb);
 #pragma unroll
               for (int k = 0; k < 3; k++)
-                sacc += Lb[3 * r + k] * __ldg(fpi + FPI_E + 3 * bb + k);
+                sacc += Lb[3 * r + k] * fpi[FPI_E + 3 * bb + k];
             }
             Le[ai][r] = sacc;
           }
@@ -429,9 +431,9 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(DevPtrs d, int force_a
 
     // ================= H2-type contributions of factor i-1 (i-1 -> i)
     if (i > 0) {
-      const double *fpi = d.fpi + (s - 1) * FPI_STRIDE;
-      const double *pre = d.pre + (s - 1) * PRE_STRIDE;
-      const double *inf = d.info + (s - 1) * INFO_STRIDE;
+      const SoaR fpi{d.fpi + (s - 1), d.S};
+      const SoaR pre{d.pre + (s - 1), d.S};
+      const SoaR inf{d.info + (s - 1), d.S};
       double H2d[9];
       h2_block(fpi, dcol, H2d);
       // D2[c][dcol] = H2[c]^T Lambda_{c,dcol} H2[dcol]
@@ -468,7 +470,7 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(DevPtrs d, int force_a
         for (int r = 0; r < 3; r++)
 #pragma unroll
           for (int k = 0; k < 3; k++)
-            le[r] += L[3 * r + k] * __ldg(fpi + FPI_E + 3 * a + k);
+            le[r] += L[3 * r + k] * fpi[FPI_E + 3 * a + k];
       }
 #pragma unroll
       for (int r = 0; r < 3; r++) {
@@ -489,7 +491,7 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(DevPtrs d, int force_a
     }
 
     // ================= vicon factor of state i
-    const double *fpv = d.fpv + s * FPV_STRIDE;
+    const SoaR fpv{d.fpv + s, d.S};
     double Bv[21]; // B[dcol][0:7]  3x7
 #pragma unroll
     for (int k = 0; k < 21; k++)
@@ -501,7 +503,7 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(DevPtrs d, int force_a
       for (int r = 0; r < 6; r++)
 #pragma unroll
         for (int c = 0; c < 3; c++)
-          Ad[3 * r + c] = __ldg(fpv + FPV_A + 6 * r + co + c);
+          Ad[3 * r + c] = fpv[FPV_A + 6 * r + co + c];
       // D[c][dcol] += A_c^T A_d for c in {theta (0), p (4)}
 #pragma unroll
       for (int ci = 0; ci < 2; ci++) {
@@ -513,7 +515,7 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(DevPtrs d, int force_a
             double sacc = 0;
 #pragma unroll
             for (int k = 0; k < 6; k++)
-              sacc += __ldg(fpv + FPV_A + 6 * k + cco + r) * Ad[3 * k + cc];
+              sacc += fpv[FPV_A + 6 * k + cco + r] * Ad[3 * k + cc];
             Dcol[c][3 * r + cc] += sacc;
           }
       }
@@ -524,13 +526,13 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(DevPtrs d, int force_a
           double sacc = 0;
 #pragma unroll
           for (int k = 0; k < 6; k++)
-            sacc += Ad[3 * k + r] * __ldg(fpv + FPV_G + 7 * k + c);
+            sacc += Ad[3 * k + r] * fpv[FPV_G + 7 * k + c];
           Bv[7 * r + c] = sacc;
         }
         double sg = 0;
 #pragma unroll
         for (int k = 0; k < 6; k++)
-          sg += Ad[3 * k + r] * __ldg(fpv + FPV_R + k);
+          sg += Ad[3 * k + r] * fpv[FPV_R + k];
         gv[r] -= sg;
       }
     }
@@ -544,26 +546,29 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(DevPtrs d, int force_a
           double sacc = 0;
 #pragma unroll
           for (int k = 0; k < 6; k++)
-            sacc += __ldg(fpv + FPV_G + 7 * k + r) * __ldg(fpv + FPV_G + 7 * k + c);
+            sacc += fpv[FPV_G + 7 * k + r] * fpv[FPV_G + 7 * k + c];
           sp[7 * r + c] = sacc;
         }
         double sg = 0;
 #pragma unroll
         for (int k = 0; k < 6; k++)
-          sg += __ldg(fpv + FPV_G + 7 * k + r) * __ldg(fpv + FPV_R + k);
+          sg += fpv[FPV_G + 7 * k + r] * fpv[FPV_R + k];
         sp[49 + r] = -sg;
       }
     }
 
     // ================= store this thread's strips
+    // D is symmetric: the column strip this thread computed is written as the ROW strip 3 dcol .. 3 dcol + 2
+    // (45 contiguous doubles per thread, so each 32-byte sector is completed by back-to-back stores of one
+    // thread and merges in L2 instead of being written back partially)
     double *HD = ne + NE_D;
 #pragma unroll
-    for (int c = 0; c < 5; c++)
+    for (int cc = 0; cc < 3; cc++)
 #pragma unroll
-      for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 5; c++)
 #pragma unroll
-        for (int cc = 0; cc < 3; cc++)
-          HD[(3 * c + r) * 15 + 3 * dcol + cc] = Dcol[c][3 * r + cc];
+        for (int r = 0; r < 3; r++)
+          HD[(3 * dcol + cc) * 15 + 3 * c + r] = Dcol[c][3 * r + cc];
     double *HB = ne + NE_M + NE_MB;
 #pragma unroll
     for (int r = 0; r < 3; r++) {

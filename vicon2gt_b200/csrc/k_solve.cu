@@ -36,9 +36,12 @@ __host__ __device__ inline SegGeom seg_geom(int n, int P) {
 }
 
 // ---- per-warp shared memory (doubles): two staged normal-equation records + the broadcast buffers of the
-// factorisation (column of D [16] + row of X [16], double buffered)
-constexpr int SW_STAGE = 0, SW_CB = 2 * NE_STRIDE, SW_TOTAL = 2 * NE_STRIDE + 64;
+// factorisation (column of D [16] + row of X [16], double buffered, + 64 doubles of per-lane store scratch)
+constexpr int SW_STAGE = 0, SW_CB = 2 * NE_STRIDE, SW_TOTAL = 2 * NE_STRIDE + 128;
 constexpr int ELIM_WARPS = 4;
+#ifndef ELIM_MIN_CTAS
+#define ELIM_MIN_CTAS 3
+#endif
 
 // D[8x8] += A[8x4] B[4x8] on the FP64 tensor path; fragments (lane = 4 gid + tid):
 //   a = A[gid][tid], b = B[tid][gid], (c0, c1) = C[gid][2 tid + {0,1}]
@@ -84,9 +87,33 @@ __device__ __forceinline__ void acc_zero(ElimAcc &A) {
     A.pt[i][0] = A.pt[i][1] = 0.0;
 }
 
+// 1/x without the slow path of the IEEE division (x is a positive, normal pivot; anything else is caught by the
+// positivity check of the pivots): MUFU.RCP64H seed (~20 bits) + two Newton steps
+__device__ __forceinline__ double fast_rcp(const double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+__device__ __forceinline__ double fast_rsqrt(const double x) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  // two Newton steps on r <- r (1.5 - 0.5 x r^2)
+  double h = 0.5 * x;
+  r = r * fma(-h * r, r, 1.5);
+  r = r * fma(-h * r, r, 1.5);
+  // one correction in the residual form for the last bits
+  const double e = fma(-x * r, r, 1.0);
+  return fma(0.5 * r, e, r);
+}
+
 // LDL^T of the 15x15 block held as the tiles d00 = D[gid][2tid+e], d10 = D[8+gid][2tid+e],
 // d11 = D[8+gid][8+2tid+e] together with the Gauss-Jordan inverse of its unit-lower factor; returns
-// L^-1 = D^-1/2 L'^-1 (L = Cholesky factor) in the same tile order.  cb: 64 doubles of shared memory.
+// L^-1 = D^-1/2 L'^-1 (L = Cholesky factor) in the same tile order.  cb: 64 + 64 doubles of shared memory
+// (two broadcast buffers, then one 16-byte scratch slot per lane that absorbs the non-holders' stores so that
+// publishing a column is branch-free).
 __device__ __forceinline__ bool ldl_inverse(double (&d00)[2], double (&d10)[2], double (&d11)[2], double (&li00)[2],
                                             double (&li10)[2], double (&li11)[2], double *cb, const int gid, const int tid) {
   double x00[2], x10[2], x11[2];
@@ -96,30 +123,25 @@ __device__ __forceinline__ bool ldl_inverse(double (&d00)[2], double (&d10)[2], 
   x11[0] = x00[0];
   x11[1] = x00[1];
   double p0 = 1.0, p1 = 1.0;
-  bool ok = true;
+  double *scratch = cb + 64 + 2 * (4 * gid + tid);
 #pragma unroll
   for (int j = 0; j < 15; j++) {
     double *buf = cb + 32 * (j & 1);
     // the holders publish column j of D (rows 0..15) and row j of X (columns 0..15)
     if (j < 8) {
-      if (tid == (j >> 1)) {
-        buf[gid] = d00[j & 1];
-        buf[8 + gid] = d10[j & 1];
-      }
-      if (gid == j)
-        *reinterpret_cast<double2 *>(buf + 16 + 2 * tid) = make_double2(x00[0], x00[1]);
+      const bool hc = (tid == (j >> 1)), hr = (gid == j);
+      (hc ? buf + gid : scratch)[0] = d00[j & 1];
+      (hc ? buf + 8 + gid : scratch)[0] = d10[j & 1];
+      *reinterpret_cast<double2 *>(hr ? buf + 16 + 2 * tid : scratch) = make_double2(x00[0], x00[1]);
     } else {
-      if (tid == ((j - 8) >> 1))
-        buf[8 + gid] = d11[j & 1];
-      if (gid == j - 8) {
-        *reinterpret_cast<double2 *>(buf + 16 + 2 * tid) = make_double2(x10[0], x10[1]);
-        *reinterpret_cast<double2 *>(buf + 24 + 2 * tid) = make_double2(x11[0], x11[1]);
-      }
+      const bool hc = (tid == ((j - 8) >> 1)), hr = (gid == j - 8);
+      (hc ? buf + 8 + gid : scratch)[0] = d11[j & 1];
+      *reinterpret_cast<double2 *>(hr ? buf + 16 + 2 * tid : scratch) = make_double2(x10[0], x10[1]);
+      *reinterpret_cast<double2 *>(hr ? buf + 24 + 2 * tid : scratch) = make_double2(x11[0], x11[1]);
     }
     __syncwarp();
     const double piv = buf[j];
-    ok = ok && (piv > 0.0);
-    const double rinv = 1.0 / piv;
+    const double rinv = fast_rcp(piv);
     if (j < 8) {
       p0 = (gid == j) ? piv : p0;
       const double mr0 = (gid > j) ? buf[gid] * rinv : 0.0;
@@ -151,8 +173,10 @@ __device__ __forceinline__ bool ldl_inverse(double (&d00)[2], double (&d10)[2], 
       x11[1] = fma(-mr1, xr1.y, x11[1]);
     }
   }
-  const double s0 = rsqrt(p0);
-  const double s1 = (gid < 7) ? rsqrt(p1) : 0.0; // row 15 is padding
+  // every pivot is held by exactly one (gid, *) group: positive-definiteness check in one vote
+  const bool ok = __all_sync(0xffffffffu, (p0 > 0.0) && (p1 > 0.0));
+  const double s0 = fast_rsqrt(p0);
+  const double s1 = (gid < 7) ? fast_rsqrt(p1) : 0.0; // row 15 is padding
   li00[0] = s0 * x00[0];
   li00[1] = s0 * x00[1];
   li10[0] = s1 * x10[0];
@@ -308,7 +332,7 @@ __device__ __forceinline__ bool elim_chain(const double *__restrict__ ne0, const
 
 // ------------------------------------------------------------------------------------------------
 // grid: (ceil(P / ELIM_WARPS), T); block: ELIM_WARPS warps; warp -> segment j of trial t
-__global__ void __launch_bounds__(ELIM_WARPS * 32) k_seg_eliminate(DevPtrs d, int force_all) {
+__global__ void __launch_bounds__(ELIM_WARPS * 32, ELIM_MIN_CTAS) k_seg_eliminate(DevPtrs d, int force_all) {
   extern __shared__ __align__(16) double smem[];
   const int t = blockIdx.y;
   LmState &lm = d.lm[t];

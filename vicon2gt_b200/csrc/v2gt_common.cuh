@@ -11,10 +11,12 @@
 //   st_t    [S]        state times
 //   x       [2][S][16] JPLNavState rows (q4 bg3 v3 ba3 p3), double buffered (current / trial point)
 //   glob    [2][T][16] q_BtoI4 p_BinI3 t_off theta_x theta_y (+pad), double buffered
-//   pre     [S][64]    preintegration constants of interval slot s -> s+1 (PRE_* offsets below)
-//   info    [S][120]   P^-1 of that interval, packed lower triangle (row-major: r*(r+1)/2 + c)
-//   fpi     [S][64]    per-factor linearisation pieces of the IMU factor (FPI_* offsets)
-//   fpv     [S][88]    per-factor pieces of the vicon factor (FPV_* offsets)
+//   pre     [64][S]    preintegration constants of interval slot s -> s+1 (PRE_* offsets below)
+//   info    [120][S]   P^-1 of that interval, packed lower triangle (row-major: r*(r+1)/2 + c)
+//   fpi     [64][S]    per-factor linearisation pieces of the IMU factor (FPI_* offsets)
+//   fpv     [88][S]    per-factor pieces of the vicon factor (FPV_* offsets)
+//                      (these four are struct-of-arrays: element e of slot s at [e * S + s], so the
+//                       one-thread-per-state kernels read and write them fully coalesced)
 //   ne      [S][600]   normal-equation record per state: D 15x15 (225) | M 15x25 = [O 15 (k,k+1) | B 9 | g 1]
 //                      (one contiguous, 16-byte aligned record: streamed with cp.async by the elimination)
 //   fac     [S][832]   elimination factors per state in mma-fragment order: L^-1 (3 8x8 tiles) | W (16x40)
@@ -127,6 +129,18 @@ struct DevPtrs {
 };
 
 #if defined(__CUDACC__)
+// struct-of-arrays views of one slot: element e lives at p[e * S]
+struct SoaR {
+  const double *p;
+  long long S;
+  __device__ __forceinline__ SoaR operator+(int e) const { return SoaR{p + (long long)e * S, S}; }
+  __device__ __forceinline__ double operator[](int e) const { return __ldg(p + (long long)e * S); }
+};
+struct SoaW {
+  double *p;
+  long long S;
+  __device__ __forceinline__ double &operator[](int e) const { return p[(long long)e * S]; }
+};
 // 32-byte read-only load as two 16-byte __ldg (there is no __ldg overload for double4)
 __device__ __forceinline__ double4 ldg4(const double *p) {
   const double2 a = __ldg(reinterpret_cast<const double2 *>(p));

@@ -29,18 +29,18 @@ __device__ __forceinline__ void grav_terms(double thx, double thy, double gmag, 
 }
 
 // load the 3x3 block (a,b) of a packed-lower symmetric 15x15 matrix
-__device__ __forceinline__ void ld_sym_blk(const double *__restrict__ P, int a, int b, double *o) {
+__device__ __forceinline__ void ld_sym_blk(const SoaR P, int a, int b, double *o) {
 #pragma unroll
   for (int r = 0; r < 3; r++)
 #pragma unroll
     for (int c = 0; c < 3; c++) {
       const int R = 3 * a + r, C = 3 * b + c;
-      o[3 * r + c] = __ldg(P + (R >= C ? tri(R, C) : tri(C, R)));
+      o[3 * r + c] = P[R >= C ? tri(R, C) : tri(C, R)];
     }
 }
 
 // e^T Lambda e with Lambda packed lower
-__device__ __forceinline__ double quad_form15(const double *__restrict__ P, const double *e) {
+__device__ __forceinline__ double quad_form15(const SoaR P, const double *e) {
   double s = 0;
   int k = 0;
 #pragma unroll
@@ -48,8 +48,8 @@ __device__ __forceinline__ double quad_form15(const double *__restrict__ P, cons
     double row = 0;
 #pragma unroll
     for (int c = 0; c < r; c++)
-      row += __ldg(P + k + c) * e[c];
-    s += e[r] * (2.0 * row + __ldg(P + k + r) * e[r]);
+      row += P[k + c] * e[c];
+    s += e[r] * (2.0 * row + P[k + r] * e[r]);
     k += r + 1;
   }
   return s;
@@ -62,22 +62,22 @@ struct ImuPieces {
 
 // residual (always) and Jacobian pieces (JAC) of the IMU factor between xi and xj
 template <bool JAC>
-__device__ inline void imu_factor(const double *__restrict__ pre, const double *xi, const double *xj, const GravTerms &G,
+__device__ inline void imu_factor(const SoaR pre, const double *xi, const double *xj, const GravTerms &G,
                                   ImuPieces &o) {
-  const double dt = __ldg(pre + PRE_DT);
+  const double dt = pre[PRE_DT];
   double dbg[3], dba[3];
 #pragma unroll
   for (int k = 0; k < 3; k++) {
-    dbg[k] = xi[4 + k] - __ldg(pre + PRE_BGLIN + k);
-    dba[k] = xi[10 + k] - __ldg(pre + PRE_BALIN + k);
+    dbg[k] = xi[4 + k] - pre[PRE_BGLIN + k];
+    dba[k] = xi[10 + k] - pre[PRE_BALIN + k];
   }
   double Jq[9], qmeas[4];
 #pragma unroll
   for (int e = 0; e < 9; e++)
-    Jq[e] = __ldg(pre + PRE_JQ + e);
+    Jq[e] = pre[PRE_JQ + e];
 #pragma unroll
   for (int e = 0; e < 4; e++)
-    qmeas[e] = __ldg(pre + PRE_Q + e);
+    qmeas[e] = pre[PRE_Q + e];
   // q_b = rot_2_quat(exp_so3(-J_q (bg_k - bg_lin)))
   double th[3], Eb[9], q_b[4];
   mv3(Jq, dbg, th);
@@ -107,10 +107,10 @@ __device__ inline void imu_factor(const double *__restrict__ pre, const double *
   double Ja[9], Jb[9], Ha[9], Hb[9];
 #pragma unroll
   for (int e = 0; e < 9; e++) {
-    Jb[e] = __ldg(pre + PRE_JB + e);
-    Ja[e] = __ldg(pre + PRE_JA + e);
-    Hb[e] = __ldg(pre + PRE_HB + e);
-    Ha[e] = __ldg(pre + PRE_HA + e);
+    Jb[e] = pre[PRE_JB + e];
+    Ja[e] = pre[PRE_JA + e];
+    Hb[e] = pre[PRE_HB + e];
+    Ha[e] = pre[PRE_HA + e];
   }
   double t1[3], t2[3], t3[3], t4[3];
   mv3(Ja, dbg, t1);
@@ -121,9 +121,9 @@ __device__ inline void imu_factor(const double *__restrict__ pre, const double *
   for (int k = 0; k < 3; k++) {
     o.e[k] = 2 * q_r[k];
     o.e[3 + k] = xj[4 + k] - xi[4 + k];
-    o.e[6 + k] = ((sv[k] - t3[k]) - t4[k]) - __ldg(pre + PRE_BETA + k);
+    o.e[6 + k] = ((sv[k] - t3[k]) - t4[k]) - pre[PRE_BETA + k];
     o.e[9 + k] = xj[10 + k] - xi[10 + k];
-    o.e[12 + k] = ((sp[k] - t1[k]) - t2[k]) - __ldg(pre + PRE_ALPHA + k);
+    o.e[12 + k] = ((sp[k] - t1[k]) - t2[k]) - pre[PRE_ALPHA + k];
   }
   if (JAC) {
     // Tth = -((qn4 I - [qn]x)(qm4 I - [qm]x) + qn qm^T)
