@@ -48,6 +48,7 @@ def parse():
                     help="trials per GPU (weak scaling; 128 per GPU = the 1024-trial batch on 8 GPUs)")
     ap.add_argument("--duration", type=float, default=0.0, help="truncate the trajectory to this many seconds (0 = full)")
     ap.add_argument("--segments", type=int, default=0)
+    ap.add_argument("--target-warps", type=int, default=0, help="segment warps per elimination launch (0 = library default)")
     ap.add_argument("--cpu-sample-s", type=float, default=40.0, help="length of the CPU baseline sample trajectory")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
@@ -244,6 +245,8 @@ def main():
     opts = {}
     if args.segments > 0:
         opts["segments"] = args.segments
+    if args.target_warps > 0:
+        opts["target_warps"] = args.target_warps
     bs = api.BatchSolver(T, device=device, **opts)
 
     def stage_and_upload():

@@ -6,7 +6,7 @@ holds no test vectors of its own, so these files pin the ORACLE (oracle/, the CP
 ViconGraphSolver::build_and_solve) against regressions and give the GPU tests a fixture that does not depend on
 the simulator or the oracle being rebuilt identically:  "parity unpinned" with respect to the real reference.
 
-    python tools/make_golden.py        # rewrites tests/golden/c2_8s.npz and c1_3s.npz
+    python tools/make_golden.py        # rewrites tests/golden/c2_8s.npz and c1_6s.npz
 """
 import os
 import sys
@@ -61,4 +61,4 @@ if __name__ == "__main__":
     build.build_oracle()
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
     make("c2_8s", "C2", 11, 8.0, (1e-3, 1e-3, 1e-3, 1e-2, 1e-2, 1e-2), 30)
-    make("c1_3s", "C1", 5, 3.0, (0.0174, 0.0174, 0.0174, 0.05, 0.05, 0.05), 12)
+    make("c1_6s", "C1", 1, 6.0, (0.0174, 0.0174, 0.0174, 0.05, 0.05, 0.05), 30)

@@ -24,6 +24,9 @@ NVCC_FLAGS = [
 
 
 def lib_path(name):
+    # V2GT_LIB_CUDA points the loader at an alternative build of the CUDA library (kernel tuning experiments)
+    if name == "cuda" and os.environ.get("V2GT_LIB_CUDA"):
+        return os.environ["V2GT_LIB_CUDA"]
     return _LIBS[name]
 
 
@@ -59,10 +62,10 @@ def cuda_sources():
     return srcs, hdrs
 
 
-def build_cuda(force=False, verbose=False, extra=()):
+def build_cuda(force=False, verbose=False, extra=(), out=None, objdir_name="_obj"):
     """nvcc -> vicon2gt_b200/libvicon2gt_b200.so (sm_100a only; cross-compiles without a GPU)."""
     srcs, hdrs = cuda_sources()
-    out = _LIBS["cuda"]
+    out = out or _LIBS["cuda"]
     if not force and not _newer(out, srcs + hdrs):
         return out
     nvcc = _find("nvcc", ["/usr/local/cuda/bin/nvcc"])
@@ -73,7 +76,7 @@ def build_cuda(force=False, verbose=False, extra=()):
     # one nvcc per translation unit, in parallel, then one link step (objects live in _obj/, git-ignored)
     from concurrent.futures import ThreadPoolExecutor
 
-    objdir = os.path.join(PKG_DIR, "_obj")
+    objdir = os.path.join(PKG_DIR, objdir_name)
     os.makedirs(objdir, exist_ok=True)
     common = [nvcc] + NVCC_FLAGS + list(extra) + nccl_inc + ["-I", os.path.join(ROOT, "include")]
     if verbose:

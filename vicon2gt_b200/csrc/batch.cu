@@ -65,7 +65,8 @@ struct v2gt_batch {
   int n_max = 0; // max raw states over trials
   bool uploaded = false, built = false, values_init = false;
   // options
-  int opt_segments = 0;       // 0 = auto
+  int opt_segments = 0;       // 0 = auto (adaptive); > 0: fixed number of segments per trial
+  int opt_target_warps = 148 * 64; // segment warps the adaptive choice aims for per elimination launch
   int opt_keep_cov = 0;
   int opt_tries_per_sync = 8;
   // pinned readback
@@ -287,6 +288,8 @@ int v2gt_batch_set_option(v2gt_batch *b, const char *name, double value) {
   const std::string n(name);
   if (n == "segments")
     b->opt_segments = (int)value;
+  else if (n == "target_warps")
+    b->opt_target_warps = std::max(1, (int)value);
   else if (n == "keep_cov")
     b->opt_keep_cov = (int)value;
   else if (n == "tries_per_sync")
@@ -452,14 +455,12 @@ int v2gt_batch_upload(v2gt_batch *b) {
       C += d.n_vic;
     b->n_max = std::max<int>(b->n_max, (int)d.n_raw);
   }
-  // ---- segments per trial: enough warps to fill the GPU, never more than ~sqrt(n) per chain
+  // ---- segments per trial.  The buffers are sized for the most segments a launch may use (~sqrt(n) per chain);
+  // every round of the optimiser then picks its own count from the number of trials still running, so that the
+  // chains of the remaining trials are cut finer as the batch drains (v2gt_batch_optimize)
   int P = b->opt_segments;
-  if (P <= 0) {
-    const int target_warps = 148 * 24;
-    P = (target_warps + T - 1) / T;
-    const int cap = std::max(1, (int)std::ceil(std::sqrt((double)std::max(1, b->n_max)) * 1.0));
-    P = std::min(P, cap);
-  }
+  if (P <= 0)
+    P = std::max(1, (int)std::ceil(std::sqrt((double)std::max(1, b->n_max))));
   P = std::max(1, std::min(P, std::max(1, b->n_max / 2)));
   DevPtrs &d = b->d;
   std::memset(&d, 0, sizeof(d));
@@ -670,7 +671,13 @@ int v2gt_batch_optimize(v2gt_batch *b) {
     b->ev_pool.push_back(e);
   }
   int rounds = 0;
+  int n_running = b->T;
+  const DevPtrs &dmax = b->d;
   while (rounds < max_rounds) {
+    // segments per trial for this chunk of tries: fill the GPU with the trials that are still running
+    DevPtrs d = dmax;
+    if (b->opt_segments <= 0)
+      d.P = std::max(1, std::min(dmax.P, (b->opt_target_warps + std::max(1, n_running) - 1) / std::max(1, n_running)));
     V2_CUDA_CHECK(cudaMemsetAsync(d.n_active, 0, sizeof(int), st));
     for (int k = 0; k < chunk; k++) {
       cudaEvent_t *e = &b->ev_pool[7 * k];
@@ -707,7 +714,8 @@ int v2gt_batch_optimize(v2gt_batch *b) {
       }
     }
     b->tries_enqueued += chunk;
-    if (*b->h_active == 0)
+    n_running = *b->h_active;
+    if (n_running == 0)
       break;
   }
   V2_CUDA_CHECK(cudaEventRecord(b->ev[3], st));

@@ -38,7 +38,10 @@ __host__ __device__ inline SegGeom seg_geom(int n, int P) {
 // ---- per-warp shared memory (doubles): two staged normal-equation records + the broadcast buffers of the
 // factorisation (column of D [16] + row of X [16], double buffered, + 64 doubles of per-lane store scratch)
 constexpr int SW_STAGE = 0, SW_CB = 2 * NE_STRIDE, SW_TOTAL = 2 * NE_STRIDE + 128;
-constexpr int ELIM_WARPS = 4;
+#ifndef ELIM_WARPS_N
+#define ELIM_WARPS_N 4
+#endif
+constexpr int ELIM_WARPS = ELIM_WARPS_N;
 #ifndef ELIM_MIN_CTAS
 #define ELIM_MIN_CTAS 3
 #endif
