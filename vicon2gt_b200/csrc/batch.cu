@@ -62,6 +62,11 @@ struct v2gt_batch {
   DevPtrs d{};
   std::vector<void *> dev_allocs;
   std::vector<void *> pinned_allocs;
+  // allocation reuse: a re-upload of a batch of the same shape hands the existing buffers out again, in order
+  std::vector<size_t> dev_sizes, pin_sizes;
+  std::vector<long long> alloc_key;
+  size_t dev_cur = 0, pin_cur = 0;
+  bool reuse = false;
   int n_max = 0; // max raw states over trials
   bool uploaded = false, built = false, values_init = false;
   // options
@@ -89,6 +94,12 @@ template <typename Tp> int dev_alloc(v2gt_batch *b, Tp **p, size_t count) {
   *p = nullptr;
   if (count == 0)
     count = 1;
+  if (b->reuse) {
+    if (b->dev_cur >= b->dev_allocs.size() || b->dev_sizes[b->dev_cur] != count * sizeof(Tp))
+      return V2GT_ERR_CUDA;
+    *p = (Tp *)b->dev_allocs[b->dev_cur++];
+    return V2GT_OK;
+  }
   void *q = nullptr;
   cudaError_t e = cudaMalloc(&q, count * sizeof(Tp));
   if (e != cudaSuccess) {
@@ -96,16 +107,24 @@ template <typename Tp> int dev_alloc(v2gt_batch *b, Tp **p, size_t count) {
     return V2GT_ERR_CUDA;
   }
   b->dev_allocs.push_back(q);
+  b->dev_sizes.push_back(count * sizeof(Tp));
   *p = (Tp *)q;
   return V2GT_OK;
 }
 template <typename Tp> int pin_alloc(v2gt_batch *b, Tp **p, size_t count) {
   if (count == 0)
     count = 1;
+  if (b->reuse) {
+    if (b->pin_cur >= b->pinned_allocs.size() || b->pin_sizes[b->pin_cur] != count * sizeof(Tp))
+      return V2GT_ERR_CUDA;
+    *p = (Tp *)b->pinned_allocs[b->pin_cur++];
+    return V2GT_OK;
+  }
   void *q = nullptr;
   if (cudaMallocHost(&q, count * sizeof(Tp)) != cudaSuccess)
     return V2GT_ERR_CUDA;
   b->pinned_allocs.push_back(q);
+  b->pin_sizes.push_back(count * sizeof(Tp));
   *p = (Tp *)q;
   return V2GT_OK;
 }
@@ -116,6 +135,10 @@ void free_device(v2gt_batch *b) {
   for (void *p : b->pinned_allocs)
     cudaFreeHost(p);
   b->pinned_allocs.clear();
+  b->dev_sizes.clear();
+  b->pin_sizes.clear();
+  b->alloc_key.clear();
+  b->reuse = false;
   b->h_active = nullptr;
   b->uploaded = false;
   b->built = false;
@@ -372,8 +395,10 @@ int v2gt_batch_upload(v2gt_batch *b) {
   if (!b)
     return V2GT_ERR_INVALID_ARG;
   V2_CUDA_CHECK(cudaSetDevice(b->device));
-  free_device(b);
+  V2_CUDA_CHECK(cudaStreamSynchronize(b->stream));
   b->results_cached = false;
+  b->uploaded = false;
+  b->built = false;
   const int T = b->T;
   // ---- per-trial guards and timestamp cleaning (ViconGraphSolver.cpp:99-150)
   std::vector<TrialDev> td(T);
@@ -471,6 +496,16 @@ int v2gt_batch_upload(v2gt_batch *b) {
   d.P = P;
   d.nchunk = std::max(1, (b->n_max + V2GT_CHUNK - 1) / V2GT_CHUNK);
   const int nasm = std::max(1, asm_chunks(b->n_max));
+  {
+    const std::vector<long long> key = {T, S, M, V, C, P, d.nchunk, nasm, b->opt_keep_cov};
+    if (key == b->alloc_key && !b->dev_allocs.empty()) {
+      b->reuse = true; // same shape as the previous upload: keep every buffer
+      b->dev_cur = b->pin_cur = 0;
+    } else {
+      free_device(b);
+      b->alloc_key = key;
+    }
+  }
 
   // ---- pinned staging + device arrays
   double *h_imu_t, *h_imu_s, *h_vic_t, *h_vic_s, *h_vic_c, *h_st_t;
@@ -576,6 +611,7 @@ int v2gt_batch_upload(v2gt_batch *b) {
   V2_CUDA_CHECK(cudaMemsetAsync(d.trace, 0, sizeof(double) * T * TRACE_MAX * 5, st));
   V2_CUDA_CHECK(cudaMemsetAsync(d.xg, 0, sizeof(double) * T * 16, st));
   V2_CUDA_CHECK(cudaStreamSynchronize(st)); // td / lm are stack-owned host vectors
+  b->reuse = false;
   b->uploaded = true;
   b->built = false;
   b->values_init = false;
