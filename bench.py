@@ -38,13 +38,23 @@ ELIM_ALG_BYTES_PER_STATE = 2 * (120 + 225 + 135 + 15) * 8  # read D,O,B,g once +
 ELIM_ALG_FLOPS_PER_STATE = 19.4e3                           # block-tridiagonal-arrow Cholesky, Thomas-equivalent
 
 
+def ncu_traffic_per_state_block():
+    """DRAM bytes (read + write) per eliminated state block of k_seg_eliminate, from the committed ncu --set full capture
+    (profiles/elim_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one launch / its state blocks)."""
+    path = os.path.join(ROOT, "profiles", "elim_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return float(json.load(f)["dram_bytes_per_state_block"])
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--trials", type=int, default=int(os.environ.get("V2GT_BENCH_TRIALS", "16")),
+    ap.add_argument("--trials", type=int, default=int(os.environ.get("V2GT_BENCH_TRIALS", "128")),
                     help="trials per GPU (weak scaling; 128 per GPU = the 1024-trial batch on 8 GPUs)")
     ap.add_argument("--duration", type=float, default=0.0, help="truncate the trajectory to this many seconds (0 = full)")
     ap.add_argument("--segments", type=int, default=0)
@@ -301,6 +311,9 @@ def main():
     fp64_peak = api.measure_fp64_peak(device)
     elim_bytes = solve_units * args.steps * ELIM_ALG_BYTES_PER_STATE
     elim_flops = solve_units * args.steps * ELIM_ALG_FLOPS_PER_STATE
+    elim_launches = max(1, int((l1 - l0)[2]))
+    tpsb = ncu_traffic_per_state_block()
+    traffic = None if tpsb is None else tpsb * solve_units * args.steps / elim_launches
     achieved_gbs = elim_bytes / (elim_ms * 1e-3) / 1e9 if elim_ms > 0 else 0.0
     achieved_tf = elim_flops / (elim_ms * 1e-3) / 1e12 if elim_ms > 0 else 0.0
 
@@ -359,7 +372,9 @@ def main():
             "clocks": clocks,
             "roofline": {
                 "kernel": "k_seg_eliminate", "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "launches": elim_launches, "avg_launch_ms": elim_ms / elim_launches,
+                "algorithmic_bytes_per_launch": elim_bytes / elim_launches,
                 "share_of_step": elim_ms / max(1e-9, dev_ms),
                 "fp64": {"achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / max(fp64_peak, 1e-9),
                          "peak_source": "measured DFMA loop (v2gt_measure_fp64_peak)"},

@@ -1,0 +1,258 @@
+/*
+ * vicon2gt_b200 -- C++ host mirror of the reference's solver interface, header-only, over the C ABI
+ * (vicon2gt_b200.h).  A user of rpng/vicon2gt replaces
+ *
+ *     Propagator / Interpolator / ViconGraphSolver            (src/meas/Propagator.h:41-55,
+ *                                                              src/meas/Interpolator.h:55-81,
+ *                                                              src/solver/ViconGraphSolver.h:61-168)
+ *
+ * by the classes of the same names below: same method names, argument meaning and order.  Differences,
+ * all forced by dropping ROS / Eigen / GTSAM from the boundary:
+ *   - the ros::NodeHandle argument of the solver becomes a ViconGraphSolverParams struct (same parameter
+ *     names and defaults, ViconGraphSolver.cpp:34-88); Eigen vectors / matrices become std::array
+ *     (row-major 3x3);
+ *   - visualize() (ROS publishers) does not exist;
+ *   - failures: the reference logs and calls std::exit(EXIT_FAILURE) (ViconGraphSolver.cpp:99-150,
+ *     508-524).  Here they throw vicon2gt_b200::SolverError carrying the V2GT_ERR_* code; construct the
+ *     solver with exit_on_failure = true to get the reference's behaviour.
+ * Everything numeric runs in libvicon2gt_b200.so (CUDA, sm_100a); there is no CPU path.
+ * BatchSolver is the batch form (independent Monte-Carlo trials on one GPU, scripts/run_monte_carlo.sh shape).
+ */
+#ifndef VICON2GT_B200_HPP
+#define VICON2GT_B200_HPP
+
+#include "vicon2gt_b200.h"
+
+#include <array>
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace vicon2gt_b200 {
+
+using Vec3 = std::array<double, 3>;
+using Vec4 = std::array<double, 4>;  // JPL quaternion [x y z w]
+using Mat3 = std::array<double, 9>;  // row-major
+using Pose10 = std::array<double, 10>; // [q_VtoI(4) p_IinV(3) v_IinV(3)], as get_imu_poses of the reference
+
+class SolverError : public std::runtime_error {
+public:
+  SolverError(int code, const std::string &where)
+      : std::runtime_error("vicon2gt_b200: " + where + " failed with status " + std::to_string(code)), code_(code) {}
+  int code() const { return code_; }
+
+private:
+  int code_;
+};
+
+inline void check(int status, const char *where) {
+  if (status != V2GT_OK)
+    throw SolverError(status, where);
+}
+
+/* Parameters the reference reads from its ros::NodeHandle (names / defaults: ViconGraphSolver.cpp:34-88). */
+struct ViconGraphSolverParams : v2gt_params {
+  ViconGraphSolverParams() { v2gt_params_default(this); }
+};
+
+/* IMU store (src/meas/Propagator.h:41-55): noise densities + samples in feed order. */
+class Propagator {
+public:
+  Propagator(double sigma_w, double sigma_wb, double sigma_a, double sigma_ab)
+      : sigma_w_(sigma_w), sigma_wb_(sigma_wb), sigma_a_(sigma_a), sigma_ab_(sigma_ab) {}
+
+  void feed_imu(double timestamp, const Vec3 &wm, const Vec3 &am) {
+    t_.push_back(timestamp);
+    w_.insert(w_.end(), wm.begin(), wm.end());
+    a_.insert(a_.end(), am.begin(), am.end());
+  }
+  /* Propagator::has_bounding_imu (Propagator.cpp:165-193) for the time-ordered store */
+  bool has_bounding_imu(double timestamp) const { return !t_.empty() && t_.front() <= timestamp && t_.back() >= timestamp; }
+
+  const std::vector<double> &times() const { return t_; }
+  const std::vector<double> &gyro() const { return w_; }
+  const std::vector<double> &accel() const { return a_; }
+  double sigma_w() const { return sigma_w_; }
+  double sigma_wb() const { return sigma_wb_; }
+  double sigma_a() const { return sigma_a_; }
+  double sigma_ab() const { return sigma_ab_; }
+
+private:
+  double sigma_w_, sigma_wb_, sigma_a_, sigma_ab_;
+  std::vector<double> t_, w_, a_;
+};
+
+/* Vicon pose store (src/meas/Interpolator.h:55-81).  Sorting and the std::set de-duplication (first pose of a
+ * timestamp wins) are done by the library when the trial is staged. */
+class Interpolator {
+public:
+  void feed_pose(double timestamp, const Vec4 &q, const Vec3 &p, const Mat3 &R_q, const Mat3 &R_p) {
+    t_.push_back(timestamp);
+    q_.insert(q_.end(), q.begin(), q.end());
+    p_.insert(p_.end(), p.begin(), p.end());
+    Rq_.insert(Rq_.end(), R_q.begin(), R_q.end());
+    Rp_.insert(Rp_.end(), R_p.begin(), R_p.end());
+    if (t_.size() == 1 || timestamp < tmin_)
+      tmin_ = timestamp;
+    if (t_.size() == 1 || timestamp > tmax_)
+      tmax_ = timestamp;
+  }
+  double get_time_min() const { return tmin_; }
+  double get_time_max() const { return tmax_; }
+  size_t size() const { return t_.size(); }
+
+  const std::vector<double> &times() const { return t_; }
+  const std::vector<double> &quats() const { return q_; }
+  const std::vector<double> &positions() const { return p_; }
+  const std::vector<double> &cov_q() const { return Rq_; }
+  const std::vector<double> &cov_p() const { return Rp_; }
+
+private:
+  std::vector<double> t_, q_, p_, Rq_, Rp_;
+  double tmin_ = 0, tmax_ = 0;
+};
+
+/* A batch of independent build-and-solve problems resident on one GPU (owns the C handle). */
+class BatchSolver {
+public:
+  explicit BatchSolver(int n_trials, int device = 0) : n_(n_trials) { check(v2gt_batch_create(device, n_trials, &h_), "v2gt_batch_create"); }
+  ~BatchSolver() { v2gt_batch_destroy(h_); }
+  BatchSolver(const BatchSolver &) = delete;
+  BatchSolver &operator=(const BatchSolver &) = delete;
+
+  int size() const { return n_; }
+  v2gt_batch *handle() { return h_; }
+  void set_option(const char *name, double value) { check(v2gt_batch_set_option(h_, name, value), "v2gt_batch_set_option"); }
+
+  void set_trial(int trial, const v2gt_params &params, const Propagator &imu, const Interpolator &vicon,
+                 const std::vector<double> &timestamp_cameras) {
+    v2gt_params p = params;
+    p.sigma_w = imu.sigma_w();
+    p.sigma_wb = imu.sigma_wb();
+    p.sigma_a = imu.sigma_a();
+    p.sigma_ab = imu.sigma_ab();
+    check(v2gt_batch_set_trial(h_, trial, &p, (int64_t)imu.times().size(), imu.times().data(), imu.gyro().data(), imu.accel().data(),
+                               (int64_t)vicon.times().size(), vicon.times().data(), vicon.quats().data(), vicon.positions().data(),
+                               vicon.cov_q().data(), vicon.cov_p().data(), nullptr, (int64_t)timestamp_cameras.size(),
+                               timestamp_cameras.data()),
+          "v2gt_batch_set_trial");
+  }
+  void build_and_solve() { check(v2gt_batch_build_and_solve(h_), "v2gt_batch_build_and_solve"); }
+  v2gt_trial_info info(int trial) {
+    v2gt_trial_info inf;
+    check(v2gt_batch_get_info(h_, trial, &inf), "v2gt_batch_get_info");
+    return inf;
+  }
+  void write_to_file(int trial, const std::string &csv, const std::string &info) {
+    check(v2gt_batch_write_to_file(h_, trial, csv.c_str(), info.c_str()), "v2gt_batch_write_to_file");
+  }
+  /* times[n], states[n][16] = [q4 bg3 v3 ba3 p3] */
+  void get_states(int trial, std::vector<double> &times, std::vector<double> &states) {
+    int64_t n = 0;
+    check(v2gt_batch_get_states(h_, trial, 0, nullptr, nullptr, &n), "v2gt_batch_get_states");
+    times.assign((size_t)n, 0.0);
+    states.assign((size_t)n * V2GT_STATE_DIM, 0.0);
+    check(v2gt_batch_get_states(h_, trial, n, times.data(), states.data(), &n), "v2gt_batch_get_states");
+  }
+  void get_calibration(int trial, Vec4 &q_BtoI, Vec3 &p_BinI, double &toff, std::array<double, 2> &theta_xy) {
+    check(v2gt_batch_get_calibration(h_, trial, q_BtoI.data(), p_BinI.data(), &toff, theta_xy.data()), "v2gt_batch_get_calibration");
+  }
+
+private:
+  int n_;
+  v2gt_batch *h_ = nullptr;
+};
+
+/* Single-trajectory solver with the reference's method names (src/solver/ViconGraphSolver.h:71-110). */
+class ViconGraphSolver {
+public:
+  ViconGraphSolver(const ViconGraphSolverParams &params, std::shared_ptr<Propagator> propagator,
+                   std::shared_ptr<Interpolator> interpolator, std::vector<double> timestamp_cameras, int device = 0,
+                   bool exit_on_failure = false)
+      : params_(params), propagator_(std::move(propagator)), interpolator_(std::move(interpolator)),
+        timestamp_cameras_(std::move(timestamp_cameras)), exit_on_failure_(exit_on_failure) {
+    try {
+      batch_.reset(new BatchSolver(1, device));
+    } catch (const SolverError &e) {
+      fail(e);
+    }
+  }
+
+  /* ViconGraphSolver::build_and_solve (.cpp:96-192) */
+  void build_and_solve() {
+    try {
+      batch_->set_trial(0, params_, *propagator_, *interpolator_, timestamp_cameras_);
+      batch_->build_and_solve();
+      const v2gt_trial_info inf = batch_->info(0);
+      if (inf.status != V2GT_OK)
+        throw SolverError(inf.status, "build_and_solve");
+      info_ = inf;
+    } catch (const SolverError &e) {
+      fail(e);
+    }
+  }
+  /* ViconGraphSolver::write_to_file (.cpp:194-248): byte-compatible CSV + info text */
+  void write_to_file(const std::string &csvfilepath, const std::string &infofilepath) {
+    batch_->write_to_file(0, csvfilepath, infofilepath);
+  }
+  /* ViconGraphSolver::get_imu_poses (.cpp:357-375) */
+  void get_imu_poses(std::vector<double> &times, std::vector<Pose10> &poses) {
+    std::vector<double> x;
+    batch_->get_states(0, times, x);
+    poses.resize(times.size());
+    for (size_t i = 0; i < times.size(); i++) {
+      const double *s = &x[i * V2GT_STATE_DIM];
+      poses[i] = {s[0], s[1], s[2], s[3], s[13], s[14], s[15], s[7], s[8], s[9]};
+    }
+  }
+  /* full 16-double state rows [q4 bg3 v3 ba3 p3] (the CSV writer's inputs) */
+  void get_states(std::vector<double> &times, std::vector<double> &states) { batch_->get_states(0, times, states); }
+  /* ViconGraphSolver::get_calibration (.cpp:377-388) */
+  void get_calibration(double &toff, Mat3 &R_BtoI, Vec3 &p_BinI, Mat3 &R_GtoV) {
+    Vec4 q;
+    std::array<double, 2> th;
+    batch_->get_calibration(0, q, p_BinI, toff, th);
+    quat_2_Rot(q, R_BtoI);
+    rot_xy(th[0], th[1], R_GtoV);
+  }
+  const v2gt_trial_info &info() const { return info_; }
+
+  /* quat_2_Rot (src/utils/quat_ops.h:153-158) and rot_y(ty) rot_x(tx) (src/gtsam/RotationXY.h:62) on plain arrays */
+  static void quat_2_Rot(const Vec4 &q, Mat3 &R) {
+    const double x = q[0], y = q[1], z = q[2], w = q[3], a = 2 * w * w - 1;
+    R = {a + 2 * x * x,         2 * w * z + 2 * x * y, -2 * w * y + 2 * x * z,
+         -2 * w * z + 2 * y * x, a + 2 * y * y,         2 * w * x + 2 * y * z,
+         2 * w * y + 2 * z * x, -2 * w * x + 2 * z * y, a + 2 * z * z};
+  }
+  static void rot_xy(double tx, double ty, Mat3 &R);
+
+private:
+  void fail(const SolverError &e) const {
+    if (exit_on_failure_) {
+      std::fprintf(stderr, "[vicon2gt_b200] %s\n", e.what());
+      std::exit(EXIT_FAILURE);
+    }
+    throw e;
+  }
+  ViconGraphSolverParams params_;
+  std::shared_ptr<Propagator> propagator_;
+  std::shared_ptr<Interpolator> interpolator_;
+  std::vector<double> timestamp_cameras_;
+  bool exit_on_failure_;
+  std::unique_ptr<BatchSolver> batch_;
+  v2gt_trial_info info_{};
+};
+
+} // namespace vicon2gt_b200
+
+#include <cmath>
+inline void vicon2gt_b200::ViconGraphSolver::rot_xy(double tx, double ty, Mat3 &R) {
+  const double cx = std::cos(tx), sx = std::sin(tx), cy = std::cos(ty), sy = std::sin(ty);
+  // rot_y(ty) * rot_x(tx)   (src/utils/rpy_ops.h:28-46)
+  R = {cy, sy * sx, sy * cx, 0.0, cx, -sx, -sy, cy * sx, cy * cx};
+}
+
+#endif /* VICON2GT_B200_HPP */

@@ -84,3 +84,20 @@ def test_product_does_not_import_the_oracle():
                 if f == "build.py":
                     continue  # builds the checker (oracle/Makefile); building is not using
                 assert "oracle" not in txt.lower().replace("test infrastructure", ""), f"{f} mentions the oracle"
+
+
+def test_cpp_host_mirror_compiles_and_fails_loudly_without_a_device():
+    """include/vicon2gt_b200.hpp (C++ ViconGraphSolver / Propagator / Interpolator over the C ABI) builds with g++
+    into examples/run_simulation; on a box without a GPU the driver exits non-zero the way the reference does
+    (std::exit(EXIT_FAILURE) after logging) instead of computing anything on the CPU."""
+    import subprocess
+
+    from vicon2gt_b200 import api, build
+
+    exe = build.build_examples()
+    assert os.path.exists(exe)
+    if api.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    r = subprocess.run([exe, "--duration", "3"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+    assert r.returncode != 0
+    assert "no CUDA device" in r.stderr and "status 9" in r.stderr

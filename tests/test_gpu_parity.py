@@ -350,3 +350,32 @@ def test_cuda_path_matches_golden_fixture(name):
     assert np.max(np.abs(gl[4:] - g["final_globals"][4:])) < 1e-6
     assert abs(inf.final_error - g["final_error"]) / g["final_error"] < 1e-8
     bs.close()
+
+
+def test_cpp_driver_matches_python_mirror(tmp_path):
+    """examples/run_simulation (C++ host classes of include/vicon2gt_b200.hpp) and the Python mirror drive the same
+    C ABI: same simulated inputs -> byte-identical CSV / info files, and the printed ATE is at the simulation's level."""
+    import subprocess
+
+    from vicon2gt_b200 import api, build, sim
+
+    exe = build.build_examples()
+    csv, info = tmp_path / "cpp.csv", tmp_path / "cpp.txt"
+    r = subprocess.run([exe, "--seed", "4", "--duration", "10", "--states", str(csv), "--info", str(info)],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "rmse_ori" in r.stdout and "EST toff" in r.stdout
+    ds = sim.make_config("C1", seed=4, duration_s=10.0)
+    prop = api.Propagator(1.6968e-04, 1.9393e-05, 2.0e-3, 3.0e-3)
+    prop.feed_imu_array(ds.imu_t, ds.imu_w, ds.imu_a)
+    interp = api.Interpolator()
+    Rq, Rp = ds.vic_R_const[:9].reshape(3, 3), ds.vic_R_const[9:].reshape(3, 3)
+    for t, q, p in zip(ds.vic_t, ds.vic_q, ds.vic_p):
+        interp.feed_pose(t, q, p, Rq, Rp)
+    s = api.ViconGraphSolver(api.default_params(), prop, interp, ds.state_t)
+    s.build_and_solve()
+    s.write_to_file(str(tmp_path / "py.csv"), str(tmp_path / "py.txt"))
+    assert csv.read_bytes() == (tmp_path / "py.csv").read_bytes()
+    assert info.read_bytes() == (tmp_path / "py.txt").read_bytes()
+    rmse_pos = float(r.stdout.split("rmse_pos = ")[1].split()[0])
+    assert rmse_pos < 0.05  # sim.launch noise: 5 cm vicon position sigma

@@ -116,10 +116,26 @@ def build_oracle(force=False):
     return _LIBS["oracle"]
 
 
+def build_examples(force=False):
+    """g++ -> examples/run_simulation (host C++ over the C ABI: include/vicon2gt_b200.hpp); needs the two libraries."""
+    src = os.path.join(ROOT, "examples", "run_simulation.cpp")
+    out = os.path.join(ROOT, "examples", "run_simulation")
+    deps = [src, os.path.join(ROOT, "include", "vicon2gt_b200.hpp"), os.path.join(ROOT, "include", "vicon2gt_b200.h"), _LIBS["cuda"], _LIBS["sim"]]
+    if not force and not _newer(out, deps):
+        return out
+    gxx = _find("g++", ["/usr/bin/g++"])
+    _run([gxx, "-O2", "-std=c++14", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", HOST, "-o", out, src,
+          "-L", PKG_DIR, "-L", HOST, "-lvicon2gt_b200", "-lv2gt_sim",
+          "-Wl,-rpath," + PKG_DIR, "-Wl,-rpath," + HOST, "-Wl,-rpath,$ORIGIN/../vicon2gt_b200", "-Wl,-rpath,$ORIGIN/../vicon2gt_b200/host",
+          "-Wl,-rpath,/usr/local/cuda/lib64"])
+    return out
+
+
 def build_all(force=False, verbose=False):
     build_sim(force)
     build_cuda(force, verbose)
     build_oracle(force)
+    build_examples(force)
 
 
 if __name__ == "__main__":
