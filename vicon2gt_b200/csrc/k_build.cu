@@ -192,18 +192,19 @@ enum { B_TT = 0, B_TG, B_TV, B_TA, B_TP, B_GG, B_GV, B_GA, B_GP, B_VV, B_VA, B_V
 
 struct SmemCov {
   double *base; // points at [0][tid]
-  __device__ __forceinline__ double &at(int blk, int e) { return base[(blk * 9 + e) * PRE_NT]; }
+  int st;       // element stride: PRE_NT for the shared-memory copies ([entry][thread]), 1 for thread-local ones
+  __device__ __forceinline__ double &at(int blk, int e) { return base[(blk * 9 + e) * st]; }
   __device__ __forceinline__ void ld(int blk, double *o) const {
 #pragma unroll
     for (int e = 0; e < 9; e++)
-      o[e] = base[(blk * 9 + e) * PRE_NT];
+      o[e] = base[(blk * 9 + e) * st];
   }
   __device__ __forceinline__ void ldT(int blk, double *o) const {
 #pragma unroll
     for (int r = 0; r < 3; r++)
 #pragma unroll
       for (int c = 0; c < 3; c++)
-        o[3 * r + c] = base[(blk * 9 + 3 * c + r) * PRE_NT];
+        o[3 * r + c] = base[(blk * 9 + 3 * c + r) * st];
   }
 };
 
@@ -524,7 +525,10 @@ __device__ inline void cpi_step(CpiRegs &c, double t0, double t1, const double *
         Rh[e] = ((e % 4 == 0) ? 1.0 : 0.0) - c1 * w_x[e] + c2 * w_x_2[e];
       mm3(Rh, c.R, Rm);
     }
-    SmemCov P0{smem_thread}, Pacc{smem_thread + PB * PRE_NT}, PsA{smem_thread + 2 * PB * PRE_NT}, PsB{smem_thread + 3 * PB * PRE_NT};
+    // P and the RK4 accumulator live in shared memory; the two stage inputs are thread-local (L1-resident local
+    // memory), which keeps the shared-memory footprint at 2.1 kB per interval (3 CTAs per SM instead of 1)
+    double psa[PB], psb[PB];
+    SmemCov P0{smem_thread, PRE_NT}, Pacc{smem_thread + PB * PRE_NT, PRE_NT}, PsA{psa, 1}, PsB{psb, 1};
     double A[9], C[9], E[9];
 #pragma unroll
     for (int e = 0; e < 9; e++)
@@ -613,7 +617,7 @@ __device__ __forceinline__ double cov_entry(const SmemCov &P, int r, int c) {
 
 __device__ inline void set_status(LmState *lm, int code) { atomicCAS(&lm->status, V2GT_OK, code); }
 
-// grid: (ceil(n_max / PRE_NT), T), PRE_NT threads, dynamic smem 4*PB*PRE_NT doubles.
+// grid: (ceil(n_max / PRE_NT), T), PRE_NT threads, dynamic smem 2*PB*PRE_NT doubles.
 __global__ void __launch_bounds__(PRE_NT) k_preintegrate(DevPtrs d, int keep_cov) {
   extern __shared__ double smem[];
   const int t = blockIdx.y;
@@ -638,7 +642,7 @@ __global__ void __launch_bounds__(PRE_NT) k_preintegrate(DevPtrs d, int keep_cov
   const double *is = d.imu_s + 8 * tr.imu_off;
   const long long M = tr.n_imu;
 
-  for (int k = 0; k < 4 * PB; k++)
+  for (int k = 0; k < 2 * PB; k++)
     sm[k * PRE_NT] = 0.0;
   CpiRegs c;
   c.DT = 0;
@@ -760,9 +764,9 @@ __global__ void __launch_bounds__(PRE_NT) k_preintegrate(DevPtrs d, int keep_cov
   pr[63] = 0.0;
 
   // ---- information matrix P^-1 = L^-T L^-1 (Gaussian::Covariance, ImuFactorCPIv1.h:74)
-  SmemCov P0{sm};
-  double *Lm = sm + PB * PRE_NT;      // packed lower L  (120)
-  double *Li = sm + 2 * PB * PRE_NT;  // packed lower L^-1 (120)
+  SmemCov P0{sm, PRE_NT};
+  double *Lm = sm + PB * PRE_NT;      // packed lower L  (120), in the accumulator's shared-memory region
+  double Li[120];                     // packed lower L^-1, thread-local
   if (keep_cov && d.cov) {
     double *cv = d.cov + s * 225;
     for (int r = 0; r < 15; r++)
@@ -797,8 +801,8 @@ __global__ void __launch_bounds__(PRE_NT) k_preintegrate(DevPtrs d, int keep_cov
     for (int r = cc; r < 15; r++) {
       double sacc = (r == cc) ? 1.0 : 0.0;
       for (int k = cc; k < r; k++)
-        sacc -= Lm[tri(r, k) * PRE_NT] * Li[tri(k, cc) * PRE_NT];
-      Li[tri(r, cc) * PRE_NT] = sacc / Lm[tri(r, r) * PRE_NT];
+        sacc -= Lm[tri(r, k) * PRE_NT] * Li[tri(k, cc)];
+      Li[tri(r, cc)] = sacc / Lm[tri(r, r) * PRE_NT];
     }
   }
   const SoaW inf{d.info + s, d.S};
@@ -807,7 +811,7 @@ __global__ void __launch_bounds__(PRE_NT) k_preintegrate(DevPtrs d, int keep_cov
     for (int cc = 0; cc <= r; cc++) {
       double sacc = 0;
       for (int k = r; k < 15; k++) // (Li^T Li)[r][cc] = sum_k Li[k][r] Li[k][cc], k >= max(r,cc) = r
-        sacc += Li[tri(k, r) * PRE_NT] * Li[tri(k, cc) * PRE_NT];
+        sacc += Li[tri(k, r)] * Li[tri(k, cc)];
       inf[tri(r, cc)] = sacc;
       if (sacc != sacc)
         nan_found = true;
@@ -830,7 +834,7 @@ int launch_init_states(const DevPtrs &d, int n_max, int init_states, cudaStream_
 
 int launch_preintegrate(const DevPtrs &d, int n_max, int keep_cov, cudaStream_t st) {
   static bool attr_set = false;
-  const size_t smem = sizeof(double) * 4 * PB * PRE_NT;
+  const size_t smem = sizeof(double) * 2 * PB * PRE_NT;
   if (!attr_set) {
     V2_CUDA_CHECK(cudaFuncSetAttribute(k_preintegrate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
