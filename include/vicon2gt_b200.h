@@ -176,6 +176,39 @@ int v2gt_eval_cost(v2gt_batch *b, int32_t trial, double *cost);
 /* LM trace of the last optimise call: rows [lambda, cost_before, cost_after, lin_cost_change, accepted]. */
 int v2gt_batch_get_lm_trace(v2gt_batch *b, int32_t trial, int64_t capacity, double *rows, int64_t *n_out);
 
+/* ---- chain-sharded solve of ONE long sequence across ranks (BASELINE config 5) ----
+ * Every rank creates a 1-trial batch holding a contiguous piece of the cleaned state chain plus one halo state on
+ * each inner side, and drives the Levenberg-Marquardt rounds phase by phase; between the phases the caller moves the
+ * small buffers below with its collective library (NCCL through torch.distributed in vicon2gt_b200/chain.py):
+ *   all-reduce (sum)  V2GT_CHAIN_BUF_SUMS (8)   after phases 0 and 5      cost / model-fidelity scalars
+ *   all-reduce (sum)  V2GT_CHAIN_BUF_GAMMA (96) after phase 2             9x9 global block + gradient + linear error
+ *   all-gather        SEG_SEND -> SEG_ALL, SEPNE_SEND -> SEPNE_ALL  after phase 3   segment Schur outputs, separator records
+ *   all-gather        HALO_SEND (16) -> HALO_RECV (16 x world)      after phase 4   boundary steps
+ * The reduced (separator + 9 globals) system is then solved redundantly on every rank; all ranks take identical
+ * accept / reject decisions.  Geometry: the chain of n_total states is cut into p_total segments with the same
+ * formula as the single-GPU solve; this rank owns segments [j0, j1) and the separators in front of them, i.e. the
+ * local slots [own_lo, own_hi) of its n_local states starting at global state g_off.  Call before upload. */
+enum {
+  V2GT_CHAIN_BUF_SUMS = 0, V2GT_CHAIN_BUF_GAMMA = 1, V2GT_CHAIN_BUF_SEG_SEND = 2, V2GT_CHAIN_BUF_SEG_ALL = 3,
+  V2GT_CHAIN_BUF_SEPNE_SEND = 4, V2GT_CHAIN_BUF_SEPNE_ALL = 5, V2GT_CHAIN_BUF_HALO_SEND = 6, V2GT_CHAIN_BUF_HALO_RECV = 7
+};
+enum {
+  V2GT_CHAIN_PHASE_COST0 = 0,   /* cost of the current estimate -> SUMS                                   */
+  V2GT_CHAIN_PHASE_BEGIN = 1,   /* LM state initialisation from the (all-reduced) SUMS                    */
+  V2GT_CHAIN_PHASE_LINEARIZE = 2, /* start of a try; relinearise if the last step was accepted -> GAMMA   */
+  V2GT_CHAIN_PHASE_ELIMINATE = 3, /* eliminate the own segments -> SEG_SEND, SEPNE_SEND                   */
+  V2GT_CHAIN_PHASE_SOLVE = 4,   /* reduced system (redundant), back-substitution -> HALO_SEND             */
+  V2GT_CHAIN_PHASE_COST = 5,    /* trial point + its cost -> SUMS                                         */
+  V2GT_CHAIN_PHASE_DECIDE = 6   /* accept / reject, lambda update from the (all-reduced) SUMS             */
+};
+int v2gt_chain_configure(v2gt_batch *b, int32_t rank, int32_t world, int64_t n_total, int64_t g_off, int32_t p_total, int32_t j0,
+                         int32_t j1, int32_t own_lo, int32_t own_hi);
+int v2gt_chain_phase(v2gt_batch *b, int32_t phase);
+/* device pointer + length (doubles) of one of the exchange buffers (valid after upload) */
+int v2gt_chain_buffer(v2gt_batch *b, int32_t which, void **dev_ptr, int64_t *n_doubles);
+/* the handle's CUDA stream (cudaStream_t), so that the caller's collectives can be ordered with the kernels */
+int v2gt_batch_stream(v2gt_batch *b, void **stream);
+
 /* ---- measurement helpers ---- */
 /* Device time (ms, CUDA events on the handle's stream) spent in each phase of the last
  * build/optimise: [0] build(init+preint) [1] linearise+assemble [2] eliminate [3] reduced solve

@@ -37,6 +37,10 @@ int launch_backsub(const DevPtrs &d, int force_all, cudaStream_t st);
 int launch_lm_begin(const DevPtrs &d, cudaStream_t st);
 int launch_lm_pre_try(const DevPtrs &d, cudaStream_t st);
 int launch_lm_decide(const DevPtrs &d, int count_active, cudaStream_t st);
+int launch_chain_sum(const DevPtrs &d, cudaStream_t st);
+int launch_chain_fix(const DevPtrs &d, cudaStream_t st);
+int launch_chain_pack(const DevPtrs &d, int stride, cudaStream_t st);
+int launch_chain_halo(const DevPtrs &d, int recv, cudaStream_t st);
 int asm_chunks(int n_max);
 } // namespace v2
 
@@ -69,6 +73,10 @@ struct v2gt_batch {
   bool reuse = false;
   int n_max = 0; // max raw states over trials
   bool uploaded = false, built = false, values_init = false;
+  // chain-sharded mode (v2gt_chain_configure)
+  bool chain = false;
+  int c_rank = 0, c_world = 1, c_p = 0, c_j0 = 0, c_j1 = 0, c_lo = 0, c_hi = 0;
+  long long c_n = 0, c_goff = 0;
   // options
   int opt_segments = 0;       // 0 = auto (adaptive); > 0: fixed number of segments per trial
   int opt_target_warps = 148 * 64; // segment warps the adaptive choice aims for per elimination launch
@@ -487,6 +495,11 @@ int v2gt_batch_upload(v2gt_batch *b) {
   if (P <= 0)
     P = std::max(1, (int)std::ceil(std::sqrt((double)std::max(1, b->n_max))));
   P = std::max(1, std::min(P, std::max(1, b->n_max / 2)));
+  if (b->chain) {
+    if (T != 1)
+      return V2GT_ERR_INVALID_ARG;
+    P = b->c_p; // global segment count of the sharded chain
+  }
   DevPtrs &d = b->d;
   std::memset(&d, 0, sizeof(d));
   d.T = T;
@@ -497,7 +510,7 @@ int v2gt_batch_upload(v2gt_batch *b) {
   d.nchunk = std::max(1, (b->n_max + V2GT_CHUNK - 1) / V2GT_CHUNK);
   const int nasm = std::max(1, asm_chunks(b->n_max));
   {
-    const std::vector<long long> key = {T, S, M, V, C, P, d.nchunk, nasm, b->opt_keep_cov};
+    const std::vector<long long> key = {T, S, M, V, C, P, d.nchunk, nasm, b->opt_keep_cov, b->chain ? b->c_world : 0};
     if (key == b->alloc_key && !b->dev_allocs.empty()) {
       b->reuse = true; // same shape as the previous upload: keep every buffer
       b->dev_cur = b->pin_cur = 0;
@@ -585,6 +598,25 @@ int v2gt_batch_upload(v2gt_batch *b) {
   V2_TRY(dev_alloc(b, &d.trace, (size_t)T * TRACE_MAX * 5));
   V2_TRY(dev_alloc(b, &d.n_active, 1));
   V2_TRY(dev_alloc(b, &d.removed_no_vicon, (size_t)T));
+  if (b->chain) {
+    const int ploc = std::max(1, b->c_j1 - b->c_j0);
+    V2_TRY(dev_alloc(b, &d.c_sepne, ((size_t)P + 2) * NE_STRIDE));
+    V2_TRY(dev_alloc(b, &d.c_sums, 8));
+    V2_TRY(dev_alloc(b, &d.c_gamma_loc, 96));
+    V2_TRY(dev_alloc(b, &d.c_seg_send, (size_t)ploc * SEG_STRIDE));
+    V2_TRY(dev_alloc(b, &d.c_sepne_send, (size_t)ploc * NE_STRIDE));
+    V2_TRY(dev_alloc(b, &d.c_halo_send, 16));
+    V2_TRY(dev_alloc(b, &d.c_halo_recv, (size_t)16 * std::max(1, b->c_world)));
+    d.chain = 1;
+    d.c_n = (int)b->c_n;
+    d.c_goff = (int)b->c_goff;
+    d.c_j0 = b->c_j0;
+    d.c_j1 = b->c_j1;
+    d.c_lo = b->c_lo;
+    d.c_hi = b->c_hi;
+    d.c_rank = b->c_rank;
+    d.c_world = b->c_world;
+  }
   d.trials = p_trials;
   d.imu_t = p_imu_t;
   d.imu_s = p_imu_s;
@@ -610,6 +642,13 @@ int v2gt_batch_upload(v2gt_batch *b) {
   V2_CUDA_CHECK(cudaMemsetAsync(d.delta, 0, sizeof(double) * S * 16, st));
   V2_CUDA_CHECK(cudaMemsetAsync(d.trace, 0, sizeof(double) * T * TRACE_MAX * 5, st));
   V2_CUDA_CHECK(cudaMemsetAsync(d.xg, 0, sizeof(double) * T * 16, st));
+  if (b->chain) {
+    V2_CUDA_CHECK(cudaMemsetAsync(d.c_sums, 0, sizeof(double) * 8, st));
+    V2_CUDA_CHECK(cudaMemsetAsync(d.c_gamma_loc, 0, sizeof(double) * 96, st));
+    V2_CUDA_CHECK(cudaMemsetAsync(d.c_halo_recv, 0, sizeof(double) * 16 * std::max(1, b->c_world), st));
+    V2_CUDA_CHECK(cudaMemsetAsync(d.c_sepne, 0, sizeof(double) * ((size_t)P + 2) * NE_STRIDE, st));
+    V2_CUDA_CHECK(cudaMemsetAsync(d.seg, 0, sizeof(double) * (size_t)T * P * SEG_STRIDE, st));
+  }
   V2_CUDA_CHECK(cudaStreamSynchronize(st)); // td / lm are stack-owned host vectors
   b->reuse = false;
   b->uploaded = true;
@@ -897,6 +936,105 @@ int v2gt_batch_write_to_file(v2gt_batch *b, int32_t trial, const char *csv_path,
   of_info << "gravity norm: " << std::endl << b->trials[trial].prm.gravity_magnitude << std::endl << std::endl;
   of_info << "t_off_vicon_to_imu: " << std::endl << eigen_print(&toff, 1, 1) << std::endl << std::endl;
   of_info.close();
+  return V2GT_OK;
+}
+
+int v2gt_chain_configure(v2gt_batch *b, int32_t rank, int32_t world, int64_t n_total, int64_t g_off, int32_t p_total, int32_t j0,
+                         int32_t j1, int32_t own_lo, int32_t own_hi) {
+  if (!b || b->T != 1 || world < 1 || rank < 0 || rank >= world || n_total < 2 || p_total < 1 || j0 < 0 || j1 <= j0 || j1 > p_total ||
+      own_lo < 0 || own_hi <= own_lo || g_off < 0)
+    return V2GT_ERR_INVALID_ARG;
+  b->chain = true;
+  b->c_rank = rank;
+  b->c_world = world;
+  b->c_n = n_total;
+  b->c_goff = g_off;
+  b->c_p = p_total;
+  b->c_j0 = j0;
+  b->c_j1 = j1;
+  b->c_lo = own_lo;
+  b->c_hi = own_hi;
+  b->uploaded = false;
+  b->built = false;
+  return V2GT_OK;
+}
+
+static int seg_stride_host(long long n, int P) {
+  long long st = (n + 1 + P - 1) / P;
+  return (int)(st < 2 ? 2 : st);
+}
+
+int v2gt_chain_phase(v2gt_batch *b, int32_t phase) {
+  if (!b || !b->chain)
+    return V2GT_ERR_INVALID_ARG;
+  if (!b->built)
+    return V2GT_ERR_NOT_BUILT;
+  V2_CUDA_CHECK(cudaSetDevice(b->device));
+  b->results_cached = false;
+  cudaStream_t st = b->stream;
+  const DevPtrs &d = b->d;
+  switch (phase) {
+  case V2GT_CHAIN_PHASE_COST0:
+    V2_TRY(launch_cost(d, b->n_max, 0, 1, st));
+    V2_TRY(launch_chain_sum(d, st));
+    break;
+  case V2GT_CHAIN_PHASE_BEGIN:
+    V2_TRY(launch_lm_begin(d, st));
+    V2_TRY(solve_configure());
+    break;
+  case V2GT_CHAIN_PHASE_LINEARIZE:
+    V2_TRY(launch_lm_pre_try(d, st));
+    V2_TRY(launch_linearize(d, b->n_max, 0, st));
+    // the local part of the global block is kept separately, so the all-reduce into gamma can be repeated every try
+    V2_CUDA_CHECK(cudaMemcpyAsync(d.gamma, d.c_gamma_loc, sizeof(double) * 96, cudaMemcpyDeviceToDevice, st));
+    break;
+  case V2GT_CHAIN_PHASE_ELIMINATE:
+    V2_TRY(launch_chain_fix(d, st));
+    V2_TRY(launch_eliminate(d, 0, st));
+    V2_TRY(launch_chain_pack(d, seg_stride_host(b->c_n, d.P), st));
+    break;
+  case V2GT_CHAIN_PHASE_SOLVE:
+    V2_TRY(launch_reduced(d, 0, st));
+    V2_TRY(launch_backsub(d, 0, st));
+    V2_TRY(launch_chain_halo(d, 0, st));
+    break;
+  case V2GT_CHAIN_PHASE_COST:
+    V2_TRY(launch_chain_halo(d, 1, st));
+    V2_TRY(launch_cost(d, b->n_max, 1, 0, st));
+    V2_TRY(launch_chain_sum(d, st));
+    break;
+  case V2GT_CHAIN_PHASE_DECIDE:
+    V2_TRY(launch_lm_decide(d, 0, st));
+    break;
+  default:
+    return V2GT_ERR_INVALID_ARG;
+  }
+  return V2GT_OK;
+}
+
+int v2gt_chain_buffer(v2gt_batch *b, int32_t which, void **dev_ptr, int64_t *n_doubles) {
+  if (!b || !b->chain || !b->uploaded || !dev_ptr || !n_doubles)
+    return V2GT_ERR_INVALID_ARG;
+  const DevPtrs &d = b->d;
+  const int64_t ploc = b->c_j1 - b->c_j0;
+  switch (which) {
+  case V2GT_CHAIN_BUF_SUMS: *dev_ptr = d.c_sums; *n_doubles = 8; break;
+  case V2GT_CHAIN_BUF_GAMMA: *dev_ptr = d.gamma; *n_doubles = 96; break;
+  case V2GT_CHAIN_BUF_SEG_SEND: *dev_ptr = d.c_seg_send; *n_doubles = ploc * SEG_STRIDE; break;
+  case V2GT_CHAIN_BUF_SEG_ALL: *dev_ptr = d.seg; *n_doubles = (int64_t)d.P * SEG_STRIDE; break;
+  case V2GT_CHAIN_BUF_SEPNE_SEND: *dev_ptr = d.c_sepne_send; *n_doubles = ploc * NE_STRIDE; break;
+  case V2GT_CHAIN_BUF_SEPNE_ALL: *dev_ptr = d.c_sepne; *n_doubles = (int64_t)d.P * NE_STRIDE; break;
+  case V2GT_CHAIN_BUF_HALO_SEND: *dev_ptr = d.c_halo_send; *n_doubles = 16; break;
+  case V2GT_CHAIN_BUF_HALO_RECV: *dev_ptr = d.c_halo_recv; *n_doubles = 16LL * b->c_world; break;
+  default: return V2GT_ERR_INVALID_ARG;
+  }
+  return V2GT_OK;
+}
+
+int v2gt_batch_stream(v2gt_batch *b, void **stream) {
+  if (!b || !stream)
+    return V2GT_ERR_INVALID_ARG;
+  *stream = (void *)b->stream;
   return V2GT_OK;
 }
 

@@ -58,6 +58,9 @@ __global__ void __launch_bounds__(V2GT_CHUNK) k_factor_eval(DevPtrs d, int which
   const int i = blockIdx.x * V2GT_CHUNK + threadIdx.x;
   const int buf = which ? (1 - lm.cur) : lm.cur;
   double cost = 0.0, lin0 = 0.0, gd = 0.0, dd = 0.0;
+  // chain-sharded mode: halo slots carry the neighbours' boundary states; their vicon factors and the IMU factor
+  // that starts at them belong to the neighbour (they are evaluated where needed, but not counted here)
+  const bool own = !d.chain || (i >= d.c_lo && i < d.c_hi);
   if (i < n) {
     const long long s = tr.st_off + i;
     const double *gl = d.glob + ((long long)buf * d.T + t) * GLOB_STRIDE;
@@ -73,11 +76,13 @@ __global__ void __launch_bounds__(V2GT_CHUNK) k_factor_eval(DevPtrs d, int which
 #pragma unroll
       for (int k = 0; k < 4; k++)
         o4[k] = make_double4(xi[4 * k], xi[4 * k + 1], xi[4 * k + 2], xi[4 * k + 3]);
-      const double *gk = d.ne + s * NE_STRIDE + NE_M + NE_MG;
+      if (own) {
+        const double *gk = d.ne + s * NE_STRIDE + NE_M + NE_MG;
 #pragma unroll
-      for (int k = 0; k < 15; k++) {
-        gd += __ldg(gk + NE_MW * k) * dl[k];
-        dd += dl[k] * dl[k];
+        for (int k = 0; k < 15; k++) {
+          gd += __ldg(gk + NE_MW * k) * dl[k];
+          dd += dl[k] * dl[k];
+        }
       }
     } else {
       ld16(xb + s * X_STRIDE, xi);
@@ -87,7 +92,8 @@ __global__ void __launch_bounds__(V2GT_CHUNK) k_factor_eval(DevPtrs d, int which
       ViconPieces vp;
       const bool cc = tr.vic_cov_const != 0;
       const double *vc = cc ? tr.vic_Rconst : d.vic_c + d.vic_c_off[t];
-      vicon_factor<JAC>(tr, d.vic_t + tr.vic_off, d.vic_s + 8 * tr.vic_off, vc, cc, d.st_t[s], xi, gl, vp);
+      // a halo slot queries a time no pose can bracket, which makes the factor empty (has = 0, zero blocks)
+      vicon_factor<JAC>(tr, d.vic_t + tr.vic_off, d.vic_s + 8 * tr.vic_off, vc, cc, own ? d.st_t[s] : -1.0e300, xi, gl, vp);
       cost += huber_loss(tr.prm.huber_k, vp.dist);
       double r2 = 0;
 #pragma unroll
@@ -126,7 +132,7 @@ __global__ void __launch_bounds__(V2GT_CHUNK) k_factor_eval(DevPtrs d, int which
       grav_terms(gl[GL_THX], gl[GL_THY], tr.prm.gravity_magnitude, G);
       ImuPieces ip;
       imu_factor<JAC>(SoaR{d.pre + s, d.S}, xi, xj, G, ip);
-      const double q = 0.5 * quad_form15(SoaR{d.info + s, d.S}, ip.e);
+      const double q = own ? 0.5 * quad_form15(SoaR{d.info + s, d.S}, ip.e) : 0.0;
       cost += q;
       lin0 += q;
       if (JAC) {
@@ -368,7 +374,7 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(DevPtrs d, int force_a
           gv[r] -= sacc;
         }
       // gravity 2x2 block and gradient of this factor (thread dcol == 3 owns it)
-      if (dcol == 3) {
+      if (dcol == 3 && (!d.chain || (i >= d.c_lo && i < d.c_hi))) {
         // Lambda rows v and p applied to H3 and e
         double LH[2][6]; // (Lambda H3)[a] for a = v, p  (3x2)
         double Le[2][3];
@@ -606,10 +612,8 @@ __global__ void __launch_bounds__(64) k_reduce_gamma(DevPtrs d, int n_asm_chunks
       sacc += d.part_asm[((long long)t * n_asm_chunks + k) * PART_STRIDE + threadIdx.x];
   s_v[threadIdx.x] = sacc;
   __syncthreads();
-  double *gm = d.gamma + (long long)t * 96;
-  if (threadIdx.x < 81) {
-    // handled below by a strided loop (64 threads, 81+9 outputs)
-  }
+  // chain-sharded mode: this is only this rank's part; it is all-reduced into gamma by the host side
+  double *gm = d.chain ? d.c_gamma_loc : d.gamma + (long long)t * 96;
   for (int k = threadIdx.x; k < 90; k += 64) {
     double v = 0.0;
     if (k < 81) {
@@ -630,6 +634,8 @@ __global__ void __launch_bounds__(64) k_reduce_gamma(DevPtrs d, int n_asm_chunks
     for (int k = 0; k < usedc; k++)
       l0 += d.part_cost[((long long)t * d.nchunk + k) * 4 + 1];
     lm.lin_error0 = l0;
+    if (d.chain)
+      gm[90] = l0;
   }
 }
 

@@ -12,6 +12,8 @@
 namespace v2 {
 
 __device__ inline double sum_cost(const DevPtrs &d, int t, int which) {
+  if (d.chain)
+    return d.c_sums[which]; // all-reduced over the ranks of a chain-sharded solve
   const int n = d.n_states[t];
   const int used = (n + V2GT_CHUNK - 1) / V2GT_CHUNK;
   double s = 0;
@@ -78,7 +80,8 @@ __global__ void k_lm_decide(DevPtrs d, int count_active) {
   const v2gt_params &p = d.trials[t].prm;
   bool step_ok = false, stop_search = false;
   double new_error = INFINITY, lin_change = 0.0, cost_change = 0.0;
-  if (!lm.solve_failed) {
+  const bool failed = d.chain ? (d.c_sums[4] > 0.0) : (lm.solve_failed != 0);
+  if (!failed) {
     // g.delta and |delta|^2: the states' parts come from the trial-point evaluation, the globals' from the reduced solve
     const double *xg = d.xg + (long long)t * 16;
     const double gd = xg[10] + sum_cost(d, t, 2), dd = xg[11] + sum_cost(d, t, 3);
@@ -142,6 +145,78 @@ __global__ void k_lm_decide(DevPtrs d, int count_active) {
   }
   if (count_active && lm.lm_state == 0)
     atomicAdd(d.n_active, 1);
+}
+
+// ---- chain-sharded mode helpers (single trial)
+// local sums of the last factor evaluation -> c_sums (all-reduced by the host side afterwards)
+__global__ void k_chain_sum(DevPtrs d) {
+  if (threadIdx.x >= 5 || blockIdx.x != 0)
+    return;
+  const int n = d.n_states[0];
+  const int used = (n + V2GT_CHUNK - 1) / V2GT_CHUNK;
+  double s = 0;
+  if (threadIdx.x < 4) {
+    for (int k = 0; k < used; k++)
+      s += d.part_cost[(long long)k * 4 + threadIdx.x];
+  } else {
+    s = d.lm[0].solve_failed ? 1.0 : 0.0;
+  }
+  d.c_sums[threadIdx.x] = s;
+}
+// after the all-reduce of the global block: take the summed linear error
+__global__ void k_chain_fix(DevPtrs d) {
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    d.lm[0].lin_error0 = d.gamma[90];
+}
+// pack what the reduced (separator) system needs from this rank: the records of its separators and its segments' outputs
+__global__ void k_chain_pack(DevPtrs d, int stride) {
+  const int jl = blockIdx.x; // local segment index
+  const int j = d.c_j0 + jl;
+  if (j >= d.c_j1)
+    return;
+  const double *sg = d.seg + (long long)j * SEG_STRIDE;
+  double *so = d.c_seg_send + (long long)jl * SEG_STRIDE;
+  for (int k = threadIdx.x; k < SEG_STRIDE; k += blockDim.x)
+    so[k] = sg[k];
+  double *no = d.c_sepne_send + (long long)jl * NE_STRIDE;
+  const long long slot = (long long)j * stride - 1 - d.c_goff; // separator in front of segment j (none for j = 0)
+  for (int k = threadIdx.x; k < NE_STRIDE; k += blockDim.x)
+    no[k] = (j >= 1 && slot >= 0 && slot < d.n_states[0]) ? d.ne[(d.trials[0].st_off + slot) * NE_STRIDE + k] : 0.0;
+}
+// step of this rank's last own state -> send buffer; halo steps <- neighbours
+__global__ void k_chain_halo_send(DevPtrs d) {
+  if (threadIdx.x < 16 && d.c_hi >= 1)
+    d.c_halo_send[threadIdx.x] = d.delta[(d.trials[0].st_off + d.c_hi - 1) * 16 + threadIdx.x];
+}
+__global__ void k_chain_halo_recv(DevPtrs d) {
+  // left halo = the previous rank's last own state (an interior state of its last segment); the right halo is a
+  // separator, whose step k_reduced has already written
+  if (threadIdx.x < 16 && d.c_lo >= 1 && d.c_rank >= 1)
+    d.delta[(d.trials[0].st_off + d.c_lo - 1) * 16 + threadIdx.x] = d.c_halo_recv[(d.c_rank - 1) * 16 + threadIdx.x];
+}
+
+int launch_chain_sum(const DevPtrs &d, cudaStream_t st) {
+  k_chain_sum<<<1, 32, 0, st>>>(d);
+  V2_CUDA_CHECK(cudaGetLastError());
+  return V2GT_OK;
+}
+int launch_chain_fix(const DevPtrs &d, cudaStream_t st) {
+  k_chain_fix<<<1, 32, 0, st>>>(d);
+  V2_CUDA_CHECK(cudaGetLastError());
+  return V2GT_OK;
+}
+int launch_chain_pack(const DevPtrs &d, int stride, cudaStream_t st) {
+  k_chain_pack<<<max(1, d.c_j1 - d.c_j0), 256, 0, st>>>(d, stride);
+  V2_CUDA_CHECK(cudaGetLastError());
+  return V2GT_OK;
+}
+int launch_chain_halo(const DevPtrs &d, int recv, cudaStream_t st) {
+  if (recv)
+    k_chain_halo_recv<<<1, 32, 0, st>>>(d);
+  else
+    k_chain_halo_send<<<1, 32, 0, st>>>(d);
+  V2_CUDA_CHECK(cudaGetLastError());
+  return V2GT_OK;
 }
 
 int launch_lm_begin(const DevPtrs &d, cudaStream_t st) {

@@ -342,10 +342,10 @@ __global__ void __launch_bounds__(ELIM_WARPS * 32, ELIM_MIN_CTAS) k_seg_eliminat
   if (!force_all && (lm.lm_state != 0 || lm.status != V2GT_OK))
     return;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int j = blockIdx.x * ELIM_WARPS + wid;
-  const int n = d.n_states[t];
+  const int j = blockIdx.x * ELIM_WARPS + wid + (d.chain ? d.c_j0 : 0);
+  const int n = d.chain ? d.c_n : d.n_states[t];
   const SegGeom sg = seg_geom(n, d.P);
-  if (j >= sg.nseg)
+  if (j >= (d.chain ? min(sg.nseg, d.c_j1) : sg.nseg))
     return;
   double *w = smem + (size_t)wid * SW_TOTAL;
   const TrialDev &tr = d.trials[t];
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(ELIM_WARPS * 32, ELIM_MIN_CTAS) k_seg_eliminat
   const int a0 = j * sg.stride;
   const int b1 = min(n, (j + 1) * sg.stride - 1); // exclusive end of the interior
   const bool has_left = (j >= 1);
-  const long long s0 = tr.st_off + a0;
+  const long long s0 = tr.st_off + a0 - (d.chain ? d.c_goff : 0);
   ElimAcc A;
   acc_zero(A);
   bool ok;
@@ -416,14 +416,14 @@ __global__ void __launch_bounds__(128) k_reduced_assemble(DevPtrs d, int force_a
   const LmState &lm = d.lm[t];
   if (!force_all && (lm.lm_state != 0 || lm.status != V2GT_OK))
     return;
-  const int n = d.n_states[t];
+  const int n = d.chain ? d.c_n : d.n_states[t];
   const SegGeom sg = seg_geom(n, d.P);
   const int m = blockIdx.x + 1;
   if (m > sg.nsep)
     return;
   const TrialDev &tr = d.trials[t];
   const long long s = tr.st_off + (long long)m * sg.stride - 1;
-  const double *ne = d.ne + s * NE_STRIDE;
+  const double *ne = d.chain ? d.c_sepne + (long long)m * NE_STRIDE : d.ne + s * NE_STRIDE;
   const double *segl = d.seg + ((long long)t * d.P + (m - 1)) * SEG_STRIDE; // this separator closes segment m-1
   const bool has_r = (m < sg.nseg);                                         // ... and opens segment m
   const double *segr = d.seg + ((long long)t * d.P + m) * SEG_STRIDE;
@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(32) k_reduced(DevPtrs d, int force_all) {
     return;
   const int lane = threadIdx.x;
   const int gid = lane >> 2, tid = lane & 3;
-  const int n = d.n_states[t];
+  const int n = d.chain ? d.c_n : d.n_states[t];
   const SegGeom sg = seg_geom(n, d.P);
   const TrialDev &tr = d.trials[t];
   const double lambda = lm.lambda;
@@ -667,9 +667,11 @@ __global__ void __launch_bounds__(32) k_reduced(DevPtrs d, int force_all) {
     fac_load(F, d.red_fac + ((long long)t * d.P + m) * FAC_STRIDE, lane);
     double y0[2], y1[2];
     backsub_node(F, V, y0, y1, 0.0, gid, tid);
-    const long long s = tr.st_off + (long long)m * sg.stride - 1;
     store_x(d.xsep + ((long long)t * (d.P + 1) + m) * 16, y0, y1, gid, tid);
-    store_x(d.delta + s * 16, y0, y1, gid, tid);
+    // the separator's own step: in chain-sharded mode only where the state has a local slot (own or halo)
+    const long long slot = (long long)m * sg.stride - 1 - (d.chain ? d.c_goff : 0);
+    if (!d.chain || (slot >= 0 && slot < d.n_states[t]))
+      store_x(d.delta + (tr.st_off + slot) * 16, y0, y1, gid, tid);
   }
   if (lane == 0) {
     // trial point of the globals
@@ -692,12 +694,13 @@ __global__ void __launch_bounds__(BS_WARPS * 32) k_seg_backsub(DevPtrs d, int fo
     return;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int gid = lane >> 2, tid = lane & 3;
-  const int j = blockIdx.x * BS_WARPS + wid;
-  const int n = d.n_states[t];
+  const int j = blockIdx.x * BS_WARPS + wid + (d.chain ? d.c_j0 : 0);
+  const int n = d.chain ? d.c_n : d.n_states[t];
   const SegGeom sg = seg_geom(n, d.P);
-  if (j >= sg.nseg)
+  if (j >= (d.chain ? min(sg.nseg, d.c_j1) : sg.nseg))
     return;
   const TrialDev &tr = d.trials[t];
+  const long long base = tr.st_off - (d.chain ? d.c_goff : 0); // slot of global state 0
   const int a0 = j * sg.stride;
   const int b1 = min(n, (j + 1) * sg.stride - 1);
   const bool has_left = (j >= 1);
@@ -715,9 +718,9 @@ __global__ void __launch_bounds__(BS_WARPS * 32) k_seg_backsub(DevPtrs d, int fo
   if (b1 <= a0)
     return;
   FacRegs F, Fn;
-  fac_load(F, d.fac + (tr.st_off + b1 - 1) * FAC_STRIDE, lane);
+  fac_load(F, d.fac + (base + b1 - 1) * FAC_STRIDE, lane);
   for (int k = b1 - 1; k >= a0; k--) {
-    const long long s = tr.st_off + k;
+    const long long s = base + k;
     if (k > a0)
       fac_load(Fn, d.fac + (s - 1) * FAC_STRIDE, lane);
     double y0[2], y1[2];

@@ -126,6 +126,16 @@ struct DevPtrs {
   int *n_active;     // device counter of running trials
   int *removed_no_vicon; // [T]
   int nchunk;        // chunks (CTAs) per trial of the per-state kernels
+  // ---- chain-sharded mode (ONE long sequence split across ranks; T == 1).  This handle holds the states
+  // [c_goff, c_goff + n_states[0]) of a chain of c_n states; it owns the global segments [c_j0, c_j1) and the
+  // separators in front of them = local slots [c_lo, c_hi); the slots outside are halo copies of the neighbours'
+  // boundary states.  The segment / separator buffers (seg, red_*, xsep, c_sepne) are indexed GLOBALLY.
+  int chain;         // 0: ordinary batch
+  int c_n, c_goff, c_j0, c_j1, c_lo, c_hi, c_rank, c_world;
+  double *c_sepne;     // [P][NE_STRIDE] normal-equation records of every separator of the chain (all-gathered)
+  double *c_sums;      // [8] cost, lin_error0, g.delta, |delta|^2, solve_failed (local, then all-reduced)
+  double *c_gamma_loc; // [96] this rank's part of the global block (all-reduced into gamma)
+  double *c_seg_send, *c_sepne_send, *c_halo_send, *c_halo_recv;
 };
 
 #if defined(__CUDACC__)
