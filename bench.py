@@ -62,6 +62,11 @@ def parse():
     ap.add_argument("--cpu-sample-s", type=float, default=40.0, help="length of the CPU baseline sample trajectory")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--workload", default="mc", choices=["mc", "chain"],
+                    help="mc: Monte-Carlo batch (BASELINE configs[3], the default the metric is quoted on); chain: ONE one-hour "
+                         "sequence chain-sharded over the GPUs with NCCL (configs[4]; second half of the metric: LM latency)")
+    ap.add_argument("--segs-per-rank", type=int, default=0, help="chain workload: segments per GPU (0 = ~sqrt(states per GPU))")
+    ap.add_argument("--chain-duration", type=float, default=0.0, help="chain workload: truncate the hour to this many seconds")
     return ap.parse_args()
 
 
@@ -207,10 +212,94 @@ def run_reference(args):
     return 0
 
 
+def run_chain(args):
+    """BASELINE.json configs[4]: one ~72 k-state sequence, contiguous chain segments per GPU; per damped solve the ranks
+    exchange only the segment Schur outputs / separator records (all-gather) and the 9x9 global block (all-reduce)."""
+    import torch
+
+    from vicon2gt_b200 import api, sim
+    from vicon2gt_b200.chain import ChainSolver, DistComm, LocalComm
+
+    rank, local_rank, world = dist_env()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    device = local_rank if world > 1 else 0
+    kw = {} if args.chain_duration <= 0 else dict(duration_s=args.chain_duration)
+    ds = sim.make_config("C5", seed=5, **kw)  # identical on every rank (deterministic generator)
+    p = api.default_params()
+    comm = DistComm(dist) if dist is not None else LocalComm(1)
+    n_guess = ds.n_times
+    spr = args.segs_per_rank if args.segs_per_rank > 0 else max(2, int(round((n_guess / world) ** 0.5)))
+    cs = ChainSolver(p, ds, comm, segs_per_rank=spr, device=device)
+    stream = cs.parts[0].stream
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def step():
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record(stream)
+        cs.rebuild()
+        e1.record(stream)
+        inf = cs.optimize()
+        e2.record(stream)
+        e2.synchronize()
+        return e0.elapsed_time(e1), e1.elapsed_time(e2), inf
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(device)
+    barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    b_ms = o_ms = 0.0
+    for _ in range(args.steps):
+        b, o, inf = step()
+        b_ms += b
+        o_ms += o
+    torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.stop()
+    tot = torch.tensor([b_ms + o_ms, o_ms], dtype=torch.float64, device=f"cuda:{device}")
+    if dist is not None:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    tot_ms, opt_ms = (float(v) for v in tot.tolist())
+    if rank == 0:
+        n_states = len(cs.ts)
+        line = {
+            "metric": "lm_damped_solve_latency", "value": opt_ms / args.steps / max(1, inf.tries), "unit": "ms", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_ms / args.steps, "higher_is_better": False,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "ONE synthesised one-hour sequence (BASELINE.json configs[4]): 20 Hz states, 200 Hz IMU, 100 Hz vicon, "
+                                   "chain-sharded over %d GPU(s), %d segments per GPU; NCCL all-gather of segment Schur outputs + separator "
+                                   "records, all-reduce of the 9x9 global block" % (world, spr),
+                       "n_states": n_states, "n_imu": ds.n_imu, "n_vicon": ds.n_vicon, "segments_per_gpu": spr,
+                       "timing": "CUDA events on the solver stream, max over ranks"},
+            "lm": {"iterations": inf.iterations, "damped_solves": inf.tries, "final_error": inf.final_error, "status": inf.status,
+                   "ms_per_lm_iteration": opt_ms / args.steps / max(1, inf.iterations), "build_ms": (tot_ms - opt_ms) / args.steps,
+                   "optimize_ms": opt_ms / args.steps},
+            "trajectories_per_second": 1e3 * args.steps / tot_ms,
+            "collectives_per_damped_solve": 6, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    cs.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "chain":
+        return run_chain(args)
     rank, local_rank, world = dist_env()
     from vicon2gt_b200 import api, build
 

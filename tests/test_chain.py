@@ -141,3 +141,24 @@ def test_chain_sharded_solve_matches_single_gpu(ds_c3_small, world, spr):
     assert abs(toffc - toff1) < 1e-6 and np.max(np.abs(pc - p1)) < 1e-6 and np.max(np.abs(thc - th1)) < 1e-6
     cs.close()
     single.close()
+
+
+@pytest.mark.gpu
+def test_chain_sharded_solve_over_nccl_two_gpus():
+    """Real NCCL, one process per GPU (needs >= 2 GPUs on the box; skipped on a 1-GPU box)."""
+    import json
+    import subprocess
+    import sys
+
+    from vicon2gt_b200 import api
+
+    if api.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    port = 29700 + (os.getpid() % 200)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(root, "tools", "chain_nccl_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, V2GT_CHAIN_CHECK_S="60"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    assert json.loads(line)["ok"]

@@ -1,0 +1,59 @@
+#!/usr/bin/env python
+"""Chain-sharded solve over real NCCL (one rank per GPU) against the single-GPU solve of the same sequence.
+Launch:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/chain_nccl_check.py
+Rank 0 prints one JSON line with the differences and exits non-zero when a tolerance of BASELINE.json's north_star is exceeded
+(states / extrinsics / time offset 1e-6, chi2 1e-8 relative)."""
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    from vicon2gt_b200 import api, sim
+    from vicon2gt_b200.chain import ChainSolver, DistComm
+
+    rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(local)
+    dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    dur = float(os.environ.get("V2GT_CHAIN_CHECK_S", "120"))
+    ds = sim.make_config("C3", seed=3, duration_s=dur, vicon_sigmas=(1e-3, 1e-3, 1e-3, 1e-2, 1e-2, 1e-2))
+    p = api.default_params()
+    cs = ChainSolver(p, ds, DistComm(dist), segs_per_rank=int(os.environ.get("V2GT_CHAIN_CHECK_SPR", "4")), device=local)
+    ic = cs.optimize()
+    tc, xc = cs.states()
+    qc, pc, toffc, thc = cs.calibration()
+    rc = 0
+    if rank == 0:
+        single = api.BatchSolver(1, device=local)
+        single.set_trial_dataset(0, p, ds)
+        single.build_and_solve()
+        i1 = single.info(0)
+        t1, x1 = single.states(0)
+        q1, p1, toff1, th1 = single.calibration(0)
+        dq = np.abs(np.sum(xc[:, :4] * x1[:, :4], axis=1))
+        out = {"world": world, "n_states": int(len(t1)), "times_equal": bool(np.array_equal(tc, t1)),
+               "rel_chi2": abs(ic.final_error - i1.final_error) / i1.final_error,
+               "max_rot_rad": float((2 * np.arccos(np.clip(dq, 0, 1))).max()), "max_dx": float(np.max(np.abs(xc[:, 4:] - x1[:, 4:]))),
+               "d_toff": abs(toffc - toff1), "d_p_BinI": float(np.max(np.abs(pc - p1))), "d_theta": float(np.max(np.abs(thc - th1))),
+               "tries_chain": ic.tries, "tries_single": i1.tries, "status": ic.status}
+        ok = (out["times_equal"] and out["status"] == 0 and out["rel_chi2"] < 1e-8 and out["max_rot_rad"] < 1e-6 and out["max_dx"] < 1e-6
+              and out["d_toff"] < 1e-6 and out["d_p_BinI"] < 1e-6 and out["d_theta"] < 1e-6)
+        out["ok"] = bool(ok)
+        print(json.dumps(out))
+        rc = 0 if ok else 1
+        single.close()
+    cs.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    return rc
+
+
+if __name__ == "__main__":
+    sys.exit(main())

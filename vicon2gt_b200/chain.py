@@ -190,6 +190,14 @@ class ChainSolver:
         self.plans = chain_plan(len(self.ts), comm.world, segs_per_rank)
         self.parts = [_Part(params, ds, self.ts, self.plans[r], device, torch) for r in comm.ranks]
         self.tries = 0
+        self.check_every = 4  # host reads the replicated LM state every this many damped solves (phases of a finished
+        #                       chain are no-ops on the device, exactly as in the batch path)
+
+    def rebuild(self):
+        """Re-run the build (state initialisation + preintegration) from the uploaded inputs: a fresh solve."""
+        for p in self.parts:
+            p.bs.build(True)
+        self.tries = 0
 
     def _phase(self, ph):
         for p in self.parts:
@@ -213,8 +221,9 @@ class ChainSolver:
             c.all_reduce(P, BUF_SUMS, t)
             self._phase(PH_DECIDE)
             self.tries += 1
-            if P[0].bs.info(0).lm_state != 0:  # replicated LM state: identical on every rank
-                break
+            if self.tries % self.check_every == 0 or self.tries >= cap:
+                if P[0].bs.info(0).lm_state != 0:  # replicated LM state: identical on every rank
+                    break
         return P[0].bs.info(0)
 
     def info(self):

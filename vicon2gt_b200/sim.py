@@ -100,6 +100,8 @@ def make_trajectory(t_start, n_rows, dt=0.05, extent_m=20.0):
 TRAJ_SHAPES = {
     "tum_corridor1": dict(t_start=1520531829.301144123, n_rows=5986, dt=0.05, extent_m=20.0),
     "euroc_V1_01": dict(t_start=1403715273.26214, n_rows=2895, dt=0.05, extent_m=2.5),
+    # BASELINE.json configs[4]: no reference data file is an hour long -- synthesised
+    "one_hour": dict(t_start=1520531829.301144123, n_rows=72041, dt=0.05, extent_m=20.0),
 }
 
 
@@ -160,6 +162,7 @@ def make_config(name, seed=0, duration_s=None, **kw):
     name: "C1" sim.launch defaults (400 Hz IMU, 100 Hz vicon, 100 Hz states, corridor1 shape)
           "C2" EuRoC V1_01 shape: states at the trajectory timestamps (20 Hz), 200 Hz IMU, 100 Hz vicon
           "C3" TUM corridor1 shape: states at the trajectory timestamps (20 Hz), 200 Hz IMU, 100 Hz vicon
+          "C5" one-hour sequence: states at the trajectory timestamps (20 Hz, ~72 k), 200 Hz IMU (~720 k), 100 Hz vicon
     duration_s truncates the trajectory (smaller problems for tests).
     """
     if name == "C1":
@@ -170,6 +173,9 @@ def make_config(name, seed=0, duration_s=None, **kw):
         sim_kw = dict(freq_imu=200.0, freq_cam=20.0, freq_vicon=100.0, state_freq=0)
     elif name == "C3":
         shape = dict(TRAJ_SHAPES["tum_corridor1"])
+        sim_kw = dict(freq_imu=200.0, freq_cam=20.0, freq_vicon=100.0, state_freq=0)
+    elif name == "C5":
+        shape = dict(TRAJ_SHAPES["one_hour"])
         sim_kw = dict(freq_imu=200.0, freq_cam=20.0, freq_vicon=100.0, state_freq=0)
     else:
         raise ValueError(name)
