@@ -31,6 +31,8 @@ int launch_linearize(const DevPtrs &d, int n_max, int force_all, cudaStream_t st
 int launch_cost(const DevPtrs &d, int n_max, int which, int force_all, cudaStream_t st);
 int launch_solve(const DevPtrs &d, int force_all, cudaStream_t st);
 int solve_configure();
+int elim_warps_per_cta();
+int elim_ctas_per_sm();
 int launch_eliminate(const DevPtrs &d, int force_all, cudaStream_t st);
 int launch_reduced(const DevPtrs &d, int force_all, cudaStream_t st);
 int launch_backsub(const DevPtrs &d, int force_all, cudaStream_t st);
@@ -60,6 +62,7 @@ struct HostTrial {
 
 struct v2gt_batch {
   int device = 0;
+  int sm_count = 148;
   int T = 0;
   cudaStream_t stream = nullptr;
   std::vector<HostTrial> trials;
@@ -285,6 +288,7 @@ int v2gt_batch_create(int32_t device, int32_t n_trials, v2gt_batch **out) {
   V2_CUDA_CHECK(cudaSetDevice(device));
   v2gt_batch *b = new v2gt_batch();
   b->device = device;
+  cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, device);
   b->T = n_trials;
   b->trials.resize(n_trials);
   V2_CUDA_CHECK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
@@ -583,6 +587,7 @@ int v2gt_batch_upload(v2gt_batch *b) {
   V2_TRY(dev_alloc(b, &d.fpi, (size_t)S * FPI_STRIDE));
   V2_TRY(dev_alloc(b, &d.fpv, (size_t)S * FPV_STRIDE));
   V2_TRY(dev_alloc(b, &d.ne, (size_t)S * NE_STRIDE));
+  V2_TRY(dev_alloc(b, &d.grad, (size_t)S * 16));
   V2_TRY(dev_alloc(b, &d.fac, (size_t)S * FAC_STRIDE));
   V2_TRY(dev_alloc(b, &d.seg, (size_t)T * P * SEG_STRIDE));
   V2_TRY(dev_alloc(b, &d.red_ne, ((size_t)T * P + 2) * NE_STRIDE));
@@ -712,6 +717,30 @@ int v2gt_batch_build(v2gt_batch *b, int32_t init_states) {
   return V2GT_OK;
 }
 
+// Segments per trial for an elimination launch over n_running trials: close to target_warps / n_running, but such
+// that the grid (n_running x ceil(P / warps per CTA) CTAs of equal work) fills whole waves of the GPU's resident CTA
+// slots -- a launch of 5.5 waves costs 6.
+static int choose_segments(int target_warps, int n_running, int p_max, int sm_count) {
+  const int wpc = elim_warps_per_cta();
+  const double slots = (double)std::max(1, sm_count) * elim_ctas_per_sm();
+  const int base = std::max(1, (target_warps + n_running - 1) / n_running);
+  const int k0 = std::max(1, (int)(0.75 * base) / wpc), k1 = std::max(k0, (int)(1.25 * base + wpc - 1) / wpc);
+  int best_p = std::max(1, std::min(p_max, base));
+  double best_eff = -1.0;
+  for (int k = k0; k <= k1; k++) {
+    const int P = std::min(p_max, k * wpc);
+    const double waves = (double)n_running * ((P + wpc - 1) / wpc) / slots;
+    const double eff = waves / std::ceil(waves);
+    if (eff > best_eff + 1e-9 || (eff > best_eff - 1e-9 && std::abs(P - base) < std::abs(best_p - base))) {
+      best_eff = std::max(eff, best_eff);
+      best_p = P;
+    }
+    if (P == p_max)
+      break;
+  }
+  return std::max(1, best_p);
+}
+
 int v2gt_batch_optimize(v2gt_batch *b) {
   if (!b)
     return V2GT_ERR_INVALID_ARG;
@@ -752,7 +781,7 @@ int v2gt_batch_optimize(v2gt_batch *b) {
     // segments per trial for this chunk of tries: fill the GPU with the trials that are still running
     DevPtrs d = dmax;
     if (b->opt_segments <= 0)
-      d.P = std::max(1, std::min(dmax.P, (b->opt_target_warps + std::max(1, n_running) - 1) / std::max(1, n_running)));
+      d.P = choose_segments(b->opt_target_warps, std::max(1, n_running), dmax.P, b->sm_count);
     V2_CUDA_CHECK(cudaMemsetAsync(d.n_active, 0, sizeof(int), st));
     for (int k = 0; k < chunk; k++) {
       cudaEvent_t *e = &b->ev_pool[7 * k];

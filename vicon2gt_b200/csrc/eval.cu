@@ -279,7 +279,7 @@ int v2gt_eval_linearize(v2gt_batch *b, int32_t trial, int64_t capacity, double *
   if ((D || O || B || g) && capacity < n)
     return V2GT_ERR_INVALID_ARG;
   if (n && (D || O || B || g)) {
-    // unpack the per-state records [D 15x15 | M 15x25 = O 15, B 9, g 1]
+    // unpack the per-state records [D 15x15 | O 15x15 | BG 15x10 = B 9, g 1]
     std::vector<double> rec((size_t)n * NE_STRIDE);
     V2_CUDA_CHECK(cudaMemcpy(rec.data(), d.ne + td.st_off * NE_STRIDE, sizeof(double) * rec.size(), cudaMemcpyDeviceToHost));
     for (int i = 0; i < n; i++) {
@@ -287,13 +287,12 @@ int v2gt_eval_linearize(v2gt_batch *b, int32_t trial, int64_t capacity, double *
       if (D)
         std::memcpy(D + 225 * (size_t)i, r + NE_D, sizeof(double) * 225);
       for (int a = 0; a < 15; a++) {
-        const double *mr = r + NE_M + NE_MW * a;
         if (O)
-          std::memcpy(O + 225 * (size_t)i + 15 * a, mr, sizeof(double) * 15);
+          std::memcpy(O + 225 * (size_t)i + 15 * a, r + NE_O + 15 * a, sizeof(double) * 15);
         if (B)
-          std::memcpy(B + 135 * (size_t)i + 9 * a, mr + NE_MB, sizeof(double) * 9);
+          std::memcpy(B + 135 * (size_t)i + 9 * a, r + NE_BG + NE_BGW * a, sizeof(double) * 9);
         if (g)
-          g[15 * (size_t)i + a] = mr[NE_MG];
+          g[15 * (size_t)i + a] = r[NE_BG + NE_BGW * a + 9];
       }
     }
   }

@@ -77,10 +77,11 @@ __global__ void __launch_bounds__(V2GT_CHUNK) k_factor_eval(DevPtrs d, int which
       for (int k = 0; k < 4; k++)
         o4[k] = make_double4(xi[4 * k], xi[4 * k + 1], xi[4 * k + 2], xi[4 * k + 3]);
       if (own) {
-        const double *gk = d.ne + s * NE_STRIDE + NE_M + NE_MG;
+        double gk[16];
+        ld16(d.grad + s * 16, gk);
 #pragma unroll
         for (int k = 0; k < 15; k++) {
-          gd += __ldg(gk + NE_MW * k) * dl[k];
+          gd += gk[k] * dl[k];
           dd += dl[k] * dl[k];
         }
       }
@@ -180,8 +181,29 @@ __global__ void __launch_bounds__(V2GT_CHUNK) k_factor_eval(DevPtrs d, int which
 }
 
 // ------------------------------------------------------------------------------------------------
-constexpr int ASM_STATES = 64;            // states per CTA
+constexpr int ASM_STATES = 32;            // states per CTA (one warp per 3-column block of these states)
 constexpr int ASM_THREADS = ASM_STATES * 5;
+constexpr int ASM_STRIP = 45;             // doubles per (state, column block) strip staged in shared memory (odd: conflict-free)
+constexpr int ASM_IN_ROWS = INFO_STRIDE + FPI_VALID; // staged inputs per state: information matrix (120) + IMU factor pieces (57)
+constexpr int ASM_IN_COLS = ASM_STATES + 1;          // the CTA's states + the state in front of them (odd: conflict-free)
+constexpr int ASM_SMEM_DOUBLES = 5 * ASM_STATES * ASM_STRIP + ASM_STATES * 7 + ASM_IN_ROWS * ASM_IN_COLS;
+
+// Store one strip per state of the warp: buf[state][ASM_STRIP] (shared) -> dst + state * NE_STRIDE, `len` contiguous
+// doubles each.  The lanes write consecutive doubles, so every 32-byte sector leaves the SM complete (the direct
+// one-thread-per-state stores touched 32 sectors per instruction and doubled the DRAM write traffic).
+__device__ __forceinline__ int lane_of_warp() { return threadIdx.x & 31; }
+__device__ __forceinline__ void flush_strip(const double *buf, double *dst, const int nvalid, const int len, const int lane) {
+  __syncwarp();
+  for (int k = 0; k < nvalid; k++) {
+    const double *b = buf + k * ASM_STRIP;
+    double *o = dst + (long long)k * NE_STRIDE;
+    if (lane < len)
+      o[lane] = b[lane];
+    if (lane + 32 < len)
+      o[lane + 32] = b[lane + 32];
+  }
+  __syncwarp();
+}
 
 // 3x3 helpers on registers:  C += A B, C += A^T B, C -= ...
 __device__ __forceinline__ void mm3_acc(const double *A, const double *B, double *C) {
@@ -203,7 +225,7 @@ __device__ __forceinline__ void zero9(double *A) {
   for (int e = 0; e < 9; e++)
     A[e] = 0.0;
 }
-__device__ __forceinline__ void ld9(const SoaR p, double *o) {
+template <class View> __device__ __forceinline__ void ld9(const View p, double *o) {
 #pragma unroll
   for (int e = 0; e < 9; e++)
     o[e] = p[e];
@@ -211,8 +233,8 @@ __device__ __forceinline__ void ld9(const SoaR p, double *o) {
 
 // H1 block (row-block a, column-block dcol) of the IMU factor; returns false when the block is zero.
 // kind: 0 dense in M, 1 = -I, (others dense).   fpi: pieces row, pre: preintegration row.
-__device__ __forceinline__ bool h1_block(const SoaR fpi, const SoaR pre, int a, int dcol,
-                                         double *M) {
+template <class VF, class VP>
+__device__ __forceinline__ bool h1_block(const VF fpi, const VP pre, int a, int dcol, double *M) {
   // rows a: 0 th, 1 bg, 2 v, 3 ba, 4 p
   if (dcol == 0) {
     if (a == 0) { ld9(fpi + FPI_TTH, M); return true; }
@@ -243,7 +265,7 @@ __device__ __forceinline__ bool h1_block(const SoaR fpi, const SoaR pre, int a, 
   return false;
 }
 // H2 diagonal block c of the IMU factor
-__device__ __forceinline__ void h2_block(const SoaR fpi, int c, double *M) {
+template <class VF> __device__ __forceinline__ void h2_block(const VF fpi, int c, double *M) {
   if (c == 0)
     ld9(fpi + FPI_JTH2, M);
   else if (c == 2 || c == 4)
@@ -252,8 +274,8 @@ __device__ __forceinline__ void h2_block(const SoaR fpi, int c, double *M) {
     eye3(M);
 }
 // H3 row blocks (v and p rows), 3x2 each:  R dt g Hxy  and  1/2 R dt^2 g Hxy   (ImuFactorCPIv1.cpp:199-201)
-__device__ __forceinline__ void h3_blocks(const SoaR fpi, const SoaR pre, const GravTerms &G,
-                                          double *H3v, double *H3p) {
+template <class VF, class VP>
+__device__ __forceinline__ void h3_blocks(const VF fpi, const VP pre, const GravTerms &G, double *H3v, double *H3p) {
   double Rk[9];
   ld9(fpi + FPI_RK, Rk);
   const double dt = pre[PRE_DT];
@@ -272,7 +294,10 @@ __device__ __forceinline__ void h3_blocks(const SoaR fpi, const SoaR pre, const 
 }
 
 // grid (ceil(n_max / ASM_STATES), T), ASM_THREADS threads
-__global__ void __launch_bounds__(ASM_THREADS) k_assemble(DevPtrs d, int force_all) {
+#ifndef ASM_MIN_CTAS
+#define ASM_MIN_CTAS 2
+#endif
+__global__ void __launch_bounds__(ASM_THREADS, ASM_MIN_CTAS) k_assemble(DevPtrs d, int force_all) {
   const int t = blockIdx.y;
   const LmState &lm = d.lm[t];
   if (!force_all && (lm.lm_state != 0 || lm.status != V2GT_OK || !lm.need_lin))
@@ -283,181 +308,241 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(DevPtrs d, int force_a
   // lane <-> state makes every struct-of-arrays read coalesced
   const int li = threadIdx.x % ASM_STATES, dcol = threadIdx.x / ASM_STATES;
   const int i = blockIdx.x * ASM_STATES + li;
-  __shared__ double s_part[ASM_STATES][PART_STRIDE + 1];
-  for (int k = threadIdx.x; k < ASM_STATES * (PART_STRIDE + 1); k += ASM_THREADS)
-    (&s_part[0][0])[k] = 0.0;
-  __syncthreads();
-  if (i < n) {
-    const long long s = tr.st_off + i;
-    const double *gl = d.glob + ((long long)lm.cur * d.T + t) * GLOB_STRIDE;
-    GravTerms G;
-    grav_terms(gl[GL_THX], gl[GL_THY], tr.prm.gravity_magnitude, G);
-    double Dcol[5][9]; // D[c][dcol], c = 0..4
-    double Bg[6];      // B[dcol][7:9]  3x2
-    double gv[3];      // g[dcol]
-#pragma unroll
-    for (int c = 0; c < 5; c++)
-      zero9(Dcol[c]);
+  extern __shared__ __align__(16) double s_strip[]; // [5][ASM_STATES * ASM_STRIP]
+  double *wbuf = s_strip + dcol * (ASM_STATES * ASM_STRIP); // this warp's staging buffer
+  double *mybuf = wbuf + li * ASM_STRIP; // this state's strip
+  const int i0 = blockIdx.x * ASM_STATES;
+  const int nvalid = min(ASM_STATES, n - i0);
+  if (nvalid <= 0)
+    return;
+  double *ne0 = d.ne + (tr.st_off + i0) * NE_STRIDE; // record of the warp's first state
+  double Y[5][9];    // Y[a] = sum_b Lambda_ab H1[b][dcol] of the IMU factor i -> i+1 (zero for the last state)
+  double Bg[6];      // B[dcol][7:9]  3x2
+  double gv[3];      // g[dcol]
+  // warp dcol 3: gravity 2x2 block + gradient 2 of the IMU factor, parked in shared memory until the final reduction
+  double *part6 = s_strip + 5 * ASM_STATES * ASM_STRIP + li * 7;
+  if (dcol == 3) {
 #pragma unroll
     for (int k = 0; k < 6; k++)
-      Bg[k] = 0.0;
-    gv[0] = gv[1] = gv[2] = 0.0;
-    double *ne = d.ne + s * NE_STRIDE;
-    double *HO = ne + NE_M; // O block: row stride NE_MW
+      part6[k] = 0.0;
+  }
+  const long long s = tr.st_off + i;
+  const double *gl = d.glob + ((long long)lm.cur * d.T + t) * GLOB_STRIDE;
+  const bool act = (i < n), has_next = (i < n - 1), has_prev = act && (i > 0);
+  // ---- stage the information matrices and factor pieces of the CTA's states (+ the state in front) in shared memory:
+  // every element is read ~5 x 3 times by the block products below; from global memory those reads are what the
+  // kernel waited on (one CTA-wide coalesced copy instead)
+  double *s_in = s_strip + 5 * ASM_STATES * ASM_STRIP + ASM_STATES * 7; // [ASM_IN_ROWS][ASM_IN_COLS], column j <-> state i0 - 1 + j
+  {
+    const int lane = lane_of_warp();
+    const long long sl0 = tr.st_off + i0 - 1; // slot of column 0
+    const bool v0 = (i0 + lane - 1 >= 0) && (i0 + lane - 1 < n);
+    const bool v1 = (lane == 0) && (i0 + 31 < n);
+    for (int row = dcol; row < ASM_IN_ROWS; row += 5) {
+      const double *src = (row < INFO_STRIDE) ? d.info + (long long)row * d.S : d.fpi + (long long)(row - INFO_STRIDE) * d.S;
+      if (v0)
+        s_in[row * ASM_IN_COLS + lane] = __ldg(src + sl0 + lane);
+      if (v1)
+        s_in[row * ASM_IN_COLS + 32] = __ldg(src + sl0 + 32);
+    }
+  }
+  __syncthreads();
+  const SoaS inf{s_in + li + 1, ASM_IN_COLS};
+  const SoaS fpi{s_in + INFO_STRIDE * ASM_IN_COLS + li + 1, ASM_IN_COLS};
+  const SoaR pre{d.pre + s, d.S};
+#pragma unroll
+  for (int a = 0; a < 5; a++)
+    zero9(Y[a]);
+#pragma unroll
+  for (int k = 0; k < 6; k++)
+    Bg[k] = 0.0;
+  gv[0] = gv[1] = gv[2] = 0.0;
 
-    // ================= H1-type contributions of factor i (i -> i+1)
-    if (i < n - 1) {
-      const SoaR fpi{d.fpi + s, d.S};
-      const SoaR pre{d.pre + s, d.S};
-      const SoaR inf{d.info + s, d.S};
-      double Y[5][9]; // Y[a] = sum_b Lambda_ab H1[b][dcol]
+  // ================= (1) IMU factor i -> i+1: Y, the coupling strip O, its border / gradient terms
+  if (has_next) {
 #pragma unroll
-      for (int a = 0; a < 5; a++)
-        zero9(Y[a]);
+    for (int b = 0; b < 5; b++) {
+      double Hb[9];
+      if (!h1_block(fpi, pre, b, dcol, Hb))
+        continue;
 #pragma unroll
-      for (int b = 0; b < 5; b++) {
-        double Hb[9];
-        if (!h1_block(fpi, pre, b, dcol, Hb))
-          continue;
-#pragma unroll
-        for (int a = 0; a < 5; a++) {
-          double L[9];
-          ld_sym_blk(inf, a, b, L);
-          mm3_acc(L, Hb, Y[a]);
-        }
+      for (int a = 0; a < 5; a++) {
+        double L[9];
+        ld_sym_blk(inf, a, b, L);
+        mm3_acc(L, Hb, Y[a]);
       }
-      // D1[c][dcol] = sum_a H1[a][c]^T Y[a]
+    }
+    // O[dcol][e] = Y[e]^T H2[e][e]  -> rows 3 dcol .. 3 dcol + 2 of O (row stride 15 inside the strip)
 #pragma unroll
-      for (int c = 0; c < 5; c++) {
-#pragma unroll
-        for (int a = 0; a < 5; a++) {
-          double Hc[9];
-          if (!h1_block(fpi, pre, a, c, Hc))
-            continue;
-          mm3_tn_acc(Hc, Y[a], Dcol[c]);
-        }
-      }
-      // O[dcol][e] = Y[e]^T H2[e][e]
-#pragma unroll
-      for (int e = 0; e < 5; e++) {
-        double H2e[9], Ob[9];
-        h2_block(fpi, e, H2e);
-        zero9(Ob);
-        mm3_tn_acc(Y[e], H2e, Ob);
-#pragma unroll
-        for (int r = 0; r < 3; r++)
-#pragma unroll
-          for (int c = 0; c < 3; c++)
-            HO[(3 * dcol + r) * NE_MW + 3 * e + c] = Ob[3 * r + c];
-      }
-      // B1[dcol] = Y[v]^T H3v + Y[p]^T H3p ; g1[dcol] = -sum_a Y[a]^T e[a]
-      double H3v[6], H3p[6];
-      h3_blocks(fpi, pre, G, H3v, H3p);
+    for (int e = 0; e < 5; e++) {
+      double H2e[9], Ob[9];
+      h2_block(fpi, e, H2e);
+      zero9(Ob);
+      mm3_tn_acc(Y[e], H2e, Ob);
 #pragma unroll
       for (int r = 0; r < 3; r++)
 #pragma unroll
-        for (int c = 0; c < 2; c++) {
-          double sacc = 0;
+        for (int c = 0; c < 3; c++)
+          mybuf[r * 15 + 3 * e + c] = Ob[3 * r + c];
+    }
+    // B1[dcol] = Y[v]^T H3v + Y[p]^T H3p ; g1[dcol] = -sum_a Y[a]^T e[a]
+    double H3v[6], H3p[6];
+    {
+      GravTerms G;
+      grav_terms(gl[GL_THX], gl[GL_THY], tr.prm.gravity_magnitude, G);
+      h3_blocks(fpi, pre, G, H3v, H3p);
+    }
 #pragma unroll
-          for (int k = 0; k < 3; k++)
-            sacc += Y[2][3 * k + r] * H3v[2 * k + c] + Y[4][3 * k + r] * H3p[2 * k + c];
-          Bg[2 * r + c] += sacc;
-        }
+    for (int r = 0; r < 3; r++)
 #pragma unroll
-      for (int a = 0; a < 5; a++)
+      for (int c = 0; c < 2; c++) {
+        double sacc = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+          sacc += Y[2][3 * k + r] * H3v[2 * k + c] + Y[4][3 * k + r] * H3p[2 * k + c];
+        Bg[2 * r + c] += sacc;
+      }
+#pragma unroll
+    for (int a = 0; a < 5; a++)
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        double sacc = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+          sacc += Y[a][3 * k + r] * fpi[FPI_E + 3 * a + k];
+        gv[r] -= sacc;
+      }
+    // gravity 2x2 block and gradient of this factor (thread dcol == 3 owns it)
+    if (dcol == 3 && (!d.chain || (i >= d.c_lo && i < d.c_hi))) {
+      // Lambda rows v and p applied to H3 and e
+      double LH[2][6]; // (Lambda H3)[a] for a = v, p  (3x2)
+      double Le[2][3];
+#pragma unroll
+      for (int ai = 0; ai < 2; ai++) {
+        const int a = (ai == 0) ? 2 : 4;
+        double Lv[9], Lp[9];
+        ld_sym_blk(inf, a, 2, Lv);
+        ld_sym_blk(inf, a, 4, Lp);
 #pragma unroll
         for (int r = 0; r < 3; r++) {
-          double sacc = 0;
-#pragma unroll
-          for (int k = 0; k < 3; k++)
-            sacc += Y[a][3 * k + r] * fpi[FPI_E + 3 * a + k];
-          gv[r] -= sacc;
-        }
-      // gravity 2x2 block and gradient of this factor (thread dcol == 3 owns it)
-      if (dcol == 3 && (!d.chain || (i >= d.c_lo && i < d.c_hi))) {
-        // Lambda rows v and p applied to H3 and e
-        double LH[2][6]; // (Lambda H3)[a] for a = v, p  (3x2)
-        double Le[2][3];
-#pragma unroll
-        for (int ai = 0; ai < 2; ai++) {
-          const int a = (ai == 0) ? 2 : 4;
-          double Lv[9], Lp[9];
-          ld_sym_blk(inf, a, 2, Lv);
-          ld_sym_blk(inf, a, 4, Lp);
-#pragma unroll
-          for (int r = 0; r < 3; r++) {
-#pragma unroll
-            for (int c = 0; c < 2; c++) {
-              double sacc = 0;
-#pragma unroll
-              for (int k = 0; k < 3; k++)
-                sacc += Lv[3 * r + k] * H3v[2 * k + c] + Lp[3 * r + k] * H3p[2 * k + c];
-              LH[ai][2 * r + c] = sacc;
-            }
-          }
-#pragma unroll
-          for (int r = 0; r < 3; r++) {
-            double sacc = 0;
-#pragma unroll
-            for (int bb = 0; bb < 5; bb++) {
-              double Lb[9];
-              ld_sym_blk(inf, a, bb, Lb);
-#pragma unroll
-              for (int k = 0; k < 3; k++)
-                sacc += Lb[3 * r + k] * fpi[FPI_E + 3 * bb + k];
-            }
-            Le[ai][r] = sacc;
-          }
-        }
-        double *sp = s_part[li];
-#pragma unroll
-        for (int r = 0; r < 2; r++) {
 #pragma unroll
           for (int c = 0; c < 2; c++) {
             double sacc = 0;
 #pragma unroll
             for (int k = 0; k < 3; k++)
-              sacc += H3v[2 * k + r] * LH[0][2 * k + c] + H3p[2 * k + r] * LH[1][2 * k + c];
-            sp[56 + 2 * r + c] = sacc;
+              sacc += Lv[3 * r + k] * H3v[2 * k + c] + Lp[3 * r + k] * H3p[2 * k + c];
+            LH[ai][2 * r + c] = sacc;
           }
-          double sg = 0;
+        }
 #pragma unroll
-          for (int k = 0; k < 3; k++)
-            sg += H3v[2 * k + r] * Le[0][k] + H3p[2 * k + r] * Le[1][k];
-          sp[60 + r] = -sg;
+        for (int r = 0; r < 3; r++) {
+          double sacc = 0;
+#pragma unroll
+          for (int bb = 0; bb < 5; bb++) {
+            double Lb[9];
+            ld_sym_blk(inf, a, bb, Lb);
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+              sacc += Lb[3 * r + k] * fpi[FPI_E + 3 * bb + k];
+          }
+          Le[ai][r] = sacc;
         }
       }
-    } else {
-      // last state: no coupling block
 #pragma unroll
-      for (int r = 0; r < 3; r++)
-        for (int c = 0; c < 15; c++)
-          HO[(3 * dcol + r) * NE_MW + c] = 0.0;
+      for (int r = 0; r < 2; r++) {
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          double sacc = 0;
+#pragma unroll
+          for (int k = 0; k < 3; k++)
+            sacc += H3v[2 * k + r] * LH[0][2 * k + c] + H3p[2 * k + r] * LH[1][2 * k + c];
+          part6[2 * r + c] = sacc;
+        }
+        double sg = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+          sg += H3v[2 * k + r] * Le[0][k] + H3p[2 * k + r] * Le[1][k];
+        part6[4 + r] = -sg;
+      }
     }
+  } else if (act) {
+    // last state: no coupling block
+    for (int k = 0; k < 45; k++)
+      mybuf[k] = 0.0;
+  }
+  flush_strip(wbuf, ne0 + NE_O + 45 * dcol, nvalid, 45, lane_of_warp());
 
-    // ================= H2-type contributions of factor i-1 (i-1 -> i)
-    if (i > 0) {
-      const SoaR fpi{d.fpi + (s - 1), d.S};
-      const SoaR pre{d.pre + (s - 1), d.S};
-      const SoaR inf{d.info + (s - 1), d.S};
-      double H2d[9];
-      h2_block(fpi, dcol, H2d);
-      // D2[c][dcol] = H2[c]^T Lambda_{c,dcol} H2[dcol]
+  // ================= (2) the diagonal strip, one 3x3 block at a time:
+  //   D[c][dcol] = sum_a H1[a][c]^T Y[a]  +  H2[c]^T Lambda'_{c,dcol} H2[dcol] (factor i-1 -> i)  +  A_c^T A_dcol (vicon)
+  // D is symmetric: the column strip this thread computes is written as the ROW strip 3 dcol .. 3 dcol + 2
+  const SoaS infP{s_in + li, ASM_IN_COLS};
+  const SoaS fpiP{s_in + INFO_STRIDE * ASM_IN_COLS + li, ASM_IN_COLS};
+  const SoaR preP{d.pre + (s - 1), d.S};
+  const SoaR fpv{d.fpv + s, d.S};
+  const bool vic_col = (dcol == 0 || dcol == 4);
+  const int co = (dcol == 0) ? 0 : 3; // my columns inside the vicon A (theta | p)
+  if (act) {
+    double H2d[9];
+    if (has_prev)
+      h2_block(fpiP, dcol, H2d);
 #pragma unroll
-      for (int c = 0; c < 5; c++) {
+    for (int c = 0; c < 5; c++) {
+      double Dc[9];
+      zero9(Dc);
+      if (has_next) {
+#pragma unroll
+        for (int a = 0; a < 5; a++) {
+          double Hc[9];
+          if (!h1_block(fpi, pre, a, c, Hc))
+            continue;
+          mm3_tn_acc(Hc, Y[a], Dc);
+        }
+      }
+      if (has_prev) {
         double L[9], T[9], H2c[9];
-        ld_sym_blk(inf, c, dcol, L);
+        ld_sym_blk(infP, c, dcol, L);
         zero9(T);
         mm3_acc(L, H2d, T);
-        h2_block(fpi, c, H2c);
-        mm3_tn_acc(H2c, T, Dcol[c]);
+        h2_block(fpiP, c, H2c);
+        mm3_tn_acc(H2c, T, Dc);
       }
+      if (vic_col && (c == 0 || c == 4)) {
+        const int cco = (c == 4) ? 3 : 0;
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+          for (int cc = 0; cc < 3; cc++) {
+            double sacc = 0;
+#pragma unroll
+            for (int k = 0; k < 6; k++)
+              sacc += fpv[FPV_A + 6 * k + cco + r] * fpv[FPV_A + 6 * k + co + cc];
+            Dc[3 * r + cc] += sacc;
+          }
+      }
+#pragma unroll
+      for (int cc = 0; cc < 3; cc++)
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+          mybuf[cc * 15 + 3 * c + r] = Dc[3 * r + cc];
+    }
+  }
+  flush_strip(wbuf, ne0 + NE_D + 45 * dcol, nvalid, 45, lane_of_warp());
+
+  // ================= (3) border / gradient strip
+  if (act) {
+    if (has_prev) {
       // B2[dcol] = H2[dcol]^T (Lambda_{d,v} H3v + Lambda_{d,p} H3p) ; g2[dcol] = -H2[dcol]^T sum_a Lambda_{d,a} e_a
+      double H2d[9];
+      h2_block(fpiP, dcol, H2d);
       double H3v[6], H3p[6];
-      h3_blocks(fpi, pre, G, H3v, H3p);
+      {
+        GravTerms G;
+        grav_terms(gl[GL_THX], gl[GL_THY], tr.prm.gravity_magnitude, G);
+        h3_blocks(fpiP, preP, G, H3v, H3p);
+      }
       double Lv[9], Lp[9], U[6], le[3] = {0, 0, 0};
-      ld_sym_blk(inf, dcol, 2, Lv);
-      ld_sym_blk(inf, dcol, 4, Lp);
+      ld_sym_blk(infP, dcol, 2, Lv);
+      ld_sym_blk(infP, dcol, 4, Lp);
 #pragma unroll
       for (int r = 0; r < 3; r++)
 #pragma unroll
@@ -471,12 +556,12 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(DevPtrs d, int force_a
 #pragma unroll
       for (int a = 0; a < 5; a++) {
         double L[9];
-        ld_sym_blk(inf, dcol, a, L);
+        ld_sym_blk(infP, dcol, a, L);
 #pragma unroll
         for (int r = 0; r < 3; r++)
 #pragma unroll
           for (int k = 0; k < 3; k++)
-            le[r] += L[3 * r + k] * fpi[FPI_E + 3 * a + k];
+            le[r] += L[3 * r + k] * fpiP[FPI_E + 3 * a + k];
       }
 #pragma unroll
       for (int r = 0; r < 3; r++) {
@@ -495,104 +580,98 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(DevPtrs d, int force_a
         gv[r] -= sg;
       }
     }
-
-    // ================= vicon factor of state i
-    const SoaR fpv{d.fpv + s, d.S};
-    double Bv[21]; // B[dcol][0:7]  3x7
-#pragma unroll
-    for (int k = 0; k < 21; k++)
-      Bv[k] = 0.0;
-    if (dcol == 0 || dcol == 4) {
-      const int co = (dcol == 0) ? 0 : 3; // my columns inside A
-      double Ad[18];                      // A(:, co:co+3)  6x3
-#pragma unroll
-      for (int r = 0; r < 6; r++)
-#pragma unroll
-        for (int c = 0; c < 3; c++)
-          Ad[3 * r + c] = fpv[FPV_A + 6 * r + co + c];
-      // D[c][dcol] += A_c^T A_d for c in {theta (0), p (4)}
-#pragma unroll
-      for (int ci = 0; ci < 2; ci++) {
-        const int c = ci ? 4 : 0, cco = ci ? 3 : 0;
-#pragma unroll
-        for (int r = 0; r < 3; r++)
-#pragma unroll
-          for (int cc = 0; cc < 3; cc++) {
-            double sacc = 0;
-#pragma unroll
-            for (int k = 0; k < 6; k++)
-              sacc += fpv[FPV_A + 6 * k + cco + r] * Ad[3 * k + cc];
-            Dcol[c][3 * r + cc] += sacc;
-          }
-      }
-#pragma unroll
-      for (int r = 0; r < 3; r++) {
-#pragma unroll
-        for (int c = 0; c < 7; c++) {
-          double sacc = 0;
-#pragma unroll
-          for (int k = 0; k < 6; k++)
-            sacc += Ad[3 * k + r] * fpv[FPV_G + 7 * k + c];
-          Bv[7 * r + c] = sacc;
-        }
-        double sg = 0;
-#pragma unroll
-        for (int k = 0; k < 6; k++)
-          sg += Ad[3 * k + r] * fpv[FPV_R + k];
-        gv[r] -= sg;
-      }
-    }
-    if (dcol == 1) {
-      // global 7x7 block and gradient of the vicon factor: G^T G, -G^T r
-      double *sp = s_part[li];
-#pragma unroll
-      for (int r = 0; r < 7; r++) {
-#pragma unroll
-        for (int c = 0; c < 7; c++) {
-          double sacc = 0;
-#pragma unroll
-          for (int k = 0; k < 6; k++)
-            sacc += fpv[FPV_G + 7 * k + r] * fpv[FPV_G + 7 * k + c];
-          sp[7 * r + c] = sacc;
-        }
-        double sg = 0;
-#pragma unroll
-        for (int k = 0; k < 6; k++)
-          sg += fpv[FPV_G + 7 * k + r] * fpv[FPV_R + k];
-        sp[49 + r] = -sg;
-      }
-    }
-
-    // ================= store this thread's strips
-    // D is symmetric: the column strip this thread computed is written as the ROW strip 3 dcol .. 3 dcol + 2
-    // (45 contiguous doubles per thread, so each 32-byte sector is completed by back-to-back stores of one
-    // thread and merges in L2 instead of being written back partially)
-    double *HD = ne + NE_D;
-#pragma unroll
-    for (int cc = 0; cc < 3; cc++)
-#pragma unroll
-      for (int c = 0; c < 5; c++)
-#pragma unroll
-        for (int r = 0; r < 3; r++)
-          HD[(3 * dcol + cc) * 15 + 3 * c + r] = Dcol[c][3 * r + cc];
-    double *HB = ne + NE_M + NE_MB;
+    // vicon factor of state i: B[dcol][0:7] = A_d^T G, g[dcol] -= A_d^T r
 #pragma unroll
     for (int r = 0; r < 3; r++) {
 #pragma unroll
-      for (int c = 0; c < 7; c++)
-        HB[(3 * dcol + r) * NE_MW + c] = Bv[7 * r + c];
-      HB[(3 * dcol + r) * NE_MW + 7] = Bg[2 * r];
-      HB[(3 * dcol + r) * NE_MW + 8] = Bg[2 * r + 1];
-      ne[NE_M + (3 * dcol + r) * NE_MW + NE_MG] = gv[r];
+      for (int c = 0; c < 7; c++) {
+        double sacc = 0;
+        if (vic_col) {
+#pragma unroll
+          for (int k = 0; k < 6; k++)
+            sacc += fpv[FPV_A + 6 * k + co + r] * fpv[FPV_G + 7 * k + c];
+        }
+        mybuf[NE_BGW * r + c] = sacc;
+      }
+      if (vic_col) {
+        double sg = 0;
+#pragma unroll
+        for (int k = 0; k < 6; k++)
+          sg += fpv[FPV_A + 6 * k + co + r] * fpv[FPV_R + k];
+        gv[r] -= sg;
+      }
+      mybuf[NE_BGW * r + 7] = Bg[2 * r];
+      mybuf[NE_BGW * r + 8] = Bg[2 * r + 1];
+      mybuf[NE_BGW * r + 9] = gv[r];
+      d.grad[s * 16 + 3 * dcol + r] = gv[r];
     }
   }
-  __syncthreads();
-  // fixed-order reduction over the CTA's states
-  if (threadIdx.x < 62) {
-    double sacc = 0;
-    for (int k = 0; k < ASM_STATES; k++)
-      sacc += s_part[k][threadIdx.x];
-    d.part_asm[((long long)t * gridDim.x + blockIdx.x) * PART_STRIDE + threadIdx.x] = sacc;
+  flush_strip(wbuf, ne0 + NE_BG + 3 * NE_BGW * dcol, nvalid, 3 * NE_BGW, lane_of_warp());
+  // ================= per-CTA partial sums of the global blocks (fixed order over the CTA's states)
+  //   warp dcol 1: vicon 7x7 block G^T G (28 unique entries) and gradient -G^T r (7);  warp dcol 3: gravity 2x2 + gradient 2
+  if (dcol == 1 || dcol == 3) {
+    if (dcol == 1) {
+      if (i < n) {
+        const SoaR fpv{d.fpv + s, d.S};
+        int q = 0;
+#pragma unroll
+        for (int r = 0; r < 7; r++) {
+#pragma unroll
+          for (int c = r; c < 7; c++) {
+            double sacc = 0;
+#pragma unroll
+            for (int k = 0; k < 6; k++)
+              sacc += fpv[FPV_G + 7 * k + r] * fpv[FPV_G + 7 * k + c];
+            mybuf[q++] = sacc;
+          }
+          double sg = 0;
+#pragma unroll
+          for (int k = 0; k < 6; k++)
+            sg += fpv[FPV_G + 7 * k + r] * fpv[FPV_R + k];
+          mybuf[28 + r] = -sg;
+        }
+      } else {
+        for (int k = 0; k < 35; k++)
+          mybuf[k] = 0.0;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 6; k++)
+        mybuf[k] = part6[k];
+    }
+    __syncwarp();
+    const int lane = lane_of_warp();
+    const int ncol = (dcol == 1) ? 35 : 6;
+    double sacc = 0.0, sacc2 = 0.0;
+    for (int k = 0; k < ASM_STATES; k++) {
+      if (lane < ncol)
+        sacc += wbuf[k * ASM_STRIP + lane];
+      if (lane + 32 < ncol)
+        sacc2 += wbuf[k * ASM_STRIP + lane + 32];
+    }
+    double *po = d.part_asm + ((long long)t * gridDim.x + blockIdx.x) * PART_STRIDE;
+    if (dcol == 1) {
+      // unpack the upper triangle (row-major, q = index of (r, c >= r)) into the full 7x7 + gradient
+      auto put = [&](int q, double v) {
+        if (q < 28) {
+          int r = 0, base = 0;
+          while (q >= base + (7 - r)) {
+            base += 7 - r;
+            r++;
+          }
+          const int c = r + (q - base);
+          po[7 * r + c] = v;
+          po[7 * c + r] = v;
+        } else {
+          po[49 + (q - 28)] = v;
+        }
+      };
+      put(lane, sacc);
+      if (lane + 32 < ncol)
+        put(lane + 32, sacc2);
+    } else if (lane < 6) {
+      po[56 + lane] = sacc;
+    }
   }
 }
 
@@ -647,7 +726,13 @@ int launch_linearize(const DevPtrs &d, int n_max, int force_all, cudaStream_t st
   k_factor_eval<true><<<g1, V2GT_CHUNK, 0, st>>>(d, 0, force_all);
   const int nasm = (n_max + ASM_STATES - 1) / ASM_STATES;
   dim3 g2(nasm, d.T);
-  k_assemble<<<g2, ASM_THREADS, 0, st>>>(d, force_all);
+  constexpr size_t asm_smem = sizeof(double) * ASM_SMEM_DOUBLES;
+  static bool configured = false;
+  if (!configured) {
+    V2_CUDA_CHECK(cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asm_smem));
+    configured = true;
+  }
+  k_assemble<<<g2, ASM_THREADS, asm_smem, st>>>(d, force_all);
   k_reduce_gamma<<<d.T, 64, 0, st>>>(d, nasm, force_all);
   V2_CUDA_CHECK(cudaGetLastError());
   return V2GT_OK;

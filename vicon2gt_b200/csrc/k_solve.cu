@@ -216,15 +216,16 @@ __device__ __forceinline__ bool elim_node(const double *st, const double *__rest
     const int u = kk >> 1, e = kk & 1;
     const int r = 8 * u + 2 * tid + e;
     const bool rv = r < 15;
-    const double *mrow = st + NE_M + NE_MW * (rv ? r : 0);
-    m[kk][0] = rv ? mrow[gid] : 0.0;
+    const double *orow = st + NE_O + 15 * (rv ? r : 0);
+    const double *brow = st + NE_BG + NE_BGW * (rv ? r : 0);
+    m[kk][0] = rv ? orow[gid] : 0.0;
     double v1, v2, v3;
     if (HAS_F) {
       if (Finit) {
-        const double *fi = Finit + NE_M + (rv ? r : 0);
-        v1 = __ldg(fi);                        // F[r][0]     = O_sep[0][r]
-        v2 = __ldg(fi + NE_MW * (1 + gid));    // F[r][1+gid]
-        v3 = (gid < 6) ? __ldg(fi + NE_MW * (9 + gid)) : 0.0;
+        const double *fi = Finit + NE_O + (rv ? r : 0);
+        v1 = __ldg(fi);                     // F[r][0]     = O_sep[0][r]
+        v2 = __ldg(fi + 15 * (1 + gid));    // F[r][1+gid]
+        v3 = (gid < 6) ? __ldg(fi + 15 * (9 + gid)) : 0.0;
       } else {
         v1 = -A.cy[1][u][e];
         v2 = -A.cy[2][u][e];
@@ -233,10 +234,10 @@ __device__ __forceinline__ bool elim_node(const double *st, const double *__rest
     } else {
       v1 = v2 = v3 = 0.0;
     }
-    m[kk][1] = rv ? ((gid < 7) ? mrow[8 + gid] : v1) : 0.0;
+    m[kk][1] = rv ? ((gid < 7) ? orow[8 + gid] : v1) : 0.0;
     m[kk][2] = rv ? v2 : 0.0;
-    m[kk][3] = rv ? ((gid < 6) ? v3 : mrow[NE_MB + gid - 6] - A.cy[3][u][e]) : 0.0;
-    m[kk][4] = rv ? mrow[17 + gid] - A.cy[4][u][e] : 0.0;
+    m[kk][3] = rv ? ((gid < 6) ? v3 : brow[gid - 6] - A.cy[3][u][e]) : 0.0;
+    m[kk][4] = rv ? brow[2 + gid] - A.cy[4][u][e] : 0.0;
   }
   __syncwarp(); // every lane has consumed the staged record and the carry
   // ---- factorisation + inverse
@@ -431,23 +432,22 @@ __global__ void __launch_bounds__(128) k_reduced_assemble(DevPtrs d, int force_a
   double *out = d.red_ne + ((long long)t * d.P + m) * NE_STRIDE;
   for (int idx = threadIdx.x; idx < NE_STRIDE; idx += blockDim.x) {
     double v;
-    if (idx < NE_M) {
+    if (idx < NE_O) {
       const int i = idx / 15, jn = idx - 15 * i;
       v = ne[idx] - segl[SEG_CY + 40 * i + jn];
       if (has_r)
         v -= segr[SEG_FB + 25 * i + jn];
+    } else if (idx < NE_BG) {
+      const int q = idx - NE_O;
+      const int i = q / 15, c = q - 15 * i;
+      // coupling separator m -> m+1 through segment m:  H[m][m+1](i, c) = -S(rows: O index c, column F index i)
+      v = has_next ? -segr[SEG_CY + 40 * c + XC_F + i] : 0.0;
     } else {
-      const int q = idx - NE_M;
-      const int i = q / NE_MW, c = q - NE_MW * i;
-      if (c < 15) {
-        // coupling separator m -> m+1 through segment m:  H[m][m+1](i, c) = -S(rows: O index c, column F index i)
-        v = has_next ? -segr[SEG_CY + 40 * c + XC_F + i] : 0.0;
-      } else {
-        const int k = c - 15; // border columns 0..8, rhs 9
-        v = ne[idx] - segl[SEG_CY + 40 * i + XC_B + k];
-        if (has_r)
-          v -= segr[SEG_FB + 25 * i + 15 + k];
-      }
+      const int q = idx - NE_BG;
+      const int i = q / NE_BGW, k = q - NE_BGW * i; // border columns 0..8, rhs 9
+      v = ne[idx] - segl[SEG_CY + 40 * i + XC_B + k];
+      if (has_r)
+        v -= segr[SEG_FB + 25 * i + 15 + k];
     }
     out[idx] = v;
   }
@@ -731,6 +731,8 @@ __global__ void __launch_bounds__(BS_WARPS * 32) k_seg_backsub(DevPtrs d, int fo
 }
 
 // ------------------------------------------------------------------------------------------------
+int elim_warps_per_cta() { return ELIM_WARPS; }
+int elim_ctas_per_sm() { return ELIM_MIN_CTAS; }
 int solve_configure() {
   const size_t sm1 = sizeof(double) * SW_TOTAL * ELIM_WARPS;
   const size_t sm2 = sizeof(double) * RED_SMEM;

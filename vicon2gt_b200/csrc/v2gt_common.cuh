@@ -46,10 +46,10 @@ constexpr int FPI_E = 0, FPI_TTH = 15, FPI_TB = 24, FPI_SV = 33, FPI_SP = 36, FP
 //  r[6] = sqrt(w) W e ; A[6][6] = sqrt(w) W H1(:, [0:3, 12:15]) ; G[6][7] = sqrt(w) W [H2 H3 H4] ; has_vicon ; idx0 ; idx1 ; w
 constexpr int FPV_R = 0, FPV_A = 6, FPV_G = 42, FPV_HAS = 84, FPV_IDX0 = 85, FPV_IDX1 = 86, FPV_W = 87, FPV_STRIDE = 88;
 
-// ---- normal-equation record of one state (row-major pieces)
-//  D  15x15 at [0, 225);  M 15x25 at [225, 600): columns [0,15) = O (coupling to the next state),
-//  [15,24) = B (border to the 9 globals), 24 = g (right-hand side)
-constexpr int NE_D = 0, NE_M = 225, NE_MW = 25, NE_MB = 15, NE_MG = 24, NE_STRIDE = 600;
+// ---- normal-equation record of one state (row-major pieces, each piece contiguous so that the assembly can write
+//  it as whole 3-row strips):  D 15x15 at [0, 225);  O 15x15 at [225, 450) (coupling to the next state);
+//  BG 15x10 at [450, 600): columns [0,9) = B (border to the 9 globals), 9 = g (right-hand side)
+constexpr int NE_D = 0, NE_O = 225, NE_BG = 450, NE_BGW = 10, NE_STRIDE = 600;
 // ---- elimination factor record of one state, in the register order of the mma.m8n8k4 fragments
 //  (lane = 4 gid + tid):  L^-1 tiles (0,0) (1,0) (1,1): [tile][lane][e] = Linv[8u+gid][8v+2tid+e]   (192)
 //  W = L^-1 [O F B g] (16x40, row 15 is padding): [u][t][lane][e] = W[8u+2tid+e][8t+gid]            (640)
@@ -113,6 +113,7 @@ struct DevPtrs {
   double *pre, *info, *cov;
   double *fpi, *fpv;
   double *ne;        // [S][NE_STRIDE]
+  double *grad;      // [S][16] compact copy of the gradient g of every state (read by the trial-point evaluation)
   double *fac, *seg; // [S][FAC_STRIDE], [T][P][SEG_STRIDE]
   double *red_ne, *red_fac, *red_fb; // reduced (separator) chain: [T][P][NE_STRIDE], [T][P][FAC_STRIDE], [T][640]
   double *xsep;      // [T][P+1][16] separator steps (slot m = separator m, 1-based)
@@ -145,6 +146,13 @@ struct SoaR {
   long long S;
   __device__ __forceinline__ SoaR operator+(int e) const { return SoaR{p + (long long)e * S, S}; }
   __device__ __forceinline__ double operator[](int e) const { return __ldg(p + (long long)e * S); }
+};
+// the same view of a shared-memory tile ([element][column], column stride S): plain loads
+struct SoaS {
+  const double *p;
+  int S;
+  __device__ __forceinline__ SoaS operator+(int e) const { return SoaS{p + e * S, S}; }
+  __device__ __forceinline__ double operator[](int e) const { return p[e * S]; }
 };
 struct SoaW {
   double *p;

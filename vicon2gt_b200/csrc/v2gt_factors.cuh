@@ -29,7 +29,7 @@ __device__ __forceinline__ void grav_terms(double thx, double thy, double gmag, 
 }
 
 // load the 3x3 block (a,b) of a packed-lower symmetric 15x15 matrix
-__device__ __forceinline__ void ld_sym_blk(const SoaR P, int a, int b, double *o) {
+template <class View> __device__ __forceinline__ void ld_sym_blk(const View P, int a, int b, double *o) {
 #pragma unroll
   for (int r = 0; r < 3; r++)
 #pragma unroll
