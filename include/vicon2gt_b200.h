@@ -127,6 +127,19 @@ int v2gt_batch_set_trial(v2gt_batch *b, int32_t trial, const v2gt_params *params
                          const double *vic_Rq, const double *vic_Rp, const double *vic_R_const,
                          int64_t n_times, const double *state_t);
 
+/*
+ * The same, without the host copy: the arrays are BORROWED and must stay valid and unchanged until the next
+ * v2gt_batch_upload() (or v2gt_batch_build_and_solve() on a batch that was not uploaded yet) has returned.  The
+ * shared_ptr<Propagator> / shared_ptr<Interpolator> stores of the reference (ViconGraphSolver.h:117-120) have exactly
+ * this lifetime.  The conversion to the device layout is done by v2gt_batch_upload, on several host threads, straight
+ * into pinned staging memory.
+ */
+int v2gt_batch_set_trial_view(v2gt_batch *b, int32_t trial, const v2gt_params *params,
+                              int64_t n_imu, const double *imu_t, const double *imu_w, const double *imu_a,
+                              int64_t n_vicon, const double *vic_t, const double *vic_q, const double *vic_p,
+                              const double *vic_Rq, const double *vic_Rp, const double *vic_R_const,
+                              int64_t n_times, const double *state_t);
+
 /* Clean timestamps (ViconGraphSolver.cpp:114-159) and copy every staged trial to the device. */
 int v2gt_batch_upload(v2gt_batch *b);
 

@@ -42,6 +42,7 @@ def load_library():
     L.v2gt_batch_set_option.argtypes = [vp, C.c_char_p, C.c_double]
     L.v2gt_batch_set_trial.argtypes = [vp, C.c_int32, C.POINTER(Params), C.c_int64, c_double_p, c_double_p, c_double_p, C.c_int64,
                                        c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, C.c_int64, c_double_p]
+    L.v2gt_batch_set_trial_view.argtypes = L.v2gt_batch_set_trial.argtypes
     for n in ("v2gt_batch_upload", "v2gt_batch_optimize", "v2gt_batch_build_and_solve", "v2gt_batch_sync"):
         getattr(L, n).argtypes = [vp]
     L.v2gt_batch_build.argtypes = [vp, C.c_int32]
@@ -131,15 +132,23 @@ class BatchSolver:
     def set_option(self, name, value):
         _check(self._L.v2gt_batch_set_option(self.h, name.encode(), float(value)), f"set_option({name})")
 
-    def set_trial(self, trial, params, imu_t, imu_w, imu_a, vic_t, vic_q, vic_p, state_t, vic_Rq=None, vic_Rp=None, vic_R_const=None):
+    def set_trial(self, trial, params, imu_t, imu_w, imu_a, vic_t, vic_q, vic_p, state_t, vic_Rq=None, vic_Rp=None, vic_R_const=None,
+                  borrow=False):
+        """Stage one trial.  borrow=True hands the library views of the arrays instead of copies (v2gt_batch_set_trial_view);
+        this object keeps them alive until the next upload."""
         a = [_c(x) for x in (imu_t, imu_w, imu_a, vic_t, vic_q, vic_p, vic_Rq, vic_Rp, vic_R_const, state_t)]
-        _check(self._L.v2gt_batch_set_trial(self.h, int(trial), C.byref(params), len(a[0]), dptr(a[0]), dptr(a[1]), dptr(a[2]),
-                                            len(a[3]), dptr(a[3]), dptr(a[4]), dptr(a[5]), dptr(a[6]), dptr(a[7]), dptr(a[8]),
-                                            len(a[9]), dptr(a[9])), "v2gt_batch_set_trial")
+        fn = self._L.v2gt_batch_set_trial_view if borrow else self._L.v2gt_batch_set_trial
+        _check(fn(self.h, int(trial), C.byref(params), len(a[0]), dptr(a[0]), dptr(a[1]), dptr(a[2]),
+                  len(a[3]), dptr(a[3]), dptr(a[4]), dptr(a[5]), dptr(a[6]), dptr(a[7]), dptr(a[8]),
+                  len(a[9]), dptr(a[9])), "v2gt_batch_set_trial")
+        if borrow:
+            if not hasattr(self, "_views"):
+                self._views = {}
+            self._views[int(trial)] = a
 
-    def set_trial_dataset(self, trial, params, ds):
+    def set_trial_dataset(self, trial, params, ds, borrow=False):
         self.set_trial(trial, params, ds.imu_t, ds.imu_w, ds.imu_a, ds.vic_t, ds.vic_q, ds.vic_p, ds.state_t,
-                       vic_R_const=ds.vic_R_const)
+                       vic_R_const=ds.vic_R_const, borrow=borrow)
 
     def upload(self):
         _check(self._L.v2gt_batch_upload(self.h), "v2gt_batch_upload")
@@ -164,7 +173,7 @@ class BatchSolver:
     def states(self, trial=0):
         n = C.c_int64()
         _check(self._L.v2gt_batch_get_states(self.h, int(trial), 0, None, None, C.byref(n)), "v2gt_batch_get_states")
-        t, x = np.zeros(n.value), np.zeros((n.value, 16))
+        t, x = np.empty(n.value), np.empty((n.value, 16))
         _check(self._L.v2gt_batch_get_states(self.h, int(trial), n.value, dptr(t), dptr(x), C.byref(n)), "v2gt_batch_get_states")
         return t, x
 

@@ -22,6 +22,7 @@
 #include <sstream>
 #include <string>
 #include <sys/stat.h>
+#include <thread>
 #include <vector>
 
 namespace v2 {
@@ -48,13 +49,22 @@ int asm_chunks(int n_max);
 
 using namespace v2;
 
+// One trial's staged inputs: raw caller-layout arrays, either owned copies (v2gt_batch_set_trial) or borrowed views
+// (v2gt_batch_set_trial_view).  The conversion to the device layout happens in v2gt_batch_upload, straight into the
+// pinned staging buffers, in parallel over the trials.
 struct HostTrial {
   v2gt_params prm;
-  std::vector<double> imu_t, imu_s;        // imu_s: [M][8]
-  std::vector<double> vic_t, vic_s, vic_c; // vic_s: [V][8]; vic_c: [V][18] or empty
+  std::vector<double> own; // owned copies of the arrays below (empty for a borrowed view)
+  const double *imu_t = nullptr, *imu_w = nullptr, *imu_a = nullptr;
+  const double *vic_t_in = nullptr, *vic_q = nullptr, *vic_p = nullptr, *vic_Rq = nullptr, *vic_Rp = nullptr;
+  const double *state_t_raw = nullptr;
+  int64_t n_imu = 0, n_vic_in = 0, n_times = 0;
   double vic_Rconst[18];
   bool cov_const = true;
-  std::vector<double> state_t_raw, state_t; // before / after cleaning
+  // derived in upload
+  std::vector<int64_t> vic_order;  // empty: the fed poses are already strictly increasing in time (kept as they are)
+  int64_t n_vic = 0;               // after de-duplication
+  std::vector<double> state_t;     // after cleaning
   double vic_tmin = std::numeric_limits<double>::infinity(), vic_tmax = -std::numeric_limits<double>::infinity();
   v2gt_trial_info info{};
   bool set = false;
@@ -207,6 +217,24 @@ void make_dirs_for(const std::string &path) {
     }
 }
 
+// run f(t) for t in [0, T) on a few host threads (static interleaved partition)
+template <typename F> void parallel_trials(int T, F f) {
+  const int nthr = std::max(1, std::min({T, (int)std::thread::hardware_concurrency(), 16}));
+  if (nthr == 1) {
+    for (int t = 0; t < T; t++)
+      f(t);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (int k = 0; k < nthr; k++)
+    th.emplace_back([=]() {
+      for (int t = k; t < T; t += nthr)
+        f(t);
+    });
+  for (auto &x : th)
+    x.join();
+}
+
 } // namespace
 
 namespace v2 {
@@ -334,10 +362,10 @@ int v2gt_batch_set_option(v2gt_batch *b, const char *name, double value) {
   return V2GT_OK;
 }
 
-int v2gt_batch_set_trial(v2gt_batch *b, int32_t trial, const v2gt_params *params, int64_t n_imu, const double *imu_t,
-                         const double *imu_w, const double *imu_a, int64_t n_vicon, const double *vic_t, const double *vic_q,
-                         const double *vic_p, const double *vic_Rq, const double *vic_Rp, const double *vic_R_const,
-                         int64_t n_times, const double *state_t) {
+static int set_trial_impl(v2gt_batch *b, int32_t trial, const v2gt_params *params, int64_t n_imu, const double *imu_t,
+                          const double *imu_w, const double *imu_a, int64_t n_vicon, const double *vic_t, const double *vic_q,
+                          const double *vic_p, const double *vic_Rq, const double *vic_Rp, const double *vic_R_const,
+                          int64_t n_times, const double *state_t, bool copy) {
   if (!b || trial < 0 || trial >= b->T || !params || n_imu < 0 || n_vicon < 0 || n_times < 0)
     return V2GT_ERR_INVALID_ARG;
   if ((n_imu && (!imu_t || !imu_w || !imu_a)) || (n_vicon && (!vic_t || !vic_q || !vic_p)) || (n_times && !state_t))
@@ -347,60 +375,64 @@ int v2gt_batch_set_trial(v2gt_batch *b, int32_t trial, const v2gt_params *params
   HostTrial &h = b->trials[trial];
   h = HostTrial();
   h.prm = *params;
-  // ---- IMU: kept in feed order (Propagator::feed_imu appends)
-  h.imu_t.assign(imu_t, imu_t + n_imu);
-  h.imu_s.resize((size_t)n_imu * 8);
-  for (int64_t i = 0; i < n_imu; i++) {
-    double *o = &h.imu_s[(size_t)i * 8];
-    o[0] = imu_t[i];
-    o[1] = imu_w[3 * i];
-    o[2] = imu_w[3 * i + 1];
-    o[3] = imu_w[3 * i + 2];
-    o[4] = imu_a[3 * i];
-    o[5] = imu_a[3 * i + 1];
-    o[6] = imu_a[3 * i + 2];
-    o[7] = 0.0;
-  }
-  // ---- vicon: std::set<POSEDATA> keyed by timestamp -> stable sort + keep the first of equal keys
-  std::vector<int64_t> order((size_t)n_vicon);
-  std::iota(order.begin(), order.end(), (int64_t)0);
-  bool sorted = true;
-  for (int64_t i = 0; i + 1 < n_vicon; i++)
-    if (!(vic_t[i] < vic_t[i + 1])) {
-      sorted = false;
-      break;
-    }
-  if (!sorted)
-    std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return vic_t[x] < vic_t[y]; });
+  h.n_imu = n_imu;
+  h.n_vic_in = n_vicon;
+  h.n_times = n_times;
   h.cov_const = !(vic_Rq && vic_Rp);
-  if (h.cov_const)
+  if (h.cov_const && vic_R_const)
     std::memcpy(h.vic_Rconst, vic_R_const, sizeof(h.vic_Rconst));
-  h.vic_t.reserve((size_t)n_vicon);
-  h.vic_s.reserve((size_t)n_vicon * 8);
-  if (!h.cov_const)
-    h.vic_c.reserve((size_t)n_vicon * 18);
-  for (int64_t k = 0; k < n_vicon; k++) {
-    const int64_t i = order[(size_t)k];
-    // time_min / time_max are updated for every fed pose, duplicates included (Interpolator.cpp:35-37)
-    h.vic_tmin = std::min(h.vic_tmin, vic_t[i]);
-    h.vic_tmax = std::max(h.vic_tmax, vic_t[i]);
-    if (!h.vic_t.empty() && h.vic_t.back() == vic_t[i])
-      continue;
-    h.vic_t.push_back(vic_t[i]);
-    const double row[8] = {vic_q[4 * i], vic_q[4 * i + 1], vic_q[4 * i + 2], vic_q[4 * i + 3],
-                           vic_p[3 * i], vic_p[3 * i + 1], vic_p[3 * i + 2], 0.0};
-    h.vic_s.insert(h.vic_s.end(), row, row + 8);
+  else
+    std::memset(h.vic_Rconst, 0, sizeof(h.vic_Rconst));
+  if (copy) {
+    const size_t total = (size_t)n_imu * 7 + (size_t)n_vicon * (8 + (h.cov_const ? 0 : 18)) + (size_t)n_times;
+    h.own.resize(std::max<size_t>(1, total));
+    double *o = h.own.data();
+    auto take = [&](const double *src, size_t n) {
+      const double *r = o;
+      if (n)
+        std::memcpy(o, src, sizeof(double) * n);
+      o += n;
+      return r;
+    };
+    h.imu_t = take(imu_t, (size_t)n_imu);
+    h.imu_w = take(imu_w, (size_t)n_imu * 3);
+    h.imu_a = take(imu_a, (size_t)n_imu * 3);
+    h.vic_t_in = take(vic_t, (size_t)n_vicon);
+    h.vic_q = take(vic_q, (size_t)n_vicon * 4);
+    h.vic_p = take(vic_p, (size_t)n_vicon * 3);
     if (!h.cov_const) {
-      h.vic_c.insert(h.vic_c.end(), vic_Rq + 9 * i, vic_Rq + 9 * i + 9);
-      h.vic_c.insert(h.vic_c.end(), vic_Rp + 9 * i, vic_Rp + 9 * i + 9);
+      h.vic_Rq = take(vic_Rq, (size_t)n_vicon * 9);
+      h.vic_Rp = take(vic_Rp, (size_t)n_vicon * 9);
     }
+    h.state_t_raw = take(state_t, (size_t)n_times);
+  } else {
+    h.imu_t = imu_t; h.imu_w = imu_w; h.imu_a = imu_a;
+    h.vic_t_in = vic_t; h.vic_q = vic_q; h.vic_p = vic_p;
+    h.vic_Rq = h.cov_const ? nullptr : vic_Rq;
+    h.vic_Rp = h.cov_const ? nullptr : vic_Rp;
+    h.state_t_raw = state_t;
   }
-  h.state_t_raw.assign(state_t, state_t + n_times);
   h.set = true;
   b->uploaded = false;
   b->built = false;
   b->results_cached = false;
   return V2GT_OK;
+}
+
+int v2gt_batch_set_trial(v2gt_batch *b, int32_t trial, const v2gt_params *params, int64_t n_imu, const double *imu_t,
+                         const double *imu_w, const double *imu_a, int64_t n_vicon, const double *vic_t, const double *vic_q,
+                         const double *vic_p, const double *vic_Rq, const double *vic_Rp, const double *vic_R_const,
+                         int64_t n_times, const double *state_t) {
+  return set_trial_impl(b, trial, params, n_imu, imu_t, imu_w, imu_a, n_vicon, vic_t, vic_q, vic_p, vic_Rq, vic_Rp, vic_R_const,
+                        n_times, state_t, true);
+}
+
+int v2gt_batch_set_trial_view(v2gt_batch *b, int32_t trial, const v2gt_params *params, int64_t n_imu, const double *imu_t,
+                              const double *imu_w, const double *imu_a, int64_t n_vicon, const double *vic_t, const double *vic_q,
+                              const double *vic_p, const double *vic_Rq, const double *vic_Rp, const double *vic_R_const,
+                              int64_t n_times, const double *state_t) {
+  return set_trial_impl(b, trial, params, n_imu, imu_t, imu_w, imu_a, n_vicon, vic_t, vic_q, vic_p, vic_Rq, vic_Rp, vic_R_const,
+                        n_times, state_t, false);
 }
 
 int v2gt_batch_upload(v2gt_batch *b) {
@@ -417,17 +449,52 @@ int v2gt_batch_upload(v2gt_batch *b) {
   std::vector<LmState> lm(T);
   long long S = 0, M = 0, V = 0, C = 0;
   b->n_max = 0;
-  for (int t = 0; t < T; t++) {
-    HostTrial &h = b->trials[t];
-    if (!h.set)
+  for (int t = 0; t < T; t++)
+    if (!b->trials[t].set)
       return V2GT_ERR_INVALID_ARG;
+  // pass 1 (parallel over trials): vicon order / de-duplication, timestamp cleaning
+  parallel_trials(T, [&](int t) {
+    HostTrial &h = b->trials[t];
     h.info = v2gt_trial_info{};
     std::memset(&lm[t], 0, sizeof(LmState));
     h.state_t.clear();
+    // ---- vicon: std::set<POSEDATA> keyed by timestamp -> stable sort + keep the first of equal keys
+    h.vic_order.clear();
+    h.vic_tmin = std::numeric_limits<double>::infinity();
+    h.vic_tmax = -std::numeric_limits<double>::infinity();
+    const int64_t nv = h.n_vic_in;
+    bool increasing = true;
+    for (int64_t i = 0; i + 1 < nv; i++)
+      if (!(h.vic_t_in[i] < h.vic_t_in[i + 1])) {
+        increasing = false;
+        break;
+      }
+    if (increasing) {
+      h.n_vic = nv;
+      if (nv) {
+        h.vic_tmin = h.vic_t_in[0];
+        h.vic_tmax = h.vic_t_in[nv - 1];
+      }
+    } else {
+      std::vector<int64_t> order((size_t)nv);
+      std::iota(order.begin(), order.end(), (int64_t)0);
+      std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return h.vic_t_in[x] < h.vic_t_in[y]; });
+      h.vic_order.reserve((size_t)nv);
+      for (int64_t k = 0; k < nv; k++) {
+        const int64_t i = order[(size_t)k];
+        // time_min / time_max are updated for every fed pose, duplicates included (Interpolator.cpp:35-37)
+        h.vic_tmin = std::min(h.vic_tmin, h.vic_t_in[i]);
+        h.vic_tmax = std::max(h.vic_tmax, h.vic_t_in[i]);
+        if (!h.vic_order.empty() && h.vic_t_in[h.vic_order.back()] == h.vic_t_in[i])
+          continue;
+        h.vic_order.push_back(i);
+      }
+      h.n_vic = (int64_t)h.vic_order.size();
+    }
     int status = V2GT_OK;
-    if (h.state_t_raw.empty())
+    if (h.n_times == 0)
       status = V2GT_ERR_NO_TIMESTAMPS;
-    else if (h.vic_t.size() < 2)
+    else if (h.n_vic < 2)
       status = V2GT_ERR_NO_VICON;
     else {
       const double first = h.vic_tmin + h.prm.toff_imu_to_vicon + 2 * h.prm.time_offset_window;
@@ -435,18 +502,20 @@ int v2gt_batch_upload(v2gt_batch *b) {
       // has_bounding_imu (Propagator.cpp:165-193): some sample <= t and some sample >= t seen before the
       // scan breaks; for the time-ordered store this is t_imu[0] <= t <= t_imu[M-1].  The general
       // (unordered) case is reproduced with running prefix extrema.
-      const size_t Mi = h.imu_t.size();
+      const size_t Mi = (size_t)h.n_imu;
       bool imu_sorted = true;
       for (size_t i = 0; i + 1 < Mi; i++)
         if (h.imu_t[i + 1] < h.imu_t[i]) {
           imu_sorted = false;
           break;
         }
-      for (double ts : h.state_t_raw) {
+      h.state_t.reserve((size_t)h.n_times);
+      for (int64_t si = 0; si < h.n_times; si++) {
+        const double ts = h.state_t_raw[si];
         bool bounded = false;
         if (Mi > 0) {
           if (imu_sorted) {
-            bounded = (h.imu_t.front() <= ts) && (h.imu_t.back() >= ts);
+            bounded = (h.imu_t[0] <= ts) && (h.imu_t[Mi - 1] >= ts);
           } else {
             bool lo = false, hi = false;
             for (size_t i = 0; i < Mi; i++) {
@@ -474,12 +543,16 @@ int v2gt_batch_upload(v2gt_batch *b) {
     }
     h.info.status = status;
     lm[t].status = status;
+  });
+  for (int t = 0; t < T; t++) {
+    HostTrial &h = b->trials[t];
+    const int status = h.info.status;
     TrialDev &d = td[t];
     std::memset(&d, 0, sizeof(d));
     d.imu_off = M;
-    d.n_imu = (long long)h.imu_t.size();
+    d.n_imu = (long long)h.n_imu;
     d.vic_off = V;
-    d.n_vic = (long long)h.vic_t.size();
+    d.n_vic = (long long)h.n_vic;
     d.st_off = S;
     d.n_raw = (status == V2GT_OK) ? (long long)h.state_t.size() : 0;
     d.vic_cov_const = h.cov_const ? 1 : 0;
@@ -538,31 +611,59 @@ int v2gt_batch_upload(v2gt_batch *b) {
   V2_TRY(pin_alloc(b, &h_nst, (size_t)T));
   V2_TRY(pin_alloc(b, &h_coff, (size_t)T));
   V2_TRY(pin_alloc(b, &b->h_active, 1));
-  long long coff = 0;
-  for (int t = 0; t < T; t++) {
+  {
+    long long coff = 0;
+    for (int t = 0; t < T; t++) {
+      h_coff[t] = b->trials[t].cov_const ? -1 : coff * 18;
+      if (!b->trials[t].cov_const)
+        coff += td[t].n_vic;
+    }
+  }
+  // pass 2 (parallel over trials): caller layout -> device layout, written straight into the pinned buffers
+  parallel_trials(T, [&](int t) {
     const HostTrial &h = b->trials[t];
     const TrialDev &q = td[t];
     if (q.n_imu) {
-      std::memcpy(h_imu_t + q.imu_off, h.imu_t.data(), sizeof(double) * q.n_imu);
-      std::memcpy(h_imu_s + 8 * q.imu_off, h.imu_s.data(), sizeof(double) * 8 * q.n_imu);
+      // IMU: kept in feed order (Propagator::feed_imu appends); one 64-byte row (t, w, a, pad) per sample
+      std::memcpy(h_imu_t + q.imu_off, h.imu_t, sizeof(double) * q.n_imu);
+      double *o = h_imu_s + 8 * q.imu_off;
+      for (long long i = 0; i < q.n_imu; i++, o += 8) {
+        o[0] = h.imu_t[i];
+        o[1] = h.imu_w[3 * i];
+        o[2] = h.imu_w[3 * i + 1];
+        o[3] = h.imu_w[3 * i + 2];
+        o[4] = h.imu_a[3 * i];
+        o[5] = h.imu_a[3 * i + 1];
+        o[6] = h.imu_a[3 * i + 2];
+        o[7] = 0.0;
+      }
     }
-    if (q.n_vic) {
-      std::memcpy(h_vic_t + q.vic_off, h.vic_t.data(), sizeof(double) * q.n_vic);
-      std::memcpy(h_vic_s + 8 * q.vic_off, h.vic_s.data(), sizeof(double) * 8 * q.n_vic);
-    }
-    if (!h.cov_const) {
-      h_coff[t] = coff * 18;
-      std::memcpy(h_vic_c + 18 * coff, h.vic_c.data(), sizeof(double) * 18 * q.n_vic);
-      coff += q.n_vic;
-    } else {
-      h_coff[t] = -1;
+    const bool reorder = !h.vic_order.empty();
+    double *vt = h_vic_t + q.vic_off, *vs = h_vic_s + 8 * q.vic_off;
+    double *vc = h.cov_const ? nullptr : h_vic_c + h_coff[t];
+    for (long long k = 0; k < q.n_vic; k++) {
+      const int64_t i = reorder ? h.vic_order[(size_t)k] : k;
+      vt[k] = h.vic_t_in[i];
+      double *o = vs + 8 * k;
+      o[0] = h.vic_q[4 * i];
+      o[1] = h.vic_q[4 * i + 1];
+      o[2] = h.vic_q[4 * i + 2];
+      o[3] = h.vic_q[4 * i + 3];
+      o[4] = h.vic_p[3 * i];
+      o[5] = h.vic_p[3 * i + 1];
+      o[6] = h.vic_p[3 * i + 2];
+      o[7] = 0.0;
+      if (vc) {
+        std::memcpy(vc + 18 * k, h.vic_Rq + 9 * i, sizeof(double) * 9);
+        std::memcpy(vc + 18 * k + 9, h.vic_Rp + 9 * i, sizeof(double) * 9);
+      }
     }
     for (long long i = 0; i < q.n_raw; i++) {
       h_st_t[q.st_off + i] = h.state_t[(size_t)i];
       h_trial_of[q.st_off + i] = t;
     }
     h_nst[t] = (int)q.n_raw;
-  }
+  });
   double *p_imu_t, *p_imu_s, *p_vic_t, *p_vic_s, *p_vic_c;
   long long *p_coff;
   TrialDev *p_trials;
