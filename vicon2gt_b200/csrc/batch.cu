@@ -33,6 +33,7 @@ int launch_cost(const DevPtrs &d, int n_max, int which, int force_all, cudaStrea
 int launch_solve(const DevPtrs &d, int force_all, cudaStream_t st);
 int solve_configure();
 int elim_warps_per_cta();
+int l2_segments(int P, int l2_max);
 int elim_ctas_per_sm();
 int launch_eliminate(const DevPtrs &d, int force_all, cudaStream_t st);
 int launch_reduced(const DevPtrs &d, int force_all, cudaStream_t st);
@@ -569,8 +570,11 @@ int v2gt_batch_upload(v2gt_batch *b) {
   // every round of the optimiser then picks its own count from the number of trials still running, so that the
   // chains of the remaining trials are cut finer as the batch drains (v2gt_batch_optimize)
   int P = b->opt_segments;
-  if (P <= 0)
-    P = std::max(1, (int)std::ceil(std::sqrt((double)std::max(1, b->n_max))));
+  if (P <= 0) // up to 4 sqrt(n): the separator chain is itself eliminated in segments (nested level 2), so a small
+              // batch can cut its chains much finer than sqrt(n) before the reduced solve dominates
+    P = std::max(1, 4 * (int)std::ceil(std::sqrt((double)std::max(1, b->n_max))));
+  if (b->opt_segments <= 0)
+    P = std::min(P, std::max(1, b->n_max / 32)); // segments shorter than ~32 states only add separator work
   P = std::max(1, std::min(P, std::max(1, b->n_max / 2)));
   if (b->chain) {
     if (T != 1)
@@ -691,8 +695,20 @@ int v2gt_batch_upload(v2gt_batch *b) {
   V2_TRY(dev_alloc(b, &d.grad, (size_t)S * 16));
   V2_TRY(dev_alloc(b, &d.fac, (size_t)S * FAC_STRIDE));
   V2_TRY(dev_alloc(b, &d.seg, (size_t)T * P * SEG_STRIDE));
-  V2_TRY(dev_alloc(b, &d.red_ne, ((size_t)T * P + 2) * NE_STRIDE));
-  V2_TRY(dev_alloc(b, &d.red_fac, ((size_t)T * P + 2) * FAC_STRIDE));
+  V2_TRY(dev_alloc(b, &d.red_ne, ((size_t)T * (P + 1) + 2) * NE_STRIDE));
+  V2_TRY(dev_alloc(b, &d.red_fac, ((size_t)T * (P + 1) + 2) * FAC_STRIDE));
+  {
+    // level 2 of the nested elimination (separator chain of level 1 cut into ~sqrt(P) segments)
+    const int P2 = std::max(2, (int)std::ceil(std::sqrt((double)P)) + 1);
+    d.l2_P = P2;
+    V2_TRY(dev_alloc(b, &d.l2_trials, (size_t)T));
+    V2_TRY(dev_alloc(b, &d.l2_nstates, (size_t)T));
+    V2_TRY(dev_alloc(b, &d.l2_seg, (size_t)T * P2 * SEG_STRIDE));
+    V2_TRY(dev_alloc(b, &d.l2_red_ne, ((size_t)T * (P2 + 1) + 2) * NE_STRIDE));
+    V2_TRY(dev_alloc(b, &d.l2_red_fac, ((size_t)T * (P2 + 1) + 2) * FAC_STRIDE));
+    V2_TRY(dev_alloc(b, &d.l2_xsep, (size_t)T * (P2 + 1) * 16));
+    V2_TRY(dev_alloc(b, &d.l2_gamma_sub, (size_t)T * 96));
+  }
   V2_TRY(dev_alloc(b, &d.red_fb, (size_t)T * 640));
   V2_TRY(dev_alloc(b, &d.xsep, (size_t)T * (P + 1) * 16));
   V2_TRY(dev_alloc(b, &d.delta, (size_t)S * 16));
@@ -748,6 +764,8 @@ int v2gt_batch_upload(v2gt_batch *b) {
   V2_CUDA_CHECK(cudaMemsetAsync(d.delta, 0, sizeof(double) * S * 16, st));
   V2_CUDA_CHECK(cudaMemsetAsync(d.trace, 0, sizeof(double) * T * TRACE_MAX * 5, st));
   V2_CUDA_CHECK(cudaMemsetAsync(d.xg, 0, sizeof(double) * T * 16, st));
+  V2_CUDA_CHECK(cudaMemsetAsync(d.l2_trials, 0, sizeof(TrialDev) * T, st));
+  V2_CUDA_CHECK(cudaMemsetAsync(d.l2_nstates, 0, sizeof(int) * T, st));
   if (b->chain) {
     V2_CUDA_CHECK(cudaMemsetAsync(d.c_sums, 0, sizeof(double) * 8, st));
     V2_CUDA_CHECK(cudaMemsetAsync(d.c_gamma_loc, 0, sizeof(double) * 96, st));
@@ -902,7 +920,7 @@ int v2gt_batch_optimize(v2gt_batch *b) {
       V2_CUDA_CHECK(cudaEventRecord(e[6], st));
       b->launches[1] += 3;
       b->launches[2] += 1;
-      b->launches[3] += 2;
+      b->launches[3] += l2_segments(d.P, d.l2_P) ? 8 : 2;
       b->launches[4] += 1;
       b->launches[5] += 1;
       b->launches[6] += 2;

@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(128) k_reduced_assemble(DevPtrs d, int force_a
   const bool has_r = (m < sg.nseg);                                         // ... and opens segment m
   const double *segr = d.seg + ((long long)t * d.P + m) * SEG_STRIDE;
   const bool has_next = has_r && (m + 1 <= sg.nsep);
-  double *out = d.red_ne + ((long long)t * d.P + m) * NE_STRIDE;
+  double *out = d.red_ne + ((long long)t * (d.P + 1) + m) * NE_STRIDE;
   for (int idx = threadIdx.x; idx < NE_STRIDE; idx += blockDim.x) {
     double v;
     if (idx < NE_O) {
@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(32) k_reduced(DevPtrs d, int force_all) {
   // ---- forward elimination over the separators m = 1..nsep
   ElimAcc A;
   acc_zero(A);
-  const long long r0 = (long long)t * d.P + 1;
+  const long long r0 = (long long)t * (d.P + 1) + 1;
   bool ok = elim_chain<false>(d.red_ne + r0 * NE_STRIDE, sg.nsep, nullptr, lambda, d.red_fac + r0 * FAC_STRIDE, A, w, lane);
   // ---- global 9x9: Gamma + lambda I - sum_seg S_BB - S_BB(separator chain); rhs likewise
   double *fbr = d.red_fb + (long long)t * 640; // 25x25 scratch in global (only the B,g rows/columns are meaningful)
@@ -595,6 +595,8 @@ __global__ void __launch_bounds__(32) k_reduced(DevPtrs d, int force_all) {
     const int r = (idx < 81) ? idx / 9 : idx - 81;
     const int c = (idx < 81) ? idx - 9 * r : 9;
     double v = gm[idx] - fbr[25 * (15 + r) + 15 + c];
+    if (d.gamma_sub)
+      v -= d.gamma_sub[(long long)t * 96 + idx];
     for (int jj = 0; jj < sg.nseg; jj++)
       v -= segs[(long long)jj * SEG_STRIDE + SEG_FB + 25 * (15 + r) + 15 + c];
     if (idx < 81 && r == c)
@@ -664,7 +666,7 @@ __global__ void __launch_bounds__(32) k_reduced(DevPtrs d, int force_all) {
   backvec_init(V, xz, xz, xgs, gid);
   for (int m = sg.nsep; m >= 1; m--) {
     FacRegs F;
-    fac_load(F, d.red_fac + ((long long)t * d.P + m) * FAC_STRIDE, lane);
+    fac_load(F, d.red_fac + ((long long)t * (d.P + 1) + m) * FAC_STRIDE, lane);
     double y0[2], y1[2];
     backsub_node(F, V, y0, y1, 0.0, gid, tid);
     store_x(d.xsep + ((long long)t * (d.P + 1) + m) * 16, y0, y1, gid, tid);
@@ -747,13 +749,96 @@ int launch_eliminate(const DevPtrs &d, int force_all, cudaStream_t st) {
   V2_CUDA_CHECK(cudaGetLastError());
   return V2GT_OK;
 }
+// ------------------------------------------------------------------------------------------------
+// Level 2 of the nested elimination.  grid T, 96 threads: the Schur terms of the level-1 segments on the global
+// block (summed in segment order), and the description of the level-1 separator chain as a chain of "states".
+__global__ void __launch_bounds__(96) k_l2_prepare(DevPtrs d, int force_all) {
+  const int t = blockIdx.x;
+  const LmState &lm = d.lm[t];
+  if (!force_all && (lm.lm_state != 0 || lm.status != V2GT_OK))
+    return;
+  const int n = d.chain ? d.c_n : d.n_states[t];
+  const SegGeom sg = seg_geom(n, d.P);
+  if (threadIdx.x == 0) {
+    d.l2_nstates[t] = sg.nsep;
+    d.l2_trials[t].st_off = (long long)t * (d.P + 1) + 1;
+    d.l2_trials[t].n_raw = sg.nsep;
+  }
+  const int idx = threadIdx.x;
+  if (idx < 90) {
+    const int r = (idx < 81) ? idx / 9 : idx - 81;
+    const int c = (idx < 81) ? idx - 9 * r : 9;
+    const double *segs = d.seg + (long long)t * d.P * SEG_STRIDE;
+    double v = 0.0;
+    for (int jj = 0; jj < sg.nseg; jj++)
+      v += segs[(long long)jj * SEG_STRIDE + SEG_FB + 25 * (15 + r) + 15 + c];
+    d.l2_gamma_sub[(long long)t * 96 + idx] = v;
+  }
+}
+
+// grid (P, T), 32 threads: step of separator m = blockIdx.x + 1 from xsep into the delta slot of its state
+__global__ void __launch_bounds__(32) k_sep_delta(DevPtrs d, int force_all) {
+  const int t = blockIdx.y;
+  const LmState &lm = d.lm[t];
+  if (!force_all && (lm.lm_state != 0 || lm.status != V2GT_OK || lm.solve_failed))
+    return;
+  const int n = d.chain ? d.c_n : d.n_states[t];
+  const SegGeom sg = seg_geom(n, d.P);
+  const int m = blockIdx.x + 1;
+  if (m > sg.nsep || threadIdx.x >= 16)
+    return;
+  const long long slot = (long long)m * sg.stride - 1 - (d.chain ? d.c_goff : 0);
+  if (!d.chain || (slot >= 0 && slot < d.n_states[t]))
+    d.delta[(d.trials[t].st_off + slot) * 16 + threadIdx.x] = d.xsep[((long long)t * (d.P + 1) + m) * 16 + threadIdx.x];
+}
+
+// level-2 segment count for a level-1 chain cut into P segments (0: solve the separator chain directly)
+__host__ int l2_segments(int P, int l2_max) {
+  if (l2_max < 2 || P < 24)
+    return 0;
+  int p2 = (int)(sqrt((double)P) + 0.5);
+  p2 = p2 < 2 ? 2 : p2;
+  return p2 > l2_max ? l2_max : p2;
+}
+
 int launch_reduced(const DevPtrs &d, int force_all, cudaStream_t st) {
+  const size_t sm1 = sizeof(double) * SW_TOTAL * ELIM_WARPS;
   const size_t sm2 = sizeof(double) * RED_SMEM;
   if (d.P > 1) {
     dim3 g0(d.P - 1, d.T);
     k_reduced_assemble<<<g0, 128, 0, st>>>(d, force_all);
   }
-  k_reduced<<<d.T, 32, sm2, st>>>(d, force_all);
+  const int P2 = l2_segments(d.P, d.l2_P);
+  if (P2 == 0) {
+    k_reduced<<<d.T, 32, sm2, st>>>(d, force_all);
+    V2_CUDA_CHECK(cudaGetLastError());
+    return V2GT_OK;
+  }
+  // ---- nested: the separator chain (records red_ne, one per separator) is eliminated like a state chain
+  k_l2_prepare<<<d.T, 96, 0, st>>>(d, force_all);
+  DevPtrs d2 = d;
+  d2.chain = 0;
+  d2.P = P2;
+  d2.trials = d.l2_trials;
+  d2.n_states = d.l2_nstates;
+  d2.ne = d.red_ne;
+  d2.fac = d.red_fac;
+  d2.seg = d.l2_seg;
+  d2.red_ne = d.l2_red_ne;
+  d2.red_fac = d.l2_red_fac;
+  d2.xsep = d.l2_xsep;
+  d2.delta = d.xsep; // the "states" of level 2 are the separators of level 1
+  d2.gamma_sub = d.l2_gamma_sub;
+  d2.l2_P = 0;
+  dim3 g1((P2 + ELIM_WARPS - 1) / ELIM_WARPS, d.T);
+  k_seg_eliminate<<<g1, ELIM_WARPS * 32, sm1, st>>>(d2, force_all);
+  dim3 g2(P2 - 1, d.T);
+  k_reduced_assemble<<<g2, 128, 0, st>>>(d2, force_all);
+  k_reduced<<<d.T, 32, sm2, st>>>(d2, force_all);
+  dim3 g3((P2 + BS_WARPS - 1) / BS_WARPS, d.T);
+  k_seg_backsub<<<g3, BS_WARPS * 32, 0, st>>>(d2, force_all);
+  dim3 g4(d.P, d.T);
+  k_sep_delta<<<g4, 32, 0, st>>>(d, force_all);
   V2_CUDA_CHECK(cudaGetLastError());
   return V2GT_OK;
 }

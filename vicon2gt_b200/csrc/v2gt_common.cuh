@@ -115,12 +115,19 @@ struct DevPtrs {
   double *ne;        // [S][NE_STRIDE]
   double *grad;      // [S][16] compact copy of the gradient g of every state (read by the trial-point evaluation)
   double *fac, *seg; // [S][FAC_STRIDE], [T][P][SEG_STRIDE]
-  double *red_ne, *red_fac, *red_fb; // reduced (separator) chain: [T][P][NE_STRIDE], [T][P][FAC_STRIDE], [T][640]
+  double *red_ne, *red_fac, *red_fb; // reduced (separator) chain: [T][P+1][NE_STRIDE], [T][P+1][FAC_STRIDE], [T][640]
   double *xsep;      // [T][P+1][16] separator steps (slot m = separator m, 1-based)
   double *delta;
   double *part_asm;  // [T][nchunk][PART_STRIDE]
   double *part_cost; // [T][nchunk][4]: cost, lin_error0, g.delta, |delta|^2
   double *gamma;     // [T][96]: Gamma 81 + g 9 (assembled, undamped)
+  const double *gamma_sub; // [T][96] or null: Schur terms of a finer level, subtracted from gamma by k_reduced
+  // ---- second level of the nested elimination: the separator chain of level 1 (red_ne) is itself cut into l2_P
+  // segments and eliminated by the same kernels (launch_reduced builds the derived pointer set from these)
+  int l2_P;                 // max level-2 segments per trial (0: level 2 not allocated)
+  TrialDev *l2_trials;      // [T] st_off = slot of separator 1 of the trial in red_ne / xsep
+  int *l2_nstates;          // [T] separators of level 1 = "states" of level 2
+  double *l2_seg, *l2_red_ne, *l2_red_fac, *l2_xsep, *l2_gamma_sub;
   double *xg;        // [T][16]: global step
   LmState *lm;
   double *trace;     // [T][TRACE_MAX][5]
