@@ -233,7 +233,8 @@ def run_chain(args):
     p = api.default_params()
     comm = DistComm(dist) if dist is not None else LocalComm(1)
     n_guess = ds.n_times
-    spr = args.segs_per_rank if args.segs_per_rank > 0 else max(2, int(round((n_guess / world) ** 0.5)))
+    # ~4 sqrt(n) segments over the whole chain (the separator chain is eliminated in segments of its own, nested level 2)
+    spr = args.segs_per_rank if args.segs_per_rank > 0 else max(2, int(round(4.0 * n_guess ** 0.5 / world)))
     cs = ChainSolver(p, ds, comm, segs_per_rank=spr, device=device)
     stream = cs.parts[0].stream
 
@@ -276,15 +277,15 @@ def run_chain(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_ms / args.steps, "higher_is_better": False,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "ONE synthesised one-hour sequence (BASELINE.json configs[4]): 20 Hz states, 200 Hz IMU, 100 Hz vicon, "
-                                   "chain-sharded over %d GPU(s), %d segments per GPU; NCCL all-gather of segment Schur outputs + separator "
-                                   "records, all-reduce of the 9x9 global block" % (world, spr),
-                       "n_states": n_states, "n_imu": ds.n_imu, "n_vicon": ds.n_vicon, "segments_per_gpu": spr,
+                                   "chain-sharded over %d GPU(s), %d segments per GPU; one NCCL all-gather of segment Schur outputs + separator "
+                                   "records + global-block parts per damped solve" % (world, cs.segs_per_rank),
+                       "n_states": n_states, "n_imu": ds.n_imu, "n_vicon": ds.n_vicon, "segments_per_gpu": cs.segs_per_rank,
                        "timing": "CUDA events on the solver stream, max over ranks"},
             "lm": {"iterations": inf.iterations, "damped_solves": inf.tries, "final_error": inf.final_error, "status": inf.status,
                    "ms_per_lm_iteration": opt_ms / args.steps / max(1, inf.iterations), "build_ms": (tot_ms - opt_ms) / args.steps,
                    "optimize_ms": opt_ms / args.steps},
             "trajectories_per_second": 1e3 * args.steps / tot_ms,
-            "collectives_per_damped_solve": 6, "clocks": clocks,
+            "collectives_per_damped_solve": 3, "clocks": clocks,
         }
         print(json.dumps(line))
     cs.close()

@@ -194,23 +194,24 @@ int v2gt_batch_get_lm_trace(v2gt_batch *b, int32_t trial, int64_t capacity, doub
  * each inner side, and drives the Levenberg-Marquardt rounds phase by phase; between the phases the caller moves the
  * small buffers below with its collective library (NCCL through torch.distributed in vicon2gt_b200/chain.py):
  *   all-reduce (sum)  V2GT_CHAIN_BUF_SUMS (8)   after phases 0 and 5      cost / model-fidelity scalars
- *   all-reduce (sum)  V2GT_CHAIN_BUF_GAMMA (96) after phase 2             9x9 global block + gradient + linear error
- *   all-gather        SEG_SEND -> SEG_ALL, SEPNE_SEND -> SEPNE_ALL  after phase 3   segment Schur outputs, separator records
+ *   all-gather        PACK_SEND -> PACK_ALL (rank-major)   after phase 3   per rank: segment Schur outputs, separator records,
+ *                                                                          its part of the 9x9 global block + gradient
  *   all-gather        HALO_SEND (16) -> HALO_RECV (16 x world)      after phase 4   boundary steps
+ * i.e. three small collectives per damped solve.  Phase 4 unpacks PACK_ALL (the global block is summed in rank order).
  * The reduced (separator + 9 globals) system is then solved redundantly on every rank; all ranks take identical
  * accept / reject decisions.  Geometry: the chain of n_total states is cut into p_total segments with the same
  * formula as the single-GPU solve; this rank owns segments [j0, j1) and the separators in front of them, i.e. the
  * local slots [own_lo, own_hi) of its n_local states starting at global state g_off.  Call before upload. */
 enum {
-  V2GT_CHAIN_BUF_SUMS = 0, V2GT_CHAIN_BUF_GAMMA = 1, V2GT_CHAIN_BUF_SEG_SEND = 2, V2GT_CHAIN_BUF_SEG_ALL = 3,
-  V2GT_CHAIN_BUF_SEPNE_SEND = 4, V2GT_CHAIN_BUF_SEPNE_ALL = 5, V2GT_CHAIN_BUF_HALO_SEND = 6, V2GT_CHAIN_BUF_HALO_RECV = 7
+  V2GT_CHAIN_BUF_SUMS = 0, V2GT_CHAIN_BUF_GAMMA = 1, V2GT_CHAIN_BUF_PACK_SEND = 2, V2GT_CHAIN_BUF_SEG_ALL = 3,
+  V2GT_CHAIN_BUF_PACK_ALL = 4, V2GT_CHAIN_BUF_SEPNE_ALL = 5, V2GT_CHAIN_BUF_HALO_SEND = 6, V2GT_CHAIN_BUF_HALO_RECV = 7
 };
 enum {
   V2GT_CHAIN_PHASE_COST0 = 0,   /* cost of the current estimate -> SUMS                                   */
   V2GT_CHAIN_PHASE_BEGIN = 1,   /* LM state initialisation from the (all-reduced) SUMS                    */
-  V2GT_CHAIN_PHASE_LINEARIZE = 2, /* start of a try; relinearise if the last step was accepted -> GAMMA   */
-  V2GT_CHAIN_PHASE_ELIMINATE = 3, /* eliminate the own segments -> SEG_SEND, SEPNE_SEND                   */
-  V2GT_CHAIN_PHASE_SOLVE = 4,   /* reduced system (redundant), back-substitution -> HALO_SEND             */
+  V2GT_CHAIN_PHASE_LINEARIZE = 2, /* start of a try; relinearise if the last step was accepted            */
+  V2GT_CHAIN_PHASE_ELIMINATE = 3, /* eliminate the own segments -> PACK_SEND                              */
+  V2GT_CHAIN_PHASE_SOLVE = 4,   /* unpack PACK_ALL, reduced system (redundant), back-substitution -> HALO_SEND */
   V2GT_CHAIN_PHASE_COST = 5,    /* trial point + its cost -> SUMS                                         */
   V2GT_CHAIN_PHASE_DECIDE = 6   /* accept / reject, lambda update from the (all-reduced) SUMS             */
 };

@@ -158,7 +158,9 @@ def test_chain_sharded_solve_over_nccl_two_gpus():
     port = 29700 + (os.getpid() % 200)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(root, "tools", "chain_nccl_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, V2GT_CHAIN_CHECK_S="60"))
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, V2GT_CHAIN_CHECK_S="80"))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
-    assert json.loads(line)["ok"]
+    res = json.loads(line)
+    assert res["ok"], res
+    assert res["same_basin"], res  # this dataset's LM path does not sit on a bracket-switch discontinuity

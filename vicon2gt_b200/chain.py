@@ -3,9 +3,9 @@
 The cleaned state chain is cut into `world x segs_per_rank` segments with the single-GPU solver's geometry; rank r
 holds the states of its segments (+ one halo state on each inner side), linearises and eliminates them locally, and
 per damped solve exchanges only
-    * the Schur outputs of its segments and the normal-equation records of its separators (all-gather),
-    * its part of the 9x9 global block / gradient (all-reduce) and a handful of scalars (all-reduce),
-    * one boundary step (all-gather of 16 doubles),
+    * the Schur outputs of its segments, the normal-equation records of its separators and its part of the 9x9 global
+      block / gradient, packed into ONE all-gather (the global block is then summed in rank order on every rank),
+    * one boundary step (all-gather of 16 doubles) and a handful of cost scalars (all-reduce),
 after which every rank solves the small reduced system (separators + 9 globals) redundantly and takes the identical
 Levenberg-Marquardt decision.  Collectives go through `torch.distributed` (NCCL over NVLink on the GPUs; gloo in the
 CPU tests of the host logic) on the solver's own CUDA stream; `LocalComm` runs all ranks of a small world in one
@@ -20,7 +20,7 @@ import numpy as np
 
 from . import api
 
-(BUF_SUMS, BUF_GAMMA, BUF_SEG_SEND, BUF_SEG_ALL, BUF_SEPNE_SEND, BUF_SEPNE_ALL, BUF_HALO_SEND, BUF_HALO_RECV) = range(8)
+(BUF_SUMS, BUF_GAMMA, BUF_PACK_SEND, BUF_SEG_ALL, BUF_PACK_ALL, BUF_SEPNE_ALL, BUF_HALO_SEND, BUF_HALO_RECV) = range(8)
 (PH_COST0, PH_BEGIN, PH_LINEARIZE, PH_ELIMINATE, PH_SOLVE, PH_COST, PH_DECIDE) = range(7)
 
 
@@ -64,6 +64,18 @@ def chain_plan(n_total, world, segs_per_rank):
         n_local = end + (1 if r < world - 1 else 0) - g_off  # right halo: the next rank's leading separator
         plans.append(RankPlan(r, world, n_total, p, stride, j0, j1, g_off, n_local, start - g_off, end - g_off))
     return plans
+
+
+def fit_segments_per_rank(n_total, world, target):
+    """Largest segments-per-rank <= target whose geometry uses every segment (ceil rounding of the stride can leave the
+    last segments of a finer cut empty)."""
+    for spr in range(max(1, int(target)), 0, -1):
+        try:
+            chain_plan(n_total, world, spr)
+            return spr
+        except ValueError:
+            continue
+    raise ValueError(f"chain of {n_total} states cannot be cut for {world} ranks")
 
 
 def clean_timestamps(params, imu_t, vic_t, state_t):
@@ -187,7 +199,8 @@ class ChainSolver:
         self.comm = comm
         self.params = params
         self.ts = clean_timestamps(params, ds.imu_t, ds.vic_t, ds.state_t)
-        self.plans = chain_plan(len(self.ts), comm.world, segs_per_rank)
+        self.segs_per_rank = fit_segments_per_rank(len(self.ts), comm.world, segs_per_rank)
+        self.plans = chain_plan(len(self.ts), comm.world, self.segs_per_rank)
         self.parts = [_Part(params, ds, self.ts, self.plans[r], device, torch) for r in comm.ranks]
         self.tries = 0
         self.check_every = 4  # host reads the replicated LM state every this many damped solves (phases of a finished
@@ -211,10 +224,8 @@ class ChainSolver:
         cap = max_tries or 100000
         while self.tries < cap:
             self._phase(PH_LINEARIZE)
-            c.all_reduce(P, BUF_GAMMA, t)
             self._phase(PH_ELIMINATE)
-            c.all_gather(P, BUF_SEG_SEND, BUF_SEG_ALL, t)
-            c.all_gather(P, BUF_SEPNE_SEND, BUF_SEPNE_ALL, t)
+            c.all_gather(P, BUF_PACK_SEND, BUF_PACK_ALL, t)  # segment outputs + separator records + global block parts
             self._phase(PH_SOLVE)
             c.all_gather(P, BUF_HALO_SEND, BUF_HALO_RECV, t)
             self._phase(PH_COST)

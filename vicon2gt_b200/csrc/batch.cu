@@ -42,7 +42,7 @@ int launch_lm_begin(const DevPtrs &d, cudaStream_t st);
 int launch_lm_pre_try(const DevPtrs &d, cudaStream_t st);
 int launch_lm_decide(const DevPtrs &d, int count_active, cudaStream_t st);
 int launch_chain_sum(const DevPtrs &d, cudaStream_t st);
-int launch_chain_fix(const DevPtrs &d, cudaStream_t st);
+int launch_chain_unpack(const DevPtrs &d, cudaStream_t st);
 int launch_chain_pack(const DevPtrs &d, int stride, cudaStream_t st);
 int launch_chain_halo(const DevPtrs &d, int recv, cudaStream_t st);
 int asm_chunks(int n_max);
@@ -725,8 +725,9 @@ int v2gt_batch_upload(v2gt_batch *b) {
     V2_TRY(dev_alloc(b, &d.c_sepne, ((size_t)P + 2) * NE_STRIDE));
     V2_TRY(dev_alloc(b, &d.c_sums, 8));
     V2_TRY(dev_alloc(b, &d.c_gamma_loc, 96));
-    V2_TRY(dev_alloc(b, &d.c_seg_send, (size_t)ploc * SEG_STRIDE));
-    V2_TRY(dev_alloc(b, &d.c_sepne_send, (size_t)ploc * NE_STRIDE));
+    const size_t per_rank = (size_t)ploc * (SEG_STRIDE + NE_STRIDE) + 96;
+    V2_TRY(dev_alloc(b, &d.c_pack_send, per_rank));
+    V2_TRY(dev_alloc(b, &d.c_pack_all, per_rank * std::max(1, b->c_world)));
     V2_TRY(dev_alloc(b, &d.c_halo_send, 16));
     V2_TRY(dev_alloc(b, &d.c_halo_recv, (size_t)16 * std::max(1, b->c_world)));
     d.chain = 1;
@@ -1132,16 +1133,14 @@ int v2gt_chain_phase(v2gt_batch *b, int32_t phase) {
     break;
   case V2GT_CHAIN_PHASE_LINEARIZE:
     V2_TRY(launch_lm_pre_try(d, st));
-    V2_TRY(launch_linearize(d, b->n_max, 0, st));
-    // the local part of the global block is kept separately, so the all-reduce into gamma can be repeated every try
-    V2_CUDA_CHECK(cudaMemcpyAsync(d.gamma, d.c_gamma_loc, sizeof(double) * 96, cudaMemcpyDeviceToDevice, st));
+    V2_TRY(launch_linearize(d, b->n_max, 0, st)); // the local part of the global block stays in c_gamma_loc
     break;
   case V2GT_CHAIN_PHASE_ELIMINATE:
-    V2_TRY(launch_chain_fix(d, st));
     V2_TRY(launch_eliminate(d, 0, st));
     V2_TRY(launch_chain_pack(d, seg_stride_host(b->c_n, d.P), st));
     break;
   case V2GT_CHAIN_PHASE_SOLVE:
+    V2_TRY(launch_chain_unpack(d, st));
     V2_TRY(launch_reduced(d, 0, st));
     V2_TRY(launch_backsub(d, 0, st));
     V2_TRY(launch_chain_halo(d, 0, st));
@@ -1168,9 +1167,12 @@ int v2gt_chain_buffer(v2gt_batch *b, int32_t which, void **dev_ptr, int64_t *n_d
   switch (which) {
   case V2GT_CHAIN_BUF_SUMS: *dev_ptr = d.c_sums; *n_doubles = 8; break;
   case V2GT_CHAIN_BUF_GAMMA: *dev_ptr = d.gamma; *n_doubles = 96; break;
-  case V2GT_CHAIN_BUF_SEG_SEND: *dev_ptr = d.c_seg_send; *n_doubles = ploc * SEG_STRIDE; break;
+  case V2GT_CHAIN_BUF_PACK_SEND: *dev_ptr = d.c_pack_send; *n_doubles = ploc * (SEG_STRIDE + NE_STRIDE) + 96; break;
+  case V2GT_CHAIN_BUF_PACK_ALL:
+    *dev_ptr = d.c_pack_all;
+    *n_doubles = (ploc * (SEG_STRIDE + NE_STRIDE) + 96) * std::max(1, b->c_world);
+    break;
   case V2GT_CHAIN_BUF_SEG_ALL: *dev_ptr = d.seg; *n_doubles = (int64_t)d.P * SEG_STRIDE; break;
-  case V2GT_CHAIN_BUF_SEPNE_SEND: *dev_ptr = d.c_sepne_send; *n_doubles = ploc * NE_STRIDE; break;
   case V2GT_CHAIN_BUF_SEPNE_ALL: *dev_ptr = d.c_sepne; *n_doubles = (int64_t)d.P * NE_STRIDE; break;
   case V2GT_CHAIN_BUF_HALO_SEND: *dev_ptr = d.c_halo_send; *n_doubles = 16; break;
   case V2GT_CHAIN_BUF_HALO_RECV: *dev_ptr = d.c_halo_recv; *n_doubles = 16LL * b->c_world; break;

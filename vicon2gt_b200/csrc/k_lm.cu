@@ -163,25 +163,58 @@ __global__ void k_chain_sum(DevPtrs d) {
   }
   d.c_sums[threadIdx.x] = s;
 }
-// after the all-reduce of the global block: take the summed linear error
-__global__ void k_chain_fix(DevPtrs d) {
-  if (threadIdx.x == 0 && blockIdx.x == 0)
-    d.lm[0].lin_error0 = d.gamma[90];
-}
-// pack what the reduced (separator) system needs from this rank: the records of its separators and its segments' outputs
+// pack what the reduced (separator) system needs from this rank: its segments' outputs, the records of its separators
+// and its part of the global block.  grid: own segments + 1
 __global__ void k_chain_pack(DevPtrs d, int stride) {
+  const int ploc = d.c_j1 - d.c_j0;
   const int jl = blockIdx.x; // local segment index
-  const int j = d.c_j0 + jl;
-  if (j >= d.c_j1)
+  if (jl == ploc) {
+    double *go = d.c_pack_send + (long long)ploc * (SEG_STRIDE + NE_STRIDE);
+    for (int k = threadIdx.x; k < 96; k += blockDim.x)
+      go[k] = d.c_gamma_loc[k];
     return;
+  }
+  if (jl > ploc)
+    return;
+  const int j = d.c_j0 + jl;
   const double *sg = d.seg + (long long)j * SEG_STRIDE;
-  double *so = d.c_seg_send + (long long)jl * SEG_STRIDE;
+  double *so = d.c_pack_send + (long long)jl * SEG_STRIDE;
   for (int k = threadIdx.x; k < SEG_STRIDE; k += blockDim.x)
     so[k] = sg[k];
-  double *no = d.c_sepne_send + (long long)jl * NE_STRIDE;
+  double *no = d.c_pack_send + (long long)ploc * SEG_STRIDE + (long long)jl * NE_STRIDE;
   const long long slot = (long long)j * stride - 1 - d.c_goff; // separator in front of segment j (none for j = 0)
   for (int k = threadIdx.x; k < NE_STRIDE; k += blockDim.x)
     no[k] = (j >= 1 && slot >= 0 && slot < d.n_states[0]) ? d.ne[(d.trials[0].st_off + slot) * NE_STRIDE + k] : 0.0;
+}
+// after the all-gather: every rank's contribution into the globally indexed buffers; the global block is summed in
+// rank order (identical on every rank).  grid: all segments of the chain + 1
+__global__ void k_chain_unpack(DevPtrs d) {
+  const int ploc = d.c_j1 - d.c_j0; // the same on every rank
+  const long long per_rank = (long long)ploc * (SEG_STRIDE + NE_STRIDE) + 96;
+  const int j = blockIdx.x;
+  if (j == d.P) {
+    for (int k = threadIdx.x; k < 96; k += blockDim.x) {
+      double v = 0.0;
+      for (int r = 0; r < d.c_world; r++)
+        v += d.c_pack_all[r * per_rank + (long long)ploc * (SEG_STRIDE + NE_STRIDE) + k];
+      d.gamma[k] = v;
+      if (k == 90)
+        d.lm[0].lin_error0 = v; // the summed linear error
+    }
+    return;
+  }
+  if (j > d.P)
+    return;
+  const int r = j / ploc, jl = j - r * ploc;
+  const double *base = d.c_pack_all + r * per_rank;
+  const double *si = base + (long long)jl * SEG_STRIDE;
+  const double *ni = base + (long long)ploc * SEG_STRIDE + (long long)jl * NE_STRIDE;
+  double *so = d.seg + (long long)j * SEG_STRIDE;
+  double *no = d.c_sepne + (long long)j * NE_STRIDE;
+  for (int k = threadIdx.x; k < SEG_STRIDE; k += blockDim.x)
+    so[k] = si[k];
+  for (int k = threadIdx.x; k < NE_STRIDE; k += blockDim.x)
+    no[k] = ni[k];
 }
 // step of this rank's last own state -> send buffer; halo steps <- neighbours
 __global__ void k_chain_halo_send(DevPtrs d) {
@@ -200,13 +233,13 @@ int launch_chain_sum(const DevPtrs &d, cudaStream_t st) {
   V2_CUDA_CHECK(cudaGetLastError());
   return V2GT_OK;
 }
-int launch_chain_fix(const DevPtrs &d, cudaStream_t st) {
-  k_chain_fix<<<1, 32, 0, st>>>(d);
+int launch_chain_unpack(const DevPtrs &d, cudaStream_t st) {
+  k_chain_unpack<<<d.P + 1, 256, 0, st>>>(d);
   V2_CUDA_CHECK(cudaGetLastError());
   return V2GT_OK;
 }
 int launch_chain_pack(const DevPtrs &d, int stride, cudaStream_t st) {
-  k_chain_pack<<<max(1, d.c_j1 - d.c_j0), 256, 0, st>>>(d, stride);
+  k_chain_pack<<<d.c_j1 - d.c_j0 + 1, 256, 0, st>>>(d, stride);
   V2_CUDA_CHECK(cudaGetLastError());
   return V2GT_OK;
 }

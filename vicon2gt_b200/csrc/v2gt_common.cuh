@@ -143,7 +143,10 @@ struct DevPtrs {
   double *c_sepne;     // [P][NE_STRIDE] normal-equation records of every separator of the chain (all-gathered)
   double *c_sums;      // [8] cost, lin_error0, g.delta, |delta|^2, solve_failed (local, then all-reduced)
   double *c_gamma_loc; // [96] this rank's part of the global block (all-reduced into gamma)
-  double *c_seg_send, *c_sepne_send, *c_halo_send, *c_halo_recv;
+  double *c_halo_send, *c_halo_recv;
+  // one all-gather per damped solve: every rank contributes [its segments' outputs | its separators' records |
+  // its part of the global block] (c_pack_send), and unpacks everybody's (c_pack_all, rank-major)
+  double *c_pack_send, *c_pack_all;
 };
 
 #if defined(__CUDACC__)
