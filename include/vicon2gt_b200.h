@@ -161,6 +161,20 @@ int v2gt_batch_get_states(v2gt_batch *b, int32_t trial, int64_t capacity, double
 int v2gt_batch_get_calibration(v2gt_batch *b, int32_t trial, double *q_BtoI, double *p_BinI, double *t_off, double *theta_xy);
 /* ViconGraphSolver::write_to_file (.cpp:194-248): byte-compatible CSV + info text. */
 int v2gt_batch_write_to_file(v2gt_batch *b, int32_t trial, const char *csv_path, const char *info_path);
+/* The same for every solved trial of the batch (one device read-back, files written on several host threads):
+ * <dir>/<trial, 5 digits>_states.csv and _info.txt; with_txt != 0 adds _states.txt, the pose text file
+ * ("timestamp(s) tx ty tz qx qy qz qw") the reference's Monte-Carlo script hands to its evaluation tool after
+ * converting the CSV (scripts/run_monte_carlo.sh:66-72). */
+int v2gt_batch_write_all(v2gt_batch *b, const char *dir, int32_t with_txt, int32_t *n_written);
+
+/* Batched trajectory-error report of a simulated batch (the per-run report of src/run_simulation.cpp:198-297 with
+ * src/utils/stats.h:64-112, for all trials at once on the device).
+ * set_truth: truth10 = [n][10] = q_VtoI (JPL, 4), p_IinV (3), v_IinV (3) from Simulator::get_state_in_vicon at the n
+ * surviving state times of the trial (v2gt_batch_get_states).
+ * error_stats: stats = [n_trials][3][8] with rows (orientation deg, position m, velocity m/s) and columns
+ * rmse, mean, median, min, max, std, mean + 2.326 std, count; NaN rows for trials that did not solve. */
+int v2gt_batch_set_truth(v2gt_batch *b, int32_t trial, int64_t n, const double *truth10);
+int v2gt_batch_error_stats(v2gt_batch *b, double *stats);
 
 /* ---- evaluation-only entry points (parity tests; they run the production kernels) ---- */
 

@@ -385,3 +385,42 @@ def test_cpp_driver_matches_python_mirror(tmp_path):
     assert info.read_bytes() == (tmp_path / "py.txt").read_bytes()
     rmse_pos = float(r.stdout.split("rmse_pos = ")[1].split()[0])
     assert rmse_pos < 0.05  # sim.launch noise: 5 cm vicon position sigma
+
+
+def test_batched_error_stats_and_write_all(ds_c1_small, ds_c2_small, ds_c3_small, tmp_path):
+    """per-trial error report on the device vs the numpy restatement of run_simulation.cpp:216-218 +
+    stats.h:64-112, and the batch writer vs the per-trial writer (byte-identical CSV / info; pose text parses back)."""
+    from oracle import stats_ref as sr
+    from vicon2gt_b200 import api
+
+    dss = [ds_c1_small, ds_c2_small, ds_c3_small]
+    p = default_params(lm_max_iterations=6)
+    bs = api.BatchSolver(len(dss))
+    for i, ds in enumerate(dss):
+        bs.set_trial_dataset(i, p, ds)
+    bs.build_and_solve()
+    for i, ds in enumerate(dss):
+        bs.set_truth_from_dataset(i, ds)
+    st = bs.error_stats()
+    for i, ds in enumerate(dss):
+        t, x = bs.states(i)
+        idx = np.searchsorted(ds.state_t, t)
+        e = sr.trajectory_errors(x, ds.truth["states"][idx, 1:11])
+        for m in range(3):
+            ref = sr.stats_calculate(e[:, m])
+            assert ref[7] == st[i, m, 7] == len(t)
+            assert np.max(np.abs(st[i, m, :7] - ref[:7]) / np.abs(ref[:7])) < 1e-10, (i, m, st[i, m], ref)
+        assert np.all(np.isfinite(st[i, :, :5]))
+    n = bs.write_all(str(tmp_path / "mc"), with_txt=True)
+    assert n == len(dss)
+    for i in range(len(dss)):
+        bs.write_to_file(i, str(tmp_path / "one.csv"), str(tmp_path / "one.txt"))
+        stem = tmp_path / "mc" / ("%05d" % i)
+        assert open(str(stem) + "_states.csv", "rb").read() == open(tmp_path / "one.csv", "rb").read()
+        assert open(str(stem) + "_info.txt", "rb").read() == open(tmp_path / "one.txt", "rb").read()
+        txt = np.loadtxt(str(stem) + "_states.txt")
+        csv = np.loadtxt(str(stem) + "_states.csv", delimiter=",")
+        assert txt.shape == (csv.shape[0], 8)
+        assert np.allclose(txt[:, 0], 1e-9 * csv[:, 0], rtol=0, atol=1e-8)
+        assert np.allclose(txt[:, 1:4], csv[:, 1:4]) and np.allclose(txt[:, 4:7], csv[:, 5:8]) and np.allclose(txt[:, 7], csv[:, 4])
+    bs.close()

@@ -375,3 +375,36 @@ def test_failure_codes(ob, ds_c2_small):
     # 0.5 s trimmed at each end of the vicon window (2 * TIME_OFFSET) at 20 Hz
     assert inf.removed_before + inf.removed_after + inf.removed_no_imu + inf.removed_no_vicon + inf.n_states == len(ds.state_t)
     assert inf.removed_before >= 9 and inf.removed_after >= 9
+
+
+# ------------------------------------------------------------------------------------------ error report
+def test_stats_ref_known_answers():
+    """Stats::calculate restatement (oracle/stats_ref.py) on hand-computable inputs."""
+    from oracle import stats_ref as sr
+
+    s = sr.stats_calculate([4.0, 1.0, 3.0, 2.0])
+    assert np.allclose(s, [np.sqrt(7.5), 2.5, 2.5, 1.0, 4.0, np.sqrt(5.0 / 3.0), 2.5 + 2.326 * np.sqrt(5.0 / 3.0), 4.0], rtol=1e-15)
+    s = sr.stats_calculate([2.0, 7.0, 3.0])
+    assert s[2] == 3.0 and s[3] == 2.0 and s[4] == 7.0 and s[7] == 3.0
+    s1 = sr.stats_calculate([5.0])
+    assert s1[0] == 5.0 and s1[1] == 5.0 and s1[2] == 5.0 and np.isnan(s1[5])  # std of one value: 0 / 0 as in the reference
+    assert sr.stats_calculate([])[7] == 0.0
+
+
+def test_trajectory_errors_ref_known_answers():
+    """A 0.2 rad rotation about z and (3, 4, 0) / (0, 0, 2) offsets: ori = 0.2 rad in degrees to first order of the
+    2|vec(q)| form (2 sin(0.1)), pos = 5, vel = 2; the unique-quaternion flip makes the sign of q irrelevant."""
+    from oracle import stats_ref as sr
+
+    q_gt = np.array([0.0, 0.0, np.sin(0.1), np.cos(0.1)])
+    x = np.zeros((2, 16))
+    x[:, 3] = 1.0
+    x[1, :4] = [0.0, 0.0, 0.0, -1.0]
+    x[:, 13:16] = [3.0, 4.0, 0.0]
+    x[:, 7:10] = [0.0, 0.0, 2.0]
+    truth = np.zeros((2, 10))
+    truth[:, 0:4] = q_gt
+    e = sr.trajectory_errors(x, truth)
+    assert np.allclose(e[:, 0], 180.0 / np.pi * 2.0 * np.sin(0.1), rtol=1e-14)
+    assert np.allclose(e[:, 1], 5.0) and np.allclose(e[:, 2], 2.0)
+    assert np.allclose(sr.quat_multiply(q_gt, sr.quat_inv(q_gt)), [0, 0, 0, 1])

@@ -50,6 +50,9 @@ def load_library():
     L.v2gt_batch_get_states.argtypes = [vp, C.c_int32, C.c_int64, c_double_p, c_double_p, c_int64_p]
     L.v2gt_batch_get_calibration.argtypes = [vp, C.c_int32, c_double_p, c_double_p, c_double_p, c_double_p]
     L.v2gt_batch_write_to_file.argtypes = [vp, C.c_int32, C.c_char_p, C.c_char_p]
+    L.v2gt_batch_write_all.argtypes = [vp, C.c_char_p, C.c_int32, c_int32_p]
+    L.v2gt_batch_set_truth.argtypes = [vp, C.c_int32, C.c_int64, c_double_p]
+    L.v2gt_batch_error_stats.argtypes = [vp, c_double_p]
     L.v2gt_eval_interp.argtypes = [vp, C.c_int32, C.c_int64, c_double_p, C.c_double, c_int32_p, c_int32_p, c_int32_p, c_double_p,
                                    c_double_p, c_double_p, c_double_p]
     L.v2gt_batch_get_preint.argtypes = [vp, C.c_int32, C.c_int64, c_double_p, c_int64_p]
@@ -191,6 +194,31 @@ class BatchSolver:
     def write_to_file(self, trial, csv_path, info_path):
         _check(self._L.v2gt_batch_write_to_file(self.h, int(trial), csv_path.encode(), info_path.encode()),
                "v2gt_batch_write_to_file")
+
+    def write_all(self, directory, with_txt=True):
+        """CSV + info (+ pose text) files of every solved trial; returns the number of trials written."""
+        n = C.c_int32(0)
+        _check(self._L.v2gt_batch_write_all(self.h, str(directory).encode(), 1 if with_txt else 0, C.byref(n)), "v2gt_batch_write_all")
+        return n.value
+
+    def set_truth(self, trial, truth10):
+        t = _c(truth10)
+        _check(self._L.v2gt_batch_set_truth(self.h, int(trial), t.shape[0], dptr(t)), "v2gt_batch_set_truth")
+
+    def set_truth_from_dataset(self, trial, ds):
+        """Truth of a simulated Dataset at the trial's surviving state times (Simulator::get_state_in_vicon rows
+        [t, q_VtoI 4, p_IinV 3, v_IinV 3, bg 3, ba 3], matched by the exact time stamp)."""
+        times, _ = self.states(trial)
+        idx = np.searchsorted(ds.state_t, times)
+        if np.any(idx >= len(ds.state_t)) or not np.array_equal(ds.state_t[idx], times):
+            raise ValueError("surviving state times are not a subset of the dataset's state times")
+        self.set_truth(trial, ds.truth["states"][idx, 1:11])
+
+    def error_stats(self):
+        """[n_trials, 3, 8]: (ori deg, pos m, vel m/s) x (rmse, mean, median, min, max, std, mean + 2.326 std, count)."""
+        out = np.zeros((self.n_trials, 3, 8))
+        _check(self._L.v2gt_batch_error_stats(self.h, dptr(out)), "v2gt_batch_error_stats")
+        return out
 
     # ---- evaluation-only entry points (parity tests)
     def eval_interp(self, trial, t_query, gap_thresh):

@@ -34,6 +34,7 @@ int launch_solve(const DevPtrs &d, int force_all, cudaStream_t st);
 int solve_configure();
 int elim_warps_per_cta();
 int l2_segments(int P, int l2_max);
+int launch_error_stats(const DevPtrs &d, const double *d_truth, double *d_out, cudaStream_t st);
 int elim_ctas_per_sm();
 int launch_eliminate(const DevPtrs &d, int force_all, cudaStream_t st);
 int launch_reduced(const DevPtrs &d, int force_all, cudaStream_t st);
@@ -77,6 +78,7 @@ struct v2gt_batch {
   int T = 0;
   cudaStream_t stream = nullptr;
   std::vector<HostTrial> trials;
+  std::vector<std::vector<double>> truth; // per trial: [n][10] truth states (v2gt_batch_set_truth)
   DevPtrs d{};
   std::vector<void *> dev_allocs;
   std::vector<void *> pinned_allocs;
@@ -1040,37 +1042,60 @@ int v2gt_batch_get_calibration(v2gt_batch *b, int32_t trial, double *q_BtoI, dou
   return V2GT_OK;
 }
 
-int v2gt_batch_write_to_file(v2gt_batch *b, int32_t trial, const char *csv_path, const char *info_path) {
-  if (!b || !csv_path || !info_path)
-    return V2GT_ERR_INVALID_ARG;
-  int64_t n = 0;
-  V2_TRY(v2gt_batch_get_states(b, trial, 0, nullptr, nullptr, &n));
-  std::vector<double> times((size_t)n), X((size_t)n * 16);
-  V2_TRY(v2gt_batch_get_states(b, trial, n, times.data(), X.data(), &n));
-  double q_BtoI[4], p_BinI[3], toff, th[2];
-  V2_TRY(v2gt_batch_get_calibration(b, trial, q_BtoI, p_BinI, &toff, th));
-  std::remove(csv_path);
-  std::remove(info_path);
-  make_dirs_for(csv_path);
-  make_dirs_for(info_path);
-  std::ofstream of_state(csv_path, std::ofstream::out | std::ofstream::app);
-  if (!of_state)
-    return V2GT_ERR_INVALID_ARG;
-  of_state << "#time(ns),px,py,pz,qw,qx,qy,qz,vx,vy,vz,bwx,bwy,bwz,bax,bay,baz" << std::endl;
+// ViconGraphSolver::write_to_file (.cpp:194-248) from host copies of one trial's results.  txt_path (optional): the same
+// trajectory as the text file the Monte-Carlo script of the reference feeds to its evaluation tool
+// (scripts/run_monte_carlo.sh:66-72): "timestamp(s) tx ty tz qx qy qz qw", one pose per line.
+static int write_trial_files(const double *times, const double *X, int64_t n, const double *q_BtoI, const double *p_BinI, double toff,
+                             const double *th, double gravity, const char *csv_path, const char *info_path, const char *txt_path) {
   double R_GtoV[9], q_GtoV[4];
   v2::rot_xy(th[0], th[1], R_GtoV);
   v2::rot_2_quat(R_GtoV, q_GtoV);
+  if (csv_path) {
+    std::remove(csv_path);
+    make_dirs_for(csv_path);
+  }
+  if (txt_path) {
+    std::remove(txt_path);
+    make_dirs_for(txt_path);
+  }
+  std::ofstream of_state, of_txt;
+  if (csv_path) {
+    of_state.open(csv_path, std::ofstream::out | std::ofstream::app);
+    if (!of_state)
+      return V2GT_ERR_INVALID_ARG;
+    of_state << "#time(ns),px,py,pz,qw,qx,qy,qz,vx,vy,vz,bwx,bwy,bwz,bax,bay,baz" << std::endl;
+  }
+  if (txt_path) {
+    of_txt.open(txt_path, std::ofstream::out | std::ofstream::app);
+    if (!of_txt)
+      return V2GT_ERR_INVALID_ARG;
+    of_txt << "# timestamp(s) tx ty tz qx qy qz qw" << std::endl;
+  }
   for (int64_t i = 0; i < n; i++) {
     const double *x = &X[(size_t)i * 16];
     double q[4], p[3], v[3];
     v2::quat_mul(x, q_GtoV, q);
     v2::mv3_t(R_GtoV, x + 13, p);
     v2::mv3_t(R_GtoV, x + 7, v);
-    of_state << std::setprecision(20) << std::floor(1e9 * times[(size_t)i]) << "," << std::setprecision(6) << p[0] << "," << p[1]
-             << "," << p[2] << "," << q[3] << "," << q[0] << "," << q[1] << "," << q[2] << "," << v[0] << "," << v[1] << "," << v[2]
-             << "," << x[4] << "," << x[5] << "," << x[6] << "," << x[10] << "," << x[11] << "," << x[12] << std::endl;
+    if (csv_path)
+      of_state << std::setprecision(20) << std::floor(1e9 * times[(size_t)i]) << "," << std::setprecision(6) << p[0] << "," << p[1]
+               << "," << p[2] << "," << q[3] << "," << q[0] << "," << q[1] << "," << q[2] << "," << v[0] << "," << v[1] << "," << v[2]
+               << "," << x[4] << "," << x[5] << "," << x[6] << "," << x[10] << "," << x[11] << "," << x[12] << "\n";
+    if (txt_path) {
+      // the time the CSV holds (floor of the nanosecond count), back in seconds
+      const double ts = 1e-9 * std::floor(1e9 * times[(size_t)i]);
+      of_txt << std::fixed << std::setprecision(9) << ts << std::defaultfloat << std::setprecision(6) << " " << p[0] << " " << p[1] << " "
+             << p[2] << " " << q[0] << " " << q[1] << " " << q[2] << " " << q[3] << "\n";
+    }
   }
-  of_state.close();
+  if (csv_path)
+    of_state.close();
+  if (txt_path)
+    of_txt.close();
+  if (!info_path)
+    return V2GT_OK;
+  std::remove(info_path);
+  make_dirs_for(info_path);
   std::ofstream of_info(info_path, std::ofstream::out | std::ofstream::app);
   if (!of_info)
     return V2GT_ERR_INVALID_ARG;
@@ -1082,10 +1107,118 @@ int v2gt_batch_write_to_file(v2gt_batch *b, int32_t trial, const char *csv_path,
   of_info << "R_GtoV: " << std::endl << eigen_print(R_GtoV, 3, 3) << std::endl << std::endl;
   of_info << "R_GtoV (thetax, thetay): " << std::endl;
   of_info << th[0] << " " << th[0] << std::endl << std::endl; // thetax printed twice, as the reference does (.cpp:244)
-  of_info << "gravity norm: " << std::endl << b->trials[trial].prm.gravity_magnitude << std::endl << std::endl;
+  of_info << "gravity norm: " << std::endl << gravity << std::endl << std::endl;
   of_info << "t_off_vicon_to_imu: " << std::endl << eigen_print(&toff, 1, 1) << std::endl << std::endl;
   of_info.close();
   return V2GT_OK;
+}
+
+int v2gt_batch_write_to_file(v2gt_batch *b, int32_t trial, const char *csv_path, const char *info_path) {
+  if (!b || !csv_path || !info_path)
+    return V2GT_ERR_INVALID_ARG;
+  int64_t n = 0;
+  V2_TRY(v2gt_batch_get_states(b, trial, 0, nullptr, nullptr, &n));
+  std::vector<double> times((size_t)n), X((size_t)n * 16);
+  V2_TRY(v2gt_batch_get_states(b, trial, n, times.data(), X.data(), &n));
+  double q_BtoI[4], p_BinI[3], toff, th[2];
+  V2_TRY(v2gt_batch_get_calibration(b, trial, q_BtoI, p_BinI, &toff, th));
+  return write_trial_files(times.data(), X.data(), n, q_BtoI, p_BinI, toff, th, b->trials[trial].prm.gravity_magnitude, csv_path,
+                           info_path, nullptr);
+}
+
+// Every solved trial of the batch: <dir>/<trial, 5 digits>_states.csv, _info.txt and (with_txt) _states.txt.  One device
+// read-back for the whole batch, then the files are written on several host threads.
+int v2gt_batch_write_all(v2gt_batch *b, const char *dir, int32_t with_txt, int32_t *n_written) {
+  if (!b || !dir || !b->built)
+    return b && !b->built ? V2GT_ERR_NOT_BUILT : V2GT_ERR_INVALID_ARG;
+  V2_CUDA_CHECK(cudaSetDevice(b->device));
+  V2_TRY(fetch_results(b));
+  const int T = b->T;
+  const long long S = b->d.S;
+  std::vector<double> X((size_t)2 * S * X_STRIDE), times((size_t)S), glob((size_t)2 * T * GLOB_STRIDE);
+  std::vector<TrialDev> td((size_t)T);
+  V2_CUDA_CHECK(cudaMemcpy(X.data(), b->d.x, sizeof(double) * X.size(), cudaMemcpyDeviceToHost));
+  V2_CUDA_CHECK(cudaMemcpy(times.data(), b->d.st_t, sizeof(double) * times.size(), cudaMemcpyDeviceToHost));
+  V2_CUDA_CHECK(cudaMemcpy(glob.data(), b->d.glob, sizeof(double) * glob.size(), cudaMemcpyDeviceToHost));
+  V2_CUDA_CHECK(cudaMemcpy(td.data(), b->d.trials, sizeof(TrialDev) * T, cudaMemcpyDeviceToHost));
+  std::vector<int> rc((size_t)T, V2GT_OK), wrote((size_t)T, 0);
+  const std::string base(dir);
+  parallel_trials(T, [&](int t) {
+    if (b->h_lm[t].status != V2GT_OK)
+      return;
+    const int cur = b->h_lm[t].cur;
+    const long long off = td[t].st_off;
+    const double *g = &glob[((size_t)cur * T + t) * GLOB_STRIDE];
+    char name[32];
+    std::snprintf(name, sizeof(name), "/%05d", t);
+    const std::string stem = base + name;
+    const std::string csv = stem + "_states.csv", info = stem + "_info.txt", txt = stem + "_states.txt";
+    const double th[2] = {g[GL_THX], g[GL_THY]};
+    rc[t] = write_trial_files(&times[(size_t)off], &X[((size_t)cur * S + off) * X_STRIDE], b->h_nstates[t], g + GL_Q, g + GL_P,
+                              g[GL_TOFF], th, b->trials[t].prm.gravity_magnitude, csv.c_str(), info.c_str(),
+                              with_txt ? txt.c_str() : nullptr);
+    wrote[t] = (rc[t] == V2GT_OK) ? 1 : 0;
+  });
+  int total = 0;
+  for (int t = 0; t < T; t++) {
+    if (rc[t] != V2GT_OK)
+      return rc[t];
+    total += wrote[t];
+  }
+  if (n_written)
+    *n_written = total;
+  return V2GT_OK;
+}
+
+// ---- batched trajectory-error statistics (csrc/k_stats.cu)
+int v2gt_batch_set_truth(v2gt_batch *b, int32_t trial, int64_t n, const double *truth10) {
+  if (!b || trial < 0 || trial >= b->T || n < 0 || (n && !truth10))
+    return V2GT_ERR_INVALID_ARG;
+  if ((int)b->truth.size() != b->T)
+    b->truth.assign((size_t)b->T, std::vector<double>());
+  b->truth[trial].assign(truth10, truth10 + (size_t)n * 10);
+  return V2GT_OK;
+}
+
+int v2gt_batch_error_stats(v2gt_batch *b, double *stats) {
+  if (!b || !stats)
+    return V2GT_ERR_INVALID_ARG;
+  if (!b->built)
+    return V2GT_ERR_NOT_BUILT;
+  V2_CUDA_CHECK(cudaSetDevice(b->device));
+  V2_TRY(fetch_results(b));
+  const int T = b->T;
+  const long long S = b->d.S;
+  if ((int)b->truth.size() != T)
+    return V2GT_ERR_INVALID_ARG;
+  std::vector<TrialDev> td((size_t)T);
+  V2_CUDA_CHECK(cudaMemcpy(td.data(), b->d.trials, sizeof(TrialDev) * T, cudaMemcpyDeviceToHost));
+  std::vector<double> h((size_t)std::max<long long>(1, S) * 10, 0.0);
+  for (int t = 0; t < T; t++) {
+    if (b->h_lm[t].status != V2GT_OK)
+      continue;
+    const size_t n = (size_t)b->h_nstates[t];
+    if (b->truth[t].size() != n * 10)
+      return V2GT_ERR_INVALID_ARG; // truth must be given at the surviving state times of the trial
+    std::memcpy(&h[(size_t)td[t].st_off * 10], b->truth[t].data(), sizeof(double) * n * 10);
+  }
+  double *d_truth = nullptr, *d_out = nullptr;
+  V2_CUDA_CHECK(cudaMalloc(&d_truth, sizeof(double) * h.size()));
+  cudaError_t e = cudaMalloc(&d_out, sizeof(double) * (size_t)T * 24);
+  if (e != cudaSuccess) {
+    cudaFree(d_truth);
+    return V2GT_ERR_CUDA;
+  }
+  int rc = V2GT_OK;
+  if (cudaMemcpyAsync(d_truth, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, b->stream) != cudaSuccess)
+    rc = V2GT_ERR_CUDA;
+  if (rc == V2GT_OK)
+    rc = launch_error_stats(b->d, d_truth, d_out, b->stream);
+  if (rc == V2GT_OK && cudaMemcpy(stats, d_out, sizeof(double) * (size_t)T * 24, cudaMemcpyDeviceToHost) != cudaSuccess)
+    rc = V2GT_ERR_CUDA;
+  cudaFree(d_truth);
+  cudaFree(d_out);
+  return rc;
 }
 
 int v2gt_chain_configure(v2gt_batch *b, int32_t rank, int32_t world, int64_t n_total, int64_t g_off, int32_t p_total, int32_t j0,
