@@ -118,6 +118,8 @@ class OracleSolver:
 
     @classmethod
     def from_dataset(cls, params, ds):
+        if getattr(ds, "vic_Rq", None) is not None and getattr(ds, "vic_Rp", None) is not None:
+            return cls(params, ds.imu_t, ds.imu_w, ds.imu_a, ds.vic_t, ds.vic_q, ds.vic_p, ds.state_t, vic_Rq=ds.vic_Rq, vic_Rp=ds.vic_Rp)
         return cls(params, ds.imu_t, ds.imu_w, ds.imu_a, ds.vic_t, ds.vic_q, ds.vic_p, ds.state_t, vic_R_const=ds.vic_R_const)
 
     def close(self):

@@ -424,3 +424,44 @@ def test_batched_error_stats_and_write_all(ds_c1_small, ds_c2_small, ds_c3_small
         assert np.allclose(txt[:, 0], 1e-9 * csv[:, 0], rtol=0, atol=1e-8)
         assert np.allclose(txt[:, 1:4], csv[:, 1:4]) and np.allclose(txt[:, 4:7], csv[:, 5:8]) and np.allclose(txt[:, 7], csv[:, 4])
     bs.close()
+
+
+def test_ingested_files_with_per_pose_covariance(ds_c2_small, tmp_path):
+    """recorded-data path (files -> stores -> solve) with per-pose Odometry covariances, against the
+    oracle fed with the same arrays; and the non-ROS estimate_vicon2gt command end to end."""
+    from oracle import binding as ob
+    from vicon2gt_b200 import api, ingest
+    from vicon2gt_b200._cdefs import TrialInfo
+
+    ds = ds_c2_small
+    rng = np.random.default_rng(1)
+    vic, imu = tmp_path / "odom.txt", tmp_path / "imu.txt"
+    with open(imu, "w") as f:
+        for t, w, a in zip(ds.imu_t, ds.imu_w, ds.imu_a):
+            f.write(" ".join(repr(float(x)) for x in (t, *w, *a)) + "\n")
+    with open(vic, "w") as f:
+        for t, q, p in zip(ds.vic_t, ds.vic_q, ds.vic_p):
+            s = np.concatenate([(1e-2 * (1 + rng.random(3))) ** 2, (1e-3 * (1 + rng.random(3))) ** 2])  # x y z rx ry rz
+            f.write(" ".join(repr(float(x)) for x in (t, *p, *q, *np.diag(s).reshape(-1))) + "\n")
+    d2 = ingest.dataset_from_files(str(imu), str(vic), state_freq=20)
+    assert d2.vic_Rq is not None
+    p = default_params(lm_max_iterations=8)
+    orc = ob.OracleSolver.from_dataset(p, d2)
+    assert orc.build_and_solve() == 0
+    bs = api.BatchSolver(1)
+    bs.set_trial_dataset(0, p, d2)
+    bs.build_and_solve()
+    ig, io = bs.info(0), orc.info(TrialInfo)
+    assert ig.status == 0 and ig.n_states == io.n_states
+    _, xg = bs.states(0)
+    _, xo = orc.states()
+    assert np.max(np.abs(xg - xo)) < 1e-6
+    assert abs(ig.final_error - io.final_error) / io.final_error < 1e-8
+    bs.write_to_file(0, str(tmp_path / "a.csv"), str(tmp_path / "a.txt"))
+    bs.close()
+    rc = ingest.main(["--imu", str(imu), "--vicon", str(vic), "--states-csv", str(tmp_path / "b.csv"), "--info-txt", str(tmp_path / "b.txt"),
+                      "--state-freq", "20"])
+    assert rc == 0
+    # the command runs the full 30-iteration policy; the 8-iteration solve above is already converged to the CSV's 6 digits
+    a, b = np.loadtxt(tmp_path / "a.csv", delimiter=","), np.loadtxt(tmp_path / "b.csv", delimiter=",")
+    assert a.shape == b.shape and np.array_equal(a[:, 0], b[:, 0]) and np.max(np.abs(a[:, 1:8] - b[:, 1:8])) < 1e-4

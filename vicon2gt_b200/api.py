@@ -150,8 +150,10 @@ class BatchSolver:
             self._views[int(trial)] = a
 
     def set_trial_dataset(self, trial, params, ds, borrow=False):
+        per_pose = getattr(ds, "vic_Rq", None) is not None and getattr(ds, "vic_Rp", None) is not None
         self.set_trial(trial, params, ds.imu_t, ds.imu_w, ds.imu_a, ds.vic_t, ds.vic_q, ds.vic_p, ds.state_t,
-                       vic_R_const=ds.vic_R_const, borrow=borrow)
+                       vic_Rq=ds.vic_Rq if per_pose else None, vic_Rp=ds.vic_Rp if per_pose else None,
+                       vic_R_const=None if per_pose else ds.vic_R_const, borrow=borrow)
 
     def upload(self):
         _check(self._L.v2gt_batch_upload(self.h), "v2gt_batch_upload")

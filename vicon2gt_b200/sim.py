@@ -59,6 +59,8 @@ class Dataset:
     state_t: np.ndarray
     truth: dict = field(default_factory=dict)
     seed: int = 0
+    vic_Rq: np.ndarray = None  # optional per-pose covariances [V][9] (real data with Odometry covariances, ingest.py)
+    vic_Rp: np.ndarray = None
 
     @property
     def n_imu(self):
