@@ -192,6 +192,10 @@ constexpr int ASM_SMEM_DOUBLES = 5 * ASM_STATES * ASM_STRIP + ASM_STATES * 7 + A
 // doubles each.  The lanes write consecutive doubles, so every 32-byte sector leaves the SM complete (the direct
 // one-thread-per-state stores touched 32 sectors per instruction and doubled the DRAM write traffic).
 __device__ __forceinline__ int lane_of_warp() { return threadIdx.x & 31; }
+__device__ __forceinline__ void cp_async8(double *smem, const double *gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
+}
 __device__ __forceinline__ void flush_strip(const double *buf, double *dst, const int nvalid, const int len, const int lane) {
   __syncwarp();
   for (int k = 0; k < nvalid; k++) {
@@ -338,13 +342,16 @@ __global__ void __launch_bounds__(ASM_THREADS, ASM_MIN_CTAS) k_assemble(DevPtrs 
     const long long sl0 = tr.st_off + i0 - 1; // slot of column 0
     const bool v0 = (i0 + lane - 1 >= 0) && (i0 + lane - 1 < n);
     const bool v1 = (lane == 0) && (i0 + 31 < n);
+    // asynchronous 8-byte copies: all of a thread's ~36 loads are in flight at once, no register staging
     for (int row = dcol; row < ASM_IN_ROWS; row += 5) {
       const double *src = (row < INFO_STRIDE) ? d.info + (long long)row * d.S : d.fpi + (long long)(row - INFO_STRIDE) * d.S;
       if (v0)
-        s_in[row * ASM_IN_COLS + lane] = __ldg(src + sl0 + lane);
+        cp_async8(s_in + row * ASM_IN_COLS + lane, src + sl0 + lane);
       if (v1)
-        s_in[row * ASM_IN_COLS + 32] = __ldg(src + sl0 + 32);
+        cp_async8(s_in + row * ASM_IN_COLS + 32, src + sl0 + 32);
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   __syncthreads();
   const SoaS inf{s_in + li + 1, ASM_IN_COLS};
