@@ -140,7 +140,39 @@ public:
                                timestamp_cameras.data()),
           "v2gt_batch_set_trial");
   }
+  /* The same without the host copy: the stores and the timestamp vector are BORROWED until build_and_solve() (or an
+   * explicit upload) has returned -- the lifetime the reference's shared_ptr stores already have. */
+  void set_trial_view(int trial, const v2gt_params &params, const Propagator &imu, const Interpolator &vicon,
+                      const std::vector<double> &timestamp_cameras) {
+    v2gt_params p = params;
+    p.sigma_w = imu.sigma_w();
+    p.sigma_wb = imu.sigma_wb();
+    p.sigma_a = imu.sigma_a();
+    p.sigma_ab = imu.sigma_ab();
+    check(v2gt_batch_set_trial_view(h_, trial, &p, (int64_t)imu.times().size(), imu.times().data(), imu.gyro().data(),
+                                    imu.accel().data(), (int64_t)vicon.times().size(), vicon.times().data(), vicon.quats().data(),
+                                    vicon.positions().data(), vicon.cov_q().data(), vicon.cov_p().data(), nullptr,
+                                    (int64_t)timestamp_cameras.size(), timestamp_cameras.data()),
+          "v2gt_batch_set_trial_view");
+  }
   void build_and_solve() { check(v2gt_batch_build_and_solve(h_), "v2gt_batch_build_and_solve"); }
+  /* CSV + info (+ pose text) files of every solved trial under `dir`; returns the number of trials written. */
+  int write_all(const std::string &dir, bool with_txt = true) {
+    int32_t n = 0;
+    check(v2gt_batch_write_all(h_, dir.c_str(), with_txt ? 1 : 0, &n), "v2gt_batch_write_all");
+    return (int)n;
+  }
+  /* Error report of a simulated batch (run_simulation.cpp:198-297, stats.h:64-112) for all trials at once:
+   * truth10 = [n][10] (q_VtoI, p_IinV, v_IinV at the trial's surviving state times); stats = [n_trials][3][8] with rows
+   * (ori deg, pos m, vel m/s) and columns rmse, mean, median, min, max, std, mean + 2.326 std, count. */
+  void set_truth(int trial, const std::vector<double> &truth10) {
+    check(v2gt_batch_set_truth(h_, trial, (int64_t)(truth10.size() / 10), truth10.data()), "v2gt_batch_set_truth");
+  }
+  std::vector<double> error_stats() {
+    std::vector<double> out((size_t)n_ * 24, 0.0);
+    check(v2gt_batch_error_stats(h_, out.data()), "v2gt_batch_error_stats");
+    return out;
+  }
   v2gt_trial_info info(int trial) {
     v2gt_trial_info inf;
     check(v2gt_batch_get_info(h_, trial, &inf), "v2gt_batch_get_info");

@@ -40,7 +40,13 @@ __device__ __forceinline__ void ld16(const double *p, double *o) {
 // rows of the trial point are written to the other half of the double buffer) together with the two dot
 // products g.delta and |delta|^2 of the LM model-fidelity test.
 template <bool JAC>
-__global__ void __launch_bounds__(V2GT_CHUNK) k_factor_eval(DevPtrs d, int which, int force_all) {
+#ifndef FE_MIN_CTAS_COST
+#define FE_MIN_CTAS_COST 3
+#endif
+#ifndef FE_MIN_CTAS_JAC
+#define FE_MIN_CTAS_JAC 2
+#endif
+__global__ void __launch_bounds__(V2GT_CHUNK, JAC ? FE_MIN_CTAS_JAC : FE_MIN_CTAS_COST) k_factor_eval(DevPtrs d, int which, int force_all) {
   const int t = blockIdx.y;
   const LmState &lm = d.lm[t];
   __shared__ double s_red[4][V2GT_CHUNK / 32];
