@@ -521,3 +521,47 @@ def test_full_size_properties():
     _, x2 = b2.states(0)
     assert np.array_equal(x1, x2) and np.array_equal(g1, b2.globals10(0)) and b2.info(0).final_error == inf.final_error
     b2.close()
+
+
+def test_vicon_store_semantics_and_view_staging(ds_c2_small):
+    """Interpolator::feed_pose keeps a std::set keyed by time (Interpolator.cpp:21-38): poses fed out of order are sorted,
+    a duplicate timestamp keeps the FIRST pose fed.  The staging code (host threads inside upload) must give, bit for bit,
+    the result of the sorted unique feed -- with constant and with per-pose covariances, copied or borrowed."""
+    from vicon2gt_b200 import api
+
+    ds = ds_c2_small
+    n = len(ds.vic_t)
+    rng = np.random.default_rng(4)
+    perm = rng.permutation(n)
+    # last fed: five duplicates of already-fed stamps carrying different poses (must be ignored)
+    vt = np.concatenate([ds.vic_t[perm], ds.vic_t[:5]])
+    vq = np.concatenate([ds.vic_q[perm], ds.vic_q[5:10]])
+    vp = np.concatenate([ds.vic_p[perm], ds.vic_p[5:10] + 1.0])
+    Rq = np.tile(np.diag([1e-6, 2e-6, 3e-6]).reshape(-1), (n, 1)) * (1 + 0.1 * rng.random((n, 1)))
+    Rp = np.tile(np.diag([1e-4, 2e-4, 3e-4]).reshape(-1), (n, 1)) * (1 + 0.1 * rng.random((n, 1)))
+    Rq_f = np.concatenate([Rq[perm], 7.0 * Rq[:5]])
+    Rp_f = np.concatenate([Rp[perm], 7.0 * Rp[:5]])
+    p = default_params(lm_max_iterations=5)
+
+    def solve(cov, shuffled, borrow):
+        bs = api.BatchSolver(1)
+        kw = dict(vic_Rq=(Rq_f if shuffled else Rq), vic_Rp=(Rp_f if shuffled else Rp)) if cov else dict(vic_R_const=ds.vic_R_const)
+        if shuffled:
+            bs.set_trial(0, p, ds.imu_t, ds.imu_w, ds.imu_a, vt, vq, vp, ds.state_t, borrow=borrow, **kw)
+        else:
+            bs.set_trial(0, p, ds.imu_t, ds.imu_w, ds.imu_a, ds.vic_t, ds.vic_q, ds.vic_p, ds.state_t, borrow=borrow, **kw)
+        bs.upload()
+        q = np.linspace(ds.vic_t[2], ds.vic_t[40], 57)
+        it = bs.eval_interp(0, q, 0.1)
+        bs.build_and_solve()
+        assert bs.info(0).status == 0
+        out = (it["idx0"].copy(), it["idx1"].copy(), it["R"].copy(), bs.states(0)[1], bs.globals10(0), bs.info(0).final_error)
+        bs.close()
+        return out
+
+    for cov in (False, True):
+        ref = solve(cov, False, False)
+        for shuffled, borrow in ((True, False), (True, True), (False, True)):
+            got = solve(cov, shuffled, borrow)
+            for a, b in zip(ref, got):
+                assert np.array_equal(a, b), (cov, shuffled, borrow)
