@@ -50,13 +50,22 @@ def _gloo_worker(rank, world, port, out):
     try:
         n, spr = 1170, 4
         pl = chain_plan(n, world, spr)[rank]
-        # the exchange pattern of one damped solve on stand-in buffers: all-gather of per-segment records into the
-        # global order, all-reduce of the global block; every rank must end up with identical global data
+        # the exchange pattern of one damped solve on stand-in buffers: ONE all-gather of every rank's packed
+        # [segment records | part of the global block]; unpacked rank-major, the segment records land in the global
+        # order and the global block is summed in rank order -- every rank must end up with identical global data
         seg_send = torch.arange(pl.j0, pl.j1, dtype=torch.float64).repeat_interleave(3) + 0.25 * rank
-        seg_all = torch.zeros(pl.p_total * 3, dtype=torch.float64)
-        dist.all_gather_into_tensor(seg_all, seg_send)
-        gamma = torch.full((96,), float(rank + 1), dtype=torch.float64)
-        dist.all_reduce(gamma)
+        gamma_loc = torch.full((96,), float(rank + 1), dtype=torch.float64)
+        pack_send = torch.cat([seg_send, gamma_loc])
+        pack_all = torch.zeros(world * pack_send.numel(), dtype=torch.float64)
+        dist.all_gather_into_tensor(pack_all, pack_send)
+        per = pack_all.view(world, -1)
+        seg_all = per[:, : seg_send.numel()].reshape(-1)
+        gamma = torch.zeros(96, dtype=torch.float64)
+        for r in range(world):  # fixed rank order, as k_chain_unpack sums
+            gamma += per[r, seg_send.numel():]
+        check = gamma_loc.clone()
+        dist.all_reduce(check)
+        assert torch.equal(check, gamma)
         lo, hi = pl.own_global
         counts = torch.zeros(n, dtype=torch.float64)
         counts[lo:hi] = 1
