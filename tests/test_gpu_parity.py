@@ -565,3 +565,38 @@ def test_vicon_store_semantics_and_view_staging(ds_c2_small):
             got = solve(cov, shuffled, borrow)
             for a, b in zip(ref, got):
                 assert np.array_equal(a, b), (cov, shuffled, borrow)
+
+
+@pytest.mark.parametrize("name", ["C2", "C3"])
+def test_baseline_configs_full_size_vs_oracle(name):
+    """BASELINE.json configs[1] (EuRoC V1_01 shape: ~2.9 k states, 28.9 k IMU, 14.4 k vicon) and configs[2] (TUM corridor1
+    shape, extrinsics + time offset + gravity: ~6 k states) at FULL size against the oracle, the whole 30-iteration LM
+    policy: bracket indices of the final estimate bit-exact, states / extrinsics / time offset 1e-6, chi2 1e-8 relative."""
+    from oracle import binding as ob
+    from vicon2gt_b200 import api, sim
+    from vicon2gt_b200._cdefs import TrialInfo
+
+    ds = sim.make_config(name, seed=21)
+    p = default_params()
+    orc = ob.OracleSolver.from_dataset(p, ds)
+    assert orc.build_and_solve() == 0
+    bs = api.BatchSolver(1)
+    bs.set_trial_dataset(0, p, ds)
+    bs.build_and_solve()
+    ig, io = bs.info(0), orc.info(TrialInfo)
+    assert ig.status == 0 and ig.n_states == io.n_states
+    tg, xg = bs.states(0)
+    to, xo = orc.states()
+    assert np.array_equal(tg, to)
+    dq = np.abs(np.sum(xg[:, :4] * xo[:, :4], axis=1))
+    assert (2 * np.arccos(np.clip(dq, 0, 1))).max() < 1e-6
+    assert np.max(np.abs(xg[:, 4:] - xo[:, 4:])) < 1e-6
+    gg, go = bs.globals10(0), orc.globals10()
+    assert np.max(np.abs(gg[4:] - go[4:])) < 1e-6 and abs(abs(np.dot(gg[:4], go[:4])) - 1) < 1e-12
+    assert abs(ig.final_error - io.final_error) / io.final_error < 1e-8
+    # the vicon brackets at the converged time offset: same query times (one fp64 subtraction), same indices
+    tq = tg - gg[7]
+    a, b = bs.eval_interp(0, tq, 0.1), orc.eval_interp(tq, 0.1)
+    for k in ("idx0", "idx1", "ok"):
+        assert np.array_equal(a[k], b[k])
+    bs.close()
