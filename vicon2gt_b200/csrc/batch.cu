@@ -687,12 +687,12 @@ int v2gt_batch_upload(v2gt_batch *b) {
   V2_TRY(dev_alloc(b, &d.x, (size_t)2 * S * X_STRIDE));
   V2_TRY(dev_alloc(b, &d.glob, (size_t)2 * T * GLOB_STRIDE));
   V2_TRY(dev_alloc(b, &d.valid, (size_t)S));
-  V2_TRY(dev_alloc(b, &d.pre, (size_t)S * PRE_STRIDE));
-  V2_TRY(dev_alloc(b, &d.info, (size_t)S * INFO_STRIDE));
+  V2_TRY(dev_alloc(b, &d.pre, (size_t)soa_alloc(S, PRE_STRIDE)));
+  V2_TRY(dev_alloc(b, &d.info, (size_t)soa_alloc(S, INFO_STRIDE)));
   if (b->opt_keep_cov)
     V2_TRY(dev_alloc(b, &d.cov, (size_t)S * 225));
-  V2_TRY(dev_alloc(b, &d.fpi, (size_t)S * FPI_STRIDE));
-  V2_TRY(dev_alloc(b, &d.fpv, (size_t)S * FPV_STRIDE));
+  V2_TRY(dev_alloc(b, &d.fpi, (size_t)soa_alloc(S, FPI_STRIDE)));
+  V2_TRY(dev_alloc(b, &d.fpv, (size_t)soa_alloc(S, FPV_STRIDE)));
   V2_TRY(dev_alloc(b, &d.ne, (size_t)S * NE_STRIDE));
   V2_TRY(dev_alloc(b, &d.grad, (size_t)S * 16));
   V2_TRY(dev_alloc(b, &d.fac, (size_t)S * FAC_STRIDE));

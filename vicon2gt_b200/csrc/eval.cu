@@ -140,21 +140,24 @@ int v2gt_batch_get_preint(v2gt_batch *b, int32_t trial, int64_t capacity, double
     return V2GT_OK;
   if (capacity < m)
     return V2GT_ERR_INVALID_ARG;
-  // device layout is struct-of-arrays ([element][slot]): copy the trial's columns of every plane, then transpose
-  std::vector<double> pre((size_t)m * PRE_STRIDE), inf((size_t)m * INFO_STRIDE);
+  // device layout is the tiled struct-of-arrays (tiles of SOA_W slots, [element][slot] inside): copy the tiles that
+  // hold the trial's slots, then gather
   if (m) {
-    V2_CUDA_CHECK(cudaMemcpy2D(pre.data(), sizeof(double) * m, d.pre + td.st_off, sizeof(double) * d.S, sizeof(double) * m, PRE_STRIDE,
-                               cudaMemcpyDeviceToHost));
-    V2_CUDA_CHECK(cudaMemcpy2D(inf.data(), sizeof(double) * m, d.info + td.st_off, sizeof(double) * d.S, sizeof(double) * m,
-                               INFO_STRIDE, cudaMemcpyDeviceToHost));
-  }
-  for (int i = 0; i < m; i++) {
-    double *o = out + (size_t)i * V2GT_PREINT_DIM;
-    for (int e = 0; e < 63; e++)
-      o[e] = pre[(size_t)e * m + i]; // identical order for [0, 63)
-    for (int r = 0; r < 15; r++)
-      for (int c = 0; c < 15; c++)
-        o[63 + 15 * r + c] = inf[(size_t)((r >= c) ? tri(r, c) : tri(c, r)) * m + i];
+    const long long t0 = td.st_off / SOA_W, t1 = (td.st_off + m - 1) / SOA_W + 1; // tile range
+    std::vector<double> pre((size_t)(t1 - t0) * PRE_STRIDE * SOA_W), inf((size_t)(t1 - t0) * INFO_STRIDE * SOA_W);
+    V2_CUDA_CHECK(cudaMemcpy(pre.data(), d.pre + t0 * PRE_STRIDE * SOA_W, sizeof(double) * pre.size(), cudaMemcpyDeviceToHost));
+    V2_CUDA_CHECK(cudaMemcpy(inf.data(), d.info + t0 * INFO_STRIDE * SOA_W, sizeof(double) * inf.size(), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < m; i++) {
+      double *o = out + (size_t)i * V2GT_PREINT_DIM;
+      const long long s = td.st_off + i;
+      const double *pp = pre.data() + (soa_base(s, PRE_STRIDE) - t0 * PRE_STRIDE * SOA_W);
+      const double *ip = inf.data() + (soa_base(s, INFO_STRIDE) - t0 * INFO_STRIDE * SOA_W);
+      for (int e = 0; e < 63; e++)
+        o[e] = pp[(size_t)e * SOA_W]; // identical order for [0, 63)
+      for (int r = 0; r < 15; r++)
+        for (int c = 0; c < 15; c++)
+          o[63 + 15 * r + c] = ip[(size_t)((r >= c) ? tri(r, c) : tri(c, r)) * SOA_W];
+    }
   }
   return V2GT_OK;
 }

@@ -741,7 +741,7 @@ __global__ void __launch_bounds__(PRE_NT) k_preintegrate(DevPtrs d, int keep_cov
   }
 
   // ---- outputs
-  const SoaW pr{d.pre + s, d.S};
+  const SoaW pr = soa_w(d.pre, s, PRE_STRIDE);
   double q[4];
   rot_2_quat(c.R, q);
   pr[PRE_DT] = c.DT;
@@ -805,7 +805,7 @@ __global__ void __launch_bounds__(PRE_NT) k_preintegrate(DevPtrs d, int keep_cov
       Li[tri(r, cc)] = sacc / Lm[tri(r, r) * PRE_NT];
     }
   }
-  const SoaW inf{d.info + s, d.S};
+  const SoaW inf = soa_w(d.info, s, INFO_STRIDE);
   bool nan_found = false;
   for (int r = 0; r < 15; r++)
     for (int cc = 0; cc <= r; cc++) {

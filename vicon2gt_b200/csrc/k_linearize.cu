@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(V2GT_CHUNK, JAC ? FE_MIN_CTAS_JAC : FE_MIN_CTA
         r2 += vp.r[k] * vp.r[k];
       lin0 += 0.5 * r2;
       if (JAC) {
-        const SoaW o{d.fpv + s, d.S};
+        const SoaW o = soa_w(d.fpv, s, FPV_STRIDE);
 #pragma unroll
         for (int k = 0; k < 6; k++)
           o[FPV_R + k] = vp.r[k];
@@ -138,12 +138,12 @@ __global__ void __launch_bounds__(V2GT_CHUNK, JAC ? FE_MIN_CTAS_JAC : FE_MIN_CTA
       GravTerms G;
       grav_terms(gl[GL_THX], gl[GL_THY], tr.prm.gravity_magnitude, G);
       ImuPieces ip;
-      imu_factor<JAC>(SoaR{d.pre + s, d.S}, xi, xj, G, ip);
-      const double q = own ? 0.5 * quad_form15(SoaR{d.info + s, d.S}, ip.e) : 0.0;
+      imu_factor<JAC>(soa_r(d.pre, s, PRE_STRIDE), xi, xj, G, ip);
+      const double q = own ? 0.5 * quad_form15(soa_r(d.info, s, INFO_STRIDE), ip.e) : 0.0;
       cost += q;
       lin0 += q;
       if (JAC) {
-        const SoaW o{d.fpi + s, d.S};
+        const SoaW o = soa_w(d.fpi, s, FPI_STRIDE);
 #pragma unroll
         for (int k = 0; k < 15; k++)
           o[FPI_E + k] = ip.e[k];
@@ -349,12 +349,15 @@ __global__ void __launch_bounds__(ASM_THREADS, ASM_MIN_CTAS) k_assemble(DevPtrs 
     const bool v0 = (i0 + lane - 1 >= 0) && (i0 + lane - 1 < n);
     const bool v1 = (lane == 0) && (i0 + 31 < n);
     // asynchronous 8-byte copies: all of a thread's ~36 loads are in flight at once, no register staging
+    const double *i0p = d.info + soa_base(v0 ? sl0 + lane : 0, INFO_STRIDE), *i1p = d.info + soa_base(v1 ? sl0 + 32 : 0, INFO_STRIDE);
+    const double *f0p = d.fpi + soa_base(v0 ? sl0 + lane : 0, FPI_STRIDE), *f1p = d.fpi + soa_base(v1 ? sl0 + 32 : 0, FPI_STRIDE);
     for (int row = dcol; row < ASM_IN_ROWS; row += 5) {
-      const double *src = (row < INFO_STRIDE) ? d.info + (long long)row * d.S : d.fpi + (long long)(row - INFO_STRIDE) * d.S;
+      const bool is_info = row < INFO_STRIDE;
+      const int e = is_info ? row : row - INFO_STRIDE;
       if (v0)
-        cp_async8(s_in + row * ASM_IN_COLS + lane, src + sl0 + lane);
+        cp_async8(s_in + row * ASM_IN_COLS + lane, (is_info ? i0p : f0p) + e * SOA_W);
       if (v1)
-        cp_async8(s_in + row * ASM_IN_COLS + 32, src + sl0 + 32);
+        cp_async8(s_in + row * ASM_IN_COLS + 32, (is_info ? i1p : f1p) + e * SOA_W);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -362,7 +365,7 @@ __global__ void __launch_bounds__(ASM_THREADS, ASM_MIN_CTAS) k_assemble(DevPtrs 
   __syncthreads();
   const SoaS inf{s_in + li + 1, ASM_IN_COLS};
   const SoaS fpi{s_in + INFO_STRIDE * ASM_IN_COLS + li + 1, ASM_IN_COLS};
-  const SoaR pre{d.pre + s, d.S};
+  const SoaR pre = soa_r(d.pre, act ? s : tr.st_off, PRE_STRIDE);
 #pragma unroll
   for (int a = 0; a < 5; a++)
     zero9(Y[a]);
@@ -490,8 +493,8 @@ __global__ void __launch_bounds__(ASM_THREADS, ASM_MIN_CTAS) k_assemble(DevPtrs 
   // D is symmetric: the column strip this thread computes is written as the ROW strip 3 dcol .. 3 dcol + 2
   const SoaS infP{s_in + li, ASM_IN_COLS};
   const SoaS fpiP{s_in + INFO_STRIDE * ASM_IN_COLS + li, ASM_IN_COLS};
-  const SoaR preP{d.pre + (s - 1), d.S};
-  const SoaR fpv{d.fpv + s, d.S};
+  const SoaR preP = soa_r(d.pre, has_prev ? s - 1 : tr.st_off, PRE_STRIDE);
+  const SoaR fpv = soa_r(d.fpv, act ? s : tr.st_off, FPV_STRIDE);
   const bool vic_col = (dcol == 0 || dcol == 4);
   const int co = (dcol == 0) ? 0 : 3; // my columns inside the vicon A (theta | p)
   if (act) {
@@ -625,7 +628,7 @@ __global__ void __launch_bounds__(ASM_THREADS, ASM_MIN_CTAS) k_assemble(DevPtrs 
   if (dcol == 1 || dcol == 3) {
     if (dcol == 1) {
       if (i < n) {
-        const SoaR fpv{d.fpv + s, d.S};
+        const SoaR fpv = soa_r(d.fpv, s, FPV_STRIDE);
         int q = 0;
 #pragma unroll
         for (int r = 0; r < 7; r++) {

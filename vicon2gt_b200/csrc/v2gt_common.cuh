@@ -149,13 +149,20 @@ struct DevPtrs {
   double *c_pack_send, *c_pack_all;
 };
 
+// ---- tiled struct-of-arrays layout of the per-slot planes (pre, info, fpi, fpv): slots are grouped in tiles of
+// SOA_W = 32; inside a tile the layout is [element][slot], so the one-thread-per-state kernels read 256 contiguous
+// bytes per element and warp, and the E elements of a tile are ONE contiguous block of E x 256 bytes (an [element][S]
+// layout spread a warp's reads over E streams 30 MB apart: poor DRAM row locality, a multiply per access)
+constexpr int SOA_W = 32;
+__host__ __device__ inline long long soa_base(long long s, int E) { return (s / SOA_W) * ((long long)E * SOA_W) + (s % SOA_W); }
+__host__ __device__ inline long long soa_alloc(long long S, int E) { return ((S + SOA_W - 1) / SOA_W) * (long long)E * SOA_W; }
+
 #if defined(__CUDACC__)
-// struct-of-arrays views of one slot: element e lives at p[e * S]
+// views of one slot: element e lives at p[e * SOA_W]
 struct SoaR {
   const double *p;
-  long long S;
-  __device__ __forceinline__ SoaR operator+(int e) const { return SoaR{p + (long long)e * S, S}; }
-  __device__ __forceinline__ double operator[](int e) const { return __ldg(p + (long long)e * S); }
+  __device__ __forceinline__ SoaR operator+(int e) const { return SoaR{p + e * SOA_W}; }
+  __device__ __forceinline__ double operator[](int e) const { return __ldg(p + e * SOA_W); }
 };
 // the same view of a shared-memory tile ([element][column], column stride S): plain loads
 struct SoaS {
@@ -166,9 +173,10 @@ struct SoaS {
 };
 struct SoaW {
   double *p;
-  long long S;
-  __device__ __forceinline__ double &operator[](int e) const { return p[(long long)e * S]; }
+  __device__ __forceinline__ double &operator[](int e) const { return p[e * SOA_W]; }
 };
+__device__ __forceinline__ SoaR soa_r(const double *plane, long long s, int E) { return SoaR{plane + soa_base(s, E)}; }
+__device__ __forceinline__ SoaW soa_w(double *plane, long long s, int E) { return SoaW{plane + soa_base(s, E)}; }
 // 32-byte read-only load as two 16-byte __ldg (there is no __ldg overload for double4)
 __device__ __forceinline__ double4 ldg4(const double *p) {
   const double2 a = __ldg(reinterpret_cast<const double2 *>(p));
