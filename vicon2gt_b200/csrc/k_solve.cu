@@ -112,6 +112,19 @@ __device__ __forceinline__ double fast_rsqrt(const double x) {
   return fma(0.5 * r, e, r);
 }
 
+// predicated shared-memory stores (one STS under a predicate: no branch, and the lanes that do not hold the value
+// generate no shared-memory traffic -- the select-an-address form stored from all 32 lanes, ~4 wavefronts per store)
+__device__ __forceinline__ void sts_if(const bool p, double *dst, const double v) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.shared.f64 [%0], %1;\n\t}" ::"r"(sa), "d"(v), "r"((unsigned)p) : "memory");
+}
+__device__ __forceinline__ void sts2_if(const bool p, double *dst, const double v0, const double v1) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q st.shared.v2.f64 [%0], {%1, %2};\n\t}" ::"r"(sa), "d"(v0), "d"(v1),
+               "r"((unsigned)p)
+               : "memory");
+}
+
 // LDL^T of the 15x15 block held as the tiles d00 = D[gid][2tid+e], d10 = D[8+gid][2tid+e],
 // d11 = D[8+gid][8+2tid+e] together with the Gauss-Jordan inverse of its unit-lower factor; returns
 // L^-1 = D^-1/2 L'^-1 (L = Cholesky factor) in the same tile order.  cb: 64 + 64 doubles of shared memory
@@ -126,21 +139,20 @@ __device__ __forceinline__ bool ldl_inverse(double (&d00)[2], double (&d10)[2], 
   x11[0] = x00[0];
   x11[1] = x00[1];
   double p0 = 1.0, p1 = 1.0;
-  double *scratch = cb + 64 + 2 * (4 * gid + tid);
 #pragma unroll
   for (int j = 0; j < 15; j++) {
     double *buf = cb + 32 * (j & 1);
     // the holders publish column j of D (rows 0..15) and row j of X (columns 0..15)
     if (j < 8) {
       const bool hc = (tid == (j >> 1)), hr = (gid == j);
-      (hc ? buf + gid : scratch)[0] = d00[j & 1];
-      (hc ? buf + 8 + gid : scratch)[0] = d10[j & 1];
-      *reinterpret_cast<double2 *>(hr ? buf + 16 + 2 * tid : scratch) = make_double2(x00[0], x00[1]);
+      sts_if(hc, buf + gid, d00[j & 1]);
+      sts_if(hc, buf + 8 + gid, d10[j & 1]);
+      sts2_if(hr, buf + 16 + 2 * tid, x00[0], x00[1]);
     } else {
       const bool hc = (tid == ((j - 8) >> 1)), hr = (gid == j - 8);
-      (hc ? buf + 8 + gid : scratch)[0] = d11[j & 1];
-      *reinterpret_cast<double2 *>(hr ? buf + 16 + 2 * tid : scratch) = make_double2(x10[0], x10[1]);
-      *reinterpret_cast<double2 *>(hr ? buf + 24 + 2 * tid : scratch) = make_double2(x11[0], x11[1]);
+      sts_if(hc, buf + 8 + gid, d11[j & 1]);
+      sts2_if(hr, buf + 16 + 2 * tid, x10[0], x10[1]);
+      sts2_if(hr, buf + 24 + 2 * tid, x11[0], x11[1]);
     }
     __syncwarp();
     const double piv = buf[j];
