@@ -923,7 +923,7 @@ int v2gt_batch_optimize(v2gt_batch *b) {
       V2_CUDA_CHECK(cudaEventRecord(e[6], st));
       b->launches[1] += 3;
       b->launches[2] += 1;
-      b->launches[3] += l2_segments(d.P, d.l2_P) ? 8 : 2;
+      b->launches[3] += l2_segments(d.P, d.l2_P) ? 7 : 2;
       b->launches[4] += 1;
       b->launches[5] += 1;
       b->launches[6] += 2;
