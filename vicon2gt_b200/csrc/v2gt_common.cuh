@@ -11,14 +11,16 @@
 //   st_t    [S]        state times
 //   x       [2][S][16] JPLNavState rows (q4 bg3 v3 ba3 p3), double buffered (current / trial point)
 //   glob    [2][T][16] q_BtoI4 p_BinI3 t_off theta_x theta_y (+pad), double buffered
-//   pre     [64][S]    preintegration constants of interval slot s -> s+1 (PRE_* offsets below)
-//   info    [120][S]   P^-1 of that interval, packed lower triangle (row-major: r*(r+1)/2 + c)
-//   fpi     [64][S]    per-factor linearisation pieces of the IMU factor (FPI_* offsets)
-//   fpv     [88][S]    per-factor pieces of the vicon factor (FPV_* offsets)
-//                      (these four are struct-of-arrays: element e of slot s at [e * S + s], so the
-//                       one-thread-per-state kernels read and write them fully coalesced)
-//   ne      [S][600]   normal-equation record per state: D 15x15 (225) | M 15x25 = [O 15 (k,k+1) | B 9 | g 1]
+//   pre     [S/32][64][32]   preintegration constants of interval slot s -> s+1 (PRE_* offsets below)
+//   info    [S/32][120][32]  P^-1 of that interval, packed lower triangle (row-major: r*(r+1)/2 + c)
+//   fpi     [S/32][64][32]   per-factor linearisation pieces of the IMU factor (FPI_* offsets)
+//   fpv     [S/32][88][32]   per-factor pieces of the vicon factor (FPV_* offsets)
+//                      (these four are TILED struct-of-arrays, soa_base() below: element e of slot s at
+//                       [(s / 32) * E * 32 + e * 32 + s % 32], so the one-thread-per-state kernels read and write them
+//                       fully coalesced and a tile is one contiguous block)
+//   ne      [S][600]   normal-equation record per state: D 15x15 (225) | O 15x15 (225, coupling k,k+1) | BG 15x10 = [B 9 | g 1]
 //                      (one contiguous, 16-byte aligned record: streamed with cp.async by the elimination)
+//   grad    [S][16]    compact copy of g
 //   fac     [S][832]   elimination factors per state in mma-fragment order: L^-1 (3 8x8 tiles) | W (16x40)
 //   delta   [S][16]    LM step per state
 #pragma once
