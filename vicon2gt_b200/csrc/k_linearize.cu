@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(V2GT_CHUNK, JAC ? FE_MIN_CTAS_JAC : FE_MIN_CTA
       const bool cc = tr.vic_cov_const != 0;
       const double *vc = cc ? tr.vic_Rconst : d.vic_c + d.vic_c_off[t];
       // a halo slot queries a time no pose can bracket, which makes the factor empty (has = 0, zero blocks)
-      vicon_factor<JAC>(tr, d.vic_t + tr.vic_off, d.vic_s + 8 * tr.vic_off, vc, cc, own ? d.st_t[s] : -1.0e300, xi, gl, vp);
+      // d.valid (scratch flags of the build stage) holds every state's last bracket between evaluations
+      vicon_factor<JAC>(tr, d.vic_t + tr.vic_off, d.vic_s + 8 * tr.vic_off, vc, cc, own ? d.st_t[s] : -1.0e300, xi, gl, vp, d.valid + s);
       cost += huber_loss(tr.prm.huber_k, vp.dist);
       double r2 = 0;
 #pragma unroll

@@ -111,7 +111,7 @@ struct DevPtrs {
   const long long *vic_c_off; // [T] offset into vic_c (or -1)
   double *st_t, *st_t_tmp;
   double *x, *glob;  // double buffered
-  int *valid;        // [S] scratch flags of the build stage
+  int *valid;        // [S] scratch flags of the build stage; afterwards the last vicon bracket of every state (a search hint)
   double *pre, *info, *cov;
   double *fpi, *fpv;
   double *ne;        // [S][NE_STRIDE]

@@ -175,9 +175,13 @@ struct ViconPieces {
 template <bool JAC>
 __device__ inline void vicon_factor(const TrialDev &tr, const double *__restrict__ vt, const double *__restrict__ vs,
                                     const double *__restrict__ vc, bool cov_const, double t, const double *x, const double *gl,
-                                    ViconPieces &o) {
+                                    ViconPieces &o, int *bracket_hint = nullptr) {
   InterpResult ir;
-  vicon_interp(vt, vs, vc, cov_const, tr.n_vic, t - gl[GL_TOFF], tr.prm.interp_gap_factor, true, ir);
+  // the state's bracket at its previous evaluation is the guess for this one (lower bound = idx0 + 1)
+  vicon_interp(vt, vs, vc, cov_const, tr.n_vic, t - gl[GL_TOFF], tr.prm.interp_gap_factor, true, ir,
+               bracket_hint ? (long long)*bracket_hint : -1);
+  if (bracket_hint && ir.idx0 >= 0)
+    *bracket_hint = ir.idx0 + 1;
   o.has = ir.ok;
   o.idx0 = ir.idx0;
   o.idx1 = ir.idx1;

@@ -44,11 +44,36 @@ __device__ __forceinline__ long long upper_bound_d(const double *__restrict__ t,
   return lo;
 }
 
+// lower_bound with a guess `h` of the answer (the bracket of the same state at its previous evaluation: the query time
+// t - t_off moves by less than a vicon period between evaluations once the optimiser has settled).  Checks h, then
+// h -+ 1, with two / three loads instead of the ~15 dependent ones of the bisection; any other case falls back to it.
+// The result is the bisection's, always.
+__device__ __forceinline__ long long lower_bound_hint(const double *__restrict__ t, long long n, double tq, long long h) {
+  if (h >= 1 && h < n) {
+    const double a = __ldg(t + h - 1), b = __ldg(t + h);
+    if (a < tq) {
+      if (!(b < tq))
+        return h; // t[h-1] < tq <= t[h]
+      if (h + 1 == n)
+        return n;
+      if (!(__ldg(t + h + 1) < tq))
+        return h + 1;
+    } else {
+      if (h == 1)
+        return 0; // !(t[0] < tq)
+      if (__ldg(t + h - 2) < tq)
+        return h - 1;
+    }
+  }
+  return lower_bound_d(t, n, tq);
+}
+
 // Interpolator.cpp:175-207 / :63-95.  Returns 0 ok, 1 "lo == begin", 2 "lo == end or hi == end".
-__device__ __forceinline__ int vicon_bracket(const double *__restrict__ vt, long long n, double tq, int &idx0, int &idx1) {
+__device__ __forceinline__ int vicon_bracket(const double *__restrict__ vt, long long n, double tq, int &idx0, int &idx1,
+                                             long long hint = -1) {
   idx0 = -1;
   idx1 = -1;
-  const long long lo = lower_bound_d(vt, n, tq);
+  const long long lo = lower_bound_hint(vt, n, tq, hint);
   if (lo == 0)
     return 1;
   if (lo == n)
@@ -65,7 +90,8 @@ __device__ __forceinline__ int vicon_bracket(const double *__restrict__ vt, long
 // Interpolator.cpp:239-287 (and :127-169).  vs: pose rows [V][8] (q4 p3 pad); cov: [V][18] or the
 // trial-constant 18 doubles.
 __device__ inline void vicon_interp(const double *__restrict__ vt, const double *__restrict__ vs, const double *__restrict__ vc,
-                                    bool cov_const, long long n, double tq, double thresh, bool with_jac, InterpResult &o) {
+                                    bool cov_const, long long n, double tq, double thresh, bool with_jac, InterpResult &o,
+                                    long long hint = -1) {
   o.ok = 0;
   o.written = 1;
   o.lambda = 0;
@@ -78,7 +104,7 @@ __device__ inline void vicon_interp(const double *__restrict__ vt, const double 
 #pragma unroll
   for (int i = 0; i < 6; i++)
     o.Ht[i] = 0;
-  const int br = vicon_bracket(vt, n, tq, o.idx0, o.idx1);
+  const int br = vicon_bracket(vt, n, tq, o.idx0, o.idx1, hint);
   if (br != 0)
     return;
   const double t0 = __ldg(vt + o.idx0), t1 = __ldg(vt + o.idx1);
