@@ -221,22 +221,23 @@ void make_dirs_for(const std::string &path) {
 }
 
 // run f(t) for t in [0, T) on a few host threads (static interleaved partition)
-template <typename F> void parallel_trials(int T, F f) {
-  const int nthr = std::max(1, std::min({T, (int)std::thread::hardware_concurrency(), 16}));
-  if (nthr == 1) {
-    for (int t = 0; t < T; t++)
+template <typename F> void parallel_trials(int t0, int t1, F f) {
+  const int nthr = std::max(1, std::min({t1 - t0, (int)std::thread::hardware_concurrency(), 16}));
+  if (nthr <= 1) {
+    for (int t = t0; t < t1; t++)
       f(t);
     return;
   }
   std::vector<std::thread> th;
   for (int k = 0; k < nthr; k++)
     th.emplace_back([=]() {
-      for (int t = k; t < T; t += nthr)
+      for (int t = t0 + k; t < t1; t += nthr)
         f(t);
     });
   for (auto &x : th)
     x.join();
 }
+template <typename F> void parallel_trials(int T, F f) { parallel_trials(0, T, f); }
 
 } // namespace
 
@@ -625,8 +626,9 @@ int v2gt_batch_upload(v2gt_batch *b) {
         coff += td[t].n_vic;
     }
   }
-  // pass 2 (parallel over trials): caller layout -> device layout, written straight into the pinned buffers
-  parallel_trials(T, [&](int t) {
+  // pass 2 (parallel over trials, run below in chunks that overlap with the H2D copies of the chunk before): caller
+  // layout -> device layout, written straight into the pinned buffers
+  auto fill_trial = [&](int t) {
     const HostTrial &h = b->trials[t];
     const TrialDev &q = td[t];
     if (q.n_imu) {
@@ -669,7 +671,7 @@ int v2gt_batch_upload(v2gt_batch *b) {
       h_trial_of[q.st_off + i] = t;
     }
     h_nst[t] = (int)q.n_raw;
-  });
+  };
   double *p_imu_t, *p_imu_s, *p_vic_t, *p_vic_s, *p_vic_c;
   long long *p_coff;
   TrialDev *p_trials;
@@ -750,15 +752,42 @@ int v2gt_batch_upload(v2gt_batch *b) {
   d.vic_c = p_vic_c;
   d.vic_c_off = p_coff;
   cudaStream_t st = b->stream;
-  V2_CUDA_CHECK(cudaMemcpyAsync(p_imu_t, h_imu_t, sizeof(double) * M, cudaMemcpyHostToDevice, st));
-  V2_CUDA_CHECK(cudaMemcpyAsync(p_imu_s, h_imu_s, sizeof(double) * 8 * M, cudaMemcpyHostToDevice, st));
-  V2_CUDA_CHECK(cudaMemcpyAsync(p_vic_t, h_vic_t, sizeof(double) * V, cudaMemcpyHostToDevice, st));
-  V2_CUDA_CHECK(cudaMemcpyAsync(p_vic_s, h_vic_s, sizeof(double) * 8 * V, cudaMemcpyHostToDevice, st));
-  if (C)
-    V2_CUDA_CHECK(cudaMemcpyAsync(p_vic_c, h_vic_c, sizeof(double) * 18 * C, cudaMemcpyHostToDevice, st));
+  {
+    // chunks of consecutive trials: the pinned fill of chunk k+1 runs while chunk k's ranges (contiguous per array) are
+    // on their way to the device
+    const int nch = std::max(1, std::min(T, 6));
+    for (int ch = 0; ch < nch; ch++) {
+      const int t0 = (int)((long long)T * ch / nch), t1 = (int)((long long)T * (ch + 1) / nch);
+      if (t1 <= t0)
+        continue;
+      parallel_trials(t0, t1, fill_trial);
+      const TrialDev &a = td[t0], &z = td[t1 - 1];
+      const long long m0 = a.imu_off, m1 = z.imu_off + z.n_imu, v0 = a.vic_off, v1 = z.vic_off + z.n_vic;
+      const long long s0 = a.st_off, s1 = z.st_off + z.n_raw;
+      if (m1 > m0) {
+        V2_CUDA_CHECK(cudaMemcpyAsync(p_imu_t + m0, h_imu_t + m0, sizeof(double) * (m1 - m0), cudaMemcpyHostToDevice, st));
+        V2_CUDA_CHECK(cudaMemcpyAsync(p_imu_s + 8 * m0, h_imu_s + 8 * m0, sizeof(double) * 8 * (m1 - m0), cudaMemcpyHostToDevice, st));
+      }
+      if (v1 > v0) {
+        V2_CUDA_CHECK(cudaMemcpyAsync(p_vic_t + v0, h_vic_t + v0, sizeof(double) * (v1 - v0), cudaMemcpyHostToDevice, st));
+        V2_CUDA_CHECK(cudaMemcpyAsync(p_vic_s + 8 * v0, h_vic_s + 8 * v0, sizeof(double) * 8 * (v1 - v0), cudaMemcpyHostToDevice, st));
+      }
+      long long c0 = -1, c1 = -1; // range of the per-pose covariances of this chunk (doubles)
+      for (int t = t0; t < t1; t++)
+        if (h_coff[t] >= 0) {
+          if (c0 < 0)
+            c0 = h_coff[t];
+          c1 = h_coff[t] + 18 * td[t].n_vic;
+        }
+      if (c1 > c0 && c0 >= 0)
+        V2_CUDA_CHECK(cudaMemcpyAsync(p_vic_c + c0, h_vic_c + c0, sizeof(double) * (c1 - c0), cudaMemcpyHostToDevice, st));
+      if (s1 > s0) {
+        V2_CUDA_CHECK(cudaMemcpyAsync(d.st_t + s0, h_st_t + s0, sizeof(double) * (s1 - s0), cudaMemcpyHostToDevice, st));
+        V2_CUDA_CHECK(cudaMemcpyAsync(d.trial_of + s0, h_trial_of + s0, sizeof(int) * (s1 - s0), cudaMemcpyHostToDevice, st));
+      }
+    }
+  }
   V2_CUDA_CHECK(cudaMemcpyAsync(p_coff, h_coff, sizeof(long long) * T, cudaMemcpyHostToDevice, st));
-  V2_CUDA_CHECK(cudaMemcpyAsync(d.st_t, h_st_t, sizeof(double) * S, cudaMemcpyHostToDevice, st));
-  V2_CUDA_CHECK(cudaMemcpyAsync(d.trial_of, h_trial_of, sizeof(int) * S, cudaMemcpyHostToDevice, st));
   V2_CUDA_CHECK(cudaMemcpyAsync(d.n_states, h_nst, sizeof(int) * T, cudaMemcpyHostToDevice, st));
   V2_CUDA_CHECK(cudaMemcpyAsync(p_trials, td.data(), sizeof(TrialDev) * T, cudaMemcpyHostToDevice, st));
   V2_CUDA_CHECK(cudaMemcpyAsync(d.lm, lm.data(), sizeof(LmState) * T, cudaMemcpyHostToDevice, st));
