@@ -203,6 +203,12 @@ int v2gt_eval_cost(v2gt_batch *b, int32_t trial, double *cost);
 /* LM trace of the last optimise call: rows [lambda, cost_before, cost_after, lin_cost_change, accepted]. */
 int v2gt_batch_get_lm_trace(v2gt_batch *b, int32_t trial, int64_t capacity, double *rows, int64_t *n_out);
 
+/* Evaluation-only (host logic, works without a device): the chain cut the optimiser picks for trials of n_states
+ * states when n_running trials are still being optimised -- segments per trial at level 1 (close to target_warps /
+ * n_running, at most 4 sqrt(n), at least 32 states long, filling whole waves of the sm_count x resident-CTA slots) and
+ * at level 2 (segments of the separator chain; 0 = the separator chain is walked directly). */
+int v2gt_plan_segments(int32_t n_states, int32_t n_running, int32_t target_warps, int32_t sm_count, int32_t *p_level1, int32_t *p_level2);
+
 /* ---- chain-sharded solve of ONE long sequence across ranks (BASELINE config 5) ----
  * Every rank creates a 1-trial batch holding a contiguous piece of the cleaned state chain plus one halo state on
  * each inner side, and drives the Levenberg-Marquardt rounds phase by phase; between the phases the caller moves the

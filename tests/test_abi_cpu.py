@@ -101,3 +101,32 @@ def test_cpp_host_mirror_compiles_and_fails_loudly_without_a_device():
     r = subprocess.run([exe, "--duration", "3"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
     assert r.returncode != 0
     assert "no CUDA device" in r.stderr and "status 9" in r.stderr
+
+
+def test_segment_plan_host_logic():
+    """The optimiser's chain cut (host logic, no device): bounded by 4 sqrt(n) and by 32-state segments, whole waves of the
+    148 x 3 resident elimination CTAs (4 warps each) when the batch is large, nested level 2 from 24 segments on."""
+    import ctypes as C
+
+    from vicon2gt_b200 import api
+
+    L = api.load_library()
+    L.v2gt_plan_segments.argtypes = [C.c_int32] * 4 + [C.POINTER(C.c_int32)] * 2
+
+    def plan(n, running, target=148 * 64, sms=148):
+        p1, p2 = C.c_int32(), C.c_int32()
+        assert L.v2gt_plan_segments(n, running, target, sms, C.byref(p1), C.byref(p2)) == 0
+        return p1.value, p2.value
+
+    # the 128-trial shard: ~9472 / 128 = 74 segments wanted; 68 (17 CTAs per trial) fills 4.9 of 5 waves, 74 would fill 5.5 of 6
+    p1, p2 = plan(29802, 128)
+    ctas = 128 * ((p1 + 3) // 4)
+    waves = ctas / (148 * 3)
+    assert 56 <= p1 <= 92 and waves / np.ceil(waves) > 0.95 and 2 <= p2 <= 12
+    # a single trajectory is cut as fine as allowed: 4 sqrt(n), never below 32 states per segment
+    p1, p2 = plan(29802, 1)
+    assert p1 == 4 * int(np.ceil(np.sqrt(29802))) and 29802 // p1 >= 32 and p2 >= 20
+    p1, p2 = plan(477, 1)
+    assert p1 == 477 // 32 and p2 == 0  # short chain: few segments, separator chain walked directly
+    assert plan(40, 1)[0] == 1
+    assert L.v2gt_plan_segments(0, 1, 1, 1, None, None) != 0

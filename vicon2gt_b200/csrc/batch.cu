@@ -892,6 +892,20 @@ static int choose_segments(int target_warps, int n_running, int p_max, int sm_co
   return std::max(1, best_p);
 }
 
+// evaluation-only: the segment geometry the optimiser would pick (host logic, no device needed)
+int v2gt_plan_segments(int32_t n_states, int32_t n_running, int32_t target_warps, int32_t sm_count, int32_t *p_level1, int32_t *p_level2) {
+  if (n_states < 1 || n_running < 1 || target_warps < 1 || sm_count < 1 || !p_level1 || !p_level2)
+    return V2GT_ERR_INVALID_ARG;
+  int pmax = std::max(1, 4 * (int)std::ceil(std::sqrt((double)n_states)));
+  pmax = std::min(pmax, std::max(1, n_states / 32));
+  pmax = std::max(1, std::min(pmax, std::max(1, n_states / 2)));
+  const int P = choose_segments(target_warps, n_running, pmax, sm_count);
+  const int l2max = std::max(2, (int)std::ceil(std::sqrt((double)pmax)) + 1);
+  *p_level1 = P;
+  *p_level2 = l2_segments(P, l2max);
+  return V2GT_OK;
+}
+
 int v2gt_batch_optimize(v2gt_batch *b) {
   if (!b)
     return V2GT_ERR_INVALID_ARG;
