@@ -129,4 +129,5 @@ def test_segment_plan_host_logic():
     p1, p2 = plan(477, 1)
     assert p1 == 477 // 32 and p2 == 0  # short chain: few segments, separator chain walked directly
     assert plan(40, 1)[0] == 1
+    assert plan(29802, 20000)[0] == 1 and plan(29802, 4000)[0] == 3  # huge batches: whole chains / a few segments per trial
     assert L.v2gt_plan_segments(0, 1, 1, 1, None, None) != 0

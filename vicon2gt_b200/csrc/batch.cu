@@ -875,6 +875,8 @@ static int choose_segments(int target_warps, int n_running, int p_max, int sm_co
   const int wpc = elim_warps_per_cta();
   const double slots = (double)std::max(1, sm_count) * elim_ctas_per_sm();
   const int base = std::max(1, (target_warps + n_running - 1) / n_running);
+  if (base <= wpc) // very large batches: one CTA per trial is already more than enough warps; do not cut finer than asked
+    return std::max(1, std::min(p_max, base));
   const int k0 = std::max(1, (int)(0.75 * base) / wpc), k1 = std::max(k0, (int)(1.25 * base + wpc - 1) / wpc);
   int best_p = std::max(1, std::min(p_max, base));
   double best_eff = -1.0;
