@@ -16,6 +16,9 @@
 //                       complement onto the 9 globals, the 9x9 solve, back-substitution of the separators,
 //                       retract of the globals
 //   k_seg_backsub       back-substitution through the segment interiors (writes the step delta)
+// Nested level 2 (launch_reduced): for P >= 24 the separator chain -- records red_ne, same format as ne -- is itself
+// cut into ~sqrt(P) segments and run through k_seg_eliminate / k_reduced_assemble / k_reduced / k_seg_backsub with a
+// derived pointer set (k_l2_prepare, k_sep_delta are the glue), so that one warp only walks ~sqrt(P) separators.
 // Every trial and every segment takes the same arithmetic path in the same order: results are
 // deterministic run to run.
 #include "v2gt_common.cuh"
@@ -36,8 +39,8 @@ __host__ __device__ inline SegGeom seg_geom(int n, int P) {
 }
 
 // ---- per-warp shared memory (doubles): two staged normal-equation records + the broadcast buffers of the
-// factorisation (column of D [16] + row of X [16], double buffered, + 64 doubles of per-lane store scratch)
-constexpr int SW_STAGE = 0, SW_CB = 2 * NE_STRIDE, SW_TOTAL = 2 * NE_STRIDE + 128;
+// factorisation (column of D [16] + row of X [16], double buffered)
+constexpr int SW_STAGE = 0, SW_CB = 2 * NE_STRIDE, SW_TOTAL = 2 * NE_STRIDE + 64;
 #ifndef ELIM_WARPS_N
 #define ELIM_WARPS_N 4
 #endif
@@ -127,9 +130,8 @@ __device__ __forceinline__ void sts2_if(const bool p, double *dst, const double 
 
 // LDL^T of the 15x15 block held as the tiles d00 = D[gid][2tid+e], d10 = D[8+gid][2tid+e],
 // d11 = D[8+gid][8+2tid+e] together with the Gauss-Jordan inverse of its unit-lower factor; returns
-// L^-1 = D^-1/2 L'^-1 (L = Cholesky factor) in the same tile order.  cb: 64 + 64 doubles of shared memory
-// (two broadcast buffers, then one 16-byte scratch slot per lane that absorbs the non-holders' stores so that
-// publishing a column is branch-free).
+// L^-1 = D^-1/2 L'^-1 (L = Cholesky factor) in the same tile order.  cb: 64 doubles of shared memory (two broadcast
+// buffers); the holders of a column / row publish it with predicated stores.
 __device__ __forceinline__ bool ldl_inverse(double (&d00)[2], double (&d10)[2], double (&d11)[2], double (&li00)[2],
                                             double (&li10)[2], double (&li11)[2], double *cb, const int gid, const int tid) {
   double x00[2], x10[2], x11[2];
