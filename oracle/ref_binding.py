@@ -1,0 +1,214 @@
+"""ORACLE (test infrastructure, NOT product code).
+
+ctypes binding of oracle/_ref/libv2gt_ref.so: the reference's OWN sources for the factor-level
+part of the path (src/utils/quat_ops.h, rpy_ops.h, src/cpi/CpiV1.h, src/meas/Propagator.cpp,
+Interpolator.cpp, src/gtsam/ImuFactorCPIv1.cpp, MeasBased_ViconPoseTimeoffsetFactor.cpp,
+JPLNavState.cpp, JPLQuaternion.cpp, RotationXY.cpp) compiled where they lie under
+/root/reference by oracle/Makefile.ref against the interface stand-ins of oracle/shim/.
+Used by tests/test_ref_pin_cpu.py and tools/make_ref_golden.py only.
+
+available() is False where neither the prebuilt library nor /root/reference exists (then the
+committed tests/golden/ref_pin.npz carries the reference's outputs).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_ref", "libv2gt_ref.so")
+REFERENCE_ROOT = os.environ.get("V2GT_REFERENCE_ROOT", "/root/reference")
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+PREINT_DIM = 288
+_lib = None
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(c_double_p)
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(c_int32_p)
+
+
+def _c(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def can_build():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "cpi"))
+
+
+def build():
+    """Compile the reference sources (only where /root/reference exists)."""
+    if not can_build():
+        raise RuntimeError("reference sources not present at %s" % REFERENCE_ROOT)
+    subprocess.check_call(["make", "-s", "-C", _HERE, "-f", "Makefile.ref", "REF=" + REFERENCE_ROOT])
+
+
+def available():
+    return os.path.exists(_LIB_PATH) or can_build()
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if can_build():
+        build()  # make is a no-op when the library is current
+    L = C.CDLL(_LIB_PATH)
+    for n in ("ref_rot_2_quat", "ref_quat_2_Rot", "ref_exp_so3", "ref_log_so3", "ref_Jl_so3", "ref_rot2rpy"):
+        getattr(L, n).argtypes = [c_double_p, c_double_p]
+    L.ref_quat_multiply.argtypes = [c_double_p, c_double_p, c_double_p]
+    L.ref_propagate.argtypes = [c_double_p, C.c_int64, c_double_p, c_double_p, c_double_p, C.c_double, C.c_double, c_double_p,
+                                c_double_p, c_double_p, c_double_p]
+    L.ref_has_bounding_imu.argtypes = [C.c_int64, c_double_p, C.c_int64, c_double_p, c_int32_p]
+    L.ref_interp_create.restype = C.c_void_p
+    L.ref_interp_create.argtypes = [C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, C.c_int]
+    L.ref_interp_destroy.argtypes = [C.c_void_p]
+    L.ref_interp_size.restype = C.c_int64
+    L.ref_interp_size.argtypes = [C.c_void_p]
+    L.ref_eval_interp.argtypes = [C.c_void_p, C.c_int64, c_double_p, C.c_int, c_int32_p, c_int32_p, c_int32_p, c_double_p,
+                                  c_double_p, c_double_p, c_double_p]
+    L.ref_eval_imu_factor.argtypes = [c_double_p, C.c_double, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
+                                      c_double_p, c_double_p]
+    L.ref_eval_vicon_factor.argtypes = [C.c_void_p, c_int32_p, C.c_double, c_double_p, c_double_p, c_double_p, c_double_p,
+                                        c_double_p, c_double_p, c_double_p]
+    L.ref_retract_state.argtypes = [c_double_p, c_double_p, c_double_p]
+    L.ref_local_state.argtypes = [c_double_p, c_double_p, c_double_p]
+    L.ref_retract_quat.argtypes = [c_double_p, c_double_p, c_double_p]
+    L.ref_retract_rotxy.argtypes = [c_double_p, c_double_p, c_double_p]
+    L.ref_rotxy_rot.argtypes = [c_double_p, c_double_p]
+    _lib = L
+    return L
+
+
+def _unary(name, x, shape):
+    a, out = _c(x), np.zeros(shape)
+    getattr(lib(), name)(_d(a), _d(out))
+    return out
+
+
+def rot_2_quat(R):
+    return _unary("ref_rot_2_quat", R, 4)
+
+
+def quat_2_Rot(q):
+    return _unary("ref_quat_2_Rot", q, (3, 3))
+
+
+def exp_so3(w):
+    return _unary("ref_exp_so3", w, (3, 3))
+
+
+def log_so3(R):
+    return _unary("ref_log_so3", R, 3)
+
+
+def Jl_so3(w):
+    return _unary("ref_Jl_so3", w, (3, 3))
+
+
+def rot2rpy(R):
+    return _unary("ref_rot2rpy", R, 3)
+
+
+def rotxy_rot(th):
+    return _unary("ref_rotxy_rot", th, (3, 3))
+
+
+def quat_multiply(q, p):
+    a, b, out = _c(q), _c(p), np.zeros(4)
+    lib().ref_quat_multiply(_d(a), _d(b), _d(out))
+    return out
+
+
+def propagate(sigmas, imu_t, imu_w, imu_a, time0, time1, bg_lin=(0, 0, 0), ba_lin=(0, 0, 0)):
+    """Propagator::propagate + CpiV1 -> (preint row[288] without the information matrix, P[15,15]) or None."""
+    s, t, w, a = _c(sigmas), _c(imu_t), _c(imu_w), _c(imu_a)
+    bg, ba = _c(bg_lin), _c(ba_lin)
+    out, cov = np.zeros(PREINT_DIM), np.zeros((15, 15))
+    ok = lib().ref_propagate(_d(s), len(t), _d(t), _d(w), _d(a), float(time0), float(time1), _d(bg), _d(ba), _d(out), _d(cov))
+    return (out, cov) if ok else None
+
+
+def has_bounding_imu(imu_t, t_query):
+    t, q = _c(imu_t), _c(t_query)
+    out = np.zeros(len(q), dtype=np.int32)
+    lib().ref_has_bounding_imu(len(t), _d(t), len(q), _d(q), _i(out))
+    return out
+
+
+class RefInterpolator:
+    """The reference's Interpolator fed pose by pose (any order, duplicates allowed: std::set semantics)."""
+
+    def __init__(self, vic_t, vic_q, vic_p, Rq, Rp):
+        t, q, p, rq, rp = _c(vic_t), _c(vic_q), _c(vic_p), _c(Rq), _c(Rp)
+        per_pose = 1 if rq.size == 9 * len(t) and len(t) != 1 else 0
+        self._L = lib()
+        self.h = self._L.ref_interp_create(len(t), _d(t), _d(q), _d(p), _d(rq), _d(rp), per_pose)
+
+    def close(self):
+        if self.h:
+            self._L.ref_interp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def size(self):
+        return int(self._L.ref_interp_size(self.h))
+
+    def eval(self, t_query, with_jacobian=True):
+        t = _c(t_query)
+        n = len(t)
+        i0, i1, ok = (np.zeros(n, dtype=np.int32) for _ in range(3))
+        q, p, R, H = np.zeros((n, 4)), np.zeros((n, 3)), np.zeros((n, 36)), np.zeros((n, 6))
+        self._L.ref_eval_interp(self.h, n, _d(t), 1 if with_jacobian else 0, _i(i0), _i(i1), _i(ok), _d(q), _d(p), _d(R), _d(H))
+        return dict(idx0=i0, idx1=i1, ok=ok, q=q, p=p, R=R, H_toff=H)
+
+    def eval_vicon_factor(self, t, x16, globals10, estimate=(1, 1, 1)):
+        """estimate = (toff, ori, pos) flags of GtsamConfig."""
+        x, g = _c(x16), _c(globals10)
+        fl = np.asarray(estimate, dtype=np.int32)
+        e, H1, H2, H3, H4 = np.zeros(6), np.zeros((6, 15)), np.zeros((6, 3)), np.zeros((6, 3)), np.zeros(6)
+        self._L.ref_eval_vicon_factor(self.h, _i(fl), float(t), _d(x), _d(g), _d(e), _d(H1), _d(H2), _d(H3), _d(H4))
+        return dict(e=e, H1=H1, H2=H2, H3=H3, H4=H4)
+
+
+def eval_imu_factor(preint_row, grav_mag, xi, xj, thetaxy):
+    pr, a, b, th = _c(preint_row), _c(xi), _c(xj), _c(thetaxy)
+    e, H1, H2, H3 = np.zeros(15), np.zeros((15, 15)), np.zeros((15, 15)), np.zeros((15, 2))
+    lib().ref_eval_imu_factor(_d(pr), float(grav_mag), _d(a), _d(b), _d(th), _d(e), _d(H1), _d(H2), _d(H3))
+    return dict(e=e, H1=H1, H2=H2, H3=H3)
+
+
+def retract_state(x16, xi15):
+    x, xi, out = _c(x16), _c(xi15), np.zeros(16)
+    lib().ref_retract_state(_d(x), _d(xi), _d(out))
+    return out
+
+
+def local_state(x16, y16):
+    x, y, out = _c(x16), _c(y16), np.zeros(15)
+    lib().ref_local_state(_d(x), _d(y), _d(out))
+    return out
+
+
+def retract_quat(q4, d3):
+    a, b, out = _c(q4), _c(d3), np.zeros(4)
+    lib().ref_retract_quat(_d(a), _d(b), _d(out))
+    return out
+
+
+def retract_rotxy(th, d):
+    a, b, out = _c(th), _c(d), np.zeros(2)
+    lib().ref_retract_rotxy(_d(a), _d(b), _d(out))
+    return out

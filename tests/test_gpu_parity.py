@@ -600,3 +600,106 @@ def test_baseline_configs_full_size_vs_oracle(name):
     for k in ("idx0", "idx1", "ok"):
         assert np.array_equal(a[k], b[k])
     bs.close()
+
+
+# --------------------------------------------------------------------------------------------------
+# The CUDA path against the REFERENCE'S OWN CODE: tests/golden/ref_pin.npz holds outputs of the reference's sources
+# (CpiV1, Propagator, Interpolator, both factors) compiled where they lie under /root/reference (oracle/Makefile.ref,
+# tools/make_ref_golden.py).  No oracle call on the compared side of these tests.
+def _ref_pin():
+    from conftest import load_golden
+
+    return load_golden("ref_pin")
+
+
+def test_cuda_interpolation_against_reference_code():
+    """Vicon store fed out of order with repeated stamps and per-pose covariances, a 0.3 s and a 6 s dropout: bracket
+    indices and ok flags bit-exact against Interpolator::get_bounds / get_pose / get_pose_with_jacobian."""
+    from vicon2gt_b200 import api
+
+    G = _ref_pin()
+    t = G["in_t"]
+    imu_t = np.arange(t.min() - 0.5, t.max() + 0.5, 0.01)
+    imu_w = np.zeros((len(imu_t), 3))
+    imu_a = np.tile([0.0, 0.0, 9.81], (len(imu_t), 1))
+    st = t.min() + 0.5 + 0.05 * np.arange(20)
+    bs = api.BatchSolver(1)
+    bs.set_trial(0, default_params(), imu_t, imu_w, imu_a, t, G["in_q"], G["in_p"], st, vic_Rq=G["in_Rq"], vic_Rp=G["in_Rp"])
+    bs.upload()
+    tq = G["in_query"]
+    for gap, pre in ((0.1, "inj_"), (5.0, "inp_")):
+        b = bs.eval_interp(0, tq, gap)
+        ok = G[pre + "ok"]
+        assert np.array_equal(b["ok"], ok)
+        m = ok == 1
+        assert 100 < m.sum() < len(ok)
+        if pre == "inj_":
+            has = G["inj_idx0"] >= 0
+            assert np.array_equal(b["idx0"][has], G["inj_idx0"][has])  # bit-exact
+            assert np.array_equal(b["idx1"][has], G["inj_idx1"][has])
+            assert _relmax(b["H_toff"][m], G["inj_H_toff"][m]) < 1e-11
+        assert np.max(np.abs(b["q"][m] - G[pre + "q"][m])) < 1e-13
+        assert np.max(np.abs(b["p"][m] - G[pre + "p"][m])) < 1e-12
+        assert _relmax(b["R"][m], G[pre + "R"][m]) < 1e-12
+    bs.close()
+
+
+def test_cuda_preintegration_against_reference_code():
+    """Propagator::propagate + CpiV1::feed_IMU over an IMU store with irregular stamps, a repeated stamp and a
+    small-angular-rate stretch: one two-state trial per interval (zero bias linearisation points), all in one batch."""
+    from vicon2gt_b200 import api
+
+    G = _ref_pin()
+    t, w, a = G["pr_imu_t"], G["pr_imu_w"], G["pr_imu_a"]
+    # zero bias linearisation points (the initial guess), both states inside the IMU store (a state without bounding
+    # IMU is erased by the solver before any preintegration, ViconGraphSolver.cpp:118-136)
+    cases = [k for k, c in enumerate(G["pr_cases"]) if G["pr_ok"][k] and not np.any(c[2:8]) and c[0] >= t[0] and c[1] <= t[-1]]
+    assert len(cases) >= 6
+    vt = np.arange(t.min() - 1.0, t.max() + 1.0, 0.01)
+    vq = np.tile([0.0, 0.0, 0.0, 1.0], (len(vt), 1))
+    vp = np.zeros((len(vt), 3))
+    Rc = np.concatenate([np.eye(3).reshape(-1) * 1e-6, np.eye(3).reshape(-1) * 1e-4])
+    bs = api.BatchSolver(len(cases), keep_cov=1)
+    for i, k in enumerate(cases):
+        c = G["pr_cases"][k]
+        bs.set_trial(i, default_params(), t, w, a, vt, vq, vp, np.array([c[0], c[1]]), vic_R_const=Rc)
+    bs.upload()
+    bs.build(True)
+    for i, k in enumerate(cases):
+        assert bs.info(i).status == 0 and bs.info(i).n_states == 2, (k, bs.info(i).status)
+        row, P = bs.preint(i, cov=True)
+        ref, Pr = G["pr_row"][k], G["pr_cov"][k]
+        assert row[0, 0] == ref[0]  # DT bit-exact
+        assert np.max(np.abs(row[0, 1:11] - ref[1:11])) < 1e-13
+        assert _relmax(row[0, 17:62], ref[17:62]) < 1e-12
+        sc = np.sqrt(np.abs(np.diag(Pr.reshape(15, 15))))
+        assert np.max(np.abs(P[0] - Pr).reshape(15, 15) / (sc[:, None] * sc[None, :])) < 1e-10
+    bs.close()
+
+
+def test_cuda_build_and_linearization_against_reference_factors():
+    """A 3 s trial: cleaned state times and initial guess, the preintegration of every interval against the reference's
+    Propagator / CpiV1, then one linearisation at a perturbed estimate (Huber outliers included) against the normal
+    equations assembled in numpy from the reference's own evaluateError outputs of both factors."""
+    from test_ref_pin_cpu import _dataset_from_golden, check_linearization_against_reference_factors
+    from vicon2gt_b200 import api
+
+    G = _ref_pin()
+    bs = api.BatchSolver(1, keep_cov=1)
+    bs.set_trial_dataset(0, default_params(), _dataset_from_golden(G))
+    bs.upload()
+    bs.build(True)
+    assert bs.info(0).status == 0
+    tg, xg = bs.states(0)
+    assert np.array_equal(tg, G["ds_t"])
+    assert np.max(np.abs(xg - G["ds_x0"])) < 1e-12
+    row, P = bs.preint(0, cov=True)
+    ref, Pr = G["ds_pre_row"], G["ds_pre_cov"]
+    assert np.array_equal(row[:, 0], ref[:, 0])
+    assert np.max(np.abs(row[:, 1:11] - ref[:, 1:11])) < 1e-13
+    assert _relmax(row[:, 17:62], ref[:, 17:62]) < 1e-12
+    sc = np.sqrt(np.abs(np.einsum("nii->ni", Pr.reshape(-1, 15, 15))))
+    assert np.max(np.abs(P - Pr).reshape(-1, 15, 15) / (sc[:, :, None] * sc[:, None, :])) < 1e-10
+    bs.set_estimate(0, G["ds_x"], G["ds_g"])
+    check_linearization_against_reference_factors(G, bs.linearize(0))
+    bs.close()

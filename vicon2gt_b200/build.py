@@ -116,6 +116,21 @@ def build_oracle(force=False):
     return _LIBS["oracle"]
 
 
+def build_ref(force=False):
+    """Test infrastructure: oracle/_ref/libv2gt_ref.so from the reference's own sources where they lie under
+    /root/reference (oracle/Makefile.ref, against the interface stand-ins of oracle/shim/).  Returns None where the
+    reference is not present (the GPU box): the prebuilt library and tests/golden/ref_pin.npz travel instead."""
+    odir = os.path.join(ROOT, "oracle")
+    ref = os.environ.get("V2GT_REFERENCE_ROOT", "/root/reference")
+    out = os.path.join(odir, "_ref", "libv2gt_ref.so")
+    if not os.path.isdir(os.path.join(ref, "src", "cpi")):
+        return out if os.path.exists(out) else None
+    if force and os.path.exists(out):
+        os.remove(out)
+    _run(["make", "-s", "-C", odir, "-f", "Makefile.ref", "REF=" + ref])
+    return out
+
+
 def build_examples(force=False):
     """g++ -> examples/run_simulation (host C++ over the C ABI: include/vicon2gt_b200.hpp); needs the two libraries."""
     src = os.path.join(ROOT, "examples", "run_simulation.cpp")
