@@ -1,4 +1,4 @@
-"""ORACLE (test infrastructure, NOT product code) -- parity unpinned.
+"""ORACLE (test infrastructure, NOT product code) -- factor level pinned (oracle/_ref), optimiser level unpinned; see DESIGN.md section 2.
 
 ctypes binding of oracle/liboracle.so (the C++ CPU restatement of the reference's
 build-and-solve path).  Import only from tests/, __graft_entry__.smoke() and bench.py's

@@ -1,4 +1,4 @@
-// ORACLE (test infrastructure, NOT product code) -- parity unpinned.
+// ORACLE (test infrastructure, NOT product code) -- pinned on the reference's own sources (oracle/_ref, tests/test_ref_pin_cpu.py).
 //
 // Continuous preintegration, model 1 (piecewise-constant measurement), restated
 // from the reference's src/cpi/CpiBase.h:49-116 and src/cpi/CpiV1.h:58-341.

@@ -1,4 +1,4 @@
-// ORACLE (test infrastructure, NOT product code) -- parity unpinned.
+// ORACLE (test infrastructure, NOT product code) -- node / factor arithmetic pinned on the reference's own sources (oracle/_ref, tests/test_ref_pin_cpu.py); GTSAM noise models unpinned.
 //
 // Graph nodes and factors, restated from the reference's src/gtsam/*:
 //   JPLNavState (15 DoF), JPLQuaternion (3 DoF), RotationXY (2 DoF), Vector3, Vector1 nodes,

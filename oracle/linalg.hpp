@@ -1,4 +1,4 @@
-// ORACLE (test infrastructure, NOT product code) -- parity unpinned.
+// ORACLE (test infrastructure, NOT product code) -- container only (no reference counterpart).
 //
 // Tiny fixed-size dense matrix type used by the CPU restatement of the
 // vicon2gt build-and-solve path.  The reference uses Eigen (absent from this

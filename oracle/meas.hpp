@@ -1,4 +1,4 @@
-// ORACLE (test infrastructure, NOT product code) -- parity unpinned.
+// ORACLE (test infrastructure, NOT product code) -- pinned on the reference's own sources (oracle/_ref, tests/test_ref_pin_cpu.py).
 //
 // Measurement stores: IMU store + interval selection (Propagator) and the vicon
 // pose store with SO(3)xR^3 interpolation (Interpolator), restated from the

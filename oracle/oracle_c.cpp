@@ -1,4 +1,4 @@
-// ORACLE (test infrastructure, NOT product code) -- parity unpinned.
+// ORACLE (test infrastructure, NOT product code) -- factor level pinned (oracle/_ref), optimiser level unpinned; see DESIGN.md section 2.
 //
 // C entry points over the CPU restatement, loaded with ctypes by tests/,
 // __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs ONLY.

@@ -1,4 +1,4 @@
-// ORACLE (test infrastructure, NOT product code) -- parity unpinned.
+// ORACLE (test infrastructure, NOT product code) -- pinned on the reference's own sources (oracle/_ref, tests/test_ref_pin_cpu.py).
 //
 // JPL quaternion / SO(3) / roll-pitch helpers, restated from the reference's
 // src/utils/quat_ops.h and src/utils/rpy_ops.h (citations per function).

@@ -1,4 +1,4 @@
-// ORACLE (test infrastructure, NOT product code) -- parity unpinned.
+// ORACLE (test infrastructure, NOT product code) -- parity unpinned for this file (GTSAM's LM and the solver glue).
 //
 // CPU restatement of ViconGraphSolver (src/solver/ViconGraphSolver.{h,cpp}) with the
 // GTSAM 4.2a5 Levenberg-Marquardt policy the reference configures in

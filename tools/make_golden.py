@@ -1,10 +1,11 @@
 #!/usr/bin/env python
 """Generate tests/golden/*.npz: small fixed inputs plus the oracle's outputs on them.
 
-The reference cannot be compiled or imported in this environment (Eigen3, Boost, GTSAM 4.2a5, ROS1 absent) and
-holds no test vectors of its own, so these files pin the ORACLE (oracle/, the CPU restatement of
+The reference's solver cannot be run in this environment (GTSAM 4.2a5, Boost, ROS1 absent) and holds no test
+vectors of its own, so these files pin the ORACLE (oracle/, the CPU restatement of
 ViconGraphSolver::build_and_solve) against regressions and give the GPU tests a fixture that does not depend on
-the simulator or the oracle being rebuilt identically:  "parity unpinned" with respect to the real reference.
+the simulator or the oracle being rebuilt identically.  The reference's own factor-level code IS pinned, separately:
+tools/make_ref_golden.py -> tests/golden/ref_pin.npz.
 
     python tools/make_golden.py        # rewrites tests/golden/c2_8s.npz and c1_6s.npz
 """
