@@ -82,6 +82,18 @@ def lib():
     L.ref_retract_quat.argtypes = [c_double_p, c_double_p, c_double_p]
     L.ref_retract_rotxy.argtypes = [c_double_p, c_double_p, c_double_p]
     L.ref_rotxy_rot.argtypes = [c_double_p, c_double_p]
+    L.ref_solver_create.restype = C.c_void_p
+    L.ref_solver_create.argtypes = [c_double_p, c_double_p, c_double_p, c_double_p, C.c_int64, c_double_p, c_double_p, c_double_p,
+                                    C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, C.c_int, C.c_int64,
+                                    c_double_p]
+    L.ref_solver_destroy.argtypes = [C.c_void_p]
+    L.ref_solver_build_and_solve.argtypes = [C.c_void_p]
+    L.ref_solver_n_states.restype = C.c_int64
+    L.ref_solver_n_states.argtypes = [C.c_void_p]
+    L.ref_solver_get.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p]
+    L.ref_solver_get_trace.restype = C.c_int64
+    L.ref_solver_get_trace.argtypes = [C.c_int64, c_double_p]
+    L.ref_solver_write_to_file.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
     _lib = L
     return L
 
@@ -212,3 +224,61 @@ def retract_rotxy(th, d):
     a, b, out = _c(th), _c(d), np.zeros(2)
     lib().ref_retract_rotxy(_d(a), _d(b), _d(out))
     return out
+
+
+class RefSolver:
+    """The reference's ViconGraphSolver (src/solver/ViconGraphSolver.cpp, compiled where it lies) over one trial.
+
+    Cleaning, state erasure, initial guess, graph construction, relinearisation loop and write_to_file are the
+    reference's code; optimizer.optimize() is the dense GTSAM-LM restatement of oracle/shim/gtsam/mini_gtsam_lm.h.
+    `params` is a v2gt_params (the ROS parameters of ViconGraphSolver.cpp:34-88); max_iterations=None keeps the
+    reference's hard-coded 30, 0 hands back the initial values.
+    """
+
+    def __init__(self, params, ds, max_iterations=None):
+        self._L = lib()
+        p = params
+        R_GtoV, R_BtoI, p_BinI = (_c(list(getattr(p, k))) for k in ("R_GtoV", "R_BtoI", "p_BinI"))
+        par = _c([p.gravity_magnitude, p.toff_imu_to_vicon, p.estimate_toff_vicon_to_imu, p.estimate_ori_vicon_to_imu,
+                  p.estimate_pos_vicon_to_imu, p.num_loop_relin, p.sigma_w, p.sigma_wb, p.sigma_a, p.sigma_ab,
+                  -1 if max_iterations is None else max_iterations, 0, 0])
+        a = [_c(x) for x in (ds.imu_t, ds.imu_w, ds.imu_a, ds.vic_t, ds.vic_q, ds.vic_p, ds.state_t)]
+        if getattr(ds, "vic_Rq", None) is not None:
+            rq, rp, per = _c(ds.vic_Rq), _c(ds.vic_Rp), 1
+        else:
+            rc = _c(ds.vic_R_const)
+            rq, rp, per = _c(rc[:9]), _c(rc[9:]), 0
+        self.h = self._L.ref_solver_create(_d(R_GtoV), _d(R_BtoI), _d(p_BinI), _d(par), len(a[0]), _d(a[0]), _d(a[1]), _d(a[2]),
+                                           len(a[3]), _d(a[3]), _d(a[4]), _d(a[5]), _d(rq), _d(rp), per, len(a[6]), _d(a[6]))
+
+    def close(self):
+        if self.h:
+            self._L.ref_solver_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def build_and_solve(self):
+        return self._L.ref_solver_build_and_solve(self.h)
+
+    def result(self):
+        n = int(self._L.ref_solver_n_states(self.h))
+        t, x, g, lm = np.zeros(n), np.zeros((n, 16)), np.zeros(10), np.zeros(6)
+        self._L.ref_solver_get(self.h, _d(t), _d(x), _d(g), _d(lm))
+        return dict(times=t, states=x, globals10=g, iterations=int(lm[0]), tries=int(lm[1]), linearizations=int(lm[2]),
+                    initial_error=lm[3], final_error=lm[4], lambda_=lm[5])
+
+    def lm_trace(self):
+        """[tries, 5]: lambda, error before, error after (inf if not evaluated), linear cost change, accepted."""
+        n = int(self._L.ref_solver_get_trace(0, None))
+        rows = np.zeros((n, 5))
+        if n:
+            self._L.ref_solver_get_trace(n, _d(rows))
+        return rows
+
+    def write_to_file(self, csv, info):
+        return self._L.ref_solver_write_to_file(self.h, csv.encode(), info.encode())

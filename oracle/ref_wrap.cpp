@@ -24,6 +24,7 @@
 #include "gtsam/RotationXY.h"
 #include "meas/Interpolator.h"
 #include "meas/Propagator.h"
+#include "solver/ViconGraphSolver.h"
 #include "utils/quat_ops.h"
 #include "utils/rpy_ops.h"
 
@@ -229,6 +230,106 @@ int ref_retract_rotxy(const double *th, const double *d, double *out) {
 }
 int ref_rotxy_rot(const double *th, double *R) {
   put(gtsam::RotationXY(th[0], th[1]).rot(), R);
+  return 0;
+}
+
+// ---- src/solver/ViconGraphSolver.cpp: the reference's solver class end to end.  Timestamp cleaning, state erasure,
+// initial guess, graph construction, the relinearisation loop and write_to_file are the reference's; the optimiser
+// behind optimizer.optimize() is the GTSAM restatement of shim/gtsam/mini_gtsam_lm.h (dense, generic).
+namespace {
+struct SolverAccess : ViconGraphSolver {
+  using ViconGraphSolver::ViconGraphSolver;
+  const std::vector<double> &times() const { return timestamp_cameras; }
+  const gtsam::Values &result() const { return values_result; }
+  size_t id_of(double t) { return map_states[t]; }
+};
+struct SolverHandle {
+  std::shared_ptr<Propagator> prop;
+  std::shared_ptr<Interpolator> interp;
+  std::unique_ptr<SolverAccess> solver;
+};
+} // namespace
+
+// params13: gravity_magnitude, toff_imu_to_vicon, estimate_toff, estimate_ori, estimate_pos, num_loop_relin,
+//           sigma_w, sigma_wb, sigma_a, sigma_ab, max_iterations_override (-1 = the reference's 30), 0, 0
+void *ref_solver_create(const double *R_GtoV9, const double *R_BtoI9, const double *p_BinI3, const double *params13, int64_t n_imu,
+                        const double *imu_t, const double *imu_w, const double *imu_a, int64_t n_vic, const double *vic_t,
+                        const double *vic_q, const double *vic_p, const double *Rq, const double *Rp, int per_pose_cov, int64_t n_times,
+                        const double *state_t) {
+  ros::ParamTable &pt = ros::ParamTable::instance();
+  pt.scalars.clear();
+  pt.vectors.clear();
+  pt.vectors["R_GtoV"] = std::vector<double>(R_GtoV9, R_GtoV9 + 9);
+  pt.vectors["R_BtoI"] = std::vector<double>(R_BtoI9, R_BtoI9 + 9);
+  pt.vectors["p_BinI"] = std::vector<double>(p_BinI3, p_BinI3 + 3);
+  pt.scalars["gravity_magnitude"] = params13[0];
+  pt.scalars["toff_imu_to_vicon"] = params13[1];
+  pt.scalars["estimate_toff_vicon_to_imu"] = params13[2];
+  pt.scalars["estimate_ori_vicon_to_imu"] = params13[3];
+  pt.scalars["estimate_pos_vicon_to_imu"] = params13[4];
+  pt.scalars["num_loop_relin"] = params13[5];
+  gtsam::MiniLmLog::instance() = gtsam::MiniLmLog();
+  gtsam::MiniLmLog::instance().max_iterations_override = (int)params13[10];
+  SolverHandle *h = new SolverHandle();
+  h->prop = std::make_shared<Propagator>(params13[6], params13[7], params13[8], params13[9]);
+  for (int64_t i = 0; i < n_imu; i++)
+    h->prop->feed_imu(imu_t[i], v3(imu_w + 3 * i), v3(imu_a + 3 * i));
+  h->interp = std::make_shared<Interpolator>();
+  for (int64_t i = 0; i < n_vic; i++)
+    h->interp->feed_pose(vic_t[i], v4(vic_q + 4 * i), v3(vic_p + 3 * i), m3(per_pose_cov ? Rq + 9 * i : Rq), m3(per_pose_cov ? Rp + 9 * i : Rp));
+  ros::NodeHandle nh;
+  std::vector<double> times(state_t, state_t + n_times);
+  std::streambuf *old = std::cout.rdbuf(nullptr); // the constructor and build_and_solve print their parameters / result
+  h->solver.reset(new SolverAccess(nh, h->prop, h->interp, times));
+  std::cout.rdbuf(old);
+  return h;
+}
+void ref_solver_destroy(void *hv) { delete (SolverHandle *)hv; }
+int ref_solver_build_and_solve(void *hv) {
+  SolverHandle *h = (SolverHandle *)hv;
+  std::streambuf *old = std::cout.rdbuf(nullptr);
+  h->solver->build_and_solve();
+  std::cout.rdbuf(old);
+  return 0;
+}
+int64_t ref_solver_n_states(void *hv) { return (int64_t)((SolverHandle *)hv)->solver->times().size(); }
+// states: [n][16] = q bg v ba p;  calib10 = q_BtoI4 p_BinI3 t_off theta_x theta_y;  lm6 = iterations, damped solves,
+// linearisations, initial error, final error, lambda (summed over the relinearisation loops)
+int ref_solver_get(void *hv, double *times, double *states, double *calib10, double *lm6) {
+  using namespace gtsam::symbol_shorthand;
+  SolverHandle *h = (SolverHandle *)hv;
+  const std::vector<double> &t = h->solver->times();
+  const gtsam::Values &v = h->solver->result();
+  for (size_t i = 0; i < t.size(); i++) {
+    if (times)
+      times[i] = t[i];
+    if (states)
+      put_nav(v.at<gtsam::JPLNavState>(X(h->solver->id_of(t[i]))), states + 16 * i);
+  }
+  if (calib10) {
+    put(v.at<gtsam::JPLQuaternion>(C(0)).q(), calib10);
+    put(v.at<gtsam::Vector3>(C(1)), calib10 + 4);
+    calib10[7] = v.at<gtsam::Vector1>(T(0))(0);
+    calib10[8] = v.at<gtsam::RotationXY>(G(0)).thetax();
+    calib10[9] = v.at<gtsam::RotationXY>(G(0)).thetay();
+  }
+  if (lm6) {
+    const gtsam::MiniLmLog &l = gtsam::MiniLmLog::instance();
+    lm6[0] = l.iterations, lm6[1] = l.tries, lm6[2] = l.linearizations;
+    lm6[3] = l.initial_error, lm6[4] = l.final_error, lm6[5] = l.lambda;
+  }
+  return 0;
+}
+int64_t ref_solver_get_trace(int64_t capacity, double *rows5) {
+  const std::vector<double> &t = gtsam::MiniLmLog::instance().trace;
+  const int64_t n = (int64_t)t.size() / 5;
+  for (int64_t i = 0; i < n && i < capacity; i++)
+    for (int d = 0; d < 5; d++)
+      rows5[5 * i + d] = t[5 * i + d];
+  return n;
+}
+int ref_solver_write_to_file(void *hv, const char *csv, const char *info) {
+  ((SolverHandle *)hv)->solver->write_to_file(csv, info);
   return 0;
 }
 

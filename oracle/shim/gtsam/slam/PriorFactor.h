@@ -1,0 +1,3 @@
+// ORACLE / TEST INFRASTRUCTURE: stand-in for <gtsam/slam/PriorFactor.h>, see ../mini_gtsam_lm.h
+#pragma once
+#include "../mini_gtsam_lm.h"

@@ -208,6 +208,7 @@ public:
     a_.assign(a_.size(), 0.0);
     return *this;
   }
+  const Matrix &matrix() const { return *this; }
   Matrix &setIdentity() {
     *this = Identity(r_, c_);
     return *this;

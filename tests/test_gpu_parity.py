@@ -703,3 +703,40 @@ def test_cuda_build_and_linearization_against_reference_factors():
     bs.set_estimate(0, G["ds_x"], G["ds_g"])
     check_linearization_against_reference_factors(G, bs.linearize(0))
     bs.close()
+
+
+@pytest.mark.parametrize("name", ["e2e_c2", "e2e_c2_relin", "e2e_c3_fixed", "e2e_c1", "e2e_c2_dropout"])
+def test_cuda_build_and_solve_against_the_reference_class(name, tmp_path):
+    """End to end against the reference's ViconGraphSolver class (compiled where it lies; GTSAM's LM served by the
+    generic restatement of oracle/shim/gtsam/mini_gtsam_lm.h): surviving state times bit-exact, states / extrinsics /
+    time offset / gravity within 1e-6, final chi2 within 1e-8 relative.  No oracle call."""
+    from test_ref_pin_cpu import check_end_to_end, e2e_case
+    from vicon2gt_b200 import api
+
+    G = _ref_pin()
+    ds, p = e2e_case(G, name)
+    bs = api.BatchSolver(1)
+    bs.set_trial_dataset(0, p, ds)
+    bs.upload()
+    bs.build(True)
+    t0, x0 = bs.states(0)
+    assert np.array_equal(t0, G[name + "_times"])
+    assert np.max(np.abs(x0 - G[name + "_x0"])) < 1e-12  # initial guess (ViconGraphSolver.cpp:463-481)
+    bs.close()
+    bs = api.BatchSolver(1)
+    bs.set_trial_dataset(0, p, ds)
+    bs.build_and_solve()
+    inf = bs.info(0)
+    assert inf.status == 0
+    t, x = bs.states(0)
+    check_end_to_end(G, name, t, x, bs.globals10(0), inf.final_error)
+    if name == "e2e_c2":
+        import io
+
+        bs.write_to_file(0, str(tmp_path / "s.csv"), str(tmp_path / "i.txt"))
+        mine, ref = open(tmp_path / "s.csv", "rb").read(), G[name + "_csv"].tobytes()
+        assert mine.split(b"\n")[0] == ref.split(b"\n")[0]
+        a, b = np.loadtxt(io.BytesIO(mine), delimiter=","), np.loadtxt(io.BytesIO(ref), delimiter=",")
+        assert a.shape == b.shape and np.array_equal(a[:, 0], b[:, 0])
+        assert np.max(np.abs(a[:, 1:] - b[:, 1:]) / (np.abs(b[:, 1:]) + 1e-3)) < 2e-5
+    bs.close()

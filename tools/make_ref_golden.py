@@ -10,8 +10,14 @@ here; tests/test_ref_pin_cpu.py checks the oracle against them (and, where the l
 rebuilt, that the library still reproduces this file bit for bit), tests/test_gpu_parity.py checks
 the CUDA path against them.
 
+Also frozen: end-to-end runs of the reference's ViconGraphSolver class (src/solver/ViconGraphSolver.cpp,
+compiled where it lies: timestamp cleaning, state erasure, initial guess, graph construction,
+relinearisation loop, CSV writer are the reference's) -- with optimizer.optimize() served by the
+generic skyline-Cholesky restatement of GTSAM's LM in oracle/shim/gtsam/mini_gtsam_lm.h.
+
 Not covered (GTSAM's own code, absent from /root/reference): Gaussian::Covariance whitening, the
-Huber weights, LevenbergMarquardtOptimizer.  Those stay restated from upstream in oracle/solver.hpp.
+Huber weights, LevenbergMarquardtOptimizer.  Those are restated from upstream twice, independently
+(oracle/solver.hpp block-tridiagonal; mini_gtsam_lm.h generic), and the two are compared end to end.
 
     python tools/make_ref_golden.py       # needs /root/reference
 """
@@ -204,6 +210,68 @@ def dataset(rb, rng, out):
                fi_H1=np.array([r["H1"] for r in res]), fi_H2=np.array([r["H2"] for r in res]), fi_H3=np.array([r["H3"] for r in res]))
 
 
+E2E_CASES = {
+    # name: (config, make_config kwargs, v2gt_params overrides)
+    "e2e_c2": ("C2", dict(seed=7, duration_s=25.0, vicon_sigmas=(1e-3, 1e-3, 1e-3, 1e-2, 1e-2, 1e-2)), {}),
+    "e2e_c2_relin": ("C2", dict(seed=7, duration_s=25.0, vicon_sigmas=(1e-3, 1e-3, 1e-3, 1e-2, 1e-2, 1e-2)), dict(num_loop_relin=1)),
+    "e2e_c3_fixed": ("C3", dict(seed=3, duration_s=40.0, vicon_sigmas=(1e-3, 1e-3, 1e-3, 1e-2, 1e-2, 1e-2)),
+                     dict(estimate_toff_vicon_to_imu=0, estimate_pos_vicon_to_imu=0)),
+    "e2e_c1": ("C1", dict(seed=1, duration_s=8.0), {}),
+    # 11 s without vicon in the middle: build_problem erases the states inside the hole (get_pose refuses a query more
+    # than 5 s from either bracket end, Interpolator.cpp:119-123).  A shorter hole would keep states whose vicon factor
+    # then reads uninitialised memory in the reference (see tests/test_ref_pin_cpu.py::test_vicon_factor).
+    "e2e_c2_dropout": ("C2", dict(seed=5, duration_s=34.0, vicon_sigmas=(1e-3, 1e-3, 1e-3, 1e-2, 1e-2, 1e-2)), {}),
+}
+
+
+def dataset_digest(ds):
+    """sha256 over a trial's input arrays: the end-to-end cases store their inputs as (simulator arguments, digest)."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for a in (ds.imu_t, ds.imu_w, ds.imu_a, ds.vic_t, ds.vic_q, ds.vic_p, ds.vic_R_const, ds.state_t):
+        h.update(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+    return np.frombuffer(h.digest(), dtype=np.uint8).copy()
+
+
+def e2e_dataset(name):
+    from oracle import binding as ob
+    from vicon2gt_b200 import sim
+
+    cfg, kw, pk = E2E_CASES[name]
+    ds = sim.make_config(cfg, **kw)
+    if name.endswith("_dropout"):
+        keep = (ds.vic_t < ds.vic_t[0] + 11.5) | (ds.vic_t > ds.vic_t[0] + 22.5)
+        ds.vic_t, ds.vic_q, ds.vic_p = ds.vic_t[keep].copy(), ds.vic_q[keep].copy(), ds.vic_p[keep].copy()
+    return ds, ob.default_params(**pk)
+
+
+def end_to_end(rb, out):
+    """ViconGraphSolver::build_and_solve of the reference class: cleaned times, initial values (optimiser capped at 0
+    iterations), final states / calibration / cost, and the CSV of write_to_file."""
+    import tempfile
+
+    for name in E2E_CASES:
+        ds, p = e2e_dataset(name)
+        r0 = rb.RefSolver(p, ds, max_iterations=0)
+        r0.build_and_solve()
+        a = r0.result()
+        r0.close()
+        rs = rb.RefSolver(p, ds)
+        rs.build_and_solve()
+        b = rs.result()
+        out.update({name + "_digest": dataset_digest(ds), name + "_times": b["times"], name + "_x0": a["states"],
+                    name + "_g0": a["globals10"], name + "_initial_error": np.float64(a["initial_error"]), name + "_x": b["states"],
+                    name + "_g": b["globals10"], name + "_final_error": np.float64(b["final_error"]),
+                    name + "_iterations": np.int64(b["iterations"]), name + "_tries": np.int64(b["tries"])})
+        assert np.array_equal(a["times"], b["times"])
+        if name == "e2e_c2":
+            with tempfile.TemporaryDirectory() as d:
+                rs.write_to_file(os.path.join(d, "sub", "states.csv"), os.path.join(d, "sub", "info.txt"))
+                out[name + "_csv"] = np.frombuffer(open(os.path.join(d, "sub", "states.csv"), "rb").read(), dtype=np.uint8).copy()
+        rs.close()
+
+
 def generate():
     from oracle import ref_binding as rb
     from vicon2gt_b200 import build
@@ -217,6 +285,7 @@ def generate():
     propagation(rb, rng, out)
     interpolation(rb, rng, out)
     dataset(rb, rng, out)
+    end_to_end(rb, out)
     return out
 
 
