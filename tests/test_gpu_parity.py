@@ -705,6 +705,25 @@ def test_cuda_build_and_linearization_against_reference_factors():
     bs.close()
 
 
+@pytest.mark.parametrize("name", ["e2e_c2_full", "e2e_c3_full"])
+def test_cuda_full_size_baseline_configs_against_the_reference_class(name):
+    """BASELINE.json configs[1] (EuRoC V1_01 shape, 2.9 k states) and configs[2] (TUM corridor1 shape, 6 k states) at full
+    size, the whole 30-iteration policy, against the reference's ViconGraphSolver class: 1e-6 / 1e-8.  No oracle call."""
+    from test_ref_pin_cpu import check_end_to_end, e2e_case
+    from vicon2gt_b200 import api
+
+    G = _ref_pin()
+    ds, p = e2e_case(G, name)
+    bs = api.BatchSolver(1)
+    bs.set_trial_dataset(0, p, ds)
+    bs.build_and_solve()
+    inf = bs.info(0)
+    assert inf.status == 0 and inf.iterations == int(G[name + "_iterations"])
+    t, x = bs.states(0)
+    check_end_to_end(G, name, t, x, bs.globals10(0), inf.final_error)
+    bs.close()
+
+
 @pytest.mark.parametrize("name", ["e2e_c2", "e2e_c2_relin", "e2e_c3_fixed", "e2e_c1", "e2e_c2_dropout"])
 def test_cuda_build_and_solve_against_the_reference_class(name, tmp_path):
     """End to end against the reference's ViconGraphSolver class (compiled where it lies; GTSAM's LM served by the

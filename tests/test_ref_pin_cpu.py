@@ -47,9 +47,13 @@ def test_reference_library_reproduces_the_committed_vectors(G):
         "make_ref_golden", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "make_ref_golden.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    fresh = mod.generate()
-    assert sorted(fresh) == sorted(G)
-    for k in G:
+    import os as _os
+
+    full = _os.environ.get("V2GT_REF_FULL", "0") == "1"  # the two full-size runs take ~2 min; off by default
+    fresh = mod.generate(full=full)
+    skipped = [k for k in G if k not in fresh]
+    assert all(k.startswith(tuple(mod.E2E_FULL)) for k in skipped) and (not full or not skipped)
+    for k in fresh:
         assert np.array_equal(np.asarray(fresh[k]), G[k], equal_nan=True), k
 
 
@@ -274,7 +278,15 @@ E2E_NAMES = ["e2e_c2", "e2e_c2_relin", "e2e_c3_fixed", "e2e_c1", "e2e_c2_dropout
 
 def check_end_to_end(G, name, times, states, globals10, final_error, tol_state=1e-6, tol_chi2=1e-8):
     """Shared with the GPU test.  BASELINE.json north_star: states / extrinsics / offset 1e-6, chi2 1e-8 relative."""
-    assert np.array_equal(times, G[name + "_times"])  # same surviving states
+    if name + "_times" in G:
+        assert np.array_equal(times, G[name + "_times"])  # same surviving states
+    else:  # full-size cases: digest of the surviving times, every 4th state
+        import hashlib
+
+        assert len(times) == int(G[name + "_n"])
+        assert np.array_equal(np.frombuffer(hashlib.sha256(np.ascontiguousarray(times).tobytes()).digest(), dtype=np.uint8),
+                              G[name + "_times_digest"])
+        states = states[::4]
     assert np.max(np.abs(states - G[name + "_x"])) < tol_state
     assert np.max(np.abs(globals10 - G[name + "_g"])) < tol_state
     assert abs(final_error - G[name + "_final_error"]) / G[name + "_final_error"] < tol_chi2
@@ -316,3 +328,16 @@ def test_solver_end_to_end_against_the_reference_class(G, name):
         assert np.max(np.abs(a[:, 1:] - b[:, 1:]) / (np.abs(b[:, 1:]) + 1e-3)) < 2e-5
         same = sum(x == y for x, y in zip(mine.split(b"\n"), ref.split(b"\n")))
         assert same > 0.9 * len(ref.split(b"\n"))  # line for line identical except where a 6th digit rounds the other way
+
+
+@pytest.mark.parametrize("name", ["e2e_c2_full", "e2e_c3_full"])
+def test_full_size_baseline_configs_against_the_reference_class(G, name):
+    """BASELINE.json configs[1] / configs[2] at full size (2.9 k / 6 k states, 30 LM iterations)."""
+    from oracle import binding as ob
+    from vicon2gt_b200._cdefs import TrialInfo
+
+    ds, p = e2e_case(G, name)
+    o = ob.OracleSolver.from_dataset(p, ds)
+    assert o.build_and_solve() == 0
+    t, x = o.states()
+    check_end_to_end(G, name, t, x, o.globals10(), o.info(TrialInfo).final_error)

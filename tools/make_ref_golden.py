@@ -224,6 +224,14 @@ E2E_CASES = {
 }
 
 
+# BASELINE.json configs[1] and configs[2] at full size (about 30 s and 70 s of CPU each to regenerate): every 4th state kept
+E2E_FULL = {
+    "e2e_c2_full": ("C2", dict(seed=21), {}),
+    "e2e_c3_full": ("C3", dict(seed=21), {}),
+}
+FULL_STRIDE = 4
+
+
 def dataset_digest(ds):
     """sha256 over a trial's input arrays: the end-to-end cases store their inputs as (simulator arguments, digest)."""
     import hashlib
@@ -238,7 +246,7 @@ def e2e_dataset(name):
     from oracle import binding as ob
     from vicon2gt_b200 import sim
 
-    cfg, kw, pk = E2E_CASES[name]
+    cfg, kw, pk = (E2E_CASES[name] if name in E2E_CASES else E2E_FULL[name])
     ds = sim.make_config(cfg, **kw)
     if name.endswith("_dropout"):
         keep = (ds.vic_t < ds.vic_t[0] + 11.5) | (ds.vic_t > ds.vic_t[0] + 22.5)
@@ -272,7 +280,23 @@ def end_to_end(rb, out):
         rs.close()
 
 
-def generate():
+def end_to_end_full(rb, out):
+    import hashlib
+
+    for name in E2E_FULL:
+        ds, p = e2e_dataset(name)
+        rs = rb.RefSolver(p, ds)
+        rs.build_and_solve()
+        b = rs.result()
+        rs.close()
+        out.update({name + "_digest": dataset_digest(ds), name + "_n": np.int64(len(b["times"])),
+                    name + "_times_digest": np.frombuffer(hashlib.sha256(b["times"].tobytes()).digest(), dtype=np.uint8).copy(),
+                    name + "_x": b["states"][::FULL_STRIDE], name + "_g": b["globals10"],
+                    name + "_final_error": np.float64(b["final_error"]), name + "_iterations": np.int64(b["iterations"]),
+                    name + "_tries": np.int64(b["tries"])})
+
+
+def generate(full=True):
     from oracle import ref_binding as rb
     from vicon2gt_b200 import build
 
@@ -286,6 +310,8 @@ def generate():
     interpolation(rb, rng, out)
     dataset(rb, rng, out)
     end_to_end(rb, out)
+    if full:
+        end_to_end_full(rb, out)
     return out
 
 
