@@ -91,6 +91,14 @@ def lib():
     L.ref_solver_n_states.restype = C.c_int64
     L.ref_solver_n_states.argtypes = [C.c_void_p]
     L.ref_solver_get.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p]
+    L.ref_sim_run.restype = C.c_void_p
+    L.ref_sim_run.argtypes = [C.c_char_p, c_double_p, c_double_p]
+    L.ref_sim_destroy.argtypes = [C.c_void_p]
+    for n in ("ref_sim_n_imu", "ref_sim_n_vicon"):
+        getattr(L, n).restype = C.c_int64
+        getattr(L, n).argtypes = [C.c_void_p]
+    L.ref_sim_get.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p]
+    L.ref_sim_state_in_vicon.argtypes = [C.c_void_p, C.c_int64, c_double_p, c_double_p, c_int32_p]
     L.ref_solver_get_trace.restype = C.c_int64
     L.ref_solver_get_trace.argtypes = [C.c_int64, c_double_p]
     L.ref_solver_write_to_file.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
@@ -282,3 +290,27 @@ class RefSolver:
 
     def write_to_file(self, csv, info):
         return self._L.ref_solver_write_to_file(self.h, csv.encode(), info.encode())
+
+
+def simulate(traj_path, seed=0, freq_imu=400.0, freq_cam=20.0, freq_vicon=100.0, sigmas=(1.6968e-04, 1.9393e-05, 2.0e-3, 3.0e-3),
+             vicon_sigmas=(1e-3, 1e-3, 1e-3, 1e-2, 1e-2, 1e-2), gravity=9.81, truth_times=None):
+    """The reference's Simulator (src/sim/Simulator.cpp, BsplineSE3.cpp) driven like src/run_simulation.cpp:104-137."""
+    L = lib()
+    par = _c([seed, freq_imu, freq_cam, freq_vicon, *sigmas, gravity, 0, 0, 0, 0])
+    vs = _c(vicon_sigmas)
+    h = L.ref_sim_run(traj_path.encode(), _d(par), _d(vs))
+    try:
+        M, V = int(L.ref_sim_n_imu(h)), int(L.ref_sim_n_vicon(h))
+        imu, vic, truth = np.zeros((M, 7)), np.zeros((V, 8)), np.zeros(22)
+        L.ref_sim_get(h, _d(imu), _d(vic), _d(truth))
+        out = dict(imu_t=imu[:, 0].copy(), imu_w=imu[:, 1:4].copy(), imu_a=imu[:, 4:7].copy(), vic_t=vic[:, 0].copy(),
+                   vic_q=vic[:, 1:5].copy(), vic_p=vic[:, 5:8].copy(), R_BtoI=truth[:9].reshape(3, 3), p_BinI=truth[9:12].copy(),
+                   viconimu_dt=float(truth[12]), R_GtoV=truth[13:].reshape(3, 3))
+        if truth_times is not None:
+            t = _c(truth_times)
+            st, ok = np.zeros((len(t), 17)), np.zeros(len(t), dtype=np.int32)
+            L.ref_sim_state_in_vicon(h, len(t), _d(t), _d(st), _i(ok))
+            out["states"], out["states_ok"] = st, ok
+    finally:
+        L.ref_sim_destroy(h)
+    return out

@@ -24,6 +24,7 @@
 #include "gtsam/RotationXY.h"
 #include "meas/Interpolator.h"
 #include "meas/Propagator.h"
+#include "sim/Simulator.h"
 #include "solver/ViconGraphSolver.h"
 #include "utils/quat_ops.h"
 #include "utils/rpy_ops.h"
@@ -320,6 +321,81 @@ int ref_solver_get(void *hv, double *times, double *states, double *calib10, dou
   }
   return 0;
 }
+// ---- src/sim/Simulator.cpp + BsplineSE3.cpp driven as src/run_simulation.cpp:104-137 drives them
+namespace {
+struct SimHandle {
+  std::shared_ptr<Simulator> sim;
+  std::vector<double> imu, vic; // rows t w3 a3 / t q4 p3
+};
+} // namespace
+// par13: seed, freq_imu, freq_cam, freq_vicon, sigma_w, sigma_wb, sigma_a, sigma_ab, gravity, 0, 0, 0, 0
+void *ref_sim_run(const char *traj_path, const double *par13, const double *vicon_sigmas6) {
+  SimulatorParams params;
+  params.sim_traj_path = traj_path;
+  params.seed = (int)par13[0];
+  params.sim_freq_imu = par13[1];
+  params.sim_freq_cam = par13[2];
+  params.sim_freq_vicon = par13[3];
+  params.sigma_w = par13[4];
+  params.sigma_wb = par13[5];
+  params.sigma_a = par13[6];
+  params.sigma_ab = par13[7];
+  params.gravity_magnitude = par13[8];
+  params.sigma_vicon_pose << vicon_sigmas6[0], vicon_sigmas6[1], vicon_sigmas6[2], vicon_sigmas6[3], vicon_sigmas6[4], vicon_sigmas6[5];
+  SimHandle *h = new SimHandle();
+  FILE *old = stdout;
+  h->sim = std::make_shared<Simulator>(params);
+  (void)old;
+  while (h->sim->ok()) {
+    double time_imu;
+    Eigen::Vector3d wm, am;
+    if (h->sim->get_next_imu(time_imu, wm, am)) {
+      h->imu.push_back(time_imu);
+      for (int d = 0; d < 3; d++)
+        h->imu.push_back(wm(d));
+      for (int d = 0; d < 3; d++)
+        h->imu.push_back(am(d));
+    }
+    double time_cam;
+    h->sim->get_next_cam(time_cam);
+    double time_vicon;
+    Eigen::Vector4d q_VtoB;
+    Eigen::Vector3d p_BinV;
+    if (h->sim->get_next_vicon(time_vicon, q_VtoB, p_BinV)) {
+      h->vic.push_back(time_vicon);
+      for (int d = 0; d < 4; d++)
+        h->vic.push_back(q_VtoB(d));
+      for (int d = 0; d < 3; d++)
+        h->vic.push_back(p_BinV(d));
+    }
+  }
+  return h;
+}
+void ref_sim_destroy(void *hv) { delete (SimHandle *)hv; }
+int64_t ref_sim_n_imu(void *hv) { return (int64_t)((SimHandle *)hv)->imu.size() / 7; }
+int64_t ref_sim_n_vicon(void *hv) { return (int64_t)((SimHandle *)hv)->vic.size() / 8; }
+// truth22 = R_BtoI9 | p_BinI3 | viconimu_dt | R_GtoV9 (the perturbed values the simulator drew)
+int ref_sim_get(void *hv, double *imu7, double *vic8, double *truth22) {
+  SimHandle *h = (SimHandle *)hv;
+  std::memcpy(imu7, h->imu.data(), h->imu.size() * sizeof(double));
+  std::memcpy(vic8, h->vic.data(), h->vic.size() * sizeof(double));
+  SimulatorParams p = h->sim->get_params();
+  put(p.R_BtoI, truth22);
+  put(p.p_BinI, truth22 + 9);
+  truth22[12] = p.viconimu_dt;
+  put(p.R_GtoV, truth22 + 13);
+  return 0;
+}
+int ref_sim_state_in_vicon(void *hv, int64_t n, const double *t, double *state17, int32_t *ok) {
+  SimHandle *h = (SimHandle *)hv;
+  for (int64_t i = 0; i < n; i++) {
+    Eigen::Matrix<double, 17, 1> s;
+    ok[i] = h->sim->get_state_in_vicon(t[i], s) ? 1 : 0;
+    put(s, state17 + 17 * i);
+  }
+  return 0;
+}
+
 int64_t ref_solver_get_trace(int64_t capacity, double *rows5) {
   const std::vector<double> &t = gtsam::MiniLmLog::instance().trace;
   const int64_t n = (int64_t)t.size() / 5;

@@ -21,6 +21,9 @@
 #include <initializer_list>
 #include <iostream>
 #include <limits>
+#include <memory>
+#include <map> // the real Eigen headers pull these in; the reference relies on that (src/sim/BsplineSE3.h uses std::map)
+#include <string>
 #include <type_traits>
 #include <vector>
 
@@ -33,6 +36,8 @@ typedef Matrix<double, Dynamic, 1> VectorXd;
 template <class M> class BlockRef;
 class LLTResult;
 class QRResult;
+
+template <class T> using aligned_allocator = std::allocator<T>;
 
 inline void mini_fail(const char *what) {
   std::fprintf(stderr, "mini_eigen: %s\n", what);
@@ -110,6 +115,7 @@ public:
   }
   CommaInit &operator,(double v) { return add(v); }
   template <class E> CommaInit &operator,(const Base<E> &m) { return add(m); }
+  Target &finished() { return t_; }
 };
 
 // ---- owning matrix

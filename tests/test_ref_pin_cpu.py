@@ -341,3 +341,58 @@ def test_full_size_baseline_configs_against_the_reference_class(G, name):
     assert o.build_and_solve() == 0
     t, x = o.states()
     check_end_to_end(G, name, t, x, o.globals10(), o.info(TrialInfo).final_error)
+
+
+@pytest.mark.parametrize("tag,seed", [("sim5", 5), ("sim1234", 1234)])
+def test_host_simulator_against_the_reference_simulator(G, tag, seed, tmp_path):
+    """vicon2gt_b200/host/sim.cpp (the input generator of the benchmark and of the Monte-Carlo sweeps) against the
+    reference's Simulator + BsplineSE3 (compiled where they lie) on the same trajectory file and seed: the same number
+    of samples, the same stamps, the same random draws (the perturbed calibration agrees to an ulp), measurements to
+    round-off."""
+    import importlib.util
+    import os
+
+    from vicon2gt_b200 import sim
+
+    spec = importlib.util.spec_from_file_location(
+        "make_ref_golden", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "make_ref_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert np.array_equal(sim.make_trajectory(t_start=1403715273.26214, n_rows=200, dt=0.05, extent_m=2.5), G["sim_traj"])
+    path = str(tmp_path / "traj.txt")
+    mod.write_trajectory(G["sim_traj"], path)
+    ds = sim.simulate(traj_path=path, seed=seed, vicon_sigmas=(1e-3, 1e-3, 1e-3, 1e-2, 1e-2, 1e-2), freq_imu=400.0, freq_cam=20.0,
+                      freq_vicon=100.0, state_freq=100)
+    assert len(ds.imu_t) == int(G[tag + "_n_imu"]) and len(ds.vic_t) == int(G[tag + "_n_vicon"])
+    imu = np.column_stack([ds.imu_t, ds.imu_w, ds.imu_a])[::mod.SIM_STRIDE_IMU]
+    vic = np.column_stack([ds.vic_t, ds.vic_q, ds.vic_p])[::mod.SIM_STRIDE_VICON]
+    assert np.array_equal(imu[:, 0], G[tag + "_imu"][:, 0]) and np.array_equal(vic[:, 0], G[tag + "_vic"][:, 0])  # stamps
+    assert np.max(np.abs(imu[:, 1:4] - G[tag + "_imu"][:, 1:4])) < 1e-13  # rad/s
+    assert np.max(np.abs(imu[:, 4:7] - G[tag + "_imu"][:, 4:7])) < 1e-11  # m/s^2 (second derivative of the spline)
+    assert np.max(np.abs(vic[:, 1:] - G[tag + "_vic"][:, 1:])) < 1e-13
+    tr = ds.truth
+    mine = np.concatenate([tr["R_BtoI"].reshape(-1), tr["p_BinI"], [tr["viconimu_dt"]], tr["R_GtoV"].reshape(-1)])
+    assert np.max(np.abs(mine - G[tag + "_truth"])) < 1e-15  # the same std::mt19937 draws (rotations to an ulp)
+    assert mine[12] == G[tag + "_truth"][12] and np.array_equal(mine[9:12], G[tag + "_truth"][9:12])  # scalars bit for bit
+    st = truth_states_at(sim, path, seed, G[tag + "_state_t"])
+    assert np.array_equal(st[1], G[tag + "_states_ok"])
+    assert np.max(np.abs(st[0] - G[tag + "_states"])) < 1e-12
+
+
+def truth_states_at(sim, path, seed, times):
+    """Simulator::get_state_in_vicon of the host simulator at arbitrary times."""
+    import ctypes as C
+
+    lib = sim._load()
+    p = sim.default_sim_params(seed=int(seed), sim_freq_imu=400.0, sim_freq_cam=20.0, sim_freq_vicon=100.0, state_freq=100,
+                               sigma_vicon_pose=(1e-3, 1e-3, 1e-3, 1e-2, 1e-2, 1e-2))
+    h = lib.v2gt_sim_create(C.byref(p))
+    try:
+        assert lib.v2gt_sim_load_trajectory_file(h, path.encode()) == 0
+        assert lib.v2gt_sim_run(h) == 0
+        t = np.ascontiguousarray(times, dtype=np.float64)
+        st, ok = np.zeros((len(t), 17)), np.zeros(len(t), dtype=np.int32)
+        lib.v2gt_sim_get_state_in_vicon(h, len(t), sim.dptr(t), sim.dptr(st), ok.ctypes.data_as(sim.c_int32_p))
+    finally:
+        lib.v2gt_sim_destroy(h)
+    return st, ok

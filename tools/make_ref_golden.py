@@ -296,6 +296,38 @@ def end_to_end_full(rb, out):
                     name + "_tries": np.int64(b["tries"])})
 
 
+SIM_STRIDE_IMU, SIM_STRIDE_VICON, SIM_STRIDE_TRUTH = 8, 4, 10
+
+
+def write_trajectory(rows, path):
+    with open(path, "w") as f:
+        for r in rows:
+            f.write(" ".join(repr(float(x)) for x in r) + "\n")
+
+
+def simulator(rb, out):
+    """src/sim/Simulator.cpp + BsplineSE3.cpp driven as run_simulation.cpp:104-137 drives them, on a 10 s trajectory file:
+    the IMU / vicon streams (every 8th / 4th sample kept), the perturbed calibration it drew, get_state_in_vicon."""
+    import tempfile
+
+    from vicon2gt_b200 import sim
+
+    rows = sim.make_trajectory(t_start=1403715273.26214, n_rows=200, dt=0.05, extent_m=2.5)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "traj.txt")
+        write_trajectory(rows, path)
+        for seed, tag in ((5, "sim5"), (1234, "sim1234")):
+            r = rb.simulate(path, seed=seed, freq_imu=400.0, freq_cam=20.0, freq_vicon=100.0)
+            tt = r["vic_t"][::SIM_STRIDE_TRUTH] + 0.0031
+            r2 = rb.simulate(path, seed=seed, freq_imu=400.0, freq_cam=20.0, freq_vicon=100.0, truth_times=tt)
+            out.update({tag + "_n_imu": np.int64(len(r["imu_t"])), tag + "_n_vicon": np.int64(len(r["vic_t"])),
+                        tag + "_imu": np.column_stack([r["imu_t"], r["imu_w"], r["imu_a"]])[::SIM_STRIDE_IMU],
+                        tag + "_vic": np.column_stack([r["vic_t"], r["vic_q"], r["vic_p"]])[::SIM_STRIDE_VICON],
+                        tag + "_truth": np.concatenate([r["R_BtoI"].reshape(-1), r["p_BinI"], [r["viconimu_dt"]], r["R_GtoV"].reshape(-1)]),
+                        tag + "_state_t": tt, tag + "_states": r2["states"], tag + "_states_ok": r2["states_ok"]})
+    out["sim_traj"] = rows
+
+
 def generate(full=True):
     from oracle import ref_binding as rb
     from vicon2gt_b200 import build
@@ -310,6 +342,7 @@ def generate(full=True):
     interpolation(rb, rng, out)
     dataset(rb, rng, out)
     end_to_end(rb, out)
+    simulator(rb, out)
     if full:
         end_to_end_full(rb, out)
     return out
