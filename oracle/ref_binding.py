@@ -91,6 +91,7 @@ def lib():
     L.ref_solver_n_states.restype = C.c_int64
     L.ref_solver_n_states.argtypes = [C.c_void_p]
     L.ref_solver_get.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p]
+    L.ref_stats_calculate.argtypes = [C.c_int64, c_double_p, c_double_p]
     L.ref_sim_run.restype = C.c_void_p
     L.ref_sim_run.argtypes = [C.c_char_p, c_double_p, c_double_p]
     L.ref_sim_destroy.argtypes = [C.c_void_p]
@@ -313,4 +314,11 @@ def simulate(traj_path, seed=0, freq_imu=400.0, freq_cam=20.0, freq_vicon=100.0,
             out["states"], out["states_ok"] = st, ok
     finally:
         L.ref_sim_destroy(h)
+    return out
+
+
+def stats_calculate(values):
+    """Stats::calculate (src/utils/stats.h:64-112) -> rmse, mean, median, min, max, std, ninetynine."""
+    v, out = _c(values), np.zeros(7)
+    lib().ref_stats_calculate(len(v), _d(v), _d(out))
     return out

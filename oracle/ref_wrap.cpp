@@ -28,6 +28,7 @@
 #include "solver/ViconGraphSolver.h"
 #include "utils/quat_ops.h"
 #include "utils/rpy_ops.h"
+#include "utils/stats.h"
 
 namespace {
 
@@ -321,6 +322,15 @@ int ref_solver_get(void *hv, double *times, double *states, double *calib10, dou
   }
   return 0;
 }
+// ---- src/utils/stats.h: Stats::calculate -> rmse, mean, median, min, max, std, ninetynine
+int ref_stats_calculate(int64_t n, const double *values, double *out7) {
+  Stats st;
+  st.values.assign(values, values + n);
+  st.calculate();
+  out7[0] = st.rmse, out7[1] = st.mean, out7[2] = st.median, out7[3] = st.min, out7[4] = st.max, out7[5] = st.std, out7[6] = st.ninetynine;
+  return 0;
+}
+
 // ---- src/sim/Simulator.cpp + BsplineSE3.cpp driven as src/run_simulation.cpp:104-137 drives them
 namespace {
 struct SimHandle {

@@ -1,8 +1,10 @@
 """TEST INFRASTRUCTURE (oracle): numpy restatement of the reference's trajectory-error report.
 
 Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this; the product path
-(vicon2gt_b200/csrc/k_stats.cu) never does.  Parity unpinned: the reference ships no test vectors for these functions;
-tests/test_oracle_cpu.py pins them with known-answer cases.
+(vicon2gt_b200/csrc/k_stats.cu) never does.  stats_calculate is pinned on Stats::calculate of the reference's own
+src/utils/stats.h (compiled into oracle/_ref; tests/test_ref_pin_cpu.py::test_error_statistics_against_stats_h), the
+quaternion helpers on quat_ops.h the same way; trajectory_errors restates three lines of main() in run_simulation.cpp
+(known-answer cases in tests/test_oracle_cpu.py).
 
   quat_multiply / quat_inv   src/utils/quat_ops.h:181-196, 445-450 (JPL, vector first; result forced to w >= 0 and normalised)
   trajectory_errors          src/run_simulation.cpp:216-218

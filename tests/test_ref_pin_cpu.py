@@ -396,3 +396,18 @@ def truth_states_at(sim, path, seed, times):
     finally:
         lib.v2gt_sim_destroy(h)
     return st, ok
+
+
+def test_error_statistics_against_stats_h(G):
+    """oracle/stats_ref.py (the checker of csrc/k_stats.cu) against Stats::calculate of src/utils/stats.h."""
+    from oracle import stats_ref
+
+    for n in (1, 2, 7, 500, 2871):
+        mine = stats_ref.stats_calculate(G["st_v%d" % n])
+        ref = G["st_o%d" % n]
+        assert mine[7] == n
+        if n == 1:  # std = sqrt(0 / 0): NaN in both, and so is the 99th-percentile bound
+            assert np.isnan(ref[5]) and np.isnan(mine[5]) and np.isnan(ref[6]) and np.isnan(mine[6])
+            assert np.array_equal(mine[:5], ref[:5])
+        else:
+            assert np.max(np.abs(mine[:7] - ref) / np.abs(ref)) < 1e-15

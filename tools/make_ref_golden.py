@@ -328,6 +328,14 @@ def simulator(rb, out):
     out["sim_traj"] = rows
 
 
+def statistics(rb, rng, out):
+    """Stats::calculate (src/utils/stats.h) on samples of 1, 2, odd and even length."""
+    for n in (1, 2, 7, 500, 2871):
+        v = np.abs(rng.normal(size=n)) * 10.0 ** rng.integers(-3, 2)
+        out["st_v%d" % n] = v
+        out["st_o%d" % n] = rb.stats_calculate(v)
+
+
 def generate(full=True):
     from oracle import ref_binding as rb
     from vicon2gt_b200 import build
@@ -343,6 +351,7 @@ def generate(full=True):
     dataset(rb, rng, out)
     end_to_end(rb, out)
     simulator(rb, out)
+    statistics(rb, rng, out)
     if full:
         end_to_end_full(rb, out)
     return out
