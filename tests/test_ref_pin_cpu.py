@@ -411,3 +411,68 @@ def test_error_statistics_against_stats_h(G):
             assert np.array_equal(mine[:5], ref[:5])
         else:
             assert np.max(np.abs(mine[:7] - ref) / np.abs(ref)) < 1e-15
+
+
+def test_live_randomised_cross_check_of_oracle_and_reference_code():
+    """Beyond the frozen vectors: where the reference library is available, a few hundred random cases per function
+    (preintegration over random intervals and bias points, interpolation at random times, both factors at random
+    estimates) go through the reference's own code and through the oracle."""
+    from oracle import binding as ob
+    from oracle import ref_binding as rb
+    from vicon2gt_b200 import sim
+
+    if not rb.available():
+        pytest.skip("reference library not available on this machine; the committed vectors stand in")
+    rng = np.random.default_rng(77)
+    ds = sim.make_config("C1", seed=9, duration_s=6.0)
+    # preintegration
+    t_lo, t_hi = ds.imu_t[2], ds.imu_t[-3]
+    for _ in range(150):
+        t0 = rng.uniform(t_lo, t_hi - 0.2)
+        t1 = t0 + rng.uniform(1e-4, 0.15)
+        if rng.random() < 0.3:
+            t0 = ds.imu_t[np.searchsorted(ds.imu_t, t0)]  # starts exactly on a sample
+        bg, ba = rng.normal(size=3) * 0.01, rng.normal(size=3) * 0.1
+        a = ob.propagate(SIGMAS, ds.imu_t, ds.imu_w, ds.imu_a, t0, t1, bg, ba, faithful=True)
+        b = rb.propagate(SIGMAS, ds.imu_t, ds.imu_w, ds.imu_a, t0, t1, bg, ba)
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert a[0][0] == b[0][0]
+            _close(a[0][1:62], b[0][1:62], 8)
+            _close(a[1], b[1], 8, scale=np.max(np.abs(b[1])))
+    # interpolation + vicon factor
+    Rc = np.asarray(ds.vic_R_const)
+    ri = rb.RefInterpolator(ds.vic_t, ds.vic_q, ds.vic_p, Rc[:9], Rc[9:])
+    orc = ob.OracleSolver.from_dataset(default_params(), ds)
+    tq = rng.uniform(ds.vic_t[0] - 0.02, ds.vic_t[-1] + 0.02, 2000)
+    a, b = orc.eval_interp(tq, 0.1), ri.eval(tq, True)
+    assert np.array_equal(a["ok"], b["ok"])
+    has = b["idx0"] >= 0
+    assert np.array_equal(a["idx0"][has], b["idx0"][has]) and np.array_equal(a["idx1"][has], b["idx1"][has])
+    m = b["ok"] == 1
+    for k in ("q", "p", "R", "H_toff"):
+        _close(a[k][m], b[k][m], 16, scale=max(1e-300, np.max(np.abs(b[k][m]))))
+
+    def rq():
+        q = rng.normal(size=4)
+        return q / np.linalg.norm(q)
+
+    def rx():
+        return np.concatenate([rq(), rng.normal(size=3) * 0.01, rng.normal(size=3), rng.normal(size=3) * 0.1, rng.normal(size=3) * 3])
+
+    for _ in range(150):
+        x = rx()
+        g = np.concatenate([rq(), rng.normal(size=3) * 0.2, [rng.normal() * 0.02], rng.normal(size=2) * 0.1])
+        t = rng.uniform(ds.vic_t[2], ds.vic_t[-3])
+        fa, fb = orc.eval_vicon_factor(t, x, g), ri.eval_vicon_factor(t, x, g)
+        for k in ("e", "H1", "H2", "H3", "H4"):
+            _close(fa[k], fb[k], 64, scale=max(1.0, np.max(np.abs(fb["H1"]))))
+    # IMU factor
+    row = ob.propagate(SIGMAS, ds.imu_t, ds.imu_w, ds.imu_a, ds.state_t[30], ds.state_t[31], (0.01, -0.02, 0.03), (0.1, 0.2, -0.1),
+                       faithful=True)[0]
+    for _ in range(150):
+        xi, xj, th = rx(), rx(), rng.normal(size=2) * 0.3
+        fa, fb = ob.eval_imu_factor(row, 9.81, xi, xj, th), rb.eval_imu_factor(row, 9.81, xi, xj, th)
+        for k in ("e", "H1", "H2", "H3"):
+            _close(fa[k], fb[k], 16)
+    ri.close()
