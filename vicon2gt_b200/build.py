@@ -98,7 +98,7 @@ def build_cuda(force=False, verbose=False, extra=(), out=None, objdir_name="_obj
 
 def build_sim(force=False):
     src = os.path.join(HOST, "sim.cpp")
-    deps = [src, os.path.join(HOST, "v2gt_sim.h"), os.path.join(CSRC, "v2gt_math.cuh")]
+    deps = [src, os.path.join(HOST, "v2gt_sim.h"), os.path.join(CSRC, "v2gt_math.cuh"), os.path.join(CSRC, "v2gt_spline.cuh")]
     out = _LIBS["sim"]
     if not force and not _newer(out, deps):
         return out

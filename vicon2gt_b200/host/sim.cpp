@@ -17,6 +17,7 @@
 // "t x y z qx qy qz qw" text file this generator can synthesise a smooth trajectory of a
 // requested shape (start time, rows, dt), see v2gt_sim_make_trajectory.
 #include "../csrc/v2gt_math.cuh"
+#include "../csrc/v2gt_spline.cuh"
 #include "v2gt_sim.h"
 #include <algorithm>
 #include <array>
@@ -31,318 +32,8 @@
 #include <string>
 #include <vector>
 
-namespace {
-
-struct M4 {
-  double a[16];
-};
-M4 eye4() {
-  M4 m;
-  std::memset(m.a, 0, sizeof(m.a));
-  m.a[0] = m.a[5] = m.a[10] = m.a[15] = 1;
-  return m;
-}
-M4 mul(const M4 &A, const M4 &B) {
-  M4 C;
-  for (int r = 0; r < 4; r++)
-    for (int c = 0; c < 4; c++) {
-      double s = 0;
-      for (int k = 0; k < 4; k++)
-        s += A.a[4 * r + k] * B.a[4 * k + c];
-      C.a[4 * r + c] = s;
-    }
-  return C;
-}
-M4 add(const M4 &A, const M4 &B) {
-  M4 C;
-  for (int i = 0; i < 16; i++)
-    C.a[i] = A.a[i] + B.a[i];
-  return C;
-}
-M4 scale(double s, const M4 &A) {
-  M4 C;
-  for (int i = 0; i < 16; i++)
-    C.a[i] = s * A.a[i];
-  return C;
-}
-void getR(const M4 &T, double *R) {
-  for (int r = 0; r < 3; r++)
-    for (int c = 0; c < 3; c++)
-      R[3 * r + c] = T.a[4 * r + c];
-}
-void setR(M4 &T, const double *R) {
-  for (int r = 0; r < 3; r++)
-    for (int c = 0; c < 3; c++)
-      T.a[4 * r + c] = R[3 * r + c];
-}
-// quat_ops.h:432 Inv_se3
-M4 inv_se3(const M4 &T) {
-  M4 Ti = eye4();
-  for (int r = 0; r < 3; r++)
-    for (int c = 0; c < 3; c++)
-      Ti.a[4 * r + c] = T.a[4 * c + r];
-  for (int r = 0; r < 3; r++) {
-    double s = 0;
-    for (int c = 0; c < 3; c++)
-      s += Ti.a[4 * r + c] * T.a[4 * c + 3];
-    Ti.a[4 * r + 3] = -s;
-  }
-  return Ti;
-}
-// quat_ops.h:311-340 exp_se3
-M4 exp_se3(const double *vec) {
-  const double *w = vec, *u = vec + 3;
-  const double theta = std::sqrt(v2::dot3(w, w));
-  double S[9], S2[9];
-  v2::skew(w, S);
-  v2::mm3(S, S, S2);
-  double A, B, C;
-  if (theta < 1e-12) {
-    A = 1;
-    B = 0.5;
-    C = 1.0 / 6.0;
-  } else {
-    A = std::sin(theta) / theta;
-    B = (1 - std::cos(theta)) / (theta * theta);
-    C = (1 - A) / (theta * theta);
-  }
-  M4 m;
-  std::memset(m.a, 0, sizeof(m.a));
-  double V[9], R[9];
-  for (int i = 0; i < 9; i++) {
-    const double I = (i % 4 == 0) ? 1.0 : 0.0;
-    V[i] = I + B * S[i] + C * S2[i];
-    R[i] = I + A * S[i] + B * S2[i];
-  }
-  setR(m, R);
-  double t[3];
-  v2::mv3(V, u, t);
-  m.a[3] = t[0];
-  m.a[7] = t[1];
-  m.a[11] = t[2];
-  m.a[15] = 1;
-  return m;
-}
-// quat_ops.h:353-385 log_se3
-void log_se3(const M4 &mat, double *vec) {
-  double R[9], t[3] = {mat.a[3], mat.a[7], mat.a[11]};
-  getR(mat, R);
-  const double a = 0.5 * ((R[0] + R[4] + R[8]) - 1);
-  const double theta = (a > 1) ? std::acos(1.0) : ((a < -1) ? std::acos(-1.0) : std::acos(a));
-  double A, B, D, E;
-  if (theta < 1e-12) {
-    A = 1;
-    B = 0.5;
-    D = 0.5;
-    E = 1.0 / 12.0;
-  } else {
-    A = std::sin(theta) / theta;
-    B = (1 - std::cos(theta)) / (theta * theta);
-    D = theta / (2 * std::sin(theta));
-    E = 1 / (theta * theta) * (1 - 0.5 * A / B);
-  }
-  double W[9], W2[9], Vinv[9];
-  for (int r = 0; r < 3; r++)
-    for (int c = 0; c < 3; c++)
-      W[3 * r + c] = D * (R[3 * r + c] - R[3 * c + r]);
-  v2::mm3(W, W, W2);
-  for (int i = 0; i < 9; i++)
-    Vinv[i] = ((i % 4 == 0) ? 1.0 : 0.0) - 0.5 * W[i] + E * W2[i];
-  vec[0] = W[7];
-  vec[1] = W[2];
-  vec[2] = W[3];
-  v2::mv3(Vinv, t, vec + 3);
-}
-// quat_ops.h:397-402 hat_se3
-M4 hat_se3(const double *vec) {
-  M4 m;
-  std::memset(m.a, 0, sizeof(m.a));
-  double S[9];
-  v2::skew(vec, S);
-  setR(m, S);
-  m.a[3] = vec[3];
-  m.a[7] = vec[4];
-  m.a[11] = vec[5];
-  return m;
-}
-
-struct Spline {
-  std::map<double, M4> control_points;
-  double dt = 0, timestamp_start = 0;
-
-  // BsplineSE3.cpp:21-83
-  void feed_trajectory(const std::vector<std::array<double, 8>> &traj) {
-    double sumdt = 0;
-    for (size_t i = 0; i + 1 < traj.size(); i++)
-      sumdt += traj[i + 1][0] - traj[i][0];
-    dt = sumdt / (double)(traj.size() - 1);
-    dt = (dt < 0.05) ? 0.05 : dt;
-    std::map<double, M4> pts;
-    for (size_t i = 0; i + 1 < traj.size(); i++) { // last row unused, as in the reference
-      M4 T = eye4();
-      double R[9], Rt[9];
-      v2::quat_2_Rot(&traj[i][4], R);
-      for (int r = 0; r < 3; r++)
-        for (int c = 0; c < 3; c++)
-          Rt[3 * r + c] = R[3 * c + r];
-      setR(T, Rt);
-      T.a[3] = traj[i][1];
-      T.a[7] = traj[i][2];
-      T.a[11] = traj[i][3];
-      pts.insert({traj[i][0], T});
-    }
-    double timestamp_min = INFINITY;
-    for (const auto &p : pts)
-      if (p.first <= timestamp_min)
-        timestamp_min = p.first;
-    double timestamp_curr = timestamp_min;
-    while (true) {
-      double t0, t1;
-      M4 pose0, pose1;
-      if (!find_bounding_poses(timestamp_curr, pts, t0, pose0, t1, pose1))
-        break;
-      const double lambda = (timestamp_curr - t0) / (t1 - t0);
-      double lg[6];
-      log_se3(mul(pose1, inv_se3(pose0)), lg);
-      for (int i = 0; i < 6; i++)
-        lg[i] *= lambda;
-      control_points.insert({timestamp_curr, mul(exp_se3(lg), pose0)});
-      timestamp_curr += dt;
-    }
-    timestamp_start = timestamp_min + 2 * dt;
-  }
-
-  // BsplineSE3.cpp:242-293
-  static bool find_bounding_poses(double timestamp, const std::map<double, M4> &poses, double &t0, M4 &pose0, double &t1, M4 &pose1) {
-    t0 = -1;
-    t1 = -1;
-    bool found_older = false, found_newer = false;
-    auto lower_bound = poses.lower_bound(timestamp);
-    auto upper_bound = poses.upper_bound(timestamp);
-    if (lower_bound != poses.end()) {
-      if (lower_bound->first == timestamp) {
-        found_older = true;
-      } else if (lower_bound != poses.begin()) {
-        --lower_bound;
-        found_older = true;
-      }
-    }
-    if (upper_bound != poses.end())
-      found_newer = true;
-    if (found_older) {
-      t0 = lower_bound->first;
-      pose0 = lower_bound->second;
-    }
-    if (found_newer) {
-      t1 = upper_bound->first;
-      pose1 = upper_bound->second;
-    }
-    return found_older && found_newer;
-  }
-
-  // BsplineSE3.cpp:295-351
-  bool find_bounding_control_points(double timestamp, double &t0, M4 &pose0, double &t1, M4 &pose1, double &t2, M4 &pose2, double &t3,
-                                    M4 &pose3) const {
-    if (!find_bounding_poses(timestamp, control_points, t1, pose1, t2, pose2))
-      return false;
-    auto iter_t1 = control_points.find(t1);
-    auto iter_t2 = control_points.find(t2);
-    if (iter_t1 == control_points.begin())
-      return false;
-    auto iter_t0 = --iter_t1;
-    auto iter_t3 = ++iter_t2;
-    if (iter_t3 == control_points.end())
-      return false;
-    t0 = iter_t0->first;
-    pose0 = iter_t0->second;
-    t3 = iter_t3->first;
-    pose3 = iter_t3->second;
-    return true;
-  }
-
-  // BsplineSE3.cpp:85-240 : order 0 = pose, 1 = +velocity, 2 = +acceleration
-  bool eval(double timestamp, int order, double *R_GtoI, double *p_IinG, double *w_IinI, double *v_IinG, double *alpha_IinI,
-            double *a_IinG) const {
-    double t0, t1, t2, t3;
-    M4 pose0, pose1, pose2, pose3;
-    if (!find_bounding_control_points(timestamp, t0, pose0, t1, pose1, t2, pose2, t3, pose3))
-      return false;
-    const double DT = (t2 - t1);
-    const double u = (timestamp - t1) / DT;
-    const double b0 = 1.0 / 6.0 * (5 + 3 * u - 3 * u * u + u * u * u);
-    const double b1 = 1.0 / 6.0 * (1 + 3 * u + 3 * u * u - 2 * u * u * u);
-    const double b2 = 1.0 / 6.0 * (u * u * u);
-    const double b0dot = 1.0 / (6.0 * DT) * (3 - 6 * u + 3 * u * u);
-    const double b1dot = 1.0 / (6.0 * DT) * (3 + 6 * u - 6 * u * u);
-    const double b2dot = 1.0 / (6.0 * DT) * (3 * u * u);
-    const double b0dd = 1.0 / (6.0 * DT * DT) * (-6 + 6 * u);
-    const double b1dd = 1.0 / (6.0 * DT * DT) * (6 - 12 * u);
-    const double b2dd = 1.0 / (6.0 * DT * DT) * (6 * u);
-    double o10[6], o21[6], o32[6], s[6];
-    log_se3(mul(inv_se3(pose0), pose1), o10);
-    log_se3(mul(inv_se3(pose1), pose2), o21);
-    log_se3(mul(inv_se3(pose2), pose3), o32);
-    auto sc = [&](double b, const double *o) {
-      for (int i = 0; i < 6; i++)
-        s[i] = b * o[i];
-      return exp_se3(s);
-    };
-    const M4 A0 = sc(b0, o10), A1 = sc(b1, o21), A2 = sc(b2, o32);
-    const M4 pose_interp = mul(mul(mul(pose0, A0), A1), A2);
-    double Rt[9];
-    getR(pose_interp, Rt); // R_ItoG
-    for (int r = 0; r < 3; r++)
-      for (int c = 0; c < 3; c++)
-        R_GtoI[3 * r + c] = Rt[3 * c + r];
-    p_IinG[0] = pose_interp.a[3];
-    p_IinG[1] = pose_interp.a[7];
-    p_IinG[2] = pose_interp.a[11];
-    if (order < 1)
-      return true;
-    const M4 h10 = hat_se3(o10), h21 = hat_se3(o21), h32 = hat_se3(o32);
-    const M4 A0dot = scale(b0dot, mul(h10, A0));
-    const M4 A1dot = scale(b1dot, mul(h21, A1));
-    const M4 A2dot = scale(b2dot, mul(h32, A2));
-    const M4 vel_interp =
-        mul(pose0, add(add(mul(mul(A0dot, A1), A2), mul(mul(A0, A1dot), A2)), mul(mul(A0, A1), A2dot)));
-    double Rv[9], om[9];
-    getR(vel_interp, Rv);
-    v2::mm3_tn(Rt, Rv, om); // R^T Rdot = skew(omega)
-    w_IinI[0] = om[7];
-    w_IinI[1] = om[2];
-    w_IinI[2] = om[3];
-    v_IinG[0] = vel_interp.a[3];
-    v_IinG[1] = vel_interp.a[7];
-    v_IinG[2] = vel_interp.a[11];
-    if (order < 2)
-      return true;
-    const M4 A0dd = add(scale(b0dot, mul(h10, A0dot)), scale(b0dd, mul(h10, A0)));
-    const M4 A1dd = add(scale(b1dot, mul(h21, A1dot)), scale(b1dd, mul(h21, A1)));
-    const M4 A2dd = add(scale(b2dot, mul(h32, A2dot)), scale(b2dd, mul(h32, A2)));
-    M4 acc = mul(mul(A0dd, A1), A2);
-    acc = add(acc, mul(mul(A0, A1dd), A2));
-    acc = add(acc, mul(mul(A0, A1), A2dd));
-    acc = add(acc, scale(2, mul(mul(A0dot, A1dot), A2)));
-    acc = add(acc, scale(2, mul(mul(A0, A1dot), A2dot)));
-    acc = add(acc, scale(2, mul(mul(A0dot, A1), A2dot)));
-    const M4 acc_interp = mul(pose0, acc);
-    double Ra[9], tmp[9], al[9];
-    getR(acc_interp, Ra);
-    v2::mm3(Rv, om, tmp);
-    for (int i = 0; i < 9; i++)
-      tmp[i] = Ra[i] - tmp[i];
-    v2::mm3_tn(Rt, tmp, al);
-    alpha_IinI[0] = al[7];
-    alpha_IinI[1] = al[2];
-    alpha_IinI[2] = al[3];
-    a_IinG[0] = acc_interp.a[3];
-    a_IinG[1] = acc_interp.a[7];
-    a_IinG[2] = acc_interp.a[11];
-    return true;
-  }
-};
-
-} // namespace
+using v2sp::M4;
+using v2sp::Spline;
 
 struct v2gt_sim {
   v2gt_sim_params prm;
