@@ -243,6 +243,36 @@ int v2gt_chain_buffer(v2gt_batch *b, int32_t which, void **dev_ptr, int64_t *n_d
 /* the handle's CUDA stream (cudaStream_t), so that the caller's collectives can be ordered with the kernels */
 int v2gt_batch_stream(v2gt_batch *b, void **stream);
 
+/* ---- batched simulator on the device ----
+ * src/sim of the reference (Simulator.cpp:21-262, BsplineSE3.cpp:21-351) and the measurement loop + state grid of
+ * src/run_simulation.cpp:108-158 for ALL trials of a Monte-Carlo batch at once.  One trajectory per batch; trial t takes
+ * a v2gt_sim_params (vicon2gt_b200/host/v2gt_sim.h, the SimulatorParams mirror of the host simulator; default: seed = t);
+ * the rates, gravity magnitude, sample cap and state rate must be the same for every trial of a batch.  Each seed's
+ * streams are those of a GCC build of the reference: std::mt19937(seed) words through libstdc++'s polar
+ * normal_distribution, regenerated and compacted in parallel on the device (csrc/k_sim.cu).
+ *   plan  host only (works without a device): clock schedule, truth per seed, vicon stamps, state-time grids
+ *   run   device: spline evaluation once per stamp, noise streams, bias random walks, measurements
+ *   get   caller layout of v2gt_sim_get (any pointer may be NULL; stamps only need plan)
+ *   get_state_in_vicon   Simulator::get_state_in_vicon (Simulator.cpp:91-133) for n query times of one trial
+ * v2gt_batch_set_trial_sim stages trial `sim_trial` of a simulated batch as trial `trial` of a solver batch on the same
+ * device: the stamps are cleaned on the host as usual, the measurement rows go device -> device (no host round trip). */
+struct v2gt_sim_params;
+typedef struct v2gt_simbatch v2gt_simbatch;
+int v2gt_simbatch_create(int32_t device, int32_t n_trials, int64_t n_rows, const double *rows8, v2gt_simbatch **out);
+int v2gt_simbatch_destroy(v2gt_simbatch *s);
+int v2gt_simbatch_set_trial(v2gt_simbatch *s, int32_t trial, const struct v2gt_sim_params *p);
+int v2gt_simbatch_plan(v2gt_simbatch *s);
+int v2gt_simbatch_run(v2gt_simbatch *s);
+int v2gt_simbatch_sizes(v2gt_simbatch *s, int32_t trial, int64_t *n_imu, int64_t *n_vicon, int64_t *n_states);
+int v2gt_simbatch_get(v2gt_simbatch *s, int32_t trial, double *imu_t, double *imu_w, double *imu_a, double *vic_t, double *vic_q,
+                      double *vic_p, double *state_t);
+int v2gt_simbatch_get_truth(v2gt_simbatch *s, int32_t trial, double *R_BtoI, double *p_BinI, double *viconimu_dt, double *R_GtoV);
+int v2gt_simbatch_get_state_in_vicon(v2gt_simbatch *s, int32_t trial, int64_t n, const double *times, double *out17, int32_t *ok);
+/* device time (ms, CUDA events) of the last run: uploads of the plan + all generation kernels */
+int v2gt_simbatch_get_timing(v2gt_simbatch *s, double *ms_generate);
+int v2gt_batch_set_trial_sim(v2gt_batch *b, int32_t trial, const v2gt_params *params, v2gt_simbatch *s, int32_t sim_trial,
+                             const double *vic_R_const);
+
 /* ---- measurement helpers ---- */
 /* Device time (ms, CUDA events on the handle's stream) spent in each phase of the last
  * build/optimise: [0] build(init+preint) [1] linearise+assemble [2] eliminate [3] reduced solve

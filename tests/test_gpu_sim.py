@@ -1,0 +1,113 @@
+"""GPU tests (-m gpu) of the batched simulator (csrc/k_sim.cu) against the host simulator, which is
+pinned on the reference's Simulator / BsplineSE3 (tests/test_ref_pin_cpu.py), and of the device-to-device hand-over to
+the batch solver.  The stamps, the per-seed truth and the accept / reject pattern of the noise streams are exact; the
+measurements differ from the host's by the last bits of log() in the polar method and by FMA contraction in the spline
+evaluation -- the tolerances below are those round-off levels, written next to each assert."""
+import numpy as np
+import pytest
+
+from conftest import default_params
+
+pytestmark = pytest.mark.gpu
+
+
+def _rows(n_rows):
+    from vicon2gt_b200 import sim
+
+    return sim.make_trajectory(**{**sim.TRAJ_SHAPES["tum_corridor1"], "n_rows": n_rows})
+
+
+def _quat_angle(a, b):
+    return 2 * np.arccos(np.clip(np.abs(np.sum(a * b, axis=1)), 0, 1))
+
+
+def test_device_simulator_matches_host_simulator():
+    from vicon2gt_b200 import sim
+
+    rows = _rows(500)  # 25 s: ~9.9 k IMU samples = ~76 k accepted pairs = ~620 regenerated MT19937 blocks per trial
+    seeds = [0, 1, 7, 1023, 123456]
+    sig = np.array([[0.0174] * 3 + [0.05] * 3, [1e-3] * 3 + [1e-2] * 3, [0.005] * 3 + [0.01] * 3, [0.05] * 3 + [0.10] * 3,
+                    [0.0174] * 3 + [0.05] * 3])
+    with sim.SimBatch(rows, len(seeds), seeds=seeds, vicon_sigmas=sig) as sb:
+        sb.run()
+        assert sb.generate_ms() > 0
+        for k, seed in enumerate(seeds):
+            h = sim.simulate(traj_rows=rows, seed=seed, vicon_sigmas=sig[k])
+            d = sb.dataset(k)
+            assert np.array_equal(d.imu_t, h.imu_t) and np.array_equal(d.vic_t, h.vic_t) and np.array_equal(d.state_t, h.state_t)
+            assert h.n_imu > 9000 and h.n_vicon > 2000
+            # IMU: |w| ~ 1 rad/s, |a| ~ 10 m/s^2; a wrong stream position would show up at the noise level (1e-3 .. 1e-1)
+            assert np.abs(d.imu_w - h.imu_w).max() < 1e-11
+            assert np.abs(d.imu_a - h.imu_a).max() < 1e-10
+            assert _quat_angle(d.vic_q, h.vic_q).max() < 1e-7  # arccos near 1: 1e-7 rad is round-off of the dot product
+            assert np.abs(d.vic_q - h.vic_q).max() < 1e-12
+            assert np.abs(d.vic_p - h.vic_p).max() < 1e-11
+            # Simulator::get_state_in_vicon at the state times: pose, velocity, interpolated true biases
+            assert np.array_equal(d.truth["states_ok"], h.truth["states_ok"]) and h.truth["states_ok"].sum() > 100
+            assert np.abs(d.truth["states"] - h.truth["states"]).max() < 1e-10
+            assert np.abs(d.truth["states"][:, 11:]).max() > 0  # the bias random walk is there
+    # a second batch of the same seeds reproduces the first bit for bit (fixed stream order, no atomics)
+    with sim.SimBatch(rows, 2, seeds=[7, 1023], vicon_sigmas=sig[2:4]) as sb2:
+        sb2.run()
+        a = sb2.dataset(1, with_truth_states=False)
+    with sim.SimBatch(rows, 1, seeds=[1023], vicon_sigmas=sig[3:4]) as sb3:
+        sb3.run()
+        b = sb3.dataset(0, with_truth_states=False)
+    for x, y in ((a.imu_w, b.imu_w), (a.imu_a, b.imu_a), (a.vic_q, b.vic_q), (a.vic_p, b.vic_p)):
+        assert np.array_equal(x, y)
+
+
+def test_other_rates_and_capped_stream():
+    from vicon2gt_b200 import sim
+
+    rows = _rows(300)
+    kw = dict(freq_imu=200.0, freq_cam=20.0, freq_vicon=100.0, state_freq=0, max_imu=1111)
+    with sim.SimBatch(rows, 2, seeds=[3, 4], **kw) as sb:
+        sb.run()
+        for k, seed in enumerate([3, 4]):
+            h = sim.simulate(traj_rows=rows, seed=seed, **kw)
+            d = sb.dataset(k, with_truth_states=False)
+            assert h.n_imu == 1111 and np.array_equal(d.imu_t, h.imu_t) and np.array_equal(d.vic_t, h.vic_t)
+            assert np.abs(d.imu_w - h.imu_w).max() < 1e-11 and np.abs(d.imu_a - h.imu_a).max() < 1e-10
+            assert np.abs(d.vic_p - h.vic_p).max() < 1e-11 and np.abs(d.vic_q - h.vic_q).max() < 1e-12
+
+
+def test_simulated_batch_goes_to_the_solver_without_a_host_round_trip():
+    """v2gt_batch_set_trial_sim: the rows copied device -> device give the same solve, bit for bit, as the same rows
+    downloaded and fed through the host path; and the solve recovers the simulated truth."""
+    from vicon2gt_b200 import api, sim
+
+    rows = _rows(400)
+    seeds = [11, 12, 13]
+    p = default_params()
+    with sim.SimBatch(rows, 3, seeds=seeds, vicon_sigmas=(1e-3,) * 3 + (1e-2,) * 3) as sb:
+        sb.run()
+        with api.BatchSolver(3) as dev_fed, api.BatchSolver(3) as host_fed:
+            for k in range(3):
+                dev_fed.set_trial_sim(k, p, sb)
+                host_fed.set_trial_dataset(k, p, sb.dataset(k, with_truth_states=False))
+            dev_fed.build_and_solve()
+            host_fed.build_and_solve()
+            for k in range(3):
+                ia, ib = dev_fed.info(k), host_fed.info(k)
+                assert ia.status == 0 and ib.status == 0 and ia.n_states == ib.n_states > 1000
+                assert (ia.tries, ia.iterations) == (ib.tries, ib.iterations) and ia.final_error == ib.final_error
+                ta, xa = dev_fed.states(k)
+                tb, xb = host_fed.states(k)
+                assert np.array_equal(ta, tb) and np.array_equal(xa, xb)
+                assert np.array_equal(dev_fed.globals10(k), host_fed.globals10(k))
+                # truth recovery at the tech report's level for this noise (t_off to a fraction of a millisecond)
+                tr = sb.truth(k)
+                _, _, toff, _ = dev_fed.calibration(k)
+                assert abs(toff - tr["viconimu_dt"]) < 1e-3
+        # mixed batch: one trial from the simulator, one from host arrays
+        with api.BatchSolver(2) as mixed:
+            mixed.set_trial_dataset(0, p, sb.dataset(1, with_truth_states=False))
+            mixed.set_trial_sim(1, p, sb, sim_trial=2)
+            mixed.build_and_solve()
+            assert mixed.info(0).status == 0 and mixed.info(1).status == 0
+            with api.BatchSolver(1) as one:
+                one.set_trial_sim(0, p, sb, sim_trial=2)
+                one.build_and_solve()
+                # (a batch of another size cuts its chains differently: same solution to round-off, not bit for bit)
+                assert np.abs(one.states(0)[1] - mixed.states(1)[1]).max() < 1e-7

@@ -11,7 +11,7 @@ import os
 
 import numpy as np
 
-from ._cdefs import PREINT_DIM, STATUS_NAMES, Params, TrialInfo, c_double_p, c_int32_p, c_int64_p, dptr, i32ptr
+from ._cdefs import PREINT_DIM, STATUS_NAMES, Params, SimParams, TrialInfo, c_double_p, c_int32_p, c_int64_p, dptr, i32ptr
 from .build import lib_path
 
 _lib = None
@@ -64,6 +64,18 @@ def load_library():
     L.v2gt_batch_get_lm_trace.argtypes = [vp, C.c_int32, C.c_int64, c_double_p, c_int64_p]
     L.v2gt_batch_get_timing.argtypes = [vp, c_double_p, c_int64_p]
     L.v2gt_measure_fp64_peak.argtypes = [C.c_int32, c_double_p]
+    # batched simulator on the device (csrc/k_sim.cu); the params struct is the host simulator's (host/v2gt_sim.h)
+    L.v2gt_simbatch_create.argtypes = [C.c_int32, C.c_int32, C.c_int64, c_double_p, C.POINTER(vp)]
+    L.v2gt_simbatch_destroy.argtypes = [vp]
+    L.v2gt_simbatch_set_trial.argtypes = [vp, C.c_int32, C.POINTER(SimParams)]
+    L.v2gt_simbatch_plan.argtypes = [vp]
+    L.v2gt_simbatch_run.argtypes = [vp]
+    L.v2gt_simbatch_sizes.argtypes = [vp, C.c_int32, c_int64_p, c_int64_p, c_int64_p]
+    L.v2gt_simbatch_get.argtypes = [vp, C.c_int32] + [c_double_p] * 7
+    L.v2gt_simbatch_get_truth.argtypes = [vp, C.c_int32, c_double_p, c_double_p, c_double_p, c_double_p]
+    L.v2gt_simbatch_get_state_in_vicon.argtypes = [vp, C.c_int32, C.c_int64, c_double_p, c_double_p, c_int32_p]
+    L.v2gt_simbatch_get_timing.argtypes = [vp, c_double_p]
+    L.v2gt_batch_set_trial_sim.argtypes = [vp, C.c_int32, C.POINTER(Params), vp, C.c_int32, c_double_p]
     _lib = L
     return L
 
@@ -154,6 +166,16 @@ class BatchSolver:
         self.set_trial(trial, params, ds.imu_t, ds.imu_w, ds.imu_a, ds.vic_t, ds.vic_q, ds.vic_p, ds.state_t,
                        vic_Rq=ds.vic_Rq if per_pose else None, vic_Rp=ds.vic_Rp if per_pose else None,
                        vic_R_const=None if per_pose else ds.vic_R_const, borrow=borrow)
+
+    def set_trial_sim(self, trial, params, simbatch, sim_trial=None):
+        """Stage trial `sim_trial` of a device-simulated batch (sim.SimBatch, same GPU): the measurement rows are copied
+        device to device at upload; `simbatch` must stay alive until then."""
+        k = int(trial if sim_trial is None else sim_trial)
+        R = _c(simbatch.vic_R_const(k))
+        _check(self._L.v2gt_batch_set_trial_sim(self.h, int(trial), C.byref(params), simbatch.h, k, dptr(R)), "v2gt_batch_set_trial_sim")
+        if not hasattr(self, "_views"):
+            self._views = {}
+        self._views[int(trial)] = [simbatch, R]
 
     def upload(self):
         _check(self._L.v2gt_batch_upload(self.h), "v2gt_batch_upload")

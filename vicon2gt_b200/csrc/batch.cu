@@ -47,6 +47,8 @@ int launch_chain_unpack(const DevPtrs &d, cudaStream_t st);
 int launch_chain_pack(const DevPtrs &d, int stride, cudaStream_t st);
 int launch_chain_halo(const DevPtrs &d, int recv, cudaStream_t st);
 int asm_chunks(int n_max);
+int simbatch_view(v2gt_simbatch *s, int trial, int *device, int64_t *n_imu, const double **imu_t, const double **d_imu_s, int64_t *n_vic,
+                  const double **vic_t, const double **d_vic_s, int64_t *n_times, const double **state_t);
 } // namespace v2
 
 using namespace v2;
@@ -60,6 +62,9 @@ struct HostTrial {
   const double *imu_t = nullptr, *imu_w = nullptr, *imu_a = nullptr;
   const double *vic_t_in = nullptr, *vic_q = nullptr, *vic_p = nullptr, *vic_Rq = nullptr, *vic_Rp = nullptr;
   const double *state_t_raw = nullptr;
+  // trial staged from a simulated batch (v2gt_batch_set_trial_sim): measurement rows already on this device, in
+  // the device layout; only the stamps above are host arrays (borrowed from the simulator handle)
+  const double *dev_imu_s = nullptr, *dev_vic_s = nullptr;
   int64_t n_imu = 0, n_vic_in = 0, n_times = 0;
   double vic_Rconst[18];
   bool cov_const = true;
@@ -439,6 +444,38 @@ int v2gt_batch_set_trial_view(v2gt_batch *b, int32_t trial, const v2gt_params *p
                         n_times, state_t, false);
 }
 
+int v2gt_batch_set_trial_sim(v2gt_batch *b, int32_t trial, const v2gt_params *params, v2gt_simbatch *sb, int32_t sim_trial,
+                             const double *vic_R_const) {
+  if (!b || trial < 0 || trial >= b->T || !params || !sb || !vic_R_const)
+    return V2GT_ERR_INVALID_ARG;
+  int dev = -1;
+  int64_t n_imu = 0, n_vic = 0, n_times = 0;
+  const double *imu_t, *d_imu_s, *vic_t, *d_vic_s, *state_t;
+  const int rc = v2::simbatch_view(sb, sim_trial, &dev, &n_imu, &imu_t, &d_imu_s, &n_vic, &vic_t, &d_vic_s, &n_times, &state_t);
+  if (rc != V2GT_OK)
+    return rc;
+  if (dev != b->device)
+    return V2GT_ERR_INVALID_ARG;
+  HostTrial &h = b->trials[trial];
+  h = HostTrial();
+  h.prm = *params;
+  h.n_imu = n_imu;
+  h.n_vic_in = n_vic;
+  h.n_times = n_times;
+  h.cov_const = true;
+  std::memcpy(h.vic_Rconst, vic_R_const, sizeof(h.vic_Rconst));
+  h.imu_t = imu_t;
+  h.vic_t_in = vic_t;
+  h.state_t_raw = state_t;
+  h.dev_imu_s = d_imu_s;
+  h.dev_vic_s = d_vic_s;
+  h.set = true;
+  b->uploaded = false;
+  b->built = false;
+  b->results_cached = false;
+  return V2GT_OK;
+}
+
 int v2gt_batch_upload(v2gt_batch *b) {
   if (!b)
     return V2GT_ERR_INVALID_ARG;
@@ -479,6 +516,10 @@ int v2gt_batch_upload(v2gt_batch *b) {
         h.vic_tmin = h.vic_t_in[0];
         h.vic_tmax = h.vic_t_in[nv - 1];
       }
+    } else if (h.dev_vic_s) {
+      h.info.status = V2GT_ERR_INVALID_ARG; // simulated stamps are strictly increasing by construction
+      lm[t].status = V2GT_ERR_INVALID_ARG;
+      return;
     } else {
       std::vector<int64_t> order((size_t)nv);
       std::iota(order.begin(), order.end(), (int64_t)0);
@@ -635,7 +676,7 @@ int v2gt_batch_upload(v2gt_batch *b) {
       // IMU: kept in feed order (Propagator::feed_imu appends); one 64-byte row (t, w, a, pad) per sample
       std::memcpy(h_imu_t + q.imu_off, h.imu_t, sizeof(double) * q.n_imu);
       double *o = h_imu_s + 8 * q.imu_off;
-      for (long long i = 0; i < q.n_imu; i++, o += 8) {
+      for (long long i = 0; i < (h.dev_imu_s ? 0 : q.n_imu); i++, o += 8) {
         o[0] = h.imu_t[i];
         o[1] = h.imu_w[3 * i];
         o[2] = h.imu_w[3 * i + 1];
@@ -652,6 +693,8 @@ int v2gt_batch_upload(v2gt_batch *b) {
     for (long long k = 0; k < q.n_vic; k++) {
       const int64_t i = reorder ? h.vic_order[(size_t)k] : k;
       vt[k] = h.vic_t_in[i];
+      if (h.dev_vic_s)
+        continue;
       double *o = vs + 8 * k;
       o[0] = h.vic_q[4 * i];
       o[1] = h.vic_q[4 * i + 1];
@@ -764,13 +807,27 @@ int v2gt_batch_upload(v2gt_batch *b) {
       const TrialDev &a = td[t0], &z = td[t1 - 1];
       const long long m0 = a.imu_off, m1 = z.imu_off + z.n_imu, v0 = a.vic_off, v1 = z.vic_off + z.n_vic;
       const long long s0 = a.st_off, s1 = z.st_off + z.n_raw;
+      bool all_dev = true; // every trial of the chunk comes from a simulated batch: no measurement rows to send
+      for (int t = t0; t < t1; t++)
+        all_dev = all_dev && b->trials[t].dev_imu_s;
       if (m1 > m0) {
         V2_CUDA_CHECK(cudaMemcpyAsync(p_imu_t + m0, h_imu_t + m0, sizeof(double) * (m1 - m0), cudaMemcpyHostToDevice, st));
-        V2_CUDA_CHECK(cudaMemcpyAsync(p_imu_s + 8 * m0, h_imu_s + 8 * m0, sizeof(double) * 8 * (m1 - m0), cudaMemcpyHostToDevice, st));
+        if (!all_dev)
+          V2_CUDA_CHECK(cudaMemcpyAsync(p_imu_s + 8 * m0, h_imu_s + 8 * m0, sizeof(double) * 8 * (m1 - m0), cudaMemcpyHostToDevice, st));
       }
       if (v1 > v0) {
         V2_CUDA_CHECK(cudaMemcpyAsync(p_vic_t + v0, h_vic_t + v0, sizeof(double) * (v1 - v0), cudaMemcpyHostToDevice, st));
-        V2_CUDA_CHECK(cudaMemcpyAsync(p_vic_s + 8 * v0, h_vic_s + 8 * v0, sizeof(double) * 8 * (v1 - v0), cudaMemcpyHostToDevice, st));
+        if (!all_dev)
+          V2_CUDA_CHECK(cudaMemcpyAsync(p_vic_s + 8 * v0, h_vic_s + 8 * v0, sizeof(double) * 8 * (v1 - v0), cudaMemcpyHostToDevice, st));
+      }
+      for (int t = t0; t < t1; t++) {
+        const HostTrial &h = b->trials[t];
+        if (!h.dev_imu_s)
+          continue;
+        if (td[t].n_imu)
+          V2_CUDA_CHECK(cudaMemcpyAsync(p_imu_s + 8 * td[t].imu_off, h.dev_imu_s, sizeof(double) * 8 * td[t].n_imu, cudaMemcpyDeviceToDevice, st));
+        if (td[t].n_vic)
+          V2_CUDA_CHECK(cudaMemcpyAsync(p_vic_s + 8 * td[t].vic_off, h.dev_vic_s, sizeof(double) * 8 * td[t].n_vic, cudaMemcpyDeviceToDevice, st));
       }
       long long c0 = -1, c1 = -1; // range of the per-pose covariances of this chunk (doubles)
       for (int t = t0; t < t1; t++)

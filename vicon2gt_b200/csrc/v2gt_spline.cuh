@@ -254,8 +254,9 @@ V2_HD void spline_eval_core(const M4 &pose0, const M4 &pose1, const M4 &pose2, c
 
 } // namespace v2sp
 
-// ---- host side: control points from trajectory rows (std::map, as the reference builds them)
-#if !defined(__CUDA_ARCH__)
+// ---- host side: control points from trajectory rows (std::map, as the reference builds them); plain host code,
+// also parsed (and dropped) by nvcc's device pass of csrc/k_sim.cu
+#if 1
 #include <array>
 #include <cmath>
 #include <map>

@@ -151,11 +151,116 @@ def simulate(traj_rows=None, traj_path=None, seed=0, vicon_sigmas=(0.0174, 0.017
         truth["states_ok"] = ok
     finally:
         lib.v2gt_sim_destroy(h)
-    s = np.asarray(vicon_sigmas, dtype=np.float64)
-    R_const = np.zeros(18)
-    R_const[[0, 4, 8]] = s[:3] ** 2  # R_q diag (run_simulation.cpp:89-91)
-    R_const[[9, 13, 17]] = s[3:] ** 2  # R_p diag
+    R_const = _vic_R_const(vicon_sigmas)
     return Dataset(imu_t, imu_w, imu_a, vic_t, vic_q, vic_p, R_const, state_t, truth, int(seed))
+
+
+def _vic_R_const(sigmas):
+    s = np.asarray(sigmas, dtype=np.float64)
+    R = np.zeros(18)
+    R[[0, 4, 8]] = s[:3] ** 2  # R_q diag (run_simulation.cpp:89-91)
+    R[[9, 13, 17]] = s[3:] ** 2  # R_p diag
+    return R
+
+
+class SimBatch:
+    """The simulator for a whole Monte-Carlo batch on the GPU (csrc/k_sim.cu, `v2gt_simbatch_*` of the C ABI).
+
+    One trajectory, `n_trials` seeds (default: trial t has seed t) and per-trial vicon sigmas; the rates are shared.
+    `plan()` (host only) fixes the stamps, the per-seed truth and the state grids; `run()` generates the measurements of
+    every trial on the device, where `BatchSolver.set_trial_sim` picks them up without a host round trip.  `dataset(t)`
+    downloads one trial in the host simulator's layout (parity checks, examples)."""
+
+    def __init__(self, traj_rows, n_trials, device=0, seeds=None, vicon_sigmas=(0.0174, 0.0174, 0.0174, 0.05, 0.05, 0.05),
+                 freq_imu=400.0, freq_cam=20.0, freq_vicon=100.0, state_freq=100, max_imu=0, **noise):
+        from . import api
+
+        self._L = api.load_library()
+        self._api = api
+        rows = np.ascontiguousarray(traj_rows, dtype=np.float64)
+        self.n_trials = int(n_trials)
+        self.h = C.c_void_p()
+        api._check(self._L.v2gt_simbatch_create(int(device), self.n_trials, rows.shape[0], dptr(rows), C.byref(self.h)),
+                   "v2gt_simbatch_create")
+        sig = np.asarray(vicon_sigmas, dtype=np.float64)
+        self._sigmas = np.broadcast_to(sig, (self.n_trials, 6)) if sig.ndim == 1 else sig.reshape(self.n_trials, 6)
+        self.seeds = [int(x) for x in (range(self.n_trials) if seeds is None else seeds)]
+        for t in range(self.n_trials):
+            p = default_sim_params(seed=self.seeds[t], sim_freq_imu=float(freq_imu), sim_freq_cam=float(freq_cam),
+                                   sim_freq_vicon=float(freq_vicon), state_freq=int(state_freq), max_imu=int(max_imu),
+                                   sigma_vicon_pose=self._sigmas[t], **noise)
+            api._check(self._L.v2gt_simbatch_set_trial(self.h, t, C.byref(p)), "v2gt_simbatch_set_trial")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.v2gt_simbatch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def plan(self):
+        self._api._check(self._L.v2gt_simbatch_plan(self.h), "v2gt_simbatch_plan")
+
+    def run(self):
+        self._api._check(self._L.v2gt_simbatch_run(self.h), "v2gt_simbatch_run")
+
+    def generate_ms(self):
+        v = C.c_double()
+        self._api._check(self._L.v2gt_simbatch_get_timing(self.h, C.byref(v)), "v2gt_simbatch_get_timing")
+        return v.value
+
+    def sizes(self, trial=0):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        self._api._check(self._L.v2gt_simbatch_sizes(self.h, int(trial), C.byref(a), C.byref(b), C.byref(c)), "v2gt_simbatch_sizes")
+        return a.value, b.value, c.value
+
+    def vic_R_const(self, trial):
+        return _vic_R_const(self._sigmas[int(trial)])
+
+    def truth(self, trial):
+        R_BtoI, p_BinI, R_GtoV = np.zeros((3, 3)), np.zeros(3), np.zeros((3, 3))
+        dt = C.c_double()
+        self._api._check(self._L.v2gt_simbatch_get_truth(self.h, int(trial), dptr(R_BtoI), dptr(p_BinI), C.byref(dt), dptr(R_GtoV)),
+                         "v2gt_simbatch_get_truth")
+        return dict(R_BtoI=R_BtoI, p_BinI=p_BinI, viconimu_dt=dt.value, R_GtoV=R_GtoV)
+
+    def stamps(self, trial):
+        """(imu_t, vic_t, state_t) of a trial: host plan only, no device needed."""
+        M, V, N = self.sizes(trial)
+        imu_t, vic_t, state_t = np.zeros(M), np.zeros(V), np.zeros(N)
+        self._api._check(self._L.v2gt_simbatch_get(self.h, int(trial), dptr(imu_t), None, None, dptr(vic_t), None, None, dptr(state_t)),
+                         "v2gt_simbatch_get")
+        return imu_t, vic_t, state_t
+
+    def state_in_vicon(self, trial, times):
+        times = np.ascontiguousarray(times, dtype=np.float64)
+        out = np.zeros((len(times), 17))
+        ok = np.zeros(len(times), dtype=np.int32)
+        self._api._check(self._L.v2gt_simbatch_get_state_in_vicon(self.h, int(trial), len(times), dptr(times), dptr(out),
+                                                                  ok.ctypes.data_as(c_int32_p)), "v2gt_simbatch_get_state_in_vicon")
+        return out, ok
+
+    def dataset(self, trial, with_truth_states=True):
+        M, V, N = self.sizes(trial)
+        imu_t, imu_w, imu_a = np.zeros(M), np.zeros((M, 3)), np.zeros((M, 3))
+        vic_t, vic_q, vic_p = np.zeros(V), np.zeros((V, 4)), np.zeros((V, 3))
+        state_t = np.zeros(N)
+        self._api._check(self._L.v2gt_simbatch_get(self.h, int(trial), dptr(imu_t), dptr(imu_w), dptr(imu_a), dptr(vic_t), dptr(vic_q),
+                                                   dptr(vic_p), dptr(state_t)), "v2gt_simbatch_get")
+        truth = self.truth(trial)
+        if with_truth_states and N:
+            truth["states"], truth["states_ok"] = self.state_in_vicon(trial, state_t)
+        return Dataset(imu_t, imu_w, imu_a, vic_t, vic_q, vic_p, self.vic_R_const(trial), state_t, truth, self.seeds[int(trial)])
 
 
 def make_config(name, seed=0, duration_s=None, **kw):
