@@ -62,6 +62,7 @@ def parse():
     ap.add_argument("--cpu-sample-s", type=float, default=40.0, help="length of the CPU baseline sample trajectory")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--no-sim", action="store_true", help="skip the device-simulator leg (SURVEY 8f row 1)")
     ap.add_argument("--workload", default="mc", choices=["mc", "chain"],
                     help="mc: Monte-Carlo batch (BASELINE configs[3], the default the metric is quoted on); chain: ONE one-hour "
                          "sequence chain-sharded over the GPUs with NCCL (configs[4]; second half of the metric: LM latency)")
@@ -139,6 +140,44 @@ class ClockSampler:
                     reasons.add(nme)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def simulator_leg(api, sim, bs, p, T, seed0, duration, read_back):
+    """the same trials generated by the batched device simulator (csrc/k_sim.cu) and handed to the solver
+    device -> device, next to the host simulator timed on one trial.  One step of simulate -> stage -> solve -> read back."""
+    shape = dict(sim.TRAJ_SHAPES["tum_corridor1"])
+    if duration > 0:
+        shape["n_rows"] = max(8, min(shape["n_rows"], int(round(duration / shape["dt"])) + 1))
+    rows = sim.make_trajectory(**shape)
+    t0 = time.perf_counter()
+    sim.simulate(traj_rows=rows, seed=seed0)
+    host_s = time.perf_counter() - t0
+    sb = sim.SimBatch(rows, T, seeds=range(seed0, seed0 + T))
+    try:
+        sb.plan()
+        sb.run()  # first run allocates
+        t0 = time.perf_counter()
+        sb.plan()
+        t1 = time.perf_counter()
+        sb.run()
+        t2 = time.perf_counter()
+        for i in range(T):
+            bs.set_trial_sim(i, p, sb)
+        bs.upload()
+        t3 = time.perf_counter()
+        bs.build_and_solve()
+        t4 = time.perf_counter()
+        read_back()
+        t5 = time.perf_counter()
+        ok = sum(1 for i in range(T) if bs.info(i).status == 0)
+        M, V, N = sb.sizes(0)
+        return {"trials": T, "n_imu": M, "n_vicon": V, "n_states_raw": N, "plan_host_ms": 1e3 * (t1 - t0), "generate_wall_ms": 1e3 * (t2 - t1),
+                "generate_device_ms": sb.generate_ms(), "simulated_trials_per_s": T / (t2 - t0),
+                "host_simulator_s_per_trial_1_thread": host_s, "stage_device_to_device_ms": 1e3 * (t3 - t2),
+                "build_and_solve_ms": 1e3 * (t4 - t3), "read_back_ms": 1e3 * (t5 - t4), "trials_ok": ok,
+                "simulate_to_result_trajectories_per_s": T / (t5 - t0), "kernels_launched": 6}
+    finally:
+        sb.close()
 
 
 def measured_peaks():
@@ -428,6 +467,17 @@ def main():
     e2e_s = max_over_ranks(e2e_s)
     e2e_value = world * T * args.steps / e2e_s
 
+    # ---------------- the same trials from the device simulator (inputs never on the host); rank 0 only
+    simulator = None
+    if not args.no_sim and rank == 0:
+        try:
+            from vicon2gt_b200 import sim as _sim
+
+            simulator = simulator_leg(api, _sim, bs, p, T, rank * T, args.duration, read_back)
+        except Exception as e:  # the leg is a widened row: it must never cost the headline line
+            simulator = {"error": repr(e)}
+    barrier()
+
     # ---------------- LM iteration latency on a single trajectory (second half of the metric)
     latency = None
     if not args.no_latency and rank == 0:
@@ -489,6 +539,7 @@ def main():
             "phases_ms_per_step": {k: float(phase_ms[i]) / args.steps for i, k in
                                    enumerate(["build", "linearize", "eliminate", "reduced", "backsub", "cost", "lm", "optimize_total"])},
             "lm_iteration_latency": latency,
+            "simulator": simulator,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))

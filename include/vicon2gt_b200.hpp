@@ -115,6 +115,50 @@ private:
   double tmin_ = 0, tmax_ = 0;
 };
 
+/* The reference's Simulator (src/sim/Simulator.h) for a whole Monte-Carlo batch on the GPU: one trajectory ("t x y z qx qy
+ * qz qw" rows, JPL q_GtoI), one seed (+ vicon sigmas) per trial.  BatchSolver::set_trial_sim hands a simulated trial to the
+ * solver on the device.  Parameters: v2gt_sim_params of vicon2gt_b200/host/v2gt_sim.h -- include that header before this one
+ * to set them; without it every trial keeps the SimulatorParams defaults with seed = trial index. */
+class SimBatch {
+public:
+  SimBatch(int n_trials, const std::vector<double> &rows8, int device = 0) : n_(n_trials) {
+    check(v2gt_simbatch_create(device, n_trials, (int64_t)(rows8.size() / 8), rows8.data(), &h_), "v2gt_simbatch_create");
+  }
+  ~SimBatch() { v2gt_simbatch_destroy(h_); }
+  SimBatch(const SimBatch &) = delete;
+  SimBatch &operator=(const SimBatch &) = delete;
+  int size() const { return n_; }
+  v2gt_simbatch *handle() { return h_; }
+  void set_trial(int trial, const struct v2gt_sim_params &p) { check(v2gt_simbatch_set_trial(h_, trial, &p), "v2gt_simbatch_set_trial"); }
+  void plan() { check(v2gt_simbatch_plan(h_), "v2gt_simbatch_plan"); }
+  void run() { check(v2gt_simbatch_run(h_), "v2gt_simbatch_run"); }
+  /* Simulator::get_next_imu / get_next_vicon results of one trial, in feed order, plus the state-time grid */
+  void get(int trial, std::vector<double> &imu_t, std::vector<double> &imu_w, std::vector<double> &imu_a, std::vector<double> &vic_t,
+           std::vector<double> &vic_q, std::vector<double> &vic_p, std::vector<double> &state_t) {
+    int64_t M = 0, V = 0, N = 0;
+    check(v2gt_simbatch_sizes(h_, trial, &M, &V, &N), "v2gt_simbatch_sizes");
+    imu_t.resize((size_t)M); imu_w.resize((size_t)M * 3); imu_a.resize((size_t)M * 3);
+    vic_t.resize((size_t)V); vic_q.resize((size_t)V * 4); vic_p.resize((size_t)V * 3);
+    state_t.resize((size_t)N);
+    check(v2gt_simbatch_get(h_, trial, imu_t.data(), imu_w.data(), imu_a.data(), vic_t.data(), vic_q.data(), vic_p.data(), state_t.data()),
+          "v2gt_simbatch_get");
+  }
+  void get_truth(int trial, Mat3 &R_BtoI, Vec3 &p_BinI, double &viconimu_dt, Mat3 &R_GtoV) {
+    check(v2gt_simbatch_get_truth(h_, trial, R_BtoI.data(), p_BinI.data(), &viconimu_dt, R_GtoV.data()), "v2gt_simbatch_get_truth");
+  }
+  /* Simulator::get_state_in_vicon: rows of 17 = [t, q_VtoI(4), p_IinV(3), v_IinV(3), bg(3), ba(3)] */
+  void get_state_in_vicon(int trial, const std::vector<double> &times, std::vector<double> &out17, std::vector<int32_t> &ok) {
+    out17.resize(times.size() * 17);
+    ok.resize(times.size());
+    check(v2gt_simbatch_get_state_in_vicon(h_, trial, (int64_t)times.size(), times.data(), out17.data(), ok.data()),
+          "v2gt_simbatch_get_state_in_vicon");
+  }
+
+private:
+  int n_;
+  v2gt_simbatch *h_ = nullptr;
+};
+
 /* A batch of independent build-and-solve problems resident on one GPU (owns the C handle). */
 class BatchSolver {
 public:
@@ -154,6 +198,11 @@ public:
                                     vicon.positions().data(), vicon.cov_q().data(), vicon.cov_p().data(), nullptr,
                                     (int64_t)timestamp_cameras.size(), timestamp_cameras.data()),
           "v2gt_batch_set_trial_view");
+  }
+  /* Trial `sim_trial` of a simulated batch on the same GPU (measurements copied device -> device at upload); vic_R_const =
+   * (R_q, R_p) of run_simulation.cpp:84-96, 18 doubles.  `sim` must outlive build_and_solve(). */
+  void set_trial_sim(int trial, const v2gt_params &params, SimBatch &sim, int sim_trial, const std::array<double, 18> &vic_R_const) {
+    check(v2gt_batch_set_trial_sim(h_, trial, &params, sim.handle(), sim_trial, vic_R_const.data()), "v2gt_batch_set_trial_sim");
   }
   void build_and_solve() { check(v2gt_batch_build_and_solve(h_), "v2gt_batch_build_and_solve"); }
   /* CSV + info (+ pose text) files of every solved trial under `dir`; returns the number of trials written. */

@@ -238,6 +238,12 @@ class BatchSolver:
             raise ValueError("surviving state times are not a subset of the dataset's state times")
         self.set_truth(trial, ds.truth["states"][idx, 1:11])
 
+    def set_truth_from_sim(self, trial, simbatch, sim_trial=None):
+        """The same from a device-simulated batch: Simulator::get_state_in_vicon evaluated on the GPU at the surviving times."""
+        times, _ = self.states(trial)
+        st, _ = simbatch.state_in_vicon(int(trial if sim_trial is None else sim_trial), times)
+        self.set_truth(trial, st[:, 1:11])
+
     def error_stats(self):
         """[n_trials, 3, 8]: (ori deg, pos m, vel m/s) x (rmse, mean, median, min, max, std, mean + 2.326 std, count)."""
         out = np.zeros((self.n_trials, 3, 8))

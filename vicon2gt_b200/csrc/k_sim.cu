@@ -16,7 +16,7 @@
 //                                  reference is created fresh for its 12 (IMU sample), 6 (vicon pose) or 9 (truth)
 //                                  draws, so sample i owns accepted pairs [6i, 6i+6) and pose j pairs [3j, 3j+3) of
 //                                  the same per-seed stream (both generators are seeded with `seed`, Simulator.cpp:85-88)
-//   k_sim_bias                     thread per (trial, bias component): the random walk, summed in sample order
+//   k_sim_bias                     CTA per trial: the bias random walks, summed in sample order (tiles staged in shared memory)
 //   k_sim_imu / k_sim_vic          thread per (trial, sample): measurement = spline value (+ bias) + noise
 //                                  (Simulator.cpp:170-185, 228-258), written in the batch solver's device layout
 //   k_sim_state_in_vicon           thread per query: Simulator::get_state_in_vicon (Simulator.cpp:91-133) with a
@@ -190,34 +190,65 @@ __global__ void __launch_bounds__(128) k_sim_spline_pose(const double *cp_t, con
   o[15] = 1.0;
 }
 
-// thread per (trial, component c of [bg3 ba3]): hist[t][i + 2][c] = bias after sample i, summed in sample order
-// (Simulator.cpp:182-185); rows 0 and 1 are the two zero entries the constructor pushes (Simulator.cpp:72-77)
-__global__ void k_sim_bias(int T, long long M, const SimTrialDev *ts, const double *normals, long long np2, double *hist) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= T * 6)
-    return;
-  const int t = idx / 6, c = idx - 6 * t;
-  const double k = (c < 3) ? ts[t].k_wb : ts[t].k_ab;
-  const double *n = normals + (long long)t * np2 + 6 + c;
-  double *h = hist + (long long)t * (M + 2) * 6 + c;
-  h[0] = 0.0;
-  h[6] = 0.0;
-  double b = 0.0;
-  long long i = 0;
-  for (; i + 8 <= M; i += 8) {
-    double v[8];
+// CTA (two warps) per trial: hist[t][i + 2][c] = bias component c of [bg3 ba3] after sample i (Simulator.cpp:182-185), summed
+// in sample order by six lanes; rows 0 and 1 are the two zero entries the constructor pushes (Simulator.cpp:72-77).  The
+// increments of a tile of 128 samples are fetched coalesced one tile ahead (registers -> shared memory), the running sums
+// leave through shared memory as one contiguous block: the chain of dependent additions is all that is left in sequence.
+constexpr int BIAS_TILE = 128, BIAS_THREADS = 64, BIAS_PER_THREAD = BIAS_TILE * 6 / BIAS_THREADS;
+__global__ void __launch_bounds__(BIAS_THREADS) k_sim_bias(long long M, const SimTrialDev *ts, const double *normals, long long np2,
+                                                           double *hist) {
+  __shared__ double inc[2][BIAS_TILE * 6];
+  __shared__ double res[BIAS_TILE * 6];
+  const int t = blockIdx.x, tid = threadIdx.x;
+  const double *n = normals + (long long)t * np2;
+  double *h = hist + (long long)t * (M + 2) * 6;
+  if (tid < 12)
+    h[tid] = 0.0;
+  const double kc = (tid < 3) ? ts[t].k_wb : ts[t].k_ab;
+  const long long ntile = (M + BIAS_TILE - 1) / BIAS_TILE;
+  double r[BIAS_PER_THREAD];
+  auto load = [&](const long long tile) {
 #pragma unroll
-    for (int u = 0; u < 8; u++)
-      v[u] = __ldg(n + 12 * (i + u));
-#pragma unroll
-    for (int u = 0; u < 8; u++) {
-      b = __dadd_rn(b, __dmul_rn(k, v[u]));
-      h[6 * (i + u + 2)] = b;
+    for (int k = 0; k < BIAS_PER_THREAD; k++) {
+      const int idx = tid + BIAS_THREADS * k, smp = idx / 6, c = idx - 6 * smp;
+      const long long i = tile * BIAS_TILE + smp;
+      r[k] = (i < M) ? __ldg(n + 12 * i + 6 + c) : 0.0; // padding adds exact zeros
     }
+  };
+  auto stash = [&](const int buf) {
+#pragma unroll
+    for (int k = 0; k < BIAS_PER_THREAD; k++)
+      inc[buf][tid + BIAS_THREADS * k] = r[k];
+  };
+  if (ntile > 0) {
+    load(0);
+    stash(0);
   }
-  for (; i < M; i++) {
-    b = __dadd_rn(b, __dmul_rn(k, __ldg(n + 12 * i)));
-    h[6 * (i + 2)] = b;
+  __syncthreads();
+  double b = 0.0;
+  for (long long tile = 0; tile < ntile; tile++) {
+    const int cur = (int)(tile & 1);
+    if (tile + 1 < ntile)
+      load(tile + 1);
+    if (tid < 6) {
+#pragma unroll 8
+      for (int u = 0; u < BIAS_TILE; u++) {
+        b = __dadd_rn(b, __dmul_rn(kc, inc[cur][6 * u + tid]));
+        res[6 * u + tid] = b;
+      }
+    }
+    if (tile + 1 < ntile)
+      stash(cur ^ 1);
+    __syncthreads();
+    const long long i0 = tile * BIAS_TILE;
+    const long long cnt = ((M - i0 < BIAS_TILE) ? (M - i0) : (long long)BIAS_TILE) * 6;
+#pragma unroll
+    for (int k = 0; k < BIAS_PER_THREAD; k++) {
+      const int idx = tid + BIAS_THREADS * k;
+      if (idx < cnt)
+        h[(i0 + 2) * 6 + idx] = res[idx];
+    }
+    __syncthreads();
   }
 }
 
@@ -614,7 +645,7 @@ int v2gt_simbatch_run(v2gt_simbatch *s) {
     k_sim_spline_imu<<<(unsigned)((M + 127) / 128), 128, 0, st>>>(s->d_cp_t, s->d_cp, K, s->d_imu_clk, M, s->prm[0].gravity_magnitude, s->d_base_imu);
   if (V > 0)
     k_sim_spline_pose<<<(unsigned)((V + 127) / 128), 128, 0, st>>>(s->d_cp_t, s->d_cp, K, s->d_vic_clk, V, 0, s->d_base_vic);
-  k_sim_bias<<<(T * 6 + 63) / 64, 64, 0, st>>>(T, M, s->d_ts, s->d_normals, np2, s->d_hist);
+  k_sim_bias<<<T, BIAS_THREADS, 0, st>>>(M, s->d_ts, s->d_normals, np2, s->d_hist);
   if (M > 0)
     k_sim_imu<<<(unsigned)(((long long)T * M + 255) / 256), 256, 0, st>>>(T, M, s->d_imu_clk, s->d_base_imu, s->d_ts, s->d_normals, np2,
                                                                            s->d_hist, s->d_imu_t, s->d_imu_s);
