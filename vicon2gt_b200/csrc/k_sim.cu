@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(BIAS_THREADS) k_sim_bias(long long M, const Si
   double *h = hist + (long long)t * (M + 2) * 6;
   if (tid < 12)
     h[tid] = 0.0;
-  const double kc = (tid < 3) ? ts[t].k_wb : ts[t].k_ab;
+  const double k_wb = ts[t].k_wb, k_ab = ts[t].k_ab;
   const long long ntile = (M + BIAS_TILE - 1) / BIAS_TILE;
   double r[BIAS_PER_THREAD];
   auto load = [&](const long long tile) {
@@ -217,8 +217,10 @@ __global__ void __launch_bounds__(BIAS_THREADS) k_sim_bias(long long M, const Si
   };
   auto stash = [&](const int buf) {
 #pragma unroll
-    for (int k = 0; k < BIAS_PER_THREAD; k++)
-      inc[buf][tid + BIAS_THREADS * k] = r[k];
+    for (int k = 0; k < BIAS_PER_THREAD; k++) {
+      const int idx = tid + BIAS_THREADS * k;
+      inc[buf][idx] = __dmul_rn((idx % 6 < 3) ? k_wb : k_ab, r[k]); // the step sigma sqrt(dt) n, rounded as on the host
+    }
   };
   if (ntile > 0) {
     load(0);
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(BIAS_THREADS) k_sim_bias(long long M, const Si
     if (tid < 6) {
 #pragma unroll 8
       for (int u = 0; u < BIAS_TILE; u++) {
-        b = __dadd_rn(b, __dmul_rn(kc, inc[cur][6 * u + tid]));
+        b = __dadd_rn(b, inc[cur][6 * u + tid]);
         res[6 * u + tid] = b;
       }
     }
@@ -368,6 +370,7 @@ struct v2gt_simbatch {
   std::vector<std::vector<double>> state_t, vic_t;
   bool planned = false, ran = false;
   long long n_pairs = 0;
+  long long alloc_key[4] = {0, 0, 0, 0}; // (T, M, V, K) the device buffers were sized for
   cudaStream_t stream = nullptr;
   double *d_cp_t = nullptr, *d_imu_clk = nullptr, *d_vic_clk = nullptr, *d_bias_t = nullptr;
   v2sp::M4 *d_cp = nullptr;
@@ -610,25 +613,34 @@ int v2gt_simbatch_run(v2gt_simbatch *s) {
   V2_CUDA_CHECK(cudaSetDevice(s->device));
   if (!s->stream)
     V2_CUDA_CHECK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-  sim_free(s);
   const int T = s->T;
   const long long M = (long long)s->imu_clk.size(), V = (long long)s->vic_clk.size(), K = (long long)s->cp_t.size();
   s->n_pairs = std::max(std::max(6 * M, 3 * V), 5LL);
   const long long np2 = 2 * s->n_pairs;
-  V2_TRY(sim_alloc(s, &s->d_cp_t, (size_t)K));
-  V2_TRY(sim_alloc(s, &s->d_cp, (size_t)K));
-  V2_TRY(sim_alloc(s, &s->d_imu_clk, (size_t)M));
-  V2_TRY(sim_alloc(s, &s->d_vic_clk, (size_t)V));
-  V2_TRY(sim_alloc(s, &s->d_bias_t, (size_t)M + 2));
-  V2_TRY(sim_alloc(s, &s->d_base_imu, (size_t)M * 8));
-  V2_TRY(sim_alloc(s, &s->d_base_vic, (size_t)V * 16));
-  V2_TRY(sim_alloc(s, &s->d_normals, (size_t)T * np2));
-  V2_TRY(sim_alloc(s, &s->d_hist, (size_t)T * (M + 2) * 6));
-  V2_TRY(sim_alloc(s, &s->d_imu_t, (size_t)T * M));
-  V2_TRY(sim_alloc(s, &s->d_imu_s, (size_t)T * M * 8));
-  V2_TRY(sim_alloc(s, &s->d_vic_t, (size_t)T * V));
-  V2_TRY(sim_alloc(s, &s->d_vic_s, (size_t)T * V * 8));
-  V2_TRY(sim_alloc(s, &s->d_ts, (size_t)T));
+  const bool reuse = !s->allocs.empty() && s->alloc_key[0] == T && s->alloc_key[1] == M && s->alloc_key[2] == V && s->alloc_key[3] == K;
+  if (!reuse) {
+    sim_free(s);
+    s->alloc_key[0] = 0;
+    V2_TRY(sim_alloc(s, &s->d_cp_t, (size_t)K));
+    V2_TRY(sim_alloc(s, &s->d_cp, (size_t)K));
+    V2_TRY(sim_alloc(s, &s->d_imu_clk, (size_t)M));
+    V2_TRY(sim_alloc(s, &s->d_vic_clk, (size_t)V));
+    V2_TRY(sim_alloc(s, &s->d_bias_t, (size_t)M + 2));
+    V2_TRY(sim_alloc(s, &s->d_base_imu, (size_t)M * 8));
+    V2_TRY(sim_alloc(s, &s->d_base_vic, (size_t)V * 16));
+    V2_TRY(sim_alloc(s, &s->d_normals, (size_t)T * np2));
+    V2_TRY(sim_alloc(s, &s->d_hist, (size_t)T * (M + 2) * 6));
+    V2_TRY(sim_alloc(s, &s->d_imu_t, (size_t)T * M));
+    V2_TRY(sim_alloc(s, &s->d_imu_s, (size_t)T * M * 8));
+    V2_TRY(sim_alloc(s, &s->d_vic_t, (size_t)T * V));
+    V2_TRY(sim_alloc(s, &s->d_vic_s, (size_t)T * V * 8));
+    V2_TRY(sim_alloc(s, &s->d_ts, (size_t)T));
+    s->alloc_key[0] = T;
+    s->alloc_key[1] = M;
+    s->alloc_key[2] = V;
+    s->alloc_key[3] = K;
+  }
+  s->ran = false;
   cudaStream_t st = s->stream;
   cudaEvent_t e0, e1;
   V2_CUDA_CHECK(cudaEventCreate(&e0));
