@@ -394,12 +394,9 @@ def main():
         bs.upload()
 
     def read_back():
-        nbytes = 0
-        for i in range(T):
-            t, x = bs.states(i)
-            g = bs.globals10(i)
-            nbytes += t.nbytes + x.nbytes + g.nbytes
-        return nbytes
+        # every trial's states + calibration in one call (v2gt_batch_get_all_states: pinned bounce buffer, chunked)
+        _, t, x, g = bs.all_states()
+        return t.nbytes + x.nbytes + g.nbytes
 
     # ---------------- device-resident steps: inputs already in HBM
     stage_and_upload()

@@ -157,6 +157,11 @@ int v2gt_batch_sync(v2gt_batch *b);
 /* Results (HOST pointers).  get_states replaces get_imu_poses (.cpp:357-375): times[n], states[n][16]. */
 int v2gt_batch_get_info(v2gt_batch *b, int32_t trial, v2gt_trial_info *info);
 int v2gt_batch_get_states(v2gt_batch *b, int32_t trial, int64_t capacity, double *times, double *states, int64_t *n_out);
+/* The same for every trial of the batch in one pass (asynchronous copies through pinned memory, moved to the caller's
+ * arrays on several host threads): offsets[n_trials + 1] = prefix sums of the surviving-state counts, times[offsets[T]],
+ * states[offsets[T]][16], globals10[n_trials][10] = q_BtoI(4) p_BinI(3) t_off theta_x theta_y.  `capacity` = states the
+ * arrays can hold; with times = states = globals10 = NULL only the offsets are filled. */
+int v2gt_batch_get_all_states(v2gt_batch *b, int64_t capacity, int64_t *offsets, double *times, double *states, double *globals10);
 /* get_calibration (.cpp:377-388): q_BtoI[4], p_BinI[3], t_off, (theta_x, theta_y) of R_GtoV. */
 int v2gt_batch_get_calibration(v2gt_batch *b, int32_t trial, double *q_BtoI, double *p_BinI, double *t_off, double *theta_xy);
 /* ViconGraphSolver::write_to_file (.cpp:194-248): byte-compatible CSV + info text. */

@@ -238,6 +238,16 @@ public:
     states.assign((size_t)n * V2GT_STATE_DIM, 0.0);
     check(v2gt_batch_get_states(h_, trial, n, times.data(), states.data(), &n), "v2gt_batch_get_states");
   }
+  /* every trial in one read-back: trial t owns rows offsets[t] .. offsets[t+1] of times / states (16 per row); globals10 = 10 per trial */
+  void get_all_states(std::vector<int64_t> &offsets, std::vector<double> &times, std::vector<double> &states, std::vector<double> &globals10) {
+    offsets.assign((size_t)n_ + 1, 0);
+    check(v2gt_batch_get_all_states(h_, 0, offsets.data(), nullptr, nullptr, nullptr), "v2gt_batch_get_all_states");
+    const size_t n = (size_t)offsets.back();
+    times.resize(n);
+    states.resize(n * 16);
+    globals10.resize((size_t)n_ * 10);
+    check(v2gt_batch_get_all_states(h_, (int64_t)n, offsets.data(), times.data(), states.data(), globals10.data()), "v2gt_batch_get_all_states");
+  }
   void get_calibration(int trial, Vec4 &q_BtoI, Vec3 &p_BinI, double &toff, std::array<double, 2> &theta_xy) {
     check(v2gt_batch_get_calibration(h_, trial, q_BtoI.data(), p_BinI.data(), &toff, theta_xy.data()), "v2gt_batch_get_calibration");
   }

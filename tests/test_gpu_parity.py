@@ -270,7 +270,29 @@ def test_error_codes_do_not_kill_the_batch(ds_c2_small):
     assert bs.info(0).status == 0 and bs.info(0).iterations == 3
     assert bs.info(1).status == 5
     assert bs.info(2).status == 4
+    # the one-pass read-back agrees with the per-trial getters, failed trials own no rows
+    off, t, x, g = bs.all_states()
+    t0, x0 = bs.states(0)
+    assert list(off) == [0, len(t0), len(t0), len(t0)] and np.array_equal(t, t0) and np.array_equal(x, x0)
+    assert np.array_equal(g[0], bs.globals10(0))
     bs.close()
+
+
+def test_bulk_read_back_matches_per_trial_getters(ds_c1_small, ds_c2_small, ds_c3_small):
+    from vicon2gt_b200 import api
+
+    p = default_params(lm_max_iterations=4)
+    dss = [ds_c1_small, ds_c2_small, ds_c3_small, ds_c2_small, ds_c1_small]
+    with api.BatchSolver(len(dss)) as bs:
+        for k, ds in enumerate(dss):
+            bs.set_trial_dataset(k, p, ds)
+        bs.build_and_solve()
+        off, t, x, g = bs.all_states()
+        for k in range(len(dss)):
+            tk, xk = bs.states(k)
+            assert off[k + 1] - off[k] == len(tk) > 0
+            assert np.array_equal(t[off[k]:off[k + 1]], tk) and np.array_equal(x[off[k]:off[k + 1]], xk)
+            assert np.array_equal(g[k], bs.globals10(k))
 
 
 def test_write_to_file_matches_oracle(ds_c2_small, tmp_path):

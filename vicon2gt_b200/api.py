@@ -48,6 +48,7 @@ def load_library():
     L.v2gt_batch_build.argtypes = [vp, C.c_int32]
     L.v2gt_batch_get_info.argtypes = [vp, C.c_int32, C.POINTER(TrialInfo)]
     L.v2gt_batch_get_states.argtypes = [vp, C.c_int32, C.c_int64, c_double_p, c_double_p, c_int64_p]
+    L.v2gt_batch_get_all_states.argtypes = [vp, C.c_int64, c_int64_p, c_double_p, c_double_p, c_double_p]
     L.v2gt_batch_get_calibration.argtypes = [vp, C.c_int32, c_double_p, c_double_p, c_double_p, c_double_p]
     L.v2gt_batch_write_to_file.argtypes = [vp, C.c_int32, C.c_char_p, C.c_char_p]
     L.v2gt_batch_write_all.argtypes = [vp, C.c_char_p, C.c_int32, c_int32_p]
@@ -203,6 +204,17 @@ class BatchSolver:
         t, x = np.empty(n.value), np.empty((n.value, 16))
         _check(self._L.v2gt_batch_get_states(self.h, int(trial), n.value, dptr(t), dptr(x), C.byref(n)), "v2gt_batch_get_states")
         return t, x
+
+    def all_states(self):
+        """Every trial's result in one read-back: (offsets [T+1], times [n], states [n, 16], globals [T, 10]); trial t owns
+        rows offsets[t]:offsets[t+1]."""
+        off = np.zeros(self.n_trials + 1, dtype=np.int64)
+        optr = off.ctypes.data_as(c_int64_p)
+        _check(self._L.v2gt_batch_get_all_states(self.h, 0, optr, None, None, None), "v2gt_batch_get_all_states")
+        n = int(off[-1])
+        t, x, g = np.empty(n), np.empty((n, 16)), np.empty((self.n_trials, 10))
+        _check(self._L.v2gt_batch_get_all_states(self.h, n, optr, dptr(t), dptr(x), dptr(g)), "v2gt_batch_get_all_states")
+        return off, t, x, g
 
     def calibration(self, trial=0):
         q, p, th = np.zeros(4), np.zeros(3), np.zeros(2)

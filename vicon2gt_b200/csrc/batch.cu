@@ -114,6 +114,11 @@ struct v2gt_batch {
   int64_t launches[8] = {0};
   std::vector<LmState> h_lm;
   std::vector<int> h_nstates, h_removed;
+  std::vector<long long> h_st_off; // first state slot of every trial (host copy of TrialDev::st_off)
+  double *h_stage = nullptr;       // the largest pinned staging buffer of the upload (free after it): bounce buffer of
+  size_t h_stage_doubles = 0;      // v2gt_batch_get_all_states
+  double *h_rb = nullptr;          // own pinned buffer when the staging buffer is too small
+  size_t h_rb_doubles = 0;
   bool results_cached = false;
 };
 
@@ -169,6 +174,12 @@ void free_device(v2gt_batch *b) {
   b->alloc_key.clear();
   b->reuse = false;
   b->h_active = nullptr;
+  b->h_stage = nullptr;
+  b->h_stage_doubles = 0;
+  if (b->h_rb)
+    cudaFreeHost(b->h_rb);
+  b->h_rb = nullptr;
+  b->h_rb_doubles = 0;
   b->uploaded = false;
   b->built = false;
 }
@@ -610,6 +621,9 @@ int v2gt_batch_upload(v2gt_batch *b) {
       C += d.n_vic;
     b->n_max = std::max<int>(b->n_max, (int)d.n_raw);
   }
+  b->h_st_off.resize((size_t)T);
+  for (int t = 0; t < T; t++)
+    b->h_st_off[(size_t)t] = td[t].st_off;
   // ---- segments per trial.  The buffers are sized for the most segments a launch may use (~sqrt(n) per chain);
   // every round of the optimiser then picks its own count from the number of trials still running, so that the
   // chains of the remaining trials are cut finer as the batch drains (v2gt_batch_optimize)
@@ -651,6 +665,8 @@ int v2gt_batch_upload(v2gt_batch *b) {
   long long *h_coff;
   V2_TRY(pin_alloc(b, &h_imu_t, (size_t)M));
   V2_TRY(pin_alloc(b, &h_imu_s, (size_t)M * 8));
+  b->h_stage = h_imu_s;
+  b->h_stage_doubles = (size_t)M * 8;
   V2_TRY(pin_alloc(b, &h_vic_t, (size_t)V));
   V2_TRY(pin_alloc(b, &h_vic_s, (size_t)V * 8));
   V2_TRY(pin_alloc(b, &h_vic_c, (size_t)C * 18));
@@ -1121,6 +1137,86 @@ int v2gt_batch_get_states(v2gt_batch *b, int32_t trial, int64_t capacity, double
     V2_CUDA_CHECK(cudaMemcpy(states, b->d.x + ((long long)cur * b->d.S + off) * X_STRIDE, sizeof(double) * n * X_STRIDE,
                              cudaMemcpyDeviceToHost));
   return V2GT_OK;
+}
+
+int v2gt_batch_get_all_states(v2gt_batch *b, int64_t capacity, int64_t *offsets, double *times, double *states, double *globals10) {
+  if (!b || !b->built || !offsets)
+    return b && !b->built ? V2GT_ERR_NOT_BUILT : V2GT_ERR_INVALID_ARG;
+  V2_CUDA_CHECK(cudaSetDevice(b->device));
+  V2_TRY(fetch_results(b));
+  const int T = b->T;
+  offsets[0] = 0;
+  for (int t = 0; t < T; t++)
+    offsets[t + 1] = offsets[t] + b->h_nstates[t];
+  const int64_t total = offsets[T];
+  if (!times && !states && !globals10)
+    return V2GT_OK;
+  if (capacity < total)
+    return V2GT_ERR_INVALID_ARG;
+  // bounce buffer: [states 16 x total | times total | globals 2 x T x 16]
+  const size_t need = (size_t)total * 17 + (size_t)2 * T * GLOB_STRIDE;
+  double *pin = b->h_stage;
+  if (b->h_stage_doubles < need) {
+    if (b->h_rb_doubles < need) {
+      if (b->h_rb)
+        cudaFreeHost(b->h_rb);
+      b->h_rb = nullptr;
+      b->h_rb_doubles = 0;
+      V2_CUDA_CHECK(cudaMallocHost((void **)&b->h_rb, need * sizeof(double)));
+      b->h_rb_doubles = need;
+    }
+    pin = b->h_rb;
+  }
+  double *p_x = pin, *p_t = pin + (size_t)total * 16, *p_g = pin + (size_t)total * 17;
+  cudaStream_t st = b->stream;
+  const DevPtrs &d = b->d;
+  V2_CUDA_CHECK(cudaMemcpyAsync(p_g, d.glob, sizeof(double) * 2 * T * GLOB_STRIDE, cudaMemcpyDeviceToHost, st));
+  // chunks of trials: the copies of chunk k+1 are in flight while chunk k is moved to the caller's arrays on host threads
+  const int nch = std::max(1, std::min(T, 8));
+  std::vector<cudaEvent_t> ev((size_t)nch);
+  for (int ch = 0; ch < nch; ch++) {
+    const int t0 = (int)((long long)T * ch / nch), t1 = (int)((long long)T * (ch + 1) / nch);
+    for (int t = t0; t < t1; t++) {
+      const int n = b->h_nstates[t];
+      if (!n)
+        continue;
+      const long long off = b->h_st_off[(size_t)t];
+      if (states)
+        V2_CUDA_CHECK(cudaMemcpyAsync(p_x + offsets[t] * 16, d.x + ((long long)b->h_lm[t].cur * d.S + off) * X_STRIDE,
+                                      sizeof(double) * n * X_STRIDE, cudaMemcpyDeviceToHost, st));
+      if (times)
+        V2_CUDA_CHECK(cudaMemcpyAsync(p_t + offsets[t], d.st_t + off, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    }
+    V2_CUDA_CHECK(cudaEventCreateWithFlags(&ev[(size_t)ch], cudaEventDisableTiming));
+    V2_CUDA_CHECK(cudaEventRecord(ev[(size_t)ch], st));
+  }
+  int rc = V2GT_OK;
+  for (int ch = 0; ch < nch; ch++) {
+    const int t0 = (int)((long long)T * ch / nch), t1 = (int)((long long)T * (ch + 1) / nch);
+    if (cudaEventSynchronize(ev[(size_t)ch]) != cudaSuccess)
+      rc = V2GT_ERR_CUDA;
+    cudaEventDestroy(ev[(size_t)ch]);
+    if (rc != V2GT_OK || t1 <= t0)
+      continue;
+    parallel_trials(t0, t1, [&](int t) {
+      const size_t n = (size_t)b->h_nstates[t];
+      if (states && n)
+        std::memcpy(states + offsets[t] * 16, p_x + offsets[t] * 16, sizeof(double) * 16 * n);
+      if (times && n)
+        std::memcpy(times + offsets[t], p_t + offsets[t], sizeof(double) * n);
+    });
+  }
+  if (rc == V2GT_OK && globals10)
+    for (int t = 0; t < T; t++) {
+      const double *g = p_g + ((size_t)b->h_lm[t].cur * T + t) * GLOB_STRIDE;
+      double *o = globals10 + 10 * t;
+      std::memcpy(o, g + GL_Q, 4 * sizeof(double));
+      std::memcpy(o + 4, g + GL_P, 3 * sizeof(double));
+      o[7] = g[GL_TOFF];
+      o[8] = g[GL_THX];
+      o[9] = g[GL_THY];
+    }
+  return rc;
 }
 
 int v2gt_batch_get_calibration(v2gt_batch *b, int32_t trial, double *q_BtoI, double *p_BinI, double *t_off, double *theta_xy) {
