@@ -111,3 +111,39 @@ def test_simulated_batch_goes_to_the_solver_without_a_host_round_trip():
                 one.build_and_solve()
                 # (a batch of another size cuts its chains differently: same solution to round-off, not bit for bit)
                 assert np.abs(one.states(0)[1] - mixed.states(1)[1]).max() < 1e-7
+
+
+def test_full_size_batch_against_host_simulator_and_stream_properties():
+    """BASELINE configs[3] shape (sim.launch: 400 Hz IMU, 100 Hz vicon, 100 Hz states, 299 s): one seed of a batch against the
+    host simulator over all 119.6 k IMU samples / 29.9 k poses (5 860 regenerated generator blocks), and size-independent
+    properties of the batch: trials with the same seed but other vicon sigmas share the IMU stream bit for bit and their
+    vicon noise scales exactly with sigma; different seeds are uncorrelated; the noise has the configured spectral density."""
+    from vicon2gt_b200 import sim
+
+    rows = sim.make_trajectory(**sim.TRAJ_SHAPES["tum_corridor1"])
+    seeds = [17, 17, 18, 19]
+    sig = np.array([[0.0174] * 3 + [0.05] * 3, [0.0348] * 3 + [0.10] * 3, [0.0174] * 3 + [0.05] * 3, [0.0174] * 3 + [0.05] * 3])
+    with sim.SimBatch(rows, 4, seeds=seeds, vicon_sigmas=sig) as sb:
+        sb.run()
+        d = [sb.dataset(k, with_truth_states=(k == 0)) for k in range(4)]
+    h = sim.simulate(traj_rows=rows, seed=17, vicon_sigmas=sig[0])
+    assert h.n_imu > 119000 and h.n_vicon > 29000 and h.n_times > 29000
+    assert np.array_equal(d[0].imu_t, h.imu_t) and np.array_equal(d[0].vic_t, h.vic_t) and np.array_equal(d[0].state_t, h.state_t)
+    assert np.abs(d[0].imu_w - h.imu_w).max() < 1e-11 and np.abs(d[0].imu_a - h.imu_a).max() < 1e-10
+    assert np.abs(d[0].vic_q - h.vic_q).max() < 1e-12 and np.abs(d[0].vic_p - h.vic_p).max() < 1e-11
+    assert np.abs(d[0].truth["states"] - h.truth["states"]).max() < 1e-10
+    # same seed, doubled sigma: identical IMU rows; the position noise doubles exactly (power-of-two factor)
+    assert np.array_equal(d[1].imu_w, d[0].imu_w) and np.array_equal(d[1].imu_a, d[0].imu_a)
+    n1, nh = d[1].vic_p - d[0].vic_p, d[0].vic_p - h.vic_p  # sigma n (device), device - host round-off
+    assert 0.04 < n1.std() < 0.06 and np.abs(nh).max() < 1e-11
+    # ... so removing it twice from the doubled run gives the noise-free positions: smooth at the 1e-3 level of a 1 m/s walk
+    clean = d[0].vic_p - n1
+    assert np.abs(np.diff(clean, n=2, axis=0)).max() < 5e-3 and np.abs(np.diff(d[0].vic_p, n=2, axis=0)).max() > 5e-2
+    # different seeds: gyro noise uncorrelated, each with the configured density sigma_w / sqrt(dt)
+    e23 = d[2].imu_w - d[3].imu_w  # (bias + noise) differences of two seeds: white part dominates sample to sample
+    de = np.diff(e23, axis=0)  # first differences remove the slow bias walk: var = 4 sigma^2
+    sigma = 1.6968e-04 / np.sqrt(1.0 / 400.0)
+    assert abs(de.std() / (2 * sigma) - 1.0) < 0.02
+    # and the noise of the two seeds is uncorrelated: corr(n2 - n0, n3 - n0) = 1/2 for independent streams of equal variance
+    a, b = np.diff(d[2].imu_w - d[0].imu_w, axis=0)[:, 0], np.diff(d[3].imu_w - d[0].imu_w, axis=0)[:, 0]
+    assert abs(np.corrcoef(a, b)[0, 1] - 0.5) < 0.02
