@@ -3,7 +3,9 @@
 // print the trajectory errors and the converged calibration, optionally write the CSV + info files.
 //
 //   run_simulation [--seed N] [--duration S] [--freq_imu Hz] [--freq_vicon Hz] [--state_freq Hz]
-//                  [--vicon_sigmas so so so sp sp sp] [--states out.csv --info out.txt] [--device N]
+//                  [--vicon_sigmas so so so sp sp sp] [--states out.csv --info out.txt] [--device N] [--device-sim]
+// --device-sim draws the measurements and the truth with the batched device simulator (SimBatch, csrc/k_sim.cu) instead
+// of the host one: the same seed gives the same run to round-off.
 // Defaults are launch/sim.launch (400 Hz IMU, 100 Hz vicon, state_freq 100, sigmas 0.0174 / 0.05, seed 1) on a
 // synthesised trajectory of the tum_corridor1 shape (the reference's data files are not shipped).
 #include "v2gt_sim.h"
@@ -54,6 +56,7 @@ int main(int argc, char **argv) {
   double duration = 30.0, freq_imu = 400, freq_vicon = 100;
   double sig[6] = {0.0174, 0.0174, 0.0174, 0.05, 0.05, 0.05};
   std::string path_states, path_info;
+  bool device_sim = false;
   for (int i = 1; i < argc; i++) {
     const std::string a = argv[i];
     auto next = [&]() { return (i + 1 < argc) ? argv[++i] : (char *)"0"; };
@@ -65,6 +68,7 @@ int main(int argc, char **argv) {
     else if (a == "--device") device = std::atoi(next());
     else if (a == "--states") path_states = next();
     else if (a == "--info") path_info = next();
+    else if (a == "--device-sim") device_sim = true;
     else if (a == "--vicon_sigmas") for (int k = 0; k < 6; k++) sig[k] = std::atof(next());
   }
   // ---- simulate (run_simulation.cpp:100-158)
@@ -85,9 +89,24 @@ int main(int argc, char **argv) {
     std::fprintf(stderr, "simulation failed: %s\n", v2gt_sim_error(sim));
     return EXIT_FAILURE;
   }
-  const int64_t M = v2gt_sim_n_imu(sim), V = v2gt_sim_n_vicon(sim), N = v2gt_sim_n_states(sim);
+  int64_t M = v2gt_sim_n_imu(sim), V = v2gt_sim_n_vicon(sim), N = v2gt_sim_n_states(sim);
   std::vector<double> imu_t(M), imu_w(3 * M), imu_a(3 * M), vic_t(V), vic_q(4 * V), vic_p(3 * V), state_t(N);
   v2gt_sim_get(sim, imu_t.data(), imu_w.data(), imu_a.data(), vic_t.data(), vic_q.data(), vic_p.data(), state_t.data());
+  std::unique_ptr<SimBatch> dsim;
+  if (device_sim) {
+    try {
+      dsim.reset(new SimBatch(1, traj, device));
+      dsim->set_trial(0, sp);
+      dsim->run();
+      dsim->get(0, imu_t, imu_w, imu_a, vic_t, vic_q, vic_p, state_t);
+    } catch (const SolverError &e) {
+      std::fprintf(stderr, "device simulation failed: %s (status %d)\n", e.what(), e.code());
+      return EXIT_FAILURE;
+    }
+    M = (int64_t)imu_t.size();
+    V = (int64_t)vic_t.size();
+    N = (int64_t)state_t.size();
+  }
 
   auto propagator = std::make_shared<Propagator>(sp.sigma_w, sp.sigma_wb, sp.sigma_a, sp.sigma_ab);
   auto interpolator = std::make_shared<Interpolator>();
@@ -122,7 +141,10 @@ int main(int argc, char **argv) {
   solver.get_imu_poses(times, poses);
   std::vector<double> gt(17 * times.size());
   std::vector<int32_t> ok(times.size());
-  v2gt_sim_get_state_in_vicon(sim, (int64_t)times.size(), times.data(), gt.data(), ok.data());
+  if (dsim)
+    dsim->get_state_in_vicon(0, times, gt, ok);
+  else
+    v2gt_sim_get_state_in_vicon(sim, (int64_t)times.size(), times.data(), gt.data(), ok.data());
   Stats e_ori, e_pos, e_vel;
   for (size_t i = 0; i < times.size(); i++) {
     if (!ok[i])
@@ -151,7 +173,10 @@ int main(int argc, char **argv) {
   Mat3 R_BtoI, R_GtoV, gt_R_BtoI, gt_R_GtoV;
   Vec3 p_BinI, gt_p;
   solver.get_calibration(toff, R_BtoI, p_BinI, R_GtoV);
-  v2gt_sim_get_truth(sim, gt_R_BtoI.data(), gt_p.data(), &gt_toff, gt_R_GtoV.data());
+  if (dsim)
+    dsim->get_truth(0, gt_R_BtoI, gt_p, gt_toff, gt_R_GtoV);
+  else
+    v2gt_sim_get_truth(sim, gt_R_BtoI.data(), gt_p.data(), &gt_toff, gt_R_GtoV.data());
   auto rpy = [](const Mat3 &R, double *o) { // rpy_ops.h:68-74
     o[0] = std::atan2(R[7], R[8]);
     o[1] = std::atan2(-R[6], std::sqrt(R[7] * R[7] + R[8] * R[8]));

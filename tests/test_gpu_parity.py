@@ -407,6 +407,18 @@ def test_cpp_driver_matches_python_mirror(tmp_path):
     assert info.read_bytes() == (tmp_path / "py.txt").read_bytes()
     rmse_pos = float(r.stdout.split("rmse_pos = ")[1].split()[0])
     assert rmse_pos < 0.05  # sim.launch noise: 5 cm vicon position sigma
+    # the same run with the measurements and the truth from the C++ SimBatch (device simulator): inputs equal to round-off
+    csv2, info2 = tmp_path / "cpp_dev.csv", tmp_path / "cpp_dev.txt"
+    r2 = subprocess.run([exe, "--seed", "4", "--duration", "10", "--device-sim", "--states", str(csv2), "--info", str(info2)],
+                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r2.returncode == 0, r2.stderr
+    a = np.loadtxt(csv, delimiter=",", comments="#")
+    b = np.loadtxt(csv2, delimiter=",", comments="#")
+    # (the CSV prints six significant digits: a last-digit flip is 1e-5 relative)
+    assert a.shape == b.shape and np.array_equal(a[:, 0], b[:, 0])
+    assert np.all(np.abs(a[:, 1:] - b[:, 1:]) <= 2e-5 * np.abs(a[:, 1:]) + 1e-9)
+    assert abs(float(r2.stdout.split("rmse_pos = ")[1].split()[0]) - rmse_pos) < 1e-5
+    assert r2.stdout.split("GT  toff:")[1].split()[0] == r.stdout.split("GT  toff:")[1].split()[0]
 
 
 def test_batched_error_stats_and_write_all(ds_c1_small, ds_c2_small, ds_c3_small, tmp_path):
