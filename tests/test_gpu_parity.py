@@ -414,9 +414,10 @@ def test_cpp_driver_matches_python_mirror(tmp_path):
     assert r2.returncode == 0, r2.stderr
     a = np.loadtxt(csv, delimiter=",", comments="#")
     b = np.loadtxt(csv2, delimiter=",", comments="#")
-    # (the CSV prints six significant digits: a last-digit flip is 1e-5 relative)
+    # (same solution within the 1e-6 bar of the parity target; the CSV prints six significant digits, so a last-digit
+    # flip adds 1e-5 relative)
     assert a.shape == b.shape and np.array_equal(a[:, 0], b[:, 0])
-    assert np.all(np.abs(a[:, 1:] - b[:, 1:]) <= 2e-5 * np.abs(a[:, 1:]) + 1e-9)
+    assert np.all(np.abs(a[:, 1:] - b[:, 1:]) <= 2e-5 * np.abs(a[:, 1:]) + 1e-6)
     assert abs(float(r2.stdout.split("rmse_pos = ")[1].split()[0]) - rmse_pos) < 1e-5
     assert r2.stdout.split("GT  toff:")[1].split()[0] == r.stdout.split("GT  toff:")[1].split()[0]
 
