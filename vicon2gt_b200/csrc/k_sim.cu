@@ -372,6 +372,7 @@ struct v2gt_simbatch {
   long long n_pairs = 0;
   long long alloc_key[4] = {0, 0, 0, 0}; // (T, M, V, K) the device buffers were sized for
   cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr; // around one generation, on `stream`
   double *d_cp_t = nullptr, *d_imu_clk = nullptr, *d_vic_clk = nullptr, *d_bias_t = nullptr;
   v2sp::M4 *d_cp = nullptr;
   double *d_base_imu = nullptr, *d_base_vic = nullptr, *d_normals = nullptr, *d_hist = nullptr;
@@ -473,6 +474,10 @@ int v2gt_simbatch_destroy(v2gt_simbatch *s) {
   if (!s->allocs.empty() || s->stream) {
     cudaSetDevice(s->device);
     sim_free(s);
+    if (s->ev0)
+      cudaEventDestroy(s->ev0);
+    if (s->ev1)
+      cudaEventDestroy(s->ev1);
     if (s->stream)
       cudaStreamDestroy(s->stream);
   }
@@ -613,6 +618,10 @@ int v2gt_simbatch_run(v2gt_simbatch *s) {
   V2_CUDA_CHECK(cudaSetDevice(s->device));
   if (!s->stream)
     V2_CUDA_CHECK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  if (!s->ev0)
+    V2_CUDA_CHECK(cudaEventCreate(&s->ev0));
+  if (!s->ev1)
+    V2_CUDA_CHECK(cudaEventCreate(&s->ev1));
   const int T = s->T;
   const long long M = (long long)s->imu_clk.size(), V = (long long)s->vic_clk.size(), K = (long long)s->cp_t.size();
   s->n_pairs = std::max(std::max(6 * M, 3 * V), 5LL);
@@ -642,9 +651,7 @@ int v2gt_simbatch_run(v2gt_simbatch *s) {
   }
   s->ran = false;
   cudaStream_t st = s->stream;
-  cudaEvent_t e0, e1;
-  V2_CUDA_CHECK(cudaEventCreate(&e0));
-  V2_CUDA_CHECK(cudaEventCreate(&e1));
+  const cudaEvent_t e0 = s->ev0, e1 = s->ev1;
   V2_CUDA_CHECK(cudaEventRecord(e0, st));
   V2_CUDA_CHECK(cudaMemcpyAsync(s->d_cp_t, s->cp_t.data(), sizeof(double) * K, cudaMemcpyHostToDevice, st));
   V2_CUDA_CHECK(cudaMemcpyAsync(s->d_cp, s->cp.data(), sizeof(v2sp::M4) * K, cudaMemcpyHostToDevice, st));
@@ -670,8 +677,6 @@ int v2gt_simbatch_run(v2gt_simbatch *s) {
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);
   s->ms_generate = ms;
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   s->ran = true;
   return V2GT_OK;
 }
