@@ -101,6 +101,10 @@ def test_cpp_host_mirror_compiles_and_fails_loudly_without_a_device():
     r = subprocess.run([exe, "--duration", "3"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
     assert r.returncode != 0
     assert "no CUDA device" in r.stderr and "status 9" in r.stderr
+    mc = exe.replace("run_simulation", "run_monte_carlo")
+    assert os.path.exists(mc)
+    r = subprocess.run([mc, "--seeds", "2", "--duration", "3"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+    assert r.returncode != 0 and "no CUDA device" in r.stderr and "status 9" in r.stderr
 
 
 def test_segment_plan_host_logic():

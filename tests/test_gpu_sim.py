@@ -147,3 +147,41 @@ def test_full_size_batch_against_host_simulator_and_stream_properties():
     # and the noise of the two seeds is uncorrelated: corr(n2 - n0, n3 - n0) = 1/2 for independent streams of equal variance
     a, b = np.diff(d[2].imu_w - d[0].imu_w, axis=0)[:, 0], np.diff(d[3].imu_w - d[0].imu_w, axis=0)[:, 0]
     assert abs(np.corrcoef(a, b)[0, 1] - 0.5) < 0.02
+
+
+def test_cpp_monte_carlo_driver_matches_the_python_mirror(tmp_path):
+    """examples/run_monte_carlo (C++ SimBatch + BatchSolver::set_trial_sim + get_all_states + the device error report) prints
+    what the Python mirror computes for the same seeds: same batch, same kernels, same numbers."""
+    import re
+    import subprocess
+
+    from vicon2gt_b200 import api, build, sim
+
+    exe = build.build_examples().replace("run_simulation", "run_monte_carlo")
+    r = subprocess.run([exe, "--seeds", "3", "--duration", "10", "--ori_noise", "0.001", "--pos_noise", "0.01", "--out-dir", str(tmp_path)],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    pat = re.compile(r"run\s+(\d+): status (\d+), (\d+) states, (\d+) iterations, cost (\S+), mean ATE (\S+) deg / (\S+) m, toff error (\S+) ms")
+    got = [m.groups() for m in pat.finditer(r.stdout)]
+    assert len(got) == 3 and "wrote 3 runs" in r.stdout
+    rows = sim.make_trajectory(t_start=1520531829.301144123, n_rows=201, dt=0.05, extent_m=20.0)
+    p = api.default_params()
+    with sim.SimBatch(rows, 3, vicon_sigmas=(1e-3,) * 3 + (1e-2,) * 3) as sb:
+        sb.run()
+        with api.BatchSolver(3) as bs:
+            for k in range(3):
+                bs.set_trial_sim(k, p, sb)
+            bs.build_and_solve()
+            for k in range(3):
+                bs.set_truth_from_sim(k, sb)
+            st = bs.error_stats()
+            for k, g in enumerate(got):
+                inf = bs.info(k)
+                assert (int(g[0]), int(g[1]), int(g[2]), int(g[3])) == (k, 0, inf.n_states, inf.iterations)
+                assert abs(float(g[4]) - inf.final_error) <= 1e-6 * inf.final_error  # printed with seven digits
+                assert abs(float(g[5]) - st[k, 0, 1]) < 1e-5 and abs(float(g[6]) - st[k, 1, 1]) < 1e-5
+                assert abs(float(g[7]) - 1e3 * abs(bs.calibration(k)[2] - sb.truth(k)["viconimu_dt"])) < 1e-3
+            # the files of run 1 are the single-trial writer's, byte for byte
+            bs.write_to_file(1, str(tmp_path / "py.csv"), str(tmp_path / "py.txt"))
+    assert (tmp_path / "00001_states.csv").read_bytes() == (tmp_path / "py.csv").read_bytes()
+    assert (tmp_path / "00001_info.txt").read_bytes() == (tmp_path / "py.txt").read_bytes()
