@@ -137,10 +137,6 @@ __global__ void __launch_bounds__(SIM_NOISE_THREADS) k_sim_noise(const SimTrialD
   }
 }
 
-__device__ __forceinline__ bool sim_bracket(const double *cp_t, const v2sp::M4 *cp, long long K, double ts, long long &i1) {
-  return v2sp::spline_bracket(cp_t, K, ts, i1);
-}
-
 // IMU clock stamps: out[i][8] = w_IinI (3), R_GtoI (a_IinG + g e_z) (3), ok, 0
 __global__ void __launch_bounds__(128) k_sim_spline_imu(const double *cp_t, const v2sp::M4 *cp, long long K, const double *clk, long long n,
                                                         double g, double *out) {
@@ -150,7 +146,7 @@ __global__ void __launch_bounds__(128) k_sim_spline_imu(const double *cp_t, cons
   const double ts = clk[i];
   long long i1;
   double *o = out + 8 * i;
-  if (!sim_bracket(cp_t, cp, K, ts, i1)) {
+  if (!v2sp::spline_bracket(cp_t, K, ts, i1)) {
     for (int k = 0; k < 8; k++)
       o[k] = 0.0;
     return;
@@ -177,7 +173,7 @@ __global__ void __launch_bounds__(128) k_sim_spline_pose(const double *cp_t, con
   double *o = out + 16 * i;
   for (int k = 0; k < 16; k++)
     o[k] = 0.0;
-  if (!sim_bracket(cp_t, cp, K, ts, i1))
+  if (!v2sp::spline_bracket(cp_t, K, ts, i1))
     return;
   double R[9], p[3], w[3], v[3] = {0, 0, 0};
   v2sp::spline_eval_core(cp[i1 - 1], cp[i1], cp[i1 + 1], cp[i1 + 2], cp_t[i1], cp_t[i1 + 1], ts, order, R, p, w, v, nullptr, nullptr);
