@@ -185,3 +185,27 @@ def test_cpp_monte_carlo_driver_matches_the_python_mirror(tmp_path):
             bs.write_to_file(1, str(tmp_path / "py.csv"), str(tmp_path / "py.txt"))
     assert (tmp_path / "00001_states.csv").read_bytes() == (tmp_path / "py.csv").read_bytes()
     assert (tmp_path / "00001_info.txt").read_bytes() == (tmp_path / "py.txt").read_bytes()
+
+
+@pytest.mark.parametrize("k,tag", [(0, "sim5"), (1, "sim1234")])
+def test_device_simulator_against_the_reference_simulator(k, tag):
+    """The device simulator against outputs of the reference's OWN Simulator / BsplineSE3 (compiled where they lie, frozen in
+    tests/golden/ref_pin.npz: every 8th IMU sample, every 4th vicon pose, get_state_in_vicon at 98 off-grid times)."""
+    from conftest import load_golden
+    from vicon2gt_b200 import sim
+
+    G = load_golden("ref_pin")
+    with sim.SimBatch(G["sim_traj"], 2, seeds=[5, 1234], vicon_sigmas=(1e-3,) * 3 + (1e-2,) * 3, freq_imu=400.0, freq_cam=20.0,
+                      freq_vicon=100.0, state_freq=100) as sb:
+        sb.run()
+        d = sb.dataset(k, with_truth_states=False)
+        st, ok = sb.state_in_vicon(k, G[tag + "_state_t"])
+    imu = np.column_stack([d.imu_t, d.imu_w, d.imu_a])[::8]
+    vic = np.column_stack([d.vic_t, d.vic_q, d.vic_p])[::4]
+    assert (d.n_imu, d.n_vicon) == (int(G[tag + "_n_imu"]), int(G[tag + "_n_vicon"]))
+    assert np.array_equal(imu[:, 0], G[tag + "_imu"][:, 0]) and np.array_equal(vic[:, 0], G[tag + "_vic"][:, 0])  # stamps
+    assert np.max(np.abs(imu[:, 1:4] - G[tag + "_imu"][:, 1:4])) < 1e-12  # rad/s
+    assert np.max(np.abs(imu[:, 4:7] - G[tag + "_imu"][:, 4:7])) < 1e-10  # m/s^2 (second derivative of the spline)
+    assert np.max(np.abs(vic[:, 1:] - G[tag + "_vic"][:, 1:])) < 1e-12
+    assert np.array_equal(ok, G[tag + "_states_ok"])
+    assert np.max(np.abs(st - G[tag + "_states"])) < 1e-10

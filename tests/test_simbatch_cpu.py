@@ -132,3 +132,24 @@ def test_noise_stream_layout_against_libstdcxx():
     got = (c.imu_w[:m] - a.imu_w[:m]) / (1.6968e-04 / np.sqrt(1.0 / 400.0))
     want = np.stack([vals[12 * i], vals[12 * i + 1], vals[12 * i + 2]], 1)
     assert m > 100 and np.abs(got - want).max() < 1e-9
+
+
+def test_plan_against_the_reference_simulator():
+    """The host plan against outputs of the reference's OWN Simulator / BsplineSE3 (compiled where they lie and frozen in
+    tests/golden/ref_pin.npz by tools/make_ref_golden.py): same sample counts, same stamps, the same std::mt19937 draws
+    for the perturbed calibration (scalars bit for bit, rotations to an ulp)."""
+    from conftest import load_golden
+
+    G = load_golden("ref_pin")
+    tags = [("sim5", 5), ("sim1234", 1234)]
+    with sim.SimBatch(G["sim_traj"], 2, seeds=[s for _, s in tags], vicon_sigmas=(1e-3,) * 3 + (1e-2,) * 3, freq_imu=400.0, freq_cam=20.0,
+                      freq_vicon=100.0, state_freq=100) as sb:
+        sb.plan()
+        for k, (tag, _) in enumerate(tags):
+            imu_t, vic_t, _ = sb.stamps(k)
+            assert (len(imu_t), len(vic_t)) == (int(G[tag + "_n_imu"]), int(G[tag + "_n_vicon"]))
+            assert np.array_equal(imu_t[::8], G[tag + "_imu"][:, 0]) and np.array_equal(vic_t[::4], G[tag + "_vic"][:, 0])
+            tr = sb.truth(k)
+            mine = np.concatenate([tr["R_BtoI"].reshape(-1), tr["p_BinI"], [tr["viconimu_dt"]], tr["R_GtoV"].reshape(-1)])
+            assert np.max(np.abs(mine - G[tag + "_truth"])) < 1e-15
+            assert mine[12] == G[tag + "_truth"][12] and np.array_equal(mine[9:12], G[tag + "_truth"][9:12])
