@@ -65,6 +65,9 @@ def test_no_device_fails_loudly():
     assert lib.v2gt_measure_fp64_peak(0, C.byref(v)) == 9
     # null / bad handles are rejected, not dereferenced
     assert lib.v2gt_batch_upload(None) == 1 and lib.v2gt_batch_optimize(None) == 1 and lib.v2gt_batch_build(None, 1) == 1
+    assert lib.v2gt_batch_get_all_states(None, 0, None, None, None, None) == 1
+    assert lib.v2gt_simbatch_plan(None) == 1 and lib.v2gt_simbatch_run(None) == 1 and lib.v2gt_simbatch_destroy(None) == 1
+    assert lib.v2gt_batch_set_trial_sim(None, 0, None, None, 0, None) == 1
     prop, interp = api.Propagator(1e-4, 1e-5, 1e-3, 1e-3), api.Interpolator()
     prop.feed_imu(0.0, [0, 0, 0], [0, 0, 9.81])
     interp.feed_pose(0.0, [0, 0, 0, 1], [0, 0, 0], np.eye(3), np.eye(3))
