@@ -35,6 +35,7 @@
 #include <cstring>
 #include <random>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace v2 {
@@ -504,11 +505,20 @@ int v2gt_simbatch_plan(v2gt_simbatch *s) {
   }
   // ---- clock schedule (Simulator.cpp:135-262; the spline lookups only decide when the loop stops)
   const v2sp::Spline &sp = s->spline;
-  auto in_spline = [&](double ts) {
-    double t0, t1, t2, t3;
-    v2sp::M4 a, b, c, d;
-    return sp.find_bounding_control_points(ts, t0, a, t1, b, t2, c, t3, d);
+  // a stamp is inside the spline where BsplineSE3::find_bounding_control_points succeeds (v2sp::spline_bracket states the
+  // same condition on the sorted control-point times); every clock only moves forward, so each keeps a cursor = the
+  // first control point later than its last stamp instead of searching
+  const std::vector<double> &ct = s->cp_t;
+  const long long K = (long long)ct.size();
+  struct Cursor {
+    long long ub = 0;
+  } cur_imu, cur_vic, cur_start;
+  auto in_spline_at = [&](Cursor &c, double ts) {
+    while (c.ub < K && !(ct[(size_t)c.ub] > ts))
+      c.ub++;
+    return c.ub < K && c.ub >= 2 && c.ub + 1 < K;
   };
+  auto in_spline = [&](double ts) { return in_spline_at(cur_start, ts); };
   s->imu_clk.clear();
   s->vic_clk.clear();
   s->bias_t.clear();
@@ -523,7 +533,7 @@ int v2gt_simbatch_plan(v2gt_simbatch *s) {
     if (!(last_cam + 1.0 / P.sim_freq_cam < last_imu + 1.0 / P.sim_freq_imu ||
           last_vic + 1.0 / P.sim_freq_vicon < last_imu + 1.0 / P.sim_freq_imu)) {
       last_imu += 1.0 / P.sim_freq_imu;
-      if (!in_spline(last_imu) || (int64_t)s->imu_clk.size() >= cap) {
+      if (!in_spline_at(cur_imu, last_imu) || (int64_t)s->imu_clk.size() >= cap) {
         is_running = false;
       } else {
         s->imu_clk.push_back(last_imu);
@@ -536,7 +546,7 @@ int v2gt_simbatch_plan(v2gt_simbatch *s) {
     if (!(last_imu + 1.0 / P.sim_freq_imu < last_vic + 1.0 / P.sim_freq_vicon ||
           last_cam + 1.0 / P.sim_freq_cam < last_vic + 1.0 / P.sim_freq_vicon)) {
       last_vic += 1.0 / P.sim_freq_vicon;
-      if (!in_spline(last_vic))
+      if (!in_spline_at(cur_vic, last_vic))
         is_running = false;
       else
         s->vic_clk.push_back(last_vic);
@@ -545,9 +555,9 @@ int v2gt_simbatch_plan(v2gt_simbatch *s) {
   // ---- truth per seed (Simulator.cpp:29-38), noise scales, vicon stamps, state grids (run_simulation.cpp:149-158)
   const double dt = 1.0 / P.sim_freq_imu;
   s->ts.assign((size_t)s->T, SimTrialDev());
-  s->state_t.assign((size_t)s->T, {});
-  s->vic_t.assign((size_t)s->T, {});
-  for (int t = 0; t < s->T; t++) {
+  s->state_t.resize((size_t)s->T); // capacities are kept from one plan to the next
+  s->vic_t.resize((size_t)s->T);
+  auto plan_trial = [&](int t) {
     const v2gt_sim_params &Q = s->prm[(size_t)t];
     SimTrialDev &d = s->ts[(size_t)t];
     std::memset(&d, 0, sizeof(d));
@@ -584,9 +594,11 @@ int v2gt_simbatch_plan(v2gt_simbatch *s) {
     for (size_t j = 0; j < vt.size(); j++)
       vt[j] = s->vic_clk[j] - d.viconimu_dt;
     std::vector<double> &st = s->state_t[(size_t)t];
+    st.clear();
     if (Q.state_freq > 0 && !vt.empty() && vt.front() < vt.back()) {
       double temp_time = vt.front();
       const double end_time = vt.back();
+      st.reserve((size_t)((end_time - temp_time) * (double)Q.state_freq) + 16);
       while (temp_time < end_time) {
         st.push_back(temp_time);
         temp_time += 1.0 / (double)Q.state_freq;
@@ -595,6 +607,20 @@ int v2gt_simbatch_plan(v2gt_simbatch *s) {
       for (const auto &row : s->traj)
         st.push_back(row[0]);
     }
+  };
+  {
+    // independent per trial: a few host threads, static interleaved partition
+    const int nthr = std::max(1, std::min({s->T, (int)std::thread::hardware_concurrency(), 16}));
+    std::vector<std::thread> th;
+    for (int k = 1; k < nthr; k++)
+      th.emplace_back([&, k]() {
+        for (int t = k; t < s->T; t += nthr)
+          plan_trial(t);
+      });
+    for (int t = 0; t < s->T; t += nthr)
+      plan_trial(t);
+    for (auto &x : th)
+      x.join();
   }
   s->planned = true;
   s->ran = false;
