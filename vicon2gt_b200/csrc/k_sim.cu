@@ -457,10 +457,8 @@ int v2gt_simbatch_create(int32_t device, int32_t n_trials, int64_t n_rows, const
     for (int d = 0; d < 8; d++)
       s->traj[(size_t)i][d] = rows8[8 * i + d];
   s->spline.feed_trajectory(s->traj);
-  for (const auto &kv : s->spline.control_points) {
-    s->cp_t.push_back(kv.first);
-    s->cp.push_back(kv.second);
-  }
+  s->cp_t = s->spline.cp_t;
+  s->cp = s->spline.cp;
   *out = s;
   return V2GT_OK;
 }

@@ -3,8 +3,8 @@
 // Shared by the host simulator (vicon2gt_b200/host/sim.cpp, g++) and by the GPU simulator (csrc/k_sim.cu): the same
 // statements evaluate a pose / velocity / acceleration on either side.  Behaviour follows src/utils/quat_ops.h
 // (exp_se3 :311-340, log_se3 :353-385, hat_se3 :397-402, Inv_se3 :432) and src/sim/BsplineSE3.cpp (feed_trajectory
-// :21-83, get_pose / get_velocity / get_acceleration :85-240, find_bounding_poses :242-293,
-// find_bounding_control_points :295-351).  The host side is pinned on the reference's own BsplineSE3 / Simulator
+// :21-83, get_pose / get_velocity / get_acceleration :85-240; its two lookups :242-351 are one binary search over
+// sorted times here, spline_bracket below).  The host side is pinned on the reference's own BsplineSE3 / Simulator
 // (tests/test_ref_pin_cpu.py::test_host_simulator_against_the_reference_simulator).
 #pragma once
 #include "v2gt_math.cuh"
@@ -254,117 +254,88 @@ V2_HD void spline_eval_core(const M4 &pose0, const M4 &pose1, const M4 &pose2, c
 
 } // namespace v2sp
 
-// ---- host side: control points from trajectory rows (std::map, as the reference builds them); plain host code,
-// also parsed (and dropped) by nvcc's device pass of csrc/k_sim.cu
+// ---- host side: control points from trajectory rows.  The reference keeps both the trajectory poses and the control
+// points in ordered associative containers keyed by time (BsplineSE3.cpp:21-83, lookups :242-351); here both are plain
+// arrays sorted by time with repeated stamps dropped (the first one fed wins), the uniform walk over the trajectory
+// keeps a forward cursor, and a stamp is bracketed by spline_bracket() above -- the same routine the device simulator
+// uses.  Plain host code, also parsed (and dropped) by nvcc's device pass of csrc/k_sim.cu.
 #if 1
+#include <algorithm>
 #include <array>
 #include <cmath>
-#include <map>
+#include <numeric>
 #include <vector>
 namespace v2sp {
 
 struct Spline {
-  std::map<double, M4> control_points;
+  std::vector<double> cp_t; // control-point times: strictly increasing, uniform spacing dt
+  std::vector<M4> cp;       // control-point poses
   double dt = 0, timestamp_start = 0;
 
-  // BsplineSE3.cpp:21-83
   void feed_trajectory(const std::vector<std::array<double, 8>> &traj) {
-    double sumdt = 0;
-    for (size_t i = 0; i + 1 < traj.size(); i++)
-      sumdt += traj[i + 1][0] - traj[i][0];
-    dt = sumdt / (double)(traj.size() - 1);
-    dt = (dt < 0.05) ? 0.05 : dt;
-    std::map<double, M4> pts;
-    for (size_t i = 0; i + 1 < traj.size(); i++) { // last row unused, as in the reference
-      M4 T = eye4();
+    cp_t.clear();
+    cp.clear();
+    const size_t rows = traj.size();
+    double span = 0;
+    for (size_t i = 0; i + 1 < rows; i++)
+      span += traj[i + 1][0] - traj[i][0];
+    dt = std::max(0.05, span / (double)(rows - 1));
+    // trajectory poses ordered by time; the last row is not used (the reference stops one short)
+    const size_t used = rows ? rows - 1 : 0;
+    std::vector<size_t> order(used);
+    std::iota(order.begin(), order.end(), (size_t)0);
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return traj[a][0] < traj[b][0]; });
+    std::vector<double> pt;
+    std::vector<M4> pp;
+    pt.reserve(used);
+    pp.reserve(used);
+    for (size_t k : order) {
+      if (!pt.empty() && pt.back() == traj[k][0])
+        continue;
       double R[9], Rt[9];
-      v2::quat_2_Rot(&traj[i][4], R);
+      v2::quat_2_Rot(&traj[k][4], R);
       for (int r = 0; r < 3; r++)
         for (int c = 0; c < 3; c++)
           Rt[3 * r + c] = R[3 * c + r];
+      M4 T = eye4();
       setR(T, Rt);
-      T.a[3] = traj[i][1];
-      T.a[7] = traj[i][2];
-      T.a[11] = traj[i][3];
-      pts.insert({traj[i][0], T});
+      T.a[3] = traj[k][1];
+      T.a[7] = traj[k][2];
+      T.a[11] = traj[k][3];
+      pt.push_back(traj[k][0]);
+      pp.push_back(T);
     }
-    double timestamp_min = INFINITY;
-    for (const auto &p : pts)
-      if (p.first <= timestamp_min)
-        timestamp_min = p.first;
-    double timestamp_curr = timestamp_min;
-    while (true) {
-      double t0, t1;
-      M4 pose0, pose1;
-      if (!find_bounding_poses(timestamp_curr, pts, t0, pose0, t1, pose1))
+    if (pt.empty())
+      return;
+    // uniform walk from the first stamp: every control point is the SE(3) interpolation of the two trajectory poses
+    // around it; the walk ends at the first stamp with no later pose.  `nxt` = first pose later than the stamp.
+    size_t nxt = 0;
+    for (double ts = pt.front();; ts += dt) {
+      while (nxt < pt.size() && !(pt[nxt] > ts))
+        nxt++;
+      if (nxt == pt.size() || nxt == 0)
         break;
-      const double lambda = (timestamp_curr - t0) / (t1 - t0);
+      const size_t prv = nxt - 1;
+      const double lambda = (ts - pt[prv]) / (pt[nxt] - pt[prv]);
       double lg[6];
-      log_se3(mul(pose1, inv_se3(pose0)), lg);
+      log_se3(mul(pp[nxt], inv_se3(pp[prv])), lg);
       for (int i = 0; i < 6; i++)
         lg[i] *= lambda;
-      control_points.insert({timestamp_curr, mul(exp_se3(lg), pose0)});
-      timestamp_curr += dt;
+      cp_t.push_back(ts);
+      cp.push_back(mul(exp_se3(lg), pp[prv]));
     }
-    timestamp_start = timestamp_min + 2 * dt;
-  }
-
-  // BsplineSE3.cpp:242-293
-  static bool find_bounding_poses(double timestamp, const std::map<double, M4> &poses, double &t0, M4 &pose0, double &t1, M4 &pose1) {
-    t0 = -1;
-    t1 = -1;
-    bool found_older = false, found_newer = false;
-    auto lower_bound = poses.lower_bound(timestamp);
-    auto upper_bound = poses.upper_bound(timestamp);
-    if (lower_bound != poses.end()) {
-      if (lower_bound->first == timestamp) {
-        found_older = true;
-      } else if (lower_bound != poses.begin()) {
-        --lower_bound;
-        found_older = true;
-      }
-    }
-    if (upper_bound != poses.end())
-      found_newer = true;
-    if (found_older) {
-      t0 = lower_bound->first;
-      pose0 = lower_bound->second;
-    }
-    if (found_newer) {
-      t1 = upper_bound->first;
-      pose1 = upper_bound->second;
-    }
-    return found_older && found_newer;
-  }
-
-  // BsplineSE3.cpp:295-351
-  bool find_bounding_control_points(double timestamp, double &t0, M4 &pose0, double &t1, M4 &pose1, double &t2, M4 &pose2, double &t3,
-                                    M4 &pose3) const {
-    if (!find_bounding_poses(timestamp, control_points, t1, pose1, t2, pose2))
-      return false;
-    auto iter_t1 = control_points.find(t1);
-    auto iter_t2 = control_points.find(t2);
-    if (iter_t1 == control_points.begin())
-      return false;
-    auto iter_t0 = --iter_t1;
-    auto iter_t3 = ++iter_t2;
-    if (iter_t3 == control_points.end())
-      return false;
-    t0 = iter_t0->first;
-    pose0 = iter_t0->second;
-    t3 = iter_t3->first;
-    pose3 = iter_t3->second;
-    return true;
+    timestamp_start = pt.front() + 2 * dt;
   }
 
   // BsplineSE3.cpp:85-240 : order 0 = pose, 1 = +velocity, 2 = +acceleration
   bool eval(double timestamp, int order, double *R_GtoI, double *p_IinG, double *w_IinI, double *v_IinG, double *alpha_IinI,
             double *a_IinG) const {
-    double t0, t1, t2, t3;
-    M4 pose0, pose1, pose2, pose3;
-    if (!find_bounding_control_points(timestamp, t0, pose0, t1, pose1, t2, pose2, t3, pose3))
+    long long i1 = 0;
+    if (!spline_bracket(cp_t.data(), (long long)cp_t.size(), timestamp, i1))
       return false;
-    spline_eval_core(pose0, pose1, pose2, pose3, t1, t2, timestamp, order, R_GtoI, p_IinG, w_IinI, v_IinG, alpha_IinI, a_IinG);
+    const size_t k = (size_t)i1;
+    spline_eval_core(cp[k - 1], cp[k], cp[k + 1], cp[k + 2], cp_t[k], cp_t[k + 1], timestamp, order, R_GtoI, p_IinG, w_IinI, v_IinG,
+                     alpha_IinI, a_IinG);
     return true;
   }
 };
