@@ -68,6 +68,9 @@ def parse():
                          "sequence chain-sharded over the GPUs with NCCL (configs[4]; second half of the metric: LM latency)")
     ap.add_argument("--segs-per-rank", type=int, default=0, help="chain workload: segments per GPU (0 = ~sqrt(states per GPU))")
     ap.add_argument("--chain-duration", type=float, default=0.0, help="chain workload: truncate the hour to this many seconds")
+    ap.add_argument("--no-chain", action="store_true", help="skip the chain-sharded leg (configs[4]) of the default line")
+    ap.add_argument("--chain-graph-only", action="store_true", help="chain leg: skip the plain-launch pass (per-phase times)")
+    ap.add_argument("--chain-steps", type=int, default=3)
     return ap.parse_args()
 
 
@@ -251,13 +254,87 @@ def run_reference(args):
     return 0
 
 
-def run_chain(args):
-    """BASELINE.json configs[4]: one ~72 k-state sequence, contiguous chain segments per GPU; per damped solve the ranks
-    exchange only the segment Schur outputs / separator records (all-gather) and the 9x9 global block (all-reduce)."""
+def chain_leg(args, dist, device, rank, world, steps, warmup):
+    """BASELINE.json configs[4]: ONE ~72 k-state sequence, contiguous chain segments per GPU.  The Levenberg-Marquardt loop
+    runs inside the library (v2gt_chain_optimize): per damped solve two ncclAllGather calls on the solver's stream (segment
+    Schur outputs + separator records + global-block parts; cost scalars + boundary step), the kernel + collective sequence
+    of a damped solve replayed as one CUDA graph.  Returns the result dict on rank 0 (None elsewhere)."""
     import torch
 
     from vicon2gt_b200 import api, sim
-    from vicon2gt_b200.chain import ChainSolver, DistComm, LocalComm
+    from vicon2gt_b200.chain import ChainSolver, NativeComm
+
+    kw = {} if args.chain_duration <= 0 else dict(duration_s=args.chain_duration)
+    ds = sim.make_config("C5", seed=5, **kw)  # identical on every rank (deterministic generator)
+    p = api.default_params()
+    comm = NativeComm(dist)
+    # ~4 sqrt(n) segments over the whole chain (the separator chain is eliminated in segments of its own, nested level 2),
+    # but never fewer than 16 per GPU: the per-rank sequential depth is what more GPUs are there to cut
+    spr = args.segs_per_rank if args.segs_per_rank > 0 else max(16, int(round(4.0 * ds.n_times ** 0.5 / world)))
+    out = None
+    results = {}
+    for mode in (["graph", "launches"] if not args.chain_graph_only else ["graph"]):
+        cs = ChainSolver(p, ds, comm, segs_per_rank=spr, device=device, use_graph=(mode == "graph"))
+
+        def barrier():
+            if dist is not None:
+                dist.barrier()
+
+        def step():
+            cs.rebuild()
+            inf = cs.optimize()
+            m, _ = cs.timing()
+            return float(m[0]), float(m[7]), m, inf
+
+        for _ in range(warmup):
+            step()
+        sampler = ClockSampler(device)
+        barrier()
+        torch.cuda.synchronize(device)
+        sampler.start()
+        b_ms = o_ms = 0.0
+        m0, _ = cs.timing()
+        for _ in range(steps):
+            b, o, m1, inf = step()
+            b_ms += b
+            o_ms += o
+        torch.cuda.synchronize(device)
+        barrier()
+        clocks = sampler.stop()
+        phases = (m1 - m0)
+        tot = torch.tensor([b_ms + o_ms, o_ms], dtype=torch.float64, device=f"cuda:{device}")
+        if dist is not None:
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        tot_ms, opt_ms = (float(v) for v in tot.tolist())
+        results[mode] = {
+            "ms_per_damped_solve": opt_ms / steps / max(1, inf.tries), "ms_per_lm_iteration": opt_ms / steps / max(1, inf.iterations),
+            "build_ms": (tot_ms - opt_ms) / steps, "optimize_ms": opt_ms / steps, "iterations": inf.iterations,
+            "damped_solves": inf.tries, "final_error": inf.final_error, "status": inf.status, "clocks": clocks,
+        }
+        if mode == "launches":  # per-phase CUDA events exist only with plain launches (rank 0's own times)
+            names = ["linearize", "eliminate_pack", "exchangeA_reduced", "backsub", "cost", "exchangeB_decide"]
+            results[mode]["phase_ms_per_damped_solve_rank0"] = {k: float(phases[1 + i]) / steps / max(1, inf.tries)
+                                                                 for i, k in enumerate(names)}
+        n_states, segs = len(cs.ts), cs.segs_per_rank
+        brackets_ok = cs.check_brackets()
+        cs.close()
+    if rank == 0:
+        g = results["graph"]
+        out = {"workload": "ONE synthesised one-hour sequence (BASELINE.json configs[4]): 20 Hz states, 200 Hz IMU, 100 Hz vicon, "
+                           "chain-sharded over %d GPU(s)" % world,
+               "n_gpus": world, "n_states": n_states, "n_imu": ds.n_imu, "n_vicon": ds.n_vicon, "segments_per_gpu": segs,
+               "collectives_per_damped_solve": 0 if world == 1 else 2,
+               "collectives": "ncclAllGather x2 inside the library, on the solver stream, captured in the CUDA graph of a damped solve",
+               "ms_per_damped_solve": g["ms_per_damped_solve"], "ms_per_lm_iteration": g["ms_per_lm_iteration"],
+               "trajectories_per_second": 1e3 / (g["build_ms"] + g["optimize_ms"]), "brackets_inside_rank_slices": brackets_ok,
+               "timing": "CUDA events on the solver stream around build + optimise, max over ranks; %d steps after %d warm-up" % (steps, warmup),
+               "graph": g, "plain_launches": results.get("launches")}
+    return out
+
+
+def run_chain(args):
+    """`--workload chain`: the chain leg alone, as its own JSON line (metric: latency of one damped solve)."""
+    import torch
 
     rank, local_rank, world = dist_env()
     dist = None
@@ -267,67 +344,14 @@ def run_chain(args):
         torch.cuda.set_device(local_rank)
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
     device = local_rank if world > 1 else 0
-    kw = {} if args.chain_duration <= 0 else dict(duration_s=args.chain_duration)
-    ds = sim.make_config("C5", seed=5, **kw)  # identical on every rank (deterministic generator)
-    p = api.default_params()
-    comm = DistComm(dist) if dist is not None else LocalComm(1)
-    n_guess = ds.n_times
-    # ~4 sqrt(n) segments over the whole chain (the separator chain is eliminated in segments of its own, nested level 2)
-    spr = args.segs_per_rank if args.segs_per_rank > 0 else max(2, int(round(4.0 * n_guess ** 0.5 / world)))
-    cs = ChainSolver(p, ds, comm, segs_per_rank=spr, device=device)
-    stream = cs.parts[0].stream
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-
-    def step():
-        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        e0.record(stream)
-        cs.rebuild()
-        e1.record(stream)
-        inf = cs.optimize()
-        e2.record(stream)
-        e2.synchronize()
-        return e0.elapsed_time(e1), e1.elapsed_time(e2), inf
-
-    for _ in range(args.warmup):
-        step()
-    sampler = ClockSampler(device)
-    barrier()
-    torch.cuda.synchronize()
-    sampler.start()
-    b_ms = o_ms = 0.0
-    for _ in range(args.steps):
-        b, o, inf = step()
-        b_ms += b
-        o_ms += o
-    torch.cuda.synchronize()
-    barrier()
-    clocks = sampler.stop()
-    tot = torch.tensor([b_ms + o_ms, o_ms], dtype=torch.float64, device=f"cuda:{device}")
-    if dist is not None:
-        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-    tot_ms, opt_ms = (float(v) for v in tot.tolist())
+    res = chain_leg(args, dist, device, rank, world, args.steps, args.warmup)
     if rank == 0:
-        n_states = len(cs.ts)
-        line = {
-            "metric": "lm_damped_solve_latency", "value": opt_ms / args.steps / max(1, inf.tries), "unit": "ms", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_ms / args.steps, "higher_is_better": False,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "ONE synthesised one-hour sequence (BASELINE.json configs[4]): 20 Hz states, 200 Hz IMU, 100 Hz vicon, "
-                                   "chain-sharded over %d GPU(s), %d segments per GPU; one NCCL all-gather of segment Schur outputs + separator "
-                                   "records + global-block parts per damped solve" % (world, cs.segs_per_rank),
-                       "n_states": n_states, "n_imu": ds.n_imu, "n_vicon": ds.n_vicon, "segments_per_gpu": cs.segs_per_rank,
-                       "timing": "CUDA events on the solver stream, max over ranks"},
-            "lm": {"iterations": inf.iterations, "damped_solves": inf.tries, "final_error": inf.final_error, "status": inf.status,
-                   "ms_per_lm_iteration": opt_ms / args.steps / max(1, inf.iterations), "build_ms": (tot_ms - opt_ms) / args.steps,
-                   "optimize_ms": opt_ms / args.steps},
-            "trajectories_per_second": 1e3 * args.steps / tot_ms,
-            "collectives_per_damped_solve": 3, "clocks": clocks,
-        }
+        line = {"metric": "lm_damped_solve_latency", "value": res["ms_per_damped_solve"], "unit": "ms", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["graph"]["build_ms"] + res["graph"]["optimize_ms"],
+                "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": res["workload"], "n_states": res["n_states"], "segments_per_gpu": res["segments_per_gpu"]},
+                "chain": res, "clocks": res["graph"]["clocks"]}
         print(json.dumps(line))
-    cs.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -492,6 +516,17 @@ def main():
                    "ms_per_lm_iteration": float(m[7]) / max(1, inf.iterations), "ms_per_damped_solve": float(m[7]) / max(1, inf.tries)}
         one.close()
 
+    # ---------------- BASELINE.json configs[4]: one one-hour sequence chain-sharded over the same GPUs (all ranks take part)
+    chain = None
+    if not args.no_chain:
+        bs.close()
+        bs = None
+        try:
+            chain = chain_leg(args, dist, device, rank, world, args.chain_steps, 2)
+        except Exception as e:  # a widened row must never cost the headline line
+            chain = {"error": repr(e)}
+        barrier()
+
     cpu = None
     if not args.no_cpu_baseline and rank == 0:
         v, sample, _ = cpu_baseline(args.cpu_sample_s if args.duration <= 0 else min(args.cpu_sample_s, args.duration), 1)
@@ -537,10 +572,12 @@ def main():
                                    enumerate(["build", "linearize", "eliminate", "reduced", "backsub", "cost", "lm", "optimize_total"])},
             "lm_iteration_latency": latency,
             "simulator": simulator,
+            "chain": chain,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))
-    bs.close()
+    if bs is not None:
+        bs.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -215,36 +215,70 @@ int v2gt_batch_get_lm_trace(v2gt_batch *b, int32_t trial, int64_t capacity, doub
 int v2gt_plan_segments(int32_t n_states, int32_t n_running, int32_t target_warps, int32_t sm_count, int32_t *p_level1, int32_t *p_level2);
 
 /* ---- chain-sharded solve of ONE long sequence across ranks (BASELINE config 5) ----
- * Every rank creates a 1-trial batch holding a contiguous piece of the cleaned state chain plus one halo state on
- * each inner side, and drives the Levenberg-Marquardt rounds phase by phase; between the phases the caller moves the
- * small buffers below with its collective library (NCCL through torch.distributed in vicon2gt_b200/chain.py):
- *   all-reduce (sum)  V2GT_CHAIN_BUF_SUMS (8)   after phases 0 and 5      cost / model-fidelity scalars
- *   all-gather        PACK_SEND -> PACK_ALL (rank-major)   after phase 3   per rank: segment Schur outputs, separator records,
- *                                                                          its part of the 9x9 global block + gradient
- *   all-gather        HALO_SEND (16) -> HALO_RECV (16 x world)      after phase 4   boundary steps
- * i.e. three small collectives per damped solve.  Phase 4 unpacks PACK_ALL (the global block is summed in rank order).
- * The reduced (separator + 9 globals) system is then solved redundantly on every rank; all ranks take identical
- * accept / reject decisions.  Geometry: the chain of n_total states is cut into p_total segments with the same
- * formula as the single-GPU solve; this rank owns segments [j0, j1) and the separators in front of them, i.e. the
- * local slots [own_lo, own_hi) of its n_local states starting at global state g_off.  Call before upload. */
+ * Replaces, for a sequence too long for one GPU's latency budget, the single graph that
+ * ViconGraphSolver::build_problem assembles (src/solver/ViconGraphSolver.cpp:390-536): the cleaned state chain is cut
+ * into world x segs_per_rank segments; every rank creates a 1-trial batch holding its contiguous piece of the chain
+ * plus one halo state on each inner side (the IMU factor across a rank boundary reads the neighbour's state,
+ * src/gtsam/ImuFactorCPIv1.cpp:29-39).  Per damped solve the ranks exchange twice, both all-gathers in rank order:
+ *   A  PACK_SEND -> PACK_ALL   per rank: Schur outputs of its segments, normal-equation records of its separators,
+ *                              its part of the 9x9 global block + gradient (summed in rank order after the gather)
+ *   B  SUMS_SEND -> SUMS_ALL   per rank: V2GT_CHAIN_SUMS_N doubles = cost / model-fidelity scalars of its own
+ *                              factors + the step of its last own state (the next rank's left halo)
+ * B cannot ride on A: the accept / reject decision needs the summed cost of the trial point, which needs the step,
+ * which needs the reduced system gathered by A.  The reduced (separator + 9 globals) system is solved redundantly on
+ * every rank from bit-identical data, so all ranks take identical Levenberg-Marquardt decisions.
+ * Geometry: the chain of n_total states is cut into p_total segments with the same formula as the single-GPU solve;
+ * this rank owns segments [j0, j1) and the separators in front of them, i.e. the local slots [own_lo, own_hi) of its
+ * n_local states starting at global state g_off (v2gt_chain_plan computes all of it).  Call configure before upload.
+ *
+ * Two ways to drive it:
+ *   v2gt_chain_optimize   the whole Levenberg-Marquardt loop inside the library: both exchanges are ncclAllGather calls
+ *                         on the handle's stream (libnccl is loaded at run time; v2gt_chain_comm_init), the kernel +
+ *                         collective sequence of one damped solve is captured once as a CUDA graph and replayed; the
+ *                         host reads one counter every `tries_per_sync` damped solves.  world == 1 needs no NCCL.
+ *   v2gt_chain_phase      phase by phase, the caller moves the buffers itself between the phases (used to run all
+ *                         ranks of a small world on ONE device in the tests: same kernels, same buffers). */
+typedef struct v2gt_chain_plan_t {
+  int32_t rank, world;
+  int32_t p_total, stride;   /* segments of the whole chain; separators sit at m * stride - 1 */
+  int32_t j0, j1;            /* own segments [j0, j1) */
+  int32_t own_lo, own_hi;    /* own local slots */
+  int64_t n_total, g_off, n_local;
+} v2gt_chain_plan_t;
+/* Host only. Ownership of a chain of n_total cleaned states for `rank` of `world` with segs_per_rank segments each;
+ * V2GT_ERR_INVALID_ARG when the chain is too short for that cut.  v2gt_chain_fit_segments: the largest count
+ * <= target that is valid (0 if none). */
+int v2gt_chain_plan(int64_t n_total, int32_t world, int32_t segs_per_rank, int32_t rank, v2gt_chain_plan_t *plan);
+int v2gt_chain_fit_segments(int64_t n_total, int32_t world, int32_t target, int32_t *segs_per_rank);
+#define V2GT_CHAIN_SUMS_N 24
+#define V2GT_NCCL_ID_BYTES 128
 enum {
   V2GT_CHAIN_BUF_SUMS = 0, V2GT_CHAIN_BUF_GAMMA = 1, V2GT_CHAIN_BUF_PACK_SEND = 2, V2GT_CHAIN_BUF_SEG_ALL = 3,
-  V2GT_CHAIN_BUF_PACK_ALL = 4, V2GT_CHAIN_BUF_SEPNE_ALL = 5, V2GT_CHAIN_BUF_HALO_SEND = 6, V2GT_CHAIN_BUF_HALO_RECV = 7
+  V2GT_CHAIN_BUF_PACK_ALL = 4, V2GT_CHAIN_BUF_SEPNE_ALL = 5, V2GT_CHAIN_BUF_SUMS_SEND = 6, V2GT_CHAIN_BUF_SUMS_ALL = 7
 };
 enum {
-  V2GT_CHAIN_PHASE_COST0 = 0,   /* cost of the current estimate -> SUMS                                   */
-  V2GT_CHAIN_PHASE_BEGIN = 1,   /* LM state initialisation from the (all-reduced) SUMS                    */
+  V2GT_CHAIN_PHASE_COST0 = 0,   /* cost of the current estimate -> SUMS_SEND            [exchange B]      */
+  V2GT_CHAIN_PHASE_BEGIN = 1,   /* sums in rank order, LM state initialisation                            */
   V2GT_CHAIN_PHASE_LINEARIZE = 2, /* start of a try; relinearise if the last step was accepted            */
-  V2GT_CHAIN_PHASE_ELIMINATE = 3, /* eliminate the own segments -> PACK_SEND                              */
-  V2GT_CHAIN_PHASE_SOLVE = 4,   /* unpack PACK_ALL, reduced system (redundant), back-substitution -> HALO_SEND */
-  V2GT_CHAIN_PHASE_COST = 5,    /* trial point + its cost -> SUMS                                         */
-  V2GT_CHAIN_PHASE_DECIDE = 6   /* accept / reject, lambda update from the (all-reduced) SUMS             */
+  V2GT_CHAIN_PHASE_ELIMINATE = 3, /* eliminate the own segments -> PACK_SEND             [exchange A]      */
+  V2GT_CHAIN_PHASE_SOLVE = 4,   /* unpack PACK_ALL, reduced system (redundant), back-substitution         */
+  V2GT_CHAIN_PHASE_COST = 5,    /* trial point + its cost, boundary step -> SUMS_SEND   [exchange B]      */
+  V2GT_CHAIN_PHASE_DECIDE = 6   /* sums in rank order, left halo, accept / reject, lambda update          */
 };
 int v2gt_chain_configure(v2gt_batch *b, int32_t rank, int32_t world, int64_t n_total, int64_t g_off, int32_t p_total, int32_t j0,
                          int32_t j1, int32_t own_lo, int32_t own_hi);
 int v2gt_chain_phase(v2gt_batch *b, int32_t phase);
 /* device pointer + length (doubles) of one of the exchange buffers (valid after upload) */
 int v2gt_chain_buffer(v2gt_batch *b, int32_t which, void **dev_ptr, int64_t *n_doubles);
+/* NCCL inside the library.  unique_id: rank 0 calls it and hands the V2GT_NCCL_ID_BYTES bytes to every rank by any
+ * means (a file, MPI, torch.distributed); comm_init: every rank, after v2gt_chain_configure (collective: returns when
+ * all `world` ranks have joined).  V2GT_ERR_NCCL when libnccl.so.2 cannot be loaded or a call fails. */
+int v2gt_chain_nccl_unique_id(uint8_t *id_bytes);
+int v2gt_chain_comm_init(v2gt_batch *b, const uint8_t *id_bytes);
+/* The Levenberg-Marquardt loop of the sharded chain (after v2gt_batch_build): at most max_tries damped solves
+ * (<= 0: the policy's own bound).  use_graph: 1 = replay one captured CUDA graph per damped solve, 0 = plain launches
+ * (per-phase CUDA-event timing in v2gt_batch_get_timing).  Collective when world > 1. */
+int v2gt_chain_optimize(v2gt_batch *b, int32_t max_tries, int32_t use_graph);
 /* the handle's CUDA stream (cudaStream_t), so that the caller's collectives can be ordered with the kernels */
 int v2gt_batch_stream(v2gt_batch *b, void **stream);
 

@@ -38,6 +38,21 @@ def test_chain_plan_partitions_the_chain(n, world, spr):
         chain_plan(20, 4, 4)
 
 
+def test_chain_plan_entry_points_of_the_library():
+    """v2gt_chain_plan / v2gt_chain_fit_segments are host-only: they work without a device and reject bad cuts."""
+    from vicon2gt_b200.chain import chain_plan, fit_segments_per_rank, vicon_margin
+
+    assert fit_segments_per_rank(72016, 8, 134) <= 134
+    spr = fit_segments_per_rank(301, 3, 64)
+    assert 1 <= spr < 64 and len(chain_plan(301, 3, spr)) == 3
+    with pytest.raises(ValueError):
+        fit_segments_per_rank(5, 4, 8)
+    p = default_params()
+    assert vicon_margin(p) >= 2 * p.time_offset_window + p.interp_gap_init
+    p.toff_imu_to_vicon = -0.7
+    assert vicon_margin(p) >= 0.7 + 2 * p.time_offset_window + p.interp_gap_init
+
+
 def _gloo_worker(rank, world, port, out):
     import torch
     import torch.distributed as dist
@@ -66,6 +81,15 @@ def _gloo_worker(rank, world, port, out):
         check = gamma_loc.clone()
         dist.all_reduce(check)
         assert torch.equal(check, gamma)
+        # exchange B: [5 cost scalars | pad | step of the last own state]; summed in rank order, the left halo takes the
+        # previous rank's step (k_chain_sum / k_chain_reduce)
+        sums_send = torch.cat([torch.full((8,), 0.5 + rank, dtype=torch.float64), torch.full((16,), 100.0 + rank, dtype=torch.float64)])
+        sums_all = torch.zeros(world * 24, dtype=torch.float64)
+        dist.all_gather_into_tensor(sums_all, sums_send)
+        tot = sum(float(sums_all[24 * r]) for r in range(world))
+        assert tot == sum(0.5 + r for r in range(world))
+        if rank >= 1:
+            assert float(sums_all[24 * (rank - 1) + 8]) == 100.0 + rank - 1
         lo, hi = pl.own_global
         counts = torch.zeros(n, dtype=torch.float64)
         counts[lo:hi] = 1

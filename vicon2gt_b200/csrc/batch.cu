@@ -15,9 +15,12 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <dlfcn.h>
 #include <fstream>
 #include <iomanip>
 #include <limits>
+#include <map>
+#include <mutex>
 #include <numeric>
 #include <sstream>
 #include <string>
@@ -40,12 +43,13 @@ int launch_eliminate(const DevPtrs &d, int force_all, cudaStream_t st);
 int launch_reduced(const DevPtrs &d, int force_all, cudaStream_t st);
 int launch_backsub(const DevPtrs &d, int force_all, cudaStream_t st);
 int launch_lm_begin(const DevPtrs &d, cudaStream_t st);
+int launch_lm_freeze(const DevPtrs &d, int pass, cudaStream_t st);
 int launch_lm_pre_try(const DevPtrs &d, cudaStream_t st);
 int launch_lm_decide(const DevPtrs &d, int count_active, cudaStream_t st);
-int launch_chain_sum(const DevPtrs &d, cudaStream_t st);
+int launch_chain_sum(const DevPtrs &d, int with_halo, cudaStream_t st);
+int launch_chain_reduce(const DevPtrs &d, int with_halo, cudaStream_t st);
 int launch_chain_unpack(const DevPtrs &d, cudaStream_t st);
 int launch_chain_pack(const DevPtrs &d, int stride, cudaStream_t st);
-int launch_chain_halo(const DevPtrs &d, int recv, cudaStream_t st);
 int asm_chunks(int n_max);
 int simbatch_view(v2gt_simbatch *s, int trial, int *device, int64_t *n_imu, const double **imu_t, const double **d_imu_s, int64_t *n_vic,
                   const double **vic_t, const double **d_vic_s, int64_t *n_times, const double **state_t);
@@ -68,6 +72,7 @@ struct HostTrial {
   int64_t n_imu = 0, n_vic_in = 0, n_times = 0;
   double vic_Rconst[18];
   bool cov_const = true;
+  bool imu_unsorted = false; // derived in upload: IMU fed out of time order
   // derived in upload
   std::vector<int64_t> vic_order;  // empty: the fed poses are already strictly increasing in time (kept as they are)
   int64_t n_vic = 0;               // after de-duplication
@@ -98,6 +103,11 @@ struct v2gt_batch {
   bool chain = false;
   int c_rank = 0, c_world = 1, c_p = 0, c_j0 = 0, c_j1 = 0, c_lo = 0, c_hi = 0;
   long long c_n = 0, c_goff = 0;
+  void *c_comm = nullptr; // ncclComm_t of the in-library exchange (v2gt_chain_comm_init)
+  // one damped solve captured as a CUDA graph, keyed by the segment count of the launch (v2gt_chain_optimize; small
+  // batches in v2gt_batch_optimize): valid for the device buffers of the current upload
+  std::map<int, cudaGraphExec_t> try_graphs;
+  int opt_graph = -1; // -1 auto (small batches), 0 never, 1 always
   // options
   int opt_segments = 0;       // 0 = auto (adaptive); > 0: fixed number of segments per trial
   int opt_target_warps = 148 * 64; // segment warps the adaptive choice aims for per elimination launch
@@ -162,7 +172,13 @@ template <typename Tp> int pin_alloc(v2gt_batch *b, Tp **p, size_t count) {
   *p = (Tp *)q;
   return V2GT_OK;
 }
+void drop_graphs(v2gt_batch *b) {
+  for (auto &kv : b->try_graphs)
+    cudaGraphExecDestroy(kv.second);
+  b->try_graphs.clear();
+}
 void free_device(v2gt_batch *b) {
+  drop_graphs(b);
   for (void *p : b->dev_allocs)
     cudaFree(p);
   b->dev_allocs.clear();
@@ -255,6 +271,45 @@ template <typename F> void parallel_trials(int t0, int t1, F f) {
 }
 template <typename F> void parallel_trials(int T, F f) { parallel_trials(0, T, f); }
 
+// ---- NCCL, loaded at run time (libnccl.so.2: the copy already mapped into the process, e.g. PyTorch's, else the
+// system's).  Only the five entry points the chain exchange needs; declarations follow nccl.h 2.x.
+struct NcclApi {
+  typedef struct { char internal[V2GT_NCCL_ID_BYTES]; } UniqueId;
+  int (*GetUniqueId)(UniqueId *) = nullptr;
+  int (*CommInitRank)(void **, int, UniqueId, int) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+NcclApi &nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h)
+      h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h)
+      return;
+    api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+    api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
+    api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather;
+  });
+  return api;
+}
+constexpr int NCCL_FLOAT64 = 8; // ncclDouble
+int nccl_check(int rc, const char *what) {
+  if (rc == 0)
+    return V2GT_OK;
+  NcclApi &n = nccl_api();
+  fprintf(stderr, "[vicon2gt_b200] %s failed: %s\n", what, n.GetErrorString ? n.GetErrorString(rc) : "NCCL error");
+  return V2GT_ERR_NCCL;
+}
+
+
 } // namespace
 
 namespace v2 {
@@ -310,6 +365,8 @@ int v2gt_abi_struct_sizes(int32_t *params_bytes, int32_t *trial_info_bytes) {
 }
 
 int v2gt_device_count(int32_t *count) {
+  if (!count)
+    return V2GT_ERR_INVALID_ARG;
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess) {
@@ -339,9 +396,19 @@ int v2gt_batch_create(int32_t device, int32_t n_trials, v2gt_batch **out) {
   cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, device);
   b->T = n_trials;
   b->trials.resize(n_trials);
-  V2_CUDA_CHECK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
-  for (int i = 0; i < 16; i++)
-    V2_CUDA_CHECK(cudaEventCreate(&b->ev[i]));
+  bool ok = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) == cudaSuccess;
+  int n_ev = 0;
+  for (; ok && n_ev < 16; n_ev++)
+    ok = cudaEventCreate(&b->ev[n_ev]) == cudaSuccess;
+  if (!ok) { // nothing half-built is handed out or left behind
+    for (int i = 0; i + 1 < n_ev; i++)
+      cudaEventDestroy(b->ev[i]);
+    if (b->stream)
+      cudaStreamDestroy(b->stream);
+    delete b;
+    cudaGetLastError();
+    return V2GT_ERR_CUDA;
+  }
   b->ev_ok = true;
   *out = b;
   return V2GT_OK;
@@ -354,6 +421,9 @@ int v2gt_batch_destroy(v2gt_batch *b) {
   if (b->stream)
     cudaStreamSynchronize(b->stream);
   free_device(b);
+  if (b->c_comm && nccl_api().ok)
+    nccl_api().CommDestroy(b->c_comm);
+  b->c_comm = nullptr;
   if (b->ev_ok)
     for (int i = 0; i < 16; i++)
       cudaEventDestroy(b->ev[i]);
@@ -377,6 +447,8 @@ int v2gt_batch_set_option(v2gt_batch *b, const char *name, double value) {
     b->opt_keep_cov = (int)value;
   else if (n == "tries_per_sync")
     b->opt_tries_per_sync = std::max(1, (int)value);
+  else if (n == "graph")
+    b->opt_graph = (int)value;
   else
     return V2GT_ERR_INVALID_ARG;
   return V2GT_OK;
@@ -565,6 +637,7 @@ int v2gt_batch_upload(v2gt_batch *b) {
           imu_sorted = false;
           break;
         }
+      h.imu_unsorted = !imu_sorted;
       h.state_t.reserve((size_t)h.n_times);
       for (int64_t si = 0; si < h.n_times; si++) {
         const double ts = h.state_t_raw[si];
@@ -612,6 +685,7 @@ int v2gt_batch_upload(v2gt_batch *b) {
     d.st_off = S;
     d.n_raw = (status == V2GT_OK) ? (long long)h.state_t.size() : 0;
     d.vic_cov_const = h.cov_const ? 1 : 0;
+    d.imu_unsorted = h.imu_unsorted ? 1 : 0;
     std::memcpy(d.vic_Rconst, h.vic_Rconst, sizeof(d.vic_Rconst));
     d.prm = h.prm;
     M += d.n_imu;
@@ -639,6 +713,7 @@ int v2gt_batch_upload(v2gt_batch *b) {
       return V2GT_ERR_INVALID_ARG;
     P = b->c_p; // global segment count of the sharded chain
   }
+  drop_graphs(b);
   DevPtrs &d = b->d;
   std::memset(&d, 0, sizeof(d));
   d.T = T;
@@ -791,8 +866,8 @@ int v2gt_batch_upload(v2gt_batch *b) {
     const size_t per_rank = (size_t)ploc * (SEG_STRIDE + NE_STRIDE) + 96;
     V2_TRY(dev_alloc(b, &d.c_pack_send, per_rank));
     V2_TRY(dev_alloc(b, &d.c_pack_all, per_rank * std::max(1, b->c_world)));
-    V2_TRY(dev_alloc(b, &d.c_halo_send, 16));
-    V2_TRY(dev_alloc(b, &d.c_halo_recv, (size_t)16 * std::max(1, b->c_world)));
+    V2_TRY(dev_alloc(b, &d.c_sums_send, CSUM_N));
+    V2_TRY(dev_alloc(b, &d.c_sums_all, (size_t)CSUM_N * std::max(1, b->c_world)));
     d.chain = 1;
     d.c_n = (int)b->c_n;
     d.c_goff = (int)b->c_goff;
@@ -874,7 +949,8 @@ int v2gt_batch_upload(v2gt_batch *b) {
   if (b->chain) {
     V2_CUDA_CHECK(cudaMemsetAsync(d.c_sums, 0, sizeof(double) * 8, st));
     V2_CUDA_CHECK(cudaMemsetAsync(d.c_gamma_loc, 0, sizeof(double) * 96, st));
-    V2_CUDA_CHECK(cudaMemsetAsync(d.c_halo_recv, 0, sizeof(double) * 16 * std::max(1, b->c_world), st));
+    V2_CUDA_CHECK(cudaMemsetAsync(d.c_sums_send, 0, sizeof(double) * CSUM_N, st));
+    V2_CUDA_CHECK(cudaMemsetAsync(d.c_sums_all, 0, sizeof(double) * CSUM_N * std::max(1, b->c_world), st));
     V2_CUDA_CHECK(cudaMemsetAsync(d.c_sepne, 0, sizeof(double) * ((size_t)P + 2) * NE_STRIDE, st));
     V2_CUDA_CHECK(cudaMemsetAsync(d.seg, 0, sizeof(double) * (size_t)T * P * SEG_STRIDE, st));
   }
@@ -981,21 +1057,99 @@ int v2gt_plan_segments(int32_t n_states, int32_t n_running, int32_t target_warps
   return V2GT_OK;
 }
 
-int v2gt_batch_optimize(v2gt_batch *b) {
-  if (!b)
-    return V2GT_ERR_INVALID_ARG;
-  if (!b->built)
-    return V2GT_ERR_NOT_BUILT;
-  V2_CUDA_CHECK(cudaSetDevice(b->device));
-  b->results_cached = false;
+// ---- one damped solve ("try") of every running trial, enqueued on the handle's stream.
+// ev: 7 events around the phases (plain launches only), or null.  Chain mode: the two exchanges are part of it.
+static int chain_exchange(v2gt_batch *b, int which, cudaStream_t st);
+static int seg_stride_host(long long n, int P) {
+  long long st = (n + 1 + P - 1) / P;
+  return (int)(st < 2 ? 2 : st);
+}
+static int enqueue_try(v2gt_batch *b, const DevPtrs &d, int count_active, cudaEvent_t *ev) {
   cudaStream_t st = b->stream;
-  const DevPtrs &d = b->d;
-  V2_CUDA_CHECK(cudaEventRecord(b->ev[2], st));
-  V2_TRY(launch_cost(d, b->n_max, 0, 1, st));
-  V2_TRY(launch_lm_begin(d, st));
+  auto mark = [&](int k) -> int {
+    if (ev)
+      V2_CUDA_CHECK(cudaEventRecord(ev[k], st));
+    return V2GT_OK;
+  };
+  V2_TRY(launch_lm_pre_try(d, st));
+  V2_TRY(mark(0));
+  V2_TRY(launch_linearize(d, b->n_max, 0, st));
+  V2_TRY(mark(1));
+  V2_TRY(launch_eliminate(d, 0, st));
+  if (b->chain) {
+    V2_TRY(launch_chain_pack(d, seg_stride_host(b->c_n, d.P), st));
+    V2_TRY(mark(2));
+    V2_TRY(chain_exchange(b, 0, st));
+    V2_TRY(launch_chain_unpack(d, st));
+  } else {
+    V2_TRY(mark(2));
+  }
+  V2_TRY(launch_reduced(d, 0, st));
+  V2_TRY(mark(3));
+  V2_TRY(launch_backsub(d, 0, st));
+  V2_TRY(mark(4));
+  V2_TRY(launch_cost(d, b->n_max, 1, 0, st));
+  V2_TRY(mark(5));
+  if (b->chain) {
+    V2_TRY(launch_chain_sum(d, 1, st));
+    V2_TRY(chain_exchange(b, 1, st));
+    V2_TRY(launch_chain_reduce(d, 1, st));
+  }
+  V2_TRY(launch_lm_decide(d, count_active, st));
+  V2_TRY(mark(6));
+  b->launches[1] += 3;
+  b->launches[2] += 1;
+  b->launches[3] += (l2_segments(d.P, d.l2_P) ? 7 : 2) + (b->chain ? 2 : 0);
+  b->launches[4] += 1;
   b->launches[5] += 1;
-  b->launches[6] += 1;
-  // worst case number of tries: every outer iteration may walk lambda from its floor to the upper bound
+  b->launches[6] += 2 + (b->chain ? 2 : 0);
+  return V2GT_OK;
+}
+
+// The same sequence as an executable CUDA graph (captured once per segment count and upload): one graph launch per
+// damped solve instead of ~20 kernel launches -- what a small batch or a single trajectory spends its time on.
+static int try_graph(v2gt_batch *b, const DevPtrs &d, cudaGraphExec_t *out) {
+  auto it = b->try_graphs.find(d.P);
+  if (it != b->try_graphs.end()) {
+    *out = it->second;
+    return V2GT_OK;
+  }
+  cudaStream_t st = b->stream;
+  int64_t keep[8];
+  std::memcpy(keep, b->launches, sizeof(keep));
+  V2_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+  const int rc = enqueue_try(b, d, 1, nullptr);
+  cudaGraph_t g = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(st, &g);
+  std::memcpy(b->launches, keep, sizeof(keep)); // capturing launches nothing
+  if (rc != V2GT_OK || e != cudaSuccess || !g) {
+    if (g)
+      cudaGraphDestroy(g);
+    cudaGetLastError();
+    return rc != V2GT_OK ? rc : V2GT_ERR_CUDA;
+  }
+  cudaGraphExec_t ge = nullptr;
+  const cudaError_t e2 = cudaGraphInstantiate(&ge, g, 0);
+  cudaGraphDestroy(g);
+  if (e2 != cudaSuccess) {
+    fprintf(stderr, "[vicon2gt_b200] cudaGraphInstantiate failed: %s\n", cudaGetErrorString(e2));
+    return V2GT_ERR_CUDA;
+  }
+  b->try_graphs[d.P] = ge;
+  *out = ge;
+  return V2GT_OK;
+}
+static void count_try_launches(v2gt_batch *b, const DevPtrs &d) {
+  b->launches[1] += 3;
+  b->launches[2] += 1;
+  b->launches[3] += (l2_segments(d.P, d.l2_P) ? 7 : 2) + (b->chain ? 2 : 0);
+  b->launches[4] += 1;
+  b->launches[5] += 1;
+  b->launches[6] += 2 + (b->chain ? 2 : 0);
+}
+
+// worst case number of tries: every outer iteration may walk lambda from its floor to the upper bound
+static int max_rounds_of(const v2gt_batch *b) {
   int max_rounds = 0;
   for (int t = 0; t < b->T; t++) {
     const v2gt_params &p = b->trials[t].prm;
@@ -1006,62 +1160,82 @@ int v2gt_batch_optimize(v2gt_batch *b) {
       r = std::min(r, p.lm_max_tries + 1);
     max_rounds = std::max(max_rounds, r);
   }
-  V2_TRY(solve_configure());
-  // per-phase device timing: 7 events per try, re-used every chunk (the host synchronises once per chunk)
+  return max_rounds;
+}
+
+// The optimiser rounds shared by the batch and the chain-sharded solve.  Every `chunk` damped solves the host reads
+// the number of trials still running; in between nothing leaves the device.
+static int run_rounds(v2gt_batch *b, int max_rounds, bool use_graph) {
+  cudaStream_t st = b->stream;
   const int chunk = b->opt_tries_per_sync;
-  while ((int)b->ev_pool.size() < 7 * chunk) {
-    cudaEvent_t e;
-    V2_CUDA_CHECK(cudaEventCreate(&e));
-    b->ev_pool.push_back(e);
-  }
+  if (!use_graph)
+    while ((int)b->ev_pool.size() < 7 * chunk) { // per-phase device timing: 7 events per try, re-used every chunk
+      cudaEvent_t e;
+      V2_CUDA_CHECK(cudaEventCreate(&e));
+      b->ev_pool.push_back(e);
+    }
   int rounds = 0;
   int n_running = b->T;
   const DevPtrs &dmax = b->d;
   while (rounds < max_rounds) {
     // segments per trial for this chunk of tries: fill the GPU with the trials that are still running
     DevPtrs d = dmax;
-    if (b->opt_segments <= 0)
+    if (b->opt_segments <= 0 && !b->chain)
       d.P = choose_segments(b->opt_target_warps, std::max(1, n_running), dmax.P, b->sm_count);
-    V2_CUDA_CHECK(cudaMemsetAsync(d.n_active, 0, sizeof(int), st));
-    for (int k = 0; k < chunk; k++) {
-      cudaEvent_t *e = &b->ev_pool[7 * k];
-      V2_TRY(launch_lm_pre_try(d, st));
-      V2_CUDA_CHECK(cudaEventRecord(e[0], st));
-      V2_TRY(launch_linearize(d, b->n_max, 0, st));
-      V2_CUDA_CHECK(cudaEventRecord(e[1], st));
-      V2_TRY(launch_eliminate(d, 0, st));
-      V2_CUDA_CHECK(cudaEventRecord(e[2], st));
-      V2_TRY(launch_reduced(d, 0, st));
-      V2_CUDA_CHECK(cudaEventRecord(e[3], st));
-      V2_TRY(launch_backsub(d, 0, st));
-      V2_CUDA_CHECK(cudaEventRecord(e[4], st));
-      V2_TRY(launch_cost(d, b->n_max, 1, 0, st));
-      V2_CUDA_CHECK(cudaEventRecord(e[5], st));
-      V2_TRY(launch_lm_decide(d, k == chunk - 1 ? 1 : 0, st));
-      V2_CUDA_CHECK(cudaEventRecord(e[6], st));
-      b->launches[1] += 3;
-      b->launches[2] += 1;
-      b->launches[3] += l2_segments(d.P, d.l2_P) ? 7 : 2;
-      b->launches[4] += 1;
-      b->launches[5] += 1;
-      b->launches[6] += 2;
-    }
-    rounds += chunk;
-    V2_CUDA_CHECK(cudaMemcpyAsync(b->h_active, d.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
-    V2_CUDA_CHECK(cudaStreamSynchronize(st));
-    for (int k = 0; k < chunk; k++) {
-      cudaEvent_t *e = &b->ev_pool[7 * k];
-      for (int ph = 0; ph < 6; ph++) {
-        float m = 0;
-        cudaEventElapsedTime(&m, e[ph], e[ph + 1]);
-        b->ms[1 + ph] += m;
+    const int todo = std::min(chunk, max_rounds - rounds);
+    cudaGraphExec_t ge = nullptr;
+    if (use_graph)
+      V2_TRY(try_graph(b, d, &ge));
+    for (int k = 0; k < todo; k++) {
+      if (k == todo - 1)
+        V2_CUDA_CHECK(cudaMemsetAsync(d.n_active, 0, sizeof(int), st)); // only the chunk's last decision counts
+      if (use_graph) {
+        V2_CUDA_CHECK(cudaGraphLaunch(ge, st));
+        count_try_launches(b, d);
+      } else {
+        V2_TRY(enqueue_try(b, d, k == todo - 1 ? 1 : 0, &b->ev_pool[7 * k]));
       }
     }
-    b->tries_enqueued += chunk;
+    rounds += todo;
+    V2_CUDA_CHECK(cudaMemcpyAsync(b->h_active, d.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+    V2_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (!use_graph)
+      for (int k = 0; k < todo; k++) {
+        cudaEvent_t *e = &b->ev_pool[7 * k];
+        for (int ph = 0; ph < 6; ph++) {
+          float m = 0;
+          cudaEventElapsedTime(&m, e[ph], e[ph + 1]);
+          b->ms[1 + ph] += m;
+        }
+      }
+    b->tries_enqueued += todo;
     n_running = *b->h_active;
     if (n_running == 0)
       break;
   }
+  return V2GT_OK;
+}
+
+int v2gt_batch_optimize(v2gt_batch *b) {
+  if (!b)
+    return V2GT_ERR_INVALID_ARG;
+  if (!b->built)
+    return V2GT_ERR_NOT_BUILT;
+  if (b->chain)
+    return V2GT_ERR_INVALID_ARG; // a sharded chain is optimised by v2gt_chain_optimize / v2gt_chain_phase
+  V2_CUDA_CHECK(cudaSetDevice(b->device));
+  b->results_cached = false;
+  cudaStream_t st = b->stream;
+  const DevPtrs &d = b->d;
+  V2_CUDA_CHECK(cudaEventRecord(b->ev[2], st));
+  V2_TRY(launch_cost(d, b->n_max, 0, 1, st));
+  V2_TRY(launch_lm_begin(d, st));
+  b->launches[5] += 1;
+  b->launches[6] += 1;
+  V2_TRY(solve_configure());
+  // small problems are bound by the ~20 launches of a damped solve, not by the kernels: replay a captured graph
+  const bool use_graph = b->opt_graph > 0 || (b->opt_graph < 0 && (long long)b->T * b->n_max <= 400000);
+  V2_TRY(run_rounds(b, max_rounds_of(b), use_graph));
   V2_CUDA_CHECK(cudaEventRecord(b->ev[3], st));
   V2_CUDA_CHECK(cudaStreamSynchronize(st));
   float ms = 0;
@@ -1081,6 +1255,10 @@ int v2gt_batch_build_and_solve(v2gt_batch *b) {
   for (int t = 0; t < b->T; t++)
     loops = std::max(loops, (int)b->trials[t].prm.num_loop_relin);
   for (int i = 0; i <= loops; i++) {
+    // a trial takes part in passes 0..num_loop_relin of ITS parameters (the reference loops per solver,
+    // ViconGraphSolver.cpp:163); afterwards it keeps its result while the rest of the batch goes on
+    V2_CUDA_CHECK(cudaSetDevice(b->device));
+    V2_TRY(launch_lm_freeze(b->d, i, b->stream));
     V2_TRY(v2gt_batch_build(b, i == 0 ? 1 : 0));
     V2_TRY(v2gt_batch_optimize(b));
   }
@@ -1439,9 +1617,130 @@ int v2gt_chain_configure(v2gt_batch *b, int32_t rank, int32_t world, int64_t n_t
   return V2GT_OK;
 }
 
-static int seg_stride_host(long long n, int P) {
-  long long st = (n + 1 + P - 1) / P;
-  return (int)(st < 2 ? 2 : st);
+// exchange 0: PACK_SEND -> PACK_ALL, 1: SUMS_SEND -> SUMS_ALL; an all-gather in rank order on the handle's stream
+static int chain_exchange(v2gt_batch *b, int which, cudaStream_t st) {
+  const DevPtrs &d = b->d;
+  const size_t n = which == 0 ? (size_t)(b->c_j1 - b->c_j0) * (SEG_STRIDE + NE_STRIDE) + 96 : (size_t)CSUM_N;
+  const double *src = which == 0 ? d.c_pack_send : d.c_sums_send;
+  double *dst = which == 0 ? d.c_pack_all : d.c_sums_all;
+  if (b->c_world == 1) {
+    V2_CUDA_CHECK(cudaMemcpyAsync(dst, src, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    return V2GT_OK;
+  }
+  if (!b->c_comm)
+    return V2GT_ERR_NCCL; // v2gt_chain_comm_init first (or drive the phases and move the buffers yourself)
+  return nccl_check(nccl_api().AllGather(src, dst, n, NCCL_FLOAT64, b->c_comm, st), "ncclAllGather");
+}
+
+int v2gt_chain_plan(int64_t n_total, int32_t world, int32_t segs_per_rank, int32_t rank, v2gt_chain_plan_t *plan) {
+  if (!plan || world < 1 || segs_per_rank < 1 || rank < 0 || rank >= world || n_total < 2)
+    return V2GT_ERR_INVALID_ARG;
+  const long long p = (long long)world * segs_per_rank;
+  if (p > (1 << 24))
+    return V2GT_ERR_INVALID_ARG;
+  const int stride = seg_stride_host(n_total, (int)p);
+  // every segment must exist and hold at least one interior state besides its separator
+  if ((p - 1) * stride >= n_total || stride < 3)
+    return V2GT_ERR_INVALID_ARG;
+  const int j0 = rank * segs_per_rank, j1 = (rank + 1) * segs_per_rank;
+  // own states: the separators in front of the own segments and the segments themselves, i.e. the contiguous range
+  // [j0 * stride - 1, j1 * stride - 1); rank 0 starts at state 0, the last rank ends at n_total
+  const long long start = rank > 0 ? (long long)j0 * stride - 1 : 0;
+  const long long end = rank < world - 1 ? (long long)j1 * stride - 1 : n_total;
+  const long long g_off = start - (rank > 0 ? 1 : 0);                        // left halo: the previous rank's last own state
+  const long long n_local = end + (rank < world - 1 ? 1 : 0) - g_off;        // right halo: the next rank's leading separator
+  plan->rank = rank;
+  plan->world = world;
+  plan->p_total = (int32_t)p;
+  plan->stride = stride;
+  plan->j0 = j0;
+  plan->j1 = j1;
+  plan->own_lo = (int32_t)(start - g_off);
+  plan->own_hi = (int32_t)(end - g_off);
+  plan->n_total = n_total;
+  plan->g_off = g_off;
+  plan->n_local = n_local;
+  return V2GT_OK;
+}
+
+int v2gt_chain_fit_segments(int64_t n_total, int32_t world, int32_t target, int32_t *segs_per_rank) {
+  if (!segs_per_rank || world < 1)
+    return V2GT_ERR_INVALID_ARG;
+  *segs_per_rank = 0;
+  v2gt_chain_plan_t pl;
+  for (int spr = std::max(1, (int)target); spr >= 1; spr--)
+    if (v2gt_chain_plan(n_total, world, spr, 0, &pl) == V2GT_OK) {
+      *segs_per_rank = spr;
+      return V2GT_OK;
+    }
+  return V2GT_ERR_INVALID_ARG;
+}
+
+int v2gt_chain_nccl_unique_id(uint8_t *id_bytes) {
+  if (!id_bytes)
+    return V2GT_ERR_INVALID_ARG;
+  NcclApi &n = nccl_api();
+  if (!n.ok) {
+    fprintf(stderr, "[vicon2gt_b200] libnccl.so.2 could not be loaded\n");
+    return V2GT_ERR_NCCL;
+  }
+  NcclApi::UniqueId id;
+  V2_TRY(nccl_check(n.GetUniqueId(&id), "ncclGetUniqueId"));
+  std::memcpy(id_bytes, id.internal, V2GT_NCCL_ID_BYTES);
+  return V2GT_OK;
+}
+
+int v2gt_chain_comm_init(v2gt_batch *b, const uint8_t *id_bytes) {
+  if (!b || !b->chain || !id_bytes)
+    return V2GT_ERR_INVALID_ARG;
+  NcclApi &n = nccl_api();
+  if (!n.ok) {
+    fprintf(stderr, "[vicon2gt_b200] libnccl.so.2 could not be loaded\n");
+    return V2GT_ERR_NCCL;
+  }
+  V2_CUDA_CHECK(cudaSetDevice(b->device));
+  if (b->c_comm) {
+    n.CommDestroy(b->c_comm);
+    b->c_comm = nullptr;
+    drop_graphs(b);
+  }
+  NcclApi::UniqueId id;
+  std::memcpy(id.internal, id_bytes, V2GT_NCCL_ID_BYTES);
+  return nccl_check(n.CommInitRank(&b->c_comm, b->c_world, id, b->c_rank), "ncclCommInitRank");
+}
+
+int v2gt_chain_optimize(v2gt_batch *b, int32_t max_tries, int32_t use_graph) {
+  if (!b || !b->chain)
+    return V2GT_ERR_INVALID_ARG;
+  if (!b->built)
+    return V2GT_ERR_NOT_BUILT;
+  if (b->c_world > 1 && !b->c_comm)
+    return V2GT_ERR_NCCL;
+  V2_CUDA_CHECK(cudaSetDevice(b->device));
+  b->results_cached = false;
+  cudaStream_t st = b->stream;
+  const DevPtrs &d = b->d;
+  V2_CUDA_CHECK(cudaEventRecord(b->ev[2], st));
+  V2_TRY(launch_cost(d, b->n_max, 0, 1, st));
+  V2_TRY(launch_chain_sum(d, 0, st));
+  V2_TRY(chain_exchange(b, 1, st));
+  V2_TRY(launch_chain_reduce(d, 0, st));
+  V2_TRY(launch_lm_begin(d, st));
+  b->launches[5] += 1;
+  b->launches[6] += 3;
+  V2_TRY(solve_configure());
+  int cap = max_rounds_of(b);
+  if (max_tries > 0)
+    cap = std::min(cap, (int)max_tries);
+  V2_TRY(run_rounds(b, cap, use_graph != 0));
+  V2_CUDA_CHECK(cudaEventRecord(b->ev[3], st));
+  V2_CUDA_CHECK(cudaStreamSynchronize(st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, b->ev[0], b->ev[1]);
+  b->ms[0] = ms;
+  cudaEventElapsedTime(&ms, b->ev[2], b->ev[3]);
+  b->ms[7] = ms;
+  return V2GT_OK;
 }
 
 int v2gt_chain_phase(v2gt_batch *b, int32_t phase) {
@@ -1456,9 +1755,10 @@ int v2gt_chain_phase(v2gt_batch *b, int32_t phase) {
   switch (phase) {
   case V2GT_CHAIN_PHASE_COST0:
     V2_TRY(launch_cost(d, b->n_max, 0, 1, st));
-    V2_TRY(launch_chain_sum(d, st));
+    V2_TRY(launch_chain_sum(d, 0, st));
     break;
   case V2GT_CHAIN_PHASE_BEGIN:
+    V2_TRY(launch_chain_reduce(d, 0, st));
     V2_TRY(launch_lm_begin(d, st));
     V2_TRY(solve_configure());
     break;
@@ -1474,14 +1774,13 @@ int v2gt_chain_phase(v2gt_batch *b, int32_t phase) {
     V2_TRY(launch_chain_unpack(d, st));
     V2_TRY(launch_reduced(d, 0, st));
     V2_TRY(launch_backsub(d, 0, st));
-    V2_TRY(launch_chain_halo(d, 0, st));
     break;
   case V2GT_CHAIN_PHASE_COST:
-    V2_TRY(launch_chain_halo(d, 1, st));
     V2_TRY(launch_cost(d, b->n_max, 1, 0, st));
-    V2_TRY(launch_chain_sum(d, st));
+    V2_TRY(launch_chain_sum(d, 1, st));
     break;
   case V2GT_CHAIN_PHASE_DECIDE:
+    V2_TRY(launch_chain_reduce(d, 1, st));
     V2_TRY(launch_lm_decide(d, 0, st));
     break;
   default:
@@ -1505,8 +1804,8 @@ int v2gt_chain_buffer(v2gt_batch *b, int32_t which, void **dev_ptr, int64_t *n_d
     break;
   case V2GT_CHAIN_BUF_SEG_ALL: *dev_ptr = d.seg; *n_doubles = (int64_t)d.P * SEG_STRIDE; break;
   case V2GT_CHAIN_BUF_SEPNE_ALL: *dev_ptr = d.c_sepne; *n_doubles = (int64_t)d.P * NE_STRIDE; break;
-  case V2GT_CHAIN_BUF_HALO_SEND: *dev_ptr = d.c_halo_send; *n_doubles = 16; break;
-  case V2GT_CHAIN_BUF_HALO_RECV: *dev_ptr = d.c_halo_recv; *n_doubles = 16LL * b->c_world; break;
+  case V2GT_CHAIN_BUF_SUMS_SEND: *dev_ptr = d.c_sums_send; *n_doubles = CSUM_N; break;
+  case V2GT_CHAIN_BUF_SUMS_ALL: *dev_ptr = d.c_sums_all; *n_doubles = (int64_t)CSUM_N * b->c_world; break;
   default: return V2GT_ERR_INVALID_ARG;
   }
   return V2GT_OK;

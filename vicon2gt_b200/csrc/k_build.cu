@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(V2GT_CHUNK) k_init_states(DevPtrs d, int init_
   const TrialDev &tr = d.trials[t];
   const int n = d.n_states[t];
   const int i = blockIdx.x * V2GT_CHUNK + threadIdx.x;
-  if (i >= n || d.lm[t].status != V2GT_OK)
+  if (i >= n || d.lm[t].status != V2GT_OK || d.lm[t].frozen)
     return;
   const long long s = tr.st_off + i;
   const int cur = d.lm[t].cur;
@@ -131,6 +131,8 @@ __global__ void __launch_bounds__(V2GT_CHUNK) k_init_states(DevPtrs d, int init_
 // half of x into the other half; flips lm.cur and updates n_states.
 __global__ void __launch_bounds__(256) k_compact(DevPtrs d) {
   const int t = blockIdx.x;
+  if (d.lm[t].frozen)
+    return;
   const TrialDev &tr = d.trials[t];
   const int n = d.n_states[t];
   const int cur = d.lm[t].cur;
@@ -624,7 +626,7 @@ __global__ void __launch_bounds__(PRE_NT) k_preintegrate(DevPtrs d, int keep_cov
   const TrialDev &tr = d.trials[t];
   const int n = d.n_states[t];
   const int i = blockIdx.x * PRE_NT + threadIdx.x;
-  if (d.lm[t].status != V2GT_OK)
+  if (d.lm[t].status != V2GT_OK || d.lm[t].frozen)
     return;
   const bool active = (i < n - 1);
   double *sm = smem + threadIdx.x;
@@ -698,7 +700,9 @@ __global__ void __launch_bounds__(PRE_NT) k_preintegrate(DevPtrs d, int keep_cov
     n_pushed++;
   };
   if (M >= 2) {
-    long long lb = lower_bound_d(it, M, time0);
+    // time-ordered store: start at the sample in front of time0 (every earlier iteration of the reference's scan from
+    // sample 0 matches none of its three cases); unordered store: the reference's scan itself (Propagator.cpp:46)
+    long long lb = tr.imu_unsorted ? 0 : lower_bound_d(it, M, time0);
     long long ib = (lb >= 1) ? lb - 1 : 0;
     Smp d0, d1, tmp;
     load(ib, d1);
@@ -833,12 +837,9 @@ int launch_init_states(const DevPtrs &d, int n_max, int init_states, cudaStream_
 }
 
 int launch_preintegrate(const DevPtrs &d, int n_max, int keep_cov, cudaStream_t st) {
-  static bool attr_set = false;
   const size_t smem = sizeof(double) * 2 * PB * PRE_NT;
-  if (!attr_set) {
-    V2_CUDA_CHECK(cudaFuncSetAttribute(k_preintegrate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  // function attributes are per device (context): set on every launch, a handle may live on any GPU of the process
+  V2_CUDA_CHECK(cudaFuncSetAttribute(k_preintegrate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((n_max + PRE_NT - 1) / PRE_NT, d.T);
   if (grid.x == 0)
     return V2GT_OK;

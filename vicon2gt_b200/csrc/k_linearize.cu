@@ -744,11 +744,8 @@ int launch_linearize(const DevPtrs &d, int n_max, int force_all, cudaStream_t st
   const int nasm = (n_max + ASM_STATES - 1) / ASM_STATES;
   dim3 g2(nasm, d.T);
   constexpr size_t asm_smem = sizeof(double) * ASM_SMEM_DOUBLES;
-  static bool configured = false;
-  if (!configured) {
-    V2_CUDA_CHECK(cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asm_smem));
-    configured = true;
-  }
+  // per device (context), hence on every launch: a handle may live on any GPU of the process
+  V2_CUDA_CHECK(cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asm_smem));
   k_assemble<<<g2, ASM_THREADS, asm_smem, st>>>(d, force_all);
   k_reduce_gamma<<<d.T, 64, 0, st>>>(d, nasm, force_all);
   V2_CUDA_CHECK(cudaGetLastError());

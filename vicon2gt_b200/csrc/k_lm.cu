@@ -28,6 +28,8 @@ __global__ void k_lm_begin(DevPtrs d) {
   if (t >= d.T)
     return;
   LmState &lm = d.lm[t];
+  if (lm.frozen) // keeps the result and the counters of its last pass
+    return;
   const v2gt_params &p = d.trials[t].prm;
   lm.lambda = p.lm_lambda_initial;
   lm.iterations = 0;
@@ -46,6 +48,14 @@ __global__ void k_lm_begin(DevPtrs d) {
   lm.current_error = lm.error;
   if (lm.iterations >= p.lm_max_iterations) // defaultOptimize's early return
     lm.lm_state = 1;
+}
+
+// relinearisation loop of the batch (ViconGraphSolver.cpp:163-181 loops per solver): pass `pass` (0-based) only runs the
+// trials whose num_loop_relin reaches it
+__global__ void k_lm_freeze(DevPtrs d, int pass) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < d.T)
+    d.lm[t].frozen = (d.trials[t].prm.num_loop_relin < pass) ? 1 : 0;
 }
 
 // before each try
@@ -148,20 +158,56 @@ __global__ void k_lm_decide(DevPtrs d, int count_active) {
 }
 
 // ---- chain-sharded mode helpers (single trial)
-// local sums of the last factor evaluation -> c_sums (all-reduced by the host side afterwards)
-__global__ void k_chain_sum(DevPtrs d) {
-  if (threadIdx.x >= 5 || blockIdx.x != 0)
+// JPLNavState::retract of one state row (src/gtsam/JPLNavState.cpp:25-54)
+__device__ inline void retract_row(const double *x0, const double *dx, double *x1) {
+  double dq[4], q[4];
+  small_quat(dx, dq);
+  quat_mul(dq, x0, q);
+  x1[0] = q[0]; x1[1] = q[1]; x1[2] = q[2]; x1[3] = q[3];
+  for (int k = 0; k < 12; k++)
+    x1[4 + k] = x0[4 + k] + dx[3 + k];
+}
+// This rank's contribution to the second exchange of a damped solve (CSUM_N doubles, all-gathered): the local sums of
+// the last factor evaluation [cost, lin_error0, g.delta, |delta|^2, solve_failed] and, at CSUM_HALO, the step of its
+// last own state -- the next rank's left halo (with_halo; the evaluation of the current estimate has no step)
+__global__ void k_chain_sum(DevPtrs d, int with_halo) {
+  const int k = threadIdx.x;
+  if (blockIdx.x != 0 || k >= CSUM_N)
     return;
-  const int n = d.n_states[0];
-  const int used = (n + V2GT_CHUNK - 1) / V2GT_CHUNK;
   double s = 0;
-  if (threadIdx.x < 4) {
-    for (int k = 0; k < used; k++)
-      s += d.part_cost[(long long)k * 4 + threadIdx.x];
-  } else {
+  if (k < 4) {
+    const int n = d.n_states[0];
+    const int used = (n + V2GT_CHUNK - 1) / V2GT_CHUNK;
+    for (int c = 0; c < used; c++)
+      s += d.part_cost[(long long)c * 4 + k];
+  } else if (k == 4) {
     s = d.lm[0].solve_failed ? 1.0 : 0.0;
+  } else if (k >= CSUM_HALO && with_halo && d.c_hi >= 1) {
+    s = d.delta[(d.trials[0].st_off + d.c_hi - 1) * 16 + (k - CSUM_HALO)];
   }
-  d.c_sums[threadIdx.x] = s;
+  d.c_sums_send[k] = s;
+}
+// after the all-gather of the above: sums in rank order (bit-identical on every rank) -> c_sums; the left halo (the
+// previous rank's last own state, an interior state of its last segment) takes its step and its trial point.  The right
+// halo is a separator: the redundant reduced solve has already written its step.
+__global__ void k_chain_reduce(DevPtrs d, int with_halo) {
+  const int k = threadIdx.x;
+  if (blockIdx.x != 0)
+    return;
+  if (k < 5) {
+    double s = 0;
+    for (int r = 0; r < d.c_world; r++)
+      s += d.c_sums_all[r * CSUM_N + k];
+    d.c_sums[k] = s;
+  }
+  if (k == 31 && with_halo && d.c_lo >= 1 && d.c_rank >= 1) {
+    const long long s = d.trials[0].st_off + d.c_lo - 1;
+    const double *dl = d.c_sums_all + (d.c_rank - 1) * CSUM_N + CSUM_HALO;
+    for (int e = 0; e < 16; e++)
+      d.delta[s * 16 + e] = dl[e];
+    const int cur = d.lm[0].cur;
+    retract_row(d.x + ((long long)cur * d.S + s) * X_STRIDE, dl, d.x + ((long long)(1 - cur) * d.S + s) * X_STRIDE);
+  }
 }
 // pack what the reduced (separator) system needs from this rank: its segments' outputs, the records of its separators
 // and its part of the global block.  grid: own segments + 1
@@ -216,20 +262,13 @@ __global__ void k_chain_unpack(DevPtrs d) {
   for (int k = threadIdx.x; k < NE_STRIDE; k += blockDim.x)
     no[k] = ni[k];
 }
-// step of this rank's last own state -> send buffer; halo steps <- neighbours
-__global__ void k_chain_halo_send(DevPtrs d) {
-  if (threadIdx.x < 16 && d.c_hi >= 1)
-    d.c_halo_send[threadIdx.x] = d.delta[(d.trials[0].st_off + d.c_hi - 1) * 16 + threadIdx.x];
+int launch_chain_sum(const DevPtrs &d, int with_halo, cudaStream_t st) {
+  k_chain_sum<<<1, 32, 0, st>>>(d, with_halo);
+  V2_CUDA_CHECK(cudaGetLastError());
+  return V2GT_OK;
 }
-__global__ void k_chain_halo_recv(DevPtrs d) {
-  // left halo = the previous rank's last own state (an interior state of its last segment); the right halo is a
-  // separator, whose step k_reduced has already written
-  if (threadIdx.x < 16 && d.c_lo >= 1 && d.c_rank >= 1)
-    d.delta[(d.trials[0].st_off + d.c_lo - 1) * 16 + threadIdx.x] = d.c_halo_recv[(d.c_rank - 1) * 16 + threadIdx.x];
-}
-
-int launch_chain_sum(const DevPtrs &d, cudaStream_t st) {
-  k_chain_sum<<<1, 32, 0, st>>>(d);
+int launch_chain_reduce(const DevPtrs &d, int with_halo, cudaStream_t st) {
+  k_chain_reduce<<<1, 32, 0, st>>>(d, with_halo);
   V2_CUDA_CHECK(cudaGetLastError());
   return V2GT_OK;
 }
@@ -243,15 +282,11 @@ int launch_chain_pack(const DevPtrs &d, int stride, cudaStream_t st) {
   V2_CUDA_CHECK(cudaGetLastError());
   return V2GT_OK;
 }
-int launch_chain_halo(const DevPtrs &d, int recv, cudaStream_t st) {
-  if (recv)
-    k_chain_halo_recv<<<1, 32, 0, st>>>(d);
-  else
-    k_chain_halo_send<<<1, 32, 0, st>>>(d);
+int launch_lm_freeze(const DevPtrs &d, int pass, cudaStream_t st) {
+  k_lm_freeze<<<(d.T + 127) / 128, 128, 0, st>>>(d, pass);
   V2_CUDA_CHECK(cudaGetLastError());
   return V2GT_OK;
 }
-
 int launch_lm_begin(const DevPtrs &d, cudaStream_t st) {
   k_lm_begin<<<(d.T + 127) / 128, 128, 0, st>>>(d);
   V2_CUDA_CHECK(cudaGetLastError());

@@ -430,7 +430,7 @@ int simbatch_view(v2gt_simbatch *s, int trial, int *device, int64_t *n_imu, cons
 extern "C" {
 
 int v2gt_simbatch_create(int32_t device, int32_t n_trials, int64_t n_rows, const double *rows8, v2gt_simbatch **out) {
-  if (!out || n_trials <= 0 || n_rows < 4 || !rows8)
+  if (!out || device < 0 || n_trials <= 0 || n_rows < 4 || !rows8)
     return V2GT_ERR_INVALID_ARG;
   v2gt_simbatch *s = new v2gt_simbatch();
   s->device = device;
@@ -629,7 +629,7 @@ int v2gt_simbatch_run(v2gt_simbatch *s) {
   if (!s)
     return V2GT_ERR_INVALID_ARG;
   int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || s->device >= ndev) {
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || s->device < 0 || s->device >= ndev) {
     cudaGetLastError();
     return V2GT_ERR_NO_DEVICE;
   }

@@ -113,6 +113,8 @@ __global__ void __launch_bounds__(32) k_err_stats(DevPtrs d, const double *__res
 
 // d_truth: [S][10] device; d_out: [T][3][8] device
 int launch_error_stats(const DevPtrs &d, const double *d_truth, double *d_out, cudaStream_t st) {
+  if (d.T > 0 && cudaMemsetAsync(d_out, 0, sizeof(double) * 24 * (size_t)d.T, st) != cudaSuccess) // "no samples" rows
+    return V2GT_ERR_CUDA;
   if (d.S <= 0 || d.T <= 0)
     return V2GT_OK;
   double *err = nullptr, *sorted = nullptr;

@@ -66,6 +66,8 @@ constexpr int SEG_CY = 0, SEG_FB = 600, SEG_STRIDE = 1232;
 // ---- per-CTA partial sums of the assembly / cost kernels
 //  assembly: Gamma vicon 7x7 (49) + g (7) + gravity 2x2 (4) + g (2) + lin_error0 (1) -> 63 (+pad)
 constexpr int PART_STRIDE = 64;
+// ---- chain-sharded mode: per-rank record of the second exchange of a damped solve
+constexpr int CSUM_HALO = 8, CSUM_N = 24;
 
 __host__ __device__ inline int tri(int r, int c) { return r * (r + 1) / 2 + c; } // packed lower, r >= c
 
@@ -75,7 +77,7 @@ struct TrialDev {
   long long vic_off, n_vic;
   long long st_off, n_raw;
   int vic_cov_const; // 1: vic_Rconst applies to every pose
-  int pad0;
+  int imu_unsorted;  // 1: the IMU store is not in time order: intervals are selected by the reference's scan from sample 0
   double vic_Rconst[18];
   v2gt_params prm;
 };
@@ -96,7 +98,7 @@ struct LmState {
   int cur;               // which half of x/glob holds the current estimate
   int status;            // V2GT_OK or error code of the build stage
   int n_trace;
-  int pad;
+  int frozen;            // 1: the trial has used up its num_loop_relin budget; later build / optimise passes of the batch skip it
 };
 constexpr int TRACE_MAX = 1024; // rows of [lambda, cost_before, cost_after, lin_change, accepted] kept per trial
 
@@ -143,10 +145,11 @@ struct DevPtrs {
   int chain;         // 0: ordinary batch
   int c_n, c_goff, c_j0, c_j1, c_lo, c_hi, c_rank, c_world;
   double *c_sepne;     // [P][NE_STRIDE] normal-equation records of every separator of the chain (all-gathered)
-  double *c_sums;      // [8] cost, lin_error0, g.delta, |delta|^2, solve_failed (local, then all-reduced)
-  double *c_gamma_loc; // [96] this rank's part of the global block (all-reduced into gamma)
-  double *c_halo_send, *c_halo_recv;
-  // one all-gather per damped solve: every rank contributes [its segments' outputs | its separators' records |
+  double *c_sums;      // [8] cost, lin_error0, g.delta, |delta|^2, solve_failed of the whole chain (summed in rank order)
+  double *c_gamma_loc; // [96] this rank's part of the global block (summed in rank order into gamma by k_chain_unpack)
+  // second exchange of a damped solve: [5 local sums | pad | step of the last own state] per rank, all-gathered
+  double *c_sums_send, *c_sums_all; // [CSUM_N], [c_world][CSUM_N]
+  // first exchange of a damped solve: every rank contributes [its segments' outputs | its separators' records |
   // its part of the global block] (c_pack_send), and unpacks everybody's (c_pack_all, rank-major)
   double *c_pack_send, *c_pack_all;
 };
