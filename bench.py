@@ -61,6 +61,7 @@ def parse():
     ap.add_argument("--target-warps", type=int, default=0, help="segment warps per elimination launch (0 = library default)")
     ap.add_argument("--cpu-sample-s", type=float, default=40.0, help="length of the CPU baseline sample trajectory")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-budget-s", type=float, default=300.0, help="--impl reference: wall-clock budget of all steps together")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--no-sim", action="store_true", help="skip the device-simulator leg (SURVEY 8f row 1)")
     ap.add_argument("--workload", default="mc", choices=["mc", "chain"],
@@ -148,10 +149,7 @@ class ClockSampler:
 def simulator_leg(api, sim, bs, p, T, seed0, duration, read_back):
     """the same trials generated by the batched device simulator (csrc/k_sim.cu) and handed to the solver
     device -> device, next to the host simulator timed on one trial.  One step of simulate -> stage -> solve -> read back."""
-    shape = dict(sim.TRAJ_SHAPES["tum_corridor1"])
-    if duration > 0:
-        shape["n_rows"] = max(8, min(shape["n_rows"], int(round(duration / shape["dt"])) + 1))
-    rows = sim.make_trajectory(**shape)
+    rows, _ = sim.trajectory_rows("tum_corridor1", duration if duration > 0 else None)
     t0 = time.perf_counter()
     sim.simulate(traj_rows=rows, seed=seed0)
     host_s = time.perf_counter() - t0
@@ -192,17 +190,44 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_baseline(sample_s, threads):
-    """Oracle (CPU restatement of the reference) on a bounded sample: one sim.launch-shaped trial truncated to
-    `sample_s` seconds per thread.  Returns equivalent full-size trajectories / s."""
+FULL_STATES = 29798.0  # states of a full sim.launch trial after cleaning
+
+
+def workload_config(trials_per_gpu, world, trajectory):
+    """`config` of the JSON line: the same dict in both arms (the reference arm runs this workload on the host cores)."""
+    return {
+        "workload": ("MC batch of independent sim.launch-shaped trials (BASELINE.json configs[3]): 400 Hz IMU, 100 Hz vicon, "
+                     "100 Hz states, 30-iteration LM; %d trials per GPU, %d GPU(s), no communication" % (trials_per_gpu, world)),
+        "trials_per_gpu": trials_per_gpu, "n_gpus": world, "trajectory": trajectory,
+        "l2": "no flush: every trial's per-step working set (0.37 GB of blocks + factors) exceeds the 126 MB L2",
+    }
+
+
+def cpu_baseline(sample_s, threads, faithful=False, seed0=1000):
+    """Oracle (CPU restatement of the reference) on a bounded sample: one sim.launch-shaped trial per host thread, the whole
+    trajectory (sample_s <= 0) or truncated to `sample_s` seconds.  Returns equivalent full-size trajectories / s.
+    faithful: the reference's own O(N M) linear scans in Propagator::propagate / has_bounding_imu (Propagator.cpp:46, :165-193)
+    instead of the port's binary searches."""
     from oracle import binding as ob
     from vicon2gt_b200 import sim
     from vicon2gt_b200._cdefs import TrialInfo
 
-    full_states = 29798.0  # states of a full sim.launch trial after cleaning (SURVEY.md 8)
-    dss = [sim.make_config("C1", seed=1000 + i, duration_s=sample_s) for i in range(threads)]
+    kw = {} if sample_s <= 0 else dict(duration_s=sample_s)
+    dss = [None] * threads
+
+    def gen(i):
+        dss[i] = sim.make_config("C1", seed=seed0 + i, **kw)
+
+    ths = [threading.Thread(target=gen, args=(i,)) for i in range(threads)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
     p = ob.default_params()
     solvers = [ob.OracleSolver.from_dataset(p, ds) for ds in dss]
+    if faithful:
+        for sv in solvers:
+            sv.set_option("faithful_scan", 1)
     res = [None] * threads
 
     def work(i):
@@ -218,34 +243,59 @@ def cpu_baseline(sample_s, threads):
         th.join()
     dt = time.perf_counter() - t0
     n_states = sum(r[1] for r in res)
-    value = (n_states / full_states) / dt
-    sample = (f"{threads} x sim.launch-shaped trial truncated to {sample_s:.0f} s ({res[0][1]} states, {res[0][2]} damped solves, "
-              f"{res[0][3]} LM iterations each), full build_and_solve, {dt:.1f} s wall; scaled by states to the "
-              f"{int(full_states)}-state trial")
-    return value, sample, dt
+    full = sample_s <= 0
+    value = (threads if full else n_states / FULL_STATES) / dt
+    what = "whole trajectory" if full else f"truncated to {sample_s:.0f} s"
+    sample = (f"{threads} x sim.launch-shaped trial ({dss[0].truth.get('trajectory', '?')}), {what} ({res[0][1]} states, {res[0][2]} damped "
+              f"solves, {res[0][3]} LM iterations each), full build_and_solve, {dt:.1f} s wall"
+              + ("" if full else f"; scaled by states to the {int(FULL_STATES)}-state trial")
+              + ("; reference-faithful O(N M) selection scans" if faithful else ""))
+    for sv in solvers:
+        sv.close()
+    return value, sample, dt, n_states / threads
 
 
 def run_reference(args):
+    """The reference arm: the CPU restatement of the reference's path (oracle/, kind "port": GTSAM / Eigen / ROS cannot be
+    installed here, and oracle/_ref's stand-in matrix class would flatter the ratio) on all host threads, on THIS arm's
+    workload: every step solves one sim.launch-shaped trial per host thread.  Full-size trials (same config as the GPU arm)
+    when --steps + --warmup of them fit the time budget (~45 s each), else the longest truncation that does, stated in
+    `cpu_baseline.sample` and `reference_sample`."""
     rank, _, world = dist_env()
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
-    vals, dts = [], []
+    n_steps = args.warmup + args.steps
+    budget_s = args.ref_budget_s
+    est_full_s = 48.0  # one full-size trial per thread, refined after every step
+    vals, dts, fulls = [], [], []
     sample = ""
-    for k in range(args.warmup + args.steps):
-        # keep the whole run within a few minutes: shrink the sample when many steps are requested
-        sample_s = max(8.0, min(args.cpu_sample_s, 160.0 / max(1, args.warmup + args.steps)))
-        v, sample, dt = cpu_baseline(sample_s, threads)
+    t_start = time.perf_counter()
+    traj = "?"
+    for k in range(n_steps):
+        left = max(1.0, budget_s - (time.perf_counter() - t_start))
+        per_step = left / (n_steps - k)
+        frac = per_step / est_full_s
+        sample_s = 0.0 if frac >= 1.0 else max(8.0, 0.9 * frac * 299.0)
+        v, sample, dt, n_st = cpu_baseline(sample_s, threads, seed0=1000 + k * threads)
+        est_full_s = dt * FULL_STATES / max(1.0, n_st)
         if k >= args.warmup:
             vals.append(v)
             dts.append(dt)
+            fulls.append(sample_s <= 0.0)
     value = float(np.mean(vals))
+    from vicon2gt_b200 import sim
+
+    traj = "file:" + sim.TRAJ_FILES["tum_corridor1"] if sim.trajectory_file("tum_corridor1") else "synthesised, tum_corridor1 shape"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(dts)), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "MC batch of sim.launch-shaped trials (BASELINE.json configs[3]); CPU restatement of the reference "
-                               "(GTSAM/Eigen/ROS are not installable here), bounded sample per step"},
+        "config": workload_config(args.trials, args.gpus, traj),
+        "reference_sample": {"full_size_steps": int(sum(fulls)), "timed_steps": len(fulls), "time_budget_s": budget_s,
+                             "note": "each step = one trial per host thread; full-size trials when the requested number of steps "
+                                     "fits the time budget, else truncated and scaled by states (an approximation: the LM iteration "
+                                     "and damped-solve counts of the sample are in cpu_baseline.sample)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -485,6 +535,7 @@ def main():
         t4 = time.perf_counter()
         e2e_s += t4 - t0
         e2e_parts += np.array([t1 - t0, t2 - t1, t3 - t2, t4 - t3])
+    e2e_own = e2e_s
     e2e_s = max_over_ranks(e2e_s)
     e2e_value = world * T * args.steps / e2e_s
 
@@ -529,24 +580,42 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline and rank == 0:
-        v, sample, _ = cpu_baseline(args.cpu_sample_s if args.duration <= 0 else min(args.cpu_sample_s, args.duration), 1)
-        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample}
+        cs_s = args.cpu_sample_s if args.duration <= 0 else min(args.cpu_sample_s, args.duration)
+        v, sample, _, _ = cpu_baseline(cs_s, 1)
+        # second stated baseline: the same sample with the reference's own O(N M) sample-selection scans
+        vf, sample_f, _, _ = cpu_baseline(cs_s, 1, faithful=True)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+               "reference_faithful_scans": {"value": vf, "unit": UNIT, "cores": 1, "sample": sample_f,
+                                            "note": "the scans cost O(states x IMU samples): at the full 29.8 k-state trial they are "
+                                                    "~60x this sample's share (not scaled here)"}}
 
     total_states = sum_over_ranks(float(sum(inf.n_states for inf in infos)))
+    # what limits the scaling curve: every rank's own device time, damped solves and state blocks (different seeds per rank)
+    mine = [dev_ms / args.steps, float(sum(inf.tries for inf in infos)), solve_units, 1e3 * e2e_own / args.steps,
+            float(max(inf.tries for inf in infos)), float(phase_ms[2]) / args.steps]
+    per_rank = None
+    if dist is None:
+        allr = [mine]
+    else:
+        import torch
+
+        tt = torch.tensor(mine, dtype=torch.float64, device=f"cuda:{local_rank}")
+        got = [torch.zeros_like(tt) for _ in range(world)]
+        dist.all_gather(got, tt)
+        allr = [g.tolist() for g in got]
+    per_rank = {k: [r[i] for r in allr] for i, k in enumerate(["device_ms_per_step", "damped_solves_all_trials", "state_blocks_per_step",
+                                                               "e2e_ms_per_step", "max_damped_solves_of_a_trial", "eliminate_ms_per_step"])}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {
-                "workload": ("MC batch of independent sim.launch-shaped trials (BASELINE.json configs[3]): 400 Hz IMU, 100 Hz vicon, "
-                             "100 Hz states, 30-iteration LM; %d trials per GPU, %d GPU(s), no communication" % (T, world)),
-                "trials_per_gpu": T, "states_total": int(total_states), "trials_ok": ok,
-                "trajectory": "synthesised, tum_corridor1 shape" + ("" if args.duration <= 0 else f", truncated to {args.duration:.0f} s"),
-                "l2": "working set per step (%.1f GB factors + blocks per GPU) exceeds the 126 MB L2" % (total_states / world * 12.5e3 / 1e9),
-                "timing": "CUDA events on the solver stream (build + optimise), max over ranks",
-                "wall_s_timed_region": wall_s,
-            },
+            "config": workload_config(T, world, trials[0].truth.get("trajectory", "?") +
+                                      ("" if args.duration <= 0 else f", truncated to {args.duration:.0f} s")),
+            "run": {"states_total": int(total_states), "trials_ok": ok, "wall_s_timed_region": wall_s,
+                    "timing": "CUDA events on the solver stream (build + optimise), max over ranks",
+                    "working_set_gb_per_gpu": total_states / world * 11.0e3 / 1e9},
+            "per_rank": per_rank,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": {k: 1e3 * float(v) / args.steps for k, v in
                                     zip(["stage_host", "upload_h2d", "build_and_solve", "read_back_d2h"], e2e_parts)}},

@@ -58,7 +58,7 @@ def ds_c1_small():
     """sim.launch-shaped (400 Hz IMU, 100 Hz vicon, 100 Hz states; every state time hits a vicon stamp) 8 s."""
     from vicon2gt_b200 import sim
 
-    return sim.make_config("C1", seed=1, duration_s=8.0)
+    return sim.make_config("C1", seed=1, trajectory="synth", duration_s=8.0)
 
 
 @pytest.fixture(scope="session")
@@ -66,7 +66,7 @@ def ds_c3_small():
     """TUM-shaped (200 Hz IMU, 100 Hz vicon, 20 Hz states at the trajectory stamps) 40 s, low vicon noise."""
     from vicon2gt_b200 import sim
 
-    return sim.make_config("C3", seed=3, duration_s=40.0, vicon_sigmas=(1e-3, 1e-3, 1e-3, 1e-2, 1e-2, 1e-2))
+    return sim.make_config("C3", seed=3, trajectory="synth", duration_s=40.0, vicon_sigmas=(1e-3, 1e-3, 1e-3, 1e-2, 1e-2, 1e-2))
 
 
 @pytest.fixture(scope="session")
@@ -74,7 +74,7 @@ def ds_c2_small():
     """EuRoC-shaped (200 Hz IMU, 100 Hz vicon, 20 Hz states) 25 s."""
     from vicon2gt_b200 import sim
 
-    return sim.make_config("C2", seed=7, duration_s=25.0, vicon_sigmas=(1e-3, 1e-3, 1e-3, 1e-2, 1e-2, 1e-2))
+    return sim.make_config("C2", seed=7, trajectory="synth", duration_s=25.0, vicon_sigmas=(1e-3, 1e-3, 1e-3, 1e-2, 1e-2, 1e-2))
 
 
 def load_golden(name):

@@ -393,7 +393,7 @@ def test_cpp_driver_matches_python_mirror(tmp_path):
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     assert "rmse_ori" in r.stdout and "EST toff" in r.stdout
-    ds = sim.make_config("C1", seed=4, duration_s=10.0)
+    ds = sim.make_config("C1", seed=4, trajectory="synth", duration_s=10.0)
     prop = api.Propagator(1.6968e-04, 1.9393e-05, 2.0e-3, 3.0e-3)
     prop.feed_imu_array(ds.imu_t, ds.imu_w, ds.imu_a)
     interp = api.Interpolator()
@@ -763,7 +763,7 @@ def test_cuda_full_size_baseline_configs_against_the_reference_class(name):
     bs.close()
 
 
-@pytest.mark.parametrize("name", ["e2e_c2", "e2e_c2_relin", "e2e_c3_fixed", "e2e_c1", "e2e_c2_dropout"])
+@pytest.mark.parametrize("name", ["e2e_c2", "e2e_c2_relin", "e2e_c3_fixed", "e2e_c1", "e2e_c2_dropout", "e2e_c3_file"])
 def test_cuda_build_and_solve_against_the_reference_class(name, tmp_path):
     """End to end against the reference's ViconGraphSolver class (compiled where it lies; GTSAM's LM served by the
     generic restatement of oracle/shim/gtsam/mini_gtsam_lm.h): surviving state times bit-exact, states / extrinsics /

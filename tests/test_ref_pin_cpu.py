@@ -273,7 +273,7 @@ def e2e_case(G, name):
     return ds, p
 
 
-E2E_NAMES = ["e2e_c2", "e2e_c2_relin", "e2e_c3_fixed", "e2e_c1", "e2e_c2_dropout"]
+E2E_NAMES = ["e2e_c2", "e2e_c2_relin", "e2e_c3_fixed", "e2e_c1", "e2e_c2_dropout", "e2e_c3_file"]
 
 
 def check_end_to_end(G, name, times, states, globals10, final_error, tol_state=1e-6, tol_chi2=1e-8):
@@ -425,7 +425,7 @@ def test_live_randomised_cross_check_of_oracle_and_reference_code():
     if not rb.available():
         pytest.skip("reference library not available on this machine; the committed vectors stand in")
     rng = np.random.default_rng(77)
-    ds = sim.make_config("C1", seed=9, duration_s=6.0)
+    ds = sim.make_config("C1", seed=9, trajectory="synth", duration_s=6.0)
     # preintegration
     t_lo, t_hi = ds.imu_t[2], ds.imu_t[-3]
     for _ in range(150):

@@ -5,9 +5,9 @@ import numpy as np
 def test_sim_launch_shape_and_determinism():
     from vicon2gt_b200 import sim
 
-    a = sim.make_config("C1", seed=3, duration_s=6.0)
-    b = sim.make_config("C1", seed=3, duration_s=6.0)
-    c = sim.make_config("C1", seed=4, duration_s=6.0)
+    a = sim.make_config("C1", seed=3, trajectory="synth", duration_s=6.0)
+    b = sim.make_config("C1", seed=3, trajectory="synth", duration_s=6.0)
+    c = sim.make_config("C1", seed=4, trajectory="synth", duration_s=6.0)
     for k in ("imu_t", "imu_w", "imu_a", "vic_t", "vic_q", "vic_p", "state_t"):
         assert np.array_equal(getattr(a, k), getattr(b, k))  # std::mt19937(seed): same seed, same streams
     assert not np.array_equal(a.imu_w, c.imu_w) and a.truth["viconimu_dt"] != c.truth["viconimu_dt"]
@@ -27,7 +27,7 @@ def test_sim_launch_shape_and_determinism():
 def test_truth_draws_and_state_in_vicon():
     from vicon2gt_b200 import sim
 
-    ds = sim.make_config("C2", seed=9, duration_s=12.0, vicon_sigmas=(1e-4,) * 3 + (1e-4,) * 3)
+    ds = sim.make_config("C2", seed=9, trajectory="synth", duration_s=12.0, vicon_sigmas=(1e-4,) * 3 + (1e-4,) * 3)
     tr = ds.truth
     assert np.allclose(tr["R_BtoI"] @ tr["R_BtoI"].T, np.eye(3), atol=1e-12)
     assert abs(tr["viconimu_dt"]) < 0.5 and np.linalg.norm(tr["p_BinI"]) < 1.5

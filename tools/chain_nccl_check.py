@@ -23,7 +23,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
     dur = float(os.environ.get("V2GT_CHAIN_CHECK_S", "120"))
-    ds = sim.make_config("C3", seed=3, duration_s=dur, vicon_sigmas=(1e-3, 1e-3, 1e-3, 1e-2, 1e-2, 1e-2))
+    ds = sim.make_config("C3", seed=3, trajectory="synth", duration_s=dur, vicon_sigmas=(1e-3, 1e-3, 1e-3, 1e-2, 1e-2, 1e-2))
     p = api.default_params()
     cs = ChainSolver(p, ds, DistComm(dist), segs_per_rank=int(os.environ.get("V2GT_CHAIN_CHECK_SPR", "4")), device=local)
     ic = cs.optimize()

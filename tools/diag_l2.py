@@ -2,7 +2,7 @@ import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vicon2gt_b200 import api, sim
-ds = sim.make_config("C3", seed=3, duration_s=60.0, vicon_sigmas=(1e-3, 1e-3, 1e-3, 1e-2, 1e-2, 1e-2))
+ds = sim.make_config("C3", seed=3, trajectory="synth", duration_s=60.0, vicon_sigmas=(1e-3, 1e-3, 1e-3, 1e-2, 1e-2, 1e-2))
 p = api.default_params()
 for seg in (0, 20, 36, 30, 48):
     bs = api.BatchSolver(1, **({"segments": seg} if seg else {}))

@@ -5,7 +5,7 @@ from vicon2gt_b200 import sim, api
 from vicon2gt_b200._cdefs import TrialInfo
 from oracle import binding as ob
 np.set_printoptions(linewidth=220, precision=10)
-ds=sim.make_config("C2",seed=7,duration_s=25.0,vicon_sigmas=(1e-3,1e-3,1e-3,1e-2,1e-2,1e-2))
+ds=sim.make_config("C2",seed=7,trajectory="synth", duration_s=25.0,vicon_sigmas=(1e-3,1e-3,1e-3,1e-2,1e-2,1e-2))
 p=default_params()
 for faithful in (1,0):
     o=ob.OracleSolver.from_dataset(p,ds); o.set_option("faithful_linerr",faithful); o.build_and_solve()

@@ -23,7 +23,7 @@ def make(name, cfg, seed, duration, sigmas, lm_iters):
     from vicon2gt_b200 import sim
     from vicon2gt_b200._cdefs import TrialInfo
 
-    ds = sim.make_config(cfg, seed=seed, duration_s=duration, vicon_sigmas=sigmas)
+    ds = sim.make_config(cfg, seed=seed, trajectory="synth", duration_s=duration, vicon_sigmas=sigmas)
     p = ob.default_params(lm_max_iterations=lm_iters)
     o = ob.OracleSolver.from_dataset(p, ds)
     assert o.clean() == 0 and o.build(True) == 0

@@ -165,7 +165,7 @@ def dataset(rb, rng, out):
     from oracle import binding as ob
     from vicon2gt_b200 import sim
 
-    ds = sim.make_config("C2", seed=11, duration_s=3.0, vicon_sigmas=(1e-3, 1e-3, 1e-3, 1e-2, 1e-2, 1e-2))
+    ds = sim.make_config("C2", seed=11, trajectory="synth", duration_s=3.0, vicon_sigmas=(1e-3, 1e-3, 1e-3, 1e-2, 1e-2, 1e-2))
     p = ob.default_params()
     o = ob.OracleSolver.from_dataset(p, ds)     # used only for the cleaned state times and the initial guess
     assert o.clean() == 0 and o.build(True) == 0
@@ -212,25 +212,28 @@ def dataset(rb, rng, out):
 
 E2E_CASES = {
     # name: (config, make_config kwargs, v2gt_params overrides)
-    "e2e_c2": ("C2", dict(seed=7, duration_s=25.0, vicon_sigmas=(1e-3, 1e-3, 1e-3, 1e-2, 1e-2, 1e-2)), {}),
-    "e2e_c2_relin": ("C2", dict(seed=7, duration_s=25.0, vicon_sigmas=(1e-3, 1e-3, 1e-3, 1e-2, 1e-2, 1e-2)), dict(num_loop_relin=1)),
-    "e2e_c3_fixed": ("C3", dict(seed=3, duration_s=40.0, vicon_sigmas=(1e-3, 1e-3, 1e-3, 1e-2, 1e-2, 1e-2)),
+    "e2e_c2": ("C2", dict(seed=7, trajectory="synth", duration_s=25.0, vicon_sigmas=(1e-3, 1e-3, 1e-3, 1e-2, 1e-2, 1e-2)), {}),
+    "e2e_c2_relin": ("C2", dict(seed=7, trajectory="synth", duration_s=25.0, vicon_sigmas=(1e-3, 1e-3, 1e-3, 1e-2, 1e-2, 1e-2)), dict(num_loop_relin=1)),
+    "e2e_c3_fixed": ("C3", dict(seed=3, trajectory="synth", duration_s=40.0, vicon_sigmas=(1e-3, 1e-3, 1e-3, 1e-2, 1e-2, 1e-2)),
                      dict(estimate_toff_vicon_to_imu=0, estimate_pos_vicon_to_imu=0)),
-    "e2e_c1": ("C1", dict(seed=1, duration_s=8.0), {}),
+    "e2e_c1": ("C1", dict(seed=1, trajectory="synth", duration_s=8.0), {}),
     # 11 s without vicon in the middle: build_problem erases the states inside the hole (get_pose refuses a query more
     # than 5 s from either bracket end, Interpolator.cpp:119-123).  A shorter hole would keep states whose vicon factor
     # then reads uninitialised memory in the reference (see tests/test_ref_pin_cpu.py::test_vicon_factor).
-    "e2e_c2_dropout": ("C2", dict(seed=5, duration_s=34.0, vicon_sigmas=(1e-3, 1e-3, 1e-3, 1e-2, 1e-2, 1e-2)), {}),
+    "e2e_c2_dropout": ("C2", dict(seed=5, trajectory="synth", duration_s=34.0, vicon_sigmas=(1e-3, 1e-3, 1e-3, 1e-2, 1e-2, 1e-2)), {}),
+    # the first 40 s of the reference's own data/tum_corridor1_512_16_okvis.txt: jittered state times (0.043 ... 0.055 s apart)
+    "e2e_c3_file": ("C3", dict(seed=4, trajectory="file", duration_s=40.0, vicon_sigmas=(1e-3, 1e-3, 1e-3, 1e-2, 1e-2, 1e-2)), {}),
 }
 
 
-# BASELINE.json configs[1] and configs[2] at full size (about 30 s and 70 s of CPU each to regenerate; every 4th state
-# kept) and trial 0 of the benchmark's Monte-Carlo batch (configs[0] / configs[3]: sim.launch defaults, 29.8 k states,
-# about 6 min of CPU; every 16th state kept)
+# BASELINE.json configs[1] and configs[2] at full size ON THE REFERENCE'S OWN TRAJECTORY FILES (tests/golden/traj_*.txt =
+# data/euroc_V1_01_easy.txt, data/tum_corridor1_512_16_okvis.txt; about 30 s and 70 s of CPU each to regenerate; every 4th
+# state kept) and trial 0 of the benchmark's Monte-Carlo batch (configs[0] / configs[3]: sim.launch defaults on the TUM
+# file, 29.8 k states, about 6 min of CPU; every 16th state kept)
 E2E_FULL = {
-    "e2e_c2_full": ("C2", dict(seed=21), {}),
-    "e2e_c3_full": ("C3", dict(seed=21), {}),
-    "e2e_c1_full": ("C1", dict(seed=0), {}),
+    "e2e_c2_full": ("C2", dict(seed=21, trajectory="file"), {}),
+    "e2e_c3_full": ("C3", dict(seed=21, trajectory="file"), {}),
+    "e2e_c1_full": ("C1", dict(seed=0, trajectory="file"), {}),
 }
 FULL_STRIDE = {"e2e_c2_full": 4, "e2e_c3_full": 4, "e2e_c1_full": 16}
 

@@ -1026,7 +1026,9 @@ static int choose_segments(int target_warps, int n_running, int p_max, int sm_co
   const int base = std::max(1, (target_warps + n_running - 1) / n_running);
   if (base <= wpc) // very large batches: one CTA per trial is already more than enough warps; do not cut finer than asked
     return std::max(1, std::min(p_max, base));
-  const int k0 = std::max(1, (int)(0.75 * base) / wpc), k1 = std::max(k0, (int)(1.25 * base + wpc - 1) / wpc);
+  // candidates: 0.75 ... 1.25 of the aim for small CTAs; large CTAs (one per SM, whole waves are coarse) look further
+  const double lo = wpc >= 8 ? 0.6 : 0.75, hi = wpc >= 8 ? 1.7 : 1.25;
+  const int k0 = std::max(1, (int)(lo * base) / wpc), k1 = std::max(k0, (int)(hi * base + wpc - 1) / wpc);
   int best_p = std::max(1, std::min(p_max, base));
   double best_eff = -1.0;
   for (int k = k0; k <= k1; k++) {

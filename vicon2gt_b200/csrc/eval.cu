@@ -282,13 +282,15 @@ int v2gt_eval_linearize(v2gt_batch *b, int32_t trial, int64_t capacity, double *
   if ((D || O || B || g) && capacity < n)
     return V2GT_ERR_INVALID_ARG;
   if (n && (D || O || B || g)) {
-    // unpack the per-state records [D 15x15 | O 15x15 | BG 15x10 = B 9, g 1]
+    // unpack the per-state records [D packed lower triangle | O 15x15 | BG 15x10 = B 9, g 1]
     std::vector<double> rec((size_t)n * NE_STRIDE);
     V2_CUDA_CHECK(cudaMemcpy(rec.data(), d.ne + td.st_off * NE_STRIDE, sizeof(double) * rec.size(), cudaMemcpyDeviceToHost));
     for (int i = 0; i < n; i++) {
       const double *r = &rec[(size_t)i * NE_STRIDE];
       if (D)
-        std::memcpy(D + 225 * (size_t)i, r + NE_D, sizeof(double) * 225);
+        for (int a = 0; a < 15; a++)
+          for (int c = 0; c <= a; c++)
+            D[225 * (size_t)i + 15 * a + c] = D[225 * (size_t)i + 15 * c + a] = r[NE_D + tri(a, c)];
       for (int a = 0; a < 15; a++) {
         if (O)
           std::memcpy(O + 225 * (size_t)i + 15 * a, r + NE_O + 15 * a, sizeof(double) * 15);

@@ -491,7 +491,9 @@ __global__ void __launch_bounds__(ASM_THREADS, ASM_MIN_CTAS) k_assemble(DevPtrs 
 
   // ================= (2) the diagonal strip, one 3x3 block at a time:
   //   D[c][dcol] = sum_a H1[a][c]^T Y[a]  +  H2[c]^T Lambda'_{c,dcol} H2[dcol] (factor i-1 -> i)  +  A_c^T A_dcol (vicon)
-  // D is symmetric: the column strip this thread computes is written as the ROW strip 3 dcol .. 3 dcol + 2
+  // D is symmetric and stored as its packed lower triangle: the column strip this thread computes is written as the
+  // ROW strip 3 dcol .. 3 dcol + 2, whose lower part is the blocks c <= dcol (rows of 3 dcol + 1, + 2, + 3 entries,
+  // contiguous in the record: 9 dcol + 6 doubles starting at tri(3 dcol, 0)); the blocks c > dcol are not formed
   const SoaS infP{s_in + li, ASM_IN_COLS};
   const SoaS fpiP{s_in + INFO_STRIDE * ASM_IN_COLS + li, ASM_IN_COLS};
   const SoaR preP = soa_r(d.pre, has_prev ? s - 1 : tr.st_off, PRE_STRIDE);
@@ -504,6 +506,8 @@ __global__ void __launch_bounds__(ASM_THREADS, ASM_MIN_CTAS) k_assemble(DevPtrs 
       h2_block(fpiP, dcol, H2d);
 #pragma unroll
     for (int c = 0; c < 5; c++) {
+      if (c > dcol) // warp-uniform
+        continue;
       double Dc[9];
       zero9(Dc);
       if (has_next) {
@@ -536,14 +540,16 @@ __global__ void __launch_bounds__(ASM_THREADS, ASM_MIN_CTAS) k_assemble(DevPtrs 
             Dc[3 * r + cc] += sacc;
           }
       }
+      // element (row 3 dcol + cc, column 3 c + r) of D; row cc of the strip starts at cc (3 dcol) + cc (cc + 1) / 2
 #pragma unroll
       for (int cc = 0; cc < 3; cc++)
 #pragma unroll
         for (int r = 0; r < 3; r++)
-          mybuf[cc * 15 + 3 * c + r] = Dc[3 * r + cc];
+          if (c < dcol || r <= cc)
+            mybuf[cc * 3 * dcol + (cc * (cc + 1)) / 2 + 3 * c + r] = Dc[3 * r + cc];
     }
   }
-  flush_strip(wbuf, ne0 + NE_D + 45 * dcol, nvalid, 45, lane_of_warp());
+  flush_strip(wbuf, ne0 + NE_D + (3 * dcol * (3 * dcol + 1)) / 2, nvalid, 9 * dcol + 6, lane_of_warp());
 
   // ================= (3) border / gradient strip
   if (act) {

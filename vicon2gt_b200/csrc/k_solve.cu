@@ -38,9 +38,9 @@ __host__ __device__ inline SegGeom seg_geom(int n, int P) {
   return g;
 }
 
-// ---- per-warp shared memory (doubles): two staged normal-equation records + the broadcast buffers of the
-// factorisation (column of D [16] + row of X [16], double buffered)
-constexpr int SW_STAGE = 0, SW_CB = 2 * NE_STRIDE, SW_TOTAL = 2 * NE_STRIDE + 64;
+// ---- per-warp shared memory (doubles): two staged normal-equation records, the broadcast buffers of the
+// factorisation (column of D [16] + row of X [16], double buffered; unused with ELIM_SHFL), two mbarriers, and (with
+// ELIM_ACC_SMEM) the persistent Schur sums of the segment
 #ifndef ELIM_WARPS_N
 #define ELIM_WARPS_N 4
 #endif
@@ -48,6 +48,21 @@ constexpr int ELIM_WARPS = ELIM_WARPS_N;
 #ifndef ELIM_MIN_CTAS
 #define ELIM_MIN_CTAS 3
 #endif
+#ifndef ELIM_SHFL
+#define ELIM_SHFL 0 // 1: pivot column / row broadcast by warp shuffles (measured slower: 681 vs 625 ms); 0: through shared memory
+#endif
+#ifndef ELIM_ACC_SMEM
+#define ELIM_ACC_SMEM 0 // 1: the persistent Schur sums live in shared memory (34 fewer doubles in registers)
+#endif
+#ifndef ELIM_LOCKSTEP
+#define ELIM_LOCKSTEP 0 // 1: all warps of the CTA (one CTA per SM) start every state together (named barrier), see elim_chain
+#endif
+#ifndef ELIM_BULK
+#define ELIM_BULK 1 // 1: record staged by one cp.async.bulk + mbarrier per state (0: cp.async 16-byte chunks per lane)
+#endif
+constexpr int SW_STAGE = 0, SW_CB = 2 * NE_STRIDE, SW_BAR = SW_CB + 64, SW_ACC = SW_BAR + 2;
+constexpr int SW_ACC_N = ELIM_ACC_SMEM ? (6 * 64 + 5 * 8) : 0;
+constexpr int SW_TOTAL = SW_ACC + SW_ACC_N;
 
 // D[8x8] += A[8x4] B[4x8] on the FP64 tensor path; fragments (lane = 4 gid + tid):
 //   a = A[gid][tid], b = B[tid][gid], (c0, c1) = C[gid][2 tid + {0,1}]
@@ -61,10 +76,35 @@ __device__ __forceinline__ void cp_async16(double *smem, const double *gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// stream one 600-double record into shared memory (300 16-byte chunks over the warp)
+// ---- bulk asynchronous copy (TMA unit, 1-D) of one record into shared memory, completion on an mbarrier
+__device__ __forceinline__ void mbar_init(double *bar, const unsigned count) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sa), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bulk_load(double *dst, const double *src, const unsigned bytes, double *bar) {
+  const unsigned sd = (unsigned)__cvta_generic_to_shared(dst), sb = (unsigned)__cvta_generic_to_shared(bar);
+  // generic-proxy reads of the buffer (the previous state staged there) are ordered before the async-proxy write
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sb), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sd), "l"(src), "r"(bytes),
+               "r"(sb)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(double *bar, const unsigned parity) {
+  const unsigned sb = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done)
+                 : "r"(sb), "r"(parity)
+                 : "memory");
+  } while (!done);
+}
+
+// stream one record into shared memory with 16-byte cp.async chunks over the warp (ELIM_BULK == 0)
 __device__ __forceinline__ void stage_record(double *dst, const double *src, int lane) {
 #pragma unroll
-  for (int k = 0; k < 10; k++) {
+  for (int k = 0; k < (NE_STRIDE / 2 + 31) / 32; k++) {
     const int ch = lane + 32 * k;
     if (ch < NE_STRIDE / 2)
       cp_async16(dst + 2 * ch, src + 2 * ch);
@@ -75,33 +115,62 @@ __device__ __forceinline__ void stage_record(double *dst, const double *src, int
 //   cy[t][u][e] = S[8t+gid][8u+2tid+e] of the last eliminated state (u = O-row tile; tile (0,1) is unused)
 //   p15[t]      = sum over the chain of S[15][8t+gid]   (held by lanes tid == 3; F column 0 against F, B, g)
 //   pt[i][e]    = sum over the chain of tiles (2,2)(2,3)(2,4)(3,3)(3,4)(4,4): S[8ta+gid][8tb+2tid+e]
+// With ELIM_ACC_SMEM the two persistent sums live in the warp's shared memory ([i][lane] double2, [t][gid]).
 struct ElimAcc {
   double cy[5][2][2];
+#if ELIM_ACC_SMEM
+  double *sm;
+#else
   double p15[5];
   double pt[6][2];
+#endif
 };
-__device__ __forceinline__ void acc_zero(ElimAcc &A) {
+__device__ __forceinline__ void acc_zero(ElimAcc &A, double *sm_acc, const int lane) {
 #pragma unroll
-  for (int t = 0; t < 5; t++) {
-    A.p15[t] = 0.0;
+  for (int t = 0; t < 5; t++)
 #pragma unroll
     for (int u = 0; u < 2; u++)
       A.cy[t][u][0] = A.cy[t][u][1] = 0.0;
-  }
+#if ELIM_ACC_SMEM
+  A.sm = sm_acc;
+#pragma unroll
+  for (int i = 0; i < 6; i++)
+    reinterpret_cast<double2 *>(sm_acc)[32 * i + lane] = make_double2(0.0, 0.0);
+  for (int k = lane; k < 40; k += 32)
+    sm_acc[384 + k] = 0.0;
+  __syncwarp();
+#else
+#pragma unroll
+  for (int t = 0; t < 5; t++)
+    A.p15[t] = 0.0;
 #pragma unroll
   for (int i = 0; i < 6; i++)
     A.pt[i][0] = A.pt[i][1] = 0.0;
+#endif
+}
+__device__ __forceinline__ double acc_p15(const ElimAcc &A, const int t, const int gid) {
+#if ELIM_ACC_SMEM
+  return A.sm[384 + 8 * t + gid];
+#else
+  return A.p15[t];
+#endif
+}
+__device__ __forceinline__ double2 acc_pt(const ElimAcc &A, const int i, const int lane) {
+#if ELIM_ACC_SMEM
+  return reinterpret_cast<const double2 *>(A.sm)[32 * i + lane];
+#else
+  return make_double2(A.pt[i][0], A.pt[i][1]);
+#endif
 }
 
 // 1/x without the slow path of the IEEE division (x is a positive, normal pivot; anything else is caught by the
-// positivity check of the pivots): MUFU.RCP64H seed (~20 bits) + two Newton steps
-__device__ __forceinline__ double fast_rcp(const double x) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  double e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-x, r, 1.0);
-  return fma(r, e, r);
+// positivity check of the pivots): MUFU.RCP64H seed r0 (relative error e, |e| < 2^-20), then the third-order
+// correction r = r0 (1 + e + e^2) (error e^3): rcp_seed gives r0 and p = e + e^2, so that a product c / x is
+// fma(c r0, p, c r0) -- c r0 does not wait for the correction, the dependent chain is seed, e, p, product
+__device__ __forceinline__ void rcp_seed(const double x, double &r0, double &p) {
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
+  const double e = fma(-x, r0, 1.0);
+  p = fma(e, e, e);
 }
 __device__ __forceinline__ double fast_rsqrt(const double x) {
   double r;
@@ -127,11 +196,14 @@ __device__ __forceinline__ void sts2_if(const bool p, double *dst, const double 
                "r"((unsigned)p)
                : "memory");
 }
+__device__ __forceinline__ double shfl_d(const double v, const int src) { return __shfl_sync(0xffffffffu, v, src); }
 
 // LDL^T of the 15x15 block held as the tiles d00 = D[gid][2tid+e], d10 = D[8+gid][2tid+e],
 // d11 = D[8+gid][8+2tid+e] together with the Gauss-Jordan inverse of its unit-lower factor; returns
-// L^-1 = D^-1/2 L'^-1 (L = Cholesky factor) in the same tile order.  cb: 64 doubles of shared memory (two broadcast
-// buffers); the holders of a column / row publish it with predicated stores.
+// L^-1 = D^-1/2 L'^-1 (L = Cholesky factor) in the same tile order.  Per pivot j every lane needs the pivot, the
+// entries of column j of D in its own row and in its two columns (D is symmetric), and row j of X in its two columns:
+// ELIM_SHFL fetches them with warp shuffles from the lanes that hold them (no shared memory, no barrier in the 15
+// dependent steps); otherwise the holders publish column and row through cb (64 doubles of shared memory).
 __device__ __forceinline__ bool ldl_inverse(double (&d00)[2], double (&d10)[2], double (&d11)[2], double (&li00)[2],
                                             double (&li10)[2], double (&li11)[2], double *cb, const int gid, const int tid) {
   double x00[2], x10[2], x11[2];
@@ -143,51 +215,87 @@ __device__ __forceinline__ bool ldl_inverse(double (&d00)[2], double (&d10)[2], 
   double p0 = 1.0, p1 = 1.0;
 #pragma unroll
   for (int j = 0; j < 15; j++) {
+    const int jj = j & 7, h = jj >> 1, e = jj & 1; // holders of column j: lanes with tid == h, register e
+    double piv, ca_g = 0.0, cb_g, ca0 = 0.0, ca1 = 0.0, cb0, cb1, xr0, xr1, xs0 = 0.0, xs1 = 0.0;
+#if ELIM_SHFL
+    if (j < 8) {
+      const double va = d00[e], vb = d10[e];
+      piv = shfl_d(va, 4 * jj + h);
+      ca_g = shfl_d(va, 4 * gid + h);         // D[gid][j]
+      cb_g = shfl_d(vb, 4 * gid + h);         // D[8+gid][j]
+      ca0 = shfl_d(va, 4 * (2 * tid) + h);    // D[2tid][j]   = D[j][2tid]
+      ca1 = shfl_d(va, 4 * (2 * tid + 1) + h);
+      cb0 = shfl_d(vb, 4 * (2 * tid) + h);    // D[8+2tid][j]
+      cb1 = shfl_d(vb, 4 * (2 * tid + 1) + h);
+      xr0 = shfl_d(x00[0], 4 * jj + tid);     // X[j][2tid], X[j][2tid+1]
+      xr1 = shfl_d(x00[1], 4 * jj + tid);
+    } else {
+      const double vb = d11[e];
+      piv = shfl_d(vb, 4 * jj + h);
+      cb_g = shfl_d(vb, 4 * gid + h);         // D[8+gid][j]
+      cb0 = shfl_d(vb, 4 * (2 * tid) + h);
+      cb1 = shfl_d(vb, 4 * (2 * tid + 1) + h);
+      xr0 = shfl_d(x10[0], 4 * jj + tid);     // X[j][2tid+e]
+      xr1 = shfl_d(x10[1], 4 * jj + tid);
+      xs0 = shfl_d(x11[0], 4 * jj + tid);     // X[j][8+2tid+e]
+      xs1 = shfl_d(x11[1], 4 * jj + tid);
+    }
+#else
     double *buf = cb + 32 * (j & 1);
     // the holders publish column j of D (rows 0..15) and row j of X (columns 0..15)
     if (j < 8) {
-      const bool hc = (tid == (j >> 1)), hr = (gid == j);
-      sts_if(hc, buf + gid, d00[j & 1]);
-      sts_if(hc, buf + 8 + gid, d10[j & 1]);
+      const bool hc = (tid == h), hr = (gid == j);
+      sts_if(hc, buf + gid, d00[e]);
+      sts_if(hc, buf + 8 + gid, d10[e]);
       sts2_if(hr, buf + 16 + 2 * tid, x00[0], x00[1]);
     } else {
-      const bool hc = (tid == ((j - 8) >> 1)), hr = (gid == j - 8);
-      sts_if(hc, buf + 8 + gid, d11[j & 1]);
+      const bool hc = (tid == h), hr = (gid == jj);
+      sts_if(hc, buf + 8 + gid, d11[e]);
       sts2_if(hr, buf + 16 + 2 * tid, x10[0], x10[1]);
       sts2_if(hr, buf + 24 + 2 * tid, x11[0], x11[1]);
     }
     __syncwarp();
-    const double piv = buf[j];
-    const double rinv = fast_rcp(piv);
+    piv = buf[j];
+    cb_g = buf[8 + gid];
+    cb0 = buf[8 + 2 * tid];
+    cb1 = buf[9 + 2 * tid];
+    xr0 = buf[16 + 2 * tid];
+    xr1 = buf[17 + 2 * tid];
+    if (j < 8) {
+      ca_g = buf[gid];
+      ca0 = buf[2 * tid];
+      ca1 = buf[2 * tid + 1];
+    } else {
+      xs0 = buf[24 + 2 * tid];
+      xs1 = buf[25 + 2 * tid];
+    }
+#endif
+    double r0, pc;
+    rcp_seed(piv, r0, pc);
     if (j < 8) {
       p0 = (gid == j) ? piv : p0;
-      const double mr0 = (gid > j) ? buf[gid] * rinv : 0.0;
-      const double mr1 = buf[8 + gid] * rinv;
-      const double2 c0 = *reinterpret_cast<const double2 *>(buf + 2 * tid);
-      const double2 c1 = *reinterpret_cast<const double2 *>(buf + 8 + 2 * tid);
-      const double2 xr = *reinterpret_cast<const double2 *>(buf + 16 + 2 * tid);
-      d00[0] = fma(-mr0, c0.x, d00[0]);
-      d00[1] = fma(-mr0, c0.y, d00[1]);
-      d10[0] = fma(-mr1, c0.x, d10[0]);
-      d10[1] = fma(-mr1, c0.y, d10[1]);
-      d11[0] = fma(-mr1, c1.x, d11[0]);
-      d11[1] = fma(-mr1, c1.y, d11[1]);
-      x00[0] = fma(-mr0, xr.x, x00[0]);
-      x00[1] = fma(-mr0, xr.y, x00[1]);
-      x10[0] = fma(-mr1, xr.x, x10[0]);
-      x10[1] = fma(-mr1, xr.y, x10[1]);
+      const double a0 = (gid > j) ? ca_g * r0 : 0.0, a1 = cb_g * r0;
+      const double mr0 = fma(a0, pc, a0), mr1 = fma(a1, pc, a1);
+      d00[0] = fma(-mr0, ca0, d00[0]);
+      d00[1] = fma(-mr0, ca1, d00[1]);
+      d10[0] = fma(-mr1, ca0, d10[0]);
+      d10[1] = fma(-mr1, ca1, d10[1]);
+      d11[0] = fma(-mr1, cb0, d11[0]);
+      d11[1] = fma(-mr1, cb1, d11[1]);
+      x00[0] = fma(-mr0, xr0, x00[0]);
+      x00[1] = fma(-mr0, xr1, x00[1]);
+      x10[0] = fma(-mr1, xr0, x10[0]);
+      x10[1] = fma(-mr1, xr1, x10[1]);
     } else {
       p1 = (8 + gid == j) ? piv : p1;
-      const double mr1 = (8 + gid > j) ? buf[8 + gid] * rinv : 0.0;
-      const double2 c1 = *reinterpret_cast<const double2 *>(buf + 8 + 2 * tid);
-      const double2 xr0 = *reinterpret_cast<const double2 *>(buf + 16 + 2 * tid);
-      const double2 xr1 = *reinterpret_cast<const double2 *>(buf + 24 + 2 * tid);
-      d11[0] = fma(-mr1, c1.x, d11[0]);
-      d11[1] = fma(-mr1, c1.y, d11[1]);
-      x10[0] = fma(-mr1, xr0.x, x10[0]);
-      x10[1] = fma(-mr1, xr0.y, x10[1]);
-      x11[0] = fma(-mr1, xr1.x, x11[0]);
-      x11[1] = fma(-mr1, xr1.y, x11[1]);
+      const double a1 = (8 + gid > j) ? cb_g * r0 : 0.0;
+      const double mr1 = fma(a1, pc, a1);
+      d11[0] = fma(-mr1, cb0, d11[0]);
+      d11[1] = fma(-mr1, cb1, d11[1]);
+      x10[0] = fma(-mr1, xr0, x10[0]);
+      x10[1] = fma(-mr1, xr1, x10[1]);
+      x11[0] = fma(-mr1, xs0, x11[0]);
+      x11[1] = fma(-mr1, xs1, x11[1]);
     }
   }
   // every pivot is held by exactly one (gid, *) group: positive-definiteness check in one vote
@@ -210,16 +318,16 @@ template <bool HAS_F>
 __device__ __forceinline__ bool elim_node(const double *st, const double *__restrict__ Finit, const double lambda, ElimAcc &A,
                                           double *cb, double *__restrict__ fac, const int lane) {
   const int gid = lane >> 2, tid = lane & 3;
-  // ---- D = record + lambda I - carry, as tiles
+  // ---- D = record + lambda I - carry, as tiles (the record holds the lower triangle: element (r, c) at tri(max, min))
   double d00[2], d10[2], d11[2];
 #pragma unroll
   for (int e = 0; e < 2; e++) {
     const int c = 2 * tid + e;
-    d00[e] = st[NE_D + 15 * gid + c] - A.cy[0][0][e] + ((gid == c) ? lambda : 0.0);
-    d10[e] = (gid < 7) ? st[NE_D + 15 * (8 + gid) + c] - A.cy[1][0][e] : 0.0;
+    d00[e] = st[NE_D + (gid >= c ? tri(gid, c) : tri(c, gid))] - A.cy[0][0][e] + ((gid == c) ? lambda : 0.0);
+    d10[e] = (gid < 7) ? st[NE_D + tri(8 + gid, c)] - A.cy[1][0][e] : 0.0;
     const int c1 = 8 + c;
     if (gid < 7 && c1 < 15)
-      d11[e] = st[NE_D + 15 * (8 + gid) + c1] - A.cy[1][1][e] + ((gid == c) ? lambda : 0.0);
+      d11[e] = st[NE_D + (gid >= c ? tri(8 + gid, c1) : tri(c1, 8 + gid))] - A.cy[1][1][e] + ((gid == c) ? lambda : 0.0);
     else
       d11[e] = (gid == 7 && c1 == 15) ? 1.0 : 0.0;
   }
@@ -277,17 +385,23 @@ __device__ __forceinline__ bool elim_node(const double *st, const double *__rest
     w[2][t] = b0;
     w[3][t] = b1;
   }
-  // ---- factor record (fragment order, fully coalesced 16-byte stores)
+  // ---- factor record (fragment order without the structurally zero fragments; coalesced 16- and 8-byte stores)
   {
-    double2 *f2 = reinterpret_cast<double2 *>(fac);
-    f2[lane] = make_double2(li00[0], li00[1]);
-    f2[32 + lane] = make_double2(li10[0], li10[1]);
-    f2[64 + lane] = make_double2(li11[0], li11[1]);
+    const bool lo = (2 * tid <= gid);
+    if (lo)
+      *reinterpret_cast<double2 *>(fac + FAC_LI00 + 2 * tri_slot(gid, tid)) = make_double2(li00[0], li00[1]);
+    if (gid < 7) {
+      *reinterpret_cast<double2 *>(fac + FAC_LI10 + 2 * lane) = make_double2(li10[0], li10[1]);
+      if (lo)
+        *reinterpret_cast<double2 *>(fac + FAC_LI11 + 2 * tri_slot(gid, tid)) = make_double2(li11[0], li11[1]);
+    }
 #pragma unroll
-    for (int u = 0; u < 2; u++)
-#pragma unroll
-      for (int t = 0; t < 5; t++)
-        f2[FAC_W / 2 + (u * 5 + t) * 32 + lane] = make_double2(w[2 * u][t], w[2 * u + 1][t]);
+    for (int t = 0; t < 5; t++) {
+      *reinterpret_cast<double2 *>(fac + FAC_W0 + 64 * t + 2 * lane) = make_double2(w[0][t], w[1][t]);
+      fac[FAC_W1 + 56 * t + lane] = w[2][t];
+      if (tid < 3)
+        fac[FAC_W1 + 56 * t + 32 + 3 * gid + tid] = w[3][t];
+    }
   }
   // ---- Schur tiles S = W^T W
 #pragma unroll
@@ -304,9 +418,17 @@ __device__ __forceinline__ bool elim_node(const double *st, const double *__rest
       A.cy[t][u][1] = c1;
     }
   if (HAS_F) {
+#if ELIM_ACC_SMEM
+    if (tid == 3) {
+#pragma unroll
+      for (int t = 1; t < 5; t++)
+        A.sm[384 + 8 * t + gid] += A.cy[t][1][1];
+    }
+#else
 #pragma unroll
     for (int t = 1; t < 5; t++)
       A.p15[t] += A.cy[t][1][1];
+#endif
   }
   {
     int i = 0;
@@ -315,9 +437,19 @@ __device__ __forceinline__ bool elim_node(const double *st, const double *__rest
 #pragma unroll
       for (int tb = ta; tb < 5; tb++) {
         if (HAS_F || ta != 2) {
+#if ELIM_ACC_SMEM
+          double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+          for (int kk = 0; kk < 4; kk++)
+            dmma(c0, c1, w[kk][ta], w[kk][tb]);
+          double2 *q = reinterpret_cast<double2 *>(A.sm) + 32 * i + lane;
+          const double2 o = *q;
+          *q = make_double2(o.x + c0, o.y + c1);
+#else
 #pragma unroll
           for (int kk = 0; kk < 4; kk++)
             dmma(A.pt[i][0], A.pt[i][1], w[kk][ta], w[kk][tb]);
+#endif
         }
         i++;
       }
@@ -326,12 +458,46 @@ __device__ __forceinline__ bool elim_node(const double *st, const double *__rest
 }
 
 // Eliminate `count` consecutive states whose records start at ne0 (stride NE_STRIDE); factor records to fac0.
+// w: the warp's shared memory; the state's record is fetched one state ahead.
+// sync_threads > 0 (ELIM_LOCKSTEP): the warps of the CTA start every state together, for `sync_iters` states (a warp with
+// fewer states keeps arriving at the barrier).  Why: the factorisation is a chain of ~60 DEPENDENT FP64 operations per
+// state, the mma phase a stream of 90 DMMAs, and both use the one FP64 pipe of the SM sub-partition, whose arbitration
+// makes a dependent DFMA wait behind the DMMAs of every other warp (measured, tools/fp64_micro2.cu: 8.9 cycles per
+// dependent DFMA alone, 41 / 73 / 105 with one / two / three warps streaming DMMAs beside it).  Warps that run out of
+// phase spend two thirds of their time in the factorisation; warps in phase factorise on an idle pipe and then share
+// it at its full DMMA rate.
 template <bool HAS_F>
 __device__ __forceinline__ bool elim_chain(const double *__restrict__ ne0, const int count, const double *__restrict__ left_sep_ne,
-                                           const double lambda, double *__restrict__ fac0, ElimAcc &A, double *w, const int lane) {
+                                           const double lambda, double *__restrict__ fac0, ElimAcc &A, double *w, const int lane,
+                                           const int sync_threads = 0, const int sync_iters = 0) {
   double *stage = w + SW_STAGE;
   double *cb = w + SW_CB;
   bool ok = true;
+#if ELIM_BULK
+  double *bar = w + SW_BAR;
+  constexpr unsigned REC_BYTES = NE_STRIDE * sizeof(double);
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    mbar_init(bar + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  if (count > 0 && lane == 0)
+    bulk_load(stage, ne0, REC_BYTES, bar);
+  const int iters = sync_threads > 0 ? max(count, sync_iters) : count;
+  for (int k = 0; k < iters; k++) {
+    // the buffer of state k + 1 was read by state k - 1, whose lanes have all passed the __syncwarp of elim_node
+    if (k + 1 < count && lane == 0)
+      bulk_load(stage + NE_STRIDE * ((k + 1) & 1), ne0 + (long long)(k + 1) * NE_STRIDE, REC_BYTES, bar + ((k + 1) & 1));
+    if (k < count)
+      mbar_wait(bar + (k & 1), (unsigned)(k >> 1) & 1u);
+    if (sync_threads > 0)
+      asm volatile("bar.sync 1, %0;" ::"r"(sync_threads) : "memory");
+    if (k < count)
+      ok = elim_node<HAS_F>(stage + NE_STRIDE * (k & 1), (HAS_F && k == 0) ? left_sep_ne : nullptr, lambda, A, cb,
+                            fac0 + (long long)k * FAC_STRIDE, lane) && ok;
+  }
+#else
   if (count > 0)
     stage_record(stage, ne0, lane);
   cp_async_commit();
@@ -345,6 +511,7 @@ __device__ __forceinline__ bool elim_chain(const double *__restrict__ ne0, const
                           fac0 + (long long)k * FAC_STRIDE, lane) && ok;
   }
   cp_async_wait<0>();
+#endif
   return ok;
 }
 
@@ -360,22 +527,32 @@ __global__ void __launch_bounds__(ELIM_WARPS * 32, ELIM_MIN_CTAS) k_seg_eliminat
   const int j = blockIdx.x * ELIM_WARPS + wid + (d.chain ? d.c_j0 : 0);
   const int n = d.chain ? d.c_n : d.n_states[t];
   const SegGeom sg = seg_geom(n, d.P);
-  if (j >= (d.chain ? min(sg.nseg, d.c_j1) : sg.nseg))
+  const bool live = j < (d.chain ? min(sg.nseg, d.c_j1) : sg.nseg);
+#if !ELIM_LOCKSTEP
+  if (!live)
     return;
+  const int sync_threads = 0, sync_iters = 0;
+#else
+  // every warp of the CTA takes part in the per-state barrier; a full segment has stride - 1 interior states
+  const int sync_threads = ELIM_WARPS * 32, sync_iters = sg.stride - 1;
+#endif
   double *w = smem + (size_t)wid * SW_TOTAL;
   const TrialDev &tr = d.trials[t];
   const double lambda = lm.lambda;
   const int a0 = j * sg.stride;
-  const int b1 = min(n, (j + 1) * sg.stride - 1); // exclusive end of the interior
+  const int b1 = live ? min(n, (j + 1) * sg.stride - 1) : a0; // exclusive end of the interior
   const bool has_left = (j >= 1);
   const long long s0 = tr.st_off + a0 - (d.chain ? d.c_goff : 0);
   ElimAcc A;
-  acc_zero(A);
+  acc_zero(A, w + SW_ACC, lane);
   bool ok;
   if (has_left)
-    ok = elim_chain<true>(d.ne + s0 * NE_STRIDE, b1 - a0, d.ne + (s0 - 1) * NE_STRIDE, lambda, d.fac + s0 * FAC_STRIDE, A, w, lane);
+    ok = elim_chain<true>(d.ne + s0 * NE_STRIDE, b1 - a0, d.ne + (s0 - 1) * NE_STRIDE, lambda, d.fac + s0 * FAC_STRIDE, A, w, lane,
+                          sync_threads, sync_iters);
   else
-    ok = elim_chain<false>(d.ne + s0 * NE_STRIDE, b1 - a0, nullptr, lambda, d.fac + s0 * FAC_STRIDE, A, w, lane);
+    ok = elim_chain<false>(d.ne + s0 * NE_STRIDE, b1 - a0, nullptr, lambda, d.fac + s0 * FAC_STRIDE, A, w, lane, sync_threads, sync_iters);
+  if (!live)
+    return;
   // ---- segment outputs
   const int gid = lane >> 2, tid = lane & 3;
   double *so = d.seg + ((long long)t * d.P + j) * SEG_STRIDE;
@@ -395,13 +572,17 @@ __global__ void __launch_bounds__(ELIM_WARPS * 32, ELIM_MIN_CTAS) k_seg_eliminat
             cyo[40 * c + r] = A.cy[tt][u][e]; // mirror of the D part
         }
       }
+#if ELIM_ACC_SMEM
+  __syncwarp();
+#endif
   if (tid == 3) {
 #pragma unroll
     for (int tt = 1; tt < 5; tt++) {
       const int b = 8 * tt + gid - 15;
       if (b >= 0) {
-        fbo[b] = A.p15[tt];
-        fbo[25 * b] = A.p15[tt];
+        const double v = acc_p15(A, tt, gid);
+        fbo[b] = v;
+        fbo[25 * b] = v;
       }
     }
   }
@@ -411,11 +592,12 @@ __global__ void __launch_bounds__(ELIM_WARPS * 32, ELIM_MIN_CTAS) k_seg_eliminat
     for (int ta = 2; ta < 5; ta++)
 #pragma unroll
       for (int tb = ta; tb < 5; tb++) {
+        const double2 v = acc_pt(A, i, lane);
 #pragma unroll
         for (int e = 0; e < 2; e++) {
           const int a = 8 * ta + gid - 15, b = 8 * tb + 2 * tid + e - 15;
-          fbo[25 * a + b] = A.pt[i][e];
-          fbo[25 * b + a] = A.pt[i][e];
+          fbo[25 * a + b] = e ? v.y : v.x;
+          fbo[25 * b + a] = e ? v.y : v.x;
         }
         i++;
       }
@@ -447,7 +629,13 @@ __global__ void __launch_bounds__(128) k_reduced_assemble(DevPtrs d, int force_a
   for (int idx = threadIdx.x; idx < NE_STRIDE; idx += blockDim.x) {
     double v;
     if (idx < NE_O) {
-      const int i = idx / 15, jn = idx - 15 * i;
+      // packed lower triangle: idx = tri(i, jn), i >= jn
+      int i = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
+      while (tri(i + 1, 0) <= idx)
+        i++;
+      while (tri(i, 0) > idx)
+        i--;
+      const int jn = idx - tri(i, 0);
       v = ne[idx] - segl[SEG_CY + 40 * i + jn];
       if (has_r)
         v -= segr[SEG_FB + 25 * i + jn];
@@ -456,12 +644,14 @@ __global__ void __launch_bounds__(128) k_reduced_assemble(DevPtrs d, int force_a
       const int i = q / 15, c = q - 15 * i;
       // coupling separator m -> m+1 through segment m:  H[m][m+1](i, c) = -S(rows: O index c, column F index i)
       v = has_next ? -segr[SEG_CY + 40 * c + XC_F + i] : 0.0;
-    } else {
+    } else if (idx < NE_BG + 15 * NE_BGW) {
       const int q = idx - NE_BG;
       const int i = q / NE_BGW, k = q - NE_BGW * i; // border columns 0..8, rhs 9
       v = ne[idx] - segl[SEG_CY + 40 * i + XC_B + k];
       if (has_r)
         v -= segr[SEG_FB + 25 * i + 15 + k];
+    } else {
+      v = 0.0; // pad
     }
     out[idx] = v;
   }
@@ -501,14 +691,20 @@ struct FacRegs {
   double2 li[3];
   double2 w[10];
 };
+// the packed factor record back into fragment registers (the fragments that are zero by structure are not stored)
 __device__ __forceinline__ void fac_load(FacRegs &F, const double *__restrict__ fac, const int lane) {
-  const double2 *f2 = reinterpret_cast<const double2 *>(fac);
+  const int gid = lane >> 2, tid = lane & 3;
+  const bool lo = (2 * tid <= gid);
+  const double2 z = make_double2(0.0, 0.0);
+  F.li[0] = lo ? __ldcs(reinterpret_cast<const double2 *>(fac + FAC_LI00) + tri_slot(gid, tid)) : z;
+  F.li[1] = (gid < 7) ? __ldcs(reinterpret_cast<const double2 *>(fac + FAC_LI10) + lane) : z;
+  F.li[2] = (gid < 7 && lo) ? __ldcs(reinterpret_cast<const double2 *>(fac + FAC_LI11) + tri_slot(gid, tid)) : z;
 #pragma unroll
-  for (int i = 0; i < 3; i++)
-    F.li[i] = __ldcs(f2 + 32 * i + lane);
-#pragma unroll
-  for (int i = 0; i < 10; i++)
-    F.w[i] = __ldcs(f2 + FAC_W / 2 + 32 * i + lane);
+  for (int t = 0; t < 5; t++) {
+    F.w[t] = __ldcs(reinterpret_cast<const double2 *>(fac + FAC_W0 + 64 * t) + lane);
+    F.w[5 + t].x = __ldcs(fac + FAC_W1 + 56 * t + lane);
+    F.w[5 + t].y = (tid < 3) ? __ldcs(fac + FAC_W1 + 56 * t + 32 + 3 * gid + tid) : 0.0;
+  }
 }
 // x = L^-T (w_g - W_O x_next - W_F x_left - W_B x_glob); on return every lane holds x[2tid+e] in y0[e] and
 // x[8+2tid+e] in y1[e], and V follows the chain.
@@ -582,7 +778,7 @@ __global__ void __launch_bounds__(32) k_reduced(DevPtrs d, int force_all) {
   double *xz = smem + SW_TOTAL + 112; // zeros / x_next scratch (32)
   // ---- forward elimination over the separators m = 1..nsep
   ElimAcc A;
-  acc_zero(A);
+  acc_zero(A, w + SW_ACC, lane);
   const long long r0 = (long long)t * (d.P + 1) + 1;
   bool ok = elim_chain<false>(d.red_ne + r0 * NE_STRIDE, sg.nsep, nullptr, lambda, d.red_fac + r0 * FAC_STRIDE, A, w, lane);
   // ---- global 9x9: Gamma + lambda I - sum_seg S_BB - S_BB(separator chain); rhs likewise
@@ -593,11 +789,12 @@ __global__ void __launch_bounds__(32) k_reduced(DevPtrs d, int force_all) {
     for (int ta = 2; ta < 5; ta++)
 #pragma unroll
       for (int tb = ta; tb < 5; tb++) {
+        const double2 v = acc_pt(A, i, lane);
 #pragma unroll
         for (int e = 0; e < 2; e++) {
           const int a = 8 * ta + gid - 15, b = 8 * tb + 2 * tid + e - 15;
-          fbr[25 * a + b] = A.pt[i][e];
-          fbr[25 * b + a] = A.pt[i][e];
+          fbr[25 * a + b] = e ? v.y : v.x;
+          fbr[25 * b + a] = e ? v.y : v.x;
         }
         i++;
       }

@@ -18,10 +18,13 @@
 //                      (these four are TILED struct-of-arrays, soa_base() below: element e of slot s at
 //                       [(s / 32) * E * 32 + e * 32 + s % 32], so the one-thread-per-state kernels read and write them
 //                       fully coalesced and a tile is one contiguous block)
-//   ne      [S][600]   normal-equation record per state: D 15x15 (225) | O 15x15 (225, coupling k,k+1) | BG 15x10 = [B 9 | g 1]
-//                      (one contiguous, 16-byte aligned record: streamed with cp.async by the elimination)
+//   ne      [S][496]   normal-equation record per state: D packed lower triangle (120) | O 15x15 (225, coupling k,k+1) |
+//                      BG 15x10 = [B 9 | g 1] (150) | pad 1 -- 495 doubles is what the elimination has to read; one
+//                      contiguous, 16-byte aligned record of 3968 bytes, fetched by ONE bulk asynchronous copy
+//                      (cp.async.bulk + mbarrier) per state
 //   grad    [S][16]    compact copy of g
-//   fac     [S][832]   elimination factors per state in mma-fragment order: L^-1 (3 8x8 tiles) | W (16x40)
+//   fac     [S][728]   elimination factors per state in mma-fragment order, zero fragments and the padding row left
+//                      out: L^-1 (40 + 56 + 32) | W (15x40: 320 + 280)
 //   delta   [S][16]    LM step per state
 #pragma once
 #include "../../include/vicon2gt_b200.h"
@@ -49,13 +52,22 @@ constexpr int FPI_E = 0, FPI_TTH = 15, FPI_TB = 24, FPI_SV = 33, FPI_SP = 36, FP
 constexpr int FPV_R = 0, FPV_A = 6, FPV_G = 42, FPV_HAS = 84, FPV_IDX0 = 85, FPV_IDX1 = 86, FPV_W = 87, FPV_STRIDE = 88;
 
 // ---- normal-equation record of one state (row-major pieces, each piece contiguous so that the assembly can write
-//  it as whole 3-row strips):  D 15x15 at [0, 225);  O 15x15 at [225, 450) (coupling to the next state);
-//  BG 15x10 at [450, 600): columns [0,9) = B (border to the 9 globals), 9 = g (right-hand side)
-constexpr int NE_D = 0, NE_O = 225, NE_BG = 450, NE_BGW = 10, NE_STRIDE = 600;
+//  it as whole 3-row strips):  D, symmetric, as its packed lower triangle (row r at r (r + 1) / 2) at [0, 120);
+//  O 15x15 at [120, 345) (coupling to the next state);  BG 15x10 at [345, 495): columns [0,9) = B (border to the 9
+//  globals), 9 = g (right-hand side);  one pad double -> 496 (the record is a whole number of 16-byte units)
+constexpr int NE_D = 0, NE_O = 120, NE_BG = 345, NE_BGW = 10, NE_STRIDE = 496;
 // ---- elimination factor record of one state, in the register order of the mma.m8n8k4 fragments
-//  (lane = 4 gid + tid):  L^-1 tiles (0,0) (1,0) (1,1): [tile][lane][e] = Linv[8u+gid][8v+2tid+e]   (192)
-//  W = L^-1 [O F B g] (16x40, row 15 is padding): [u][t][lane][e] = W[8u+2tid+e][8t+gid]            (640)
-constexpr int FAC_LI = 0, FAC_W = 192, FAC_STRIDE = 832;
+//  (lane = 4 gid + tid), without the fragments that are zero by structure:
+//  L^-1 = [T00 0; T10 T11], element (gid, 2 tid + e) of a tile on lane (gid, tid):
+//    T00  lanes with 2 tid <= gid, double2 at slot tri_slot(gid, tid)                         (20 x 2 = 40)
+//    T10  rows 8..14: lanes with gid < 7, double2 at slot lane                                (28 x 2 = 56)
+//    T11  rows / columns 8..14: lanes with 2 tid <= gid < 7, double2 at slot tri_slot         (16 x 2 = 32)
+//  W = L^-1 [O F B g] (15x40), lane holds W[8u+2tid+e][8t+gid] for column tile t:
+//    u = 0: [t][lane] double2                                                                 (5 x 64 = 320)
+//    u = 1: row 15 does not exist: [t][e = 0: lane (32) | e = 1: 3 gid + tid, tid < 3 (24)]   (5 x 56 = 280)
+constexpr int FAC_LI00 = 0, FAC_LI10 = 40, FAC_LI11 = 96, FAC_W0 = 128, FAC_W1 = 448, FAC_STRIDE = 728;
+// slot of lane (gid, tid) among the lanes with 2 tid <= gid, in lane order: 0 1 | 2 3 | 4 5 | 6 7 8 | ...
+__host__ __device__ inline int tri_slot(int gid, int tid) { return ((gid + 1) >> 1) * ((gid >> 1) + 1) + tid; }
 // ---- extended column order of one elimination step: [O 0..14 | F 15..29 | B 30..38 | g 39]
 constexpr int XC_F = 15, XC_B = 30, XC_G = 39, XC_N = 40;
 // ---- per-segment outputs, all "+S" (the consumer subtracts):

@@ -263,31 +263,71 @@ class SimBatch:
         return Dataset(imu_t, imu_w, imu_a, vic_t, vic_q, vic_p, self.vic_R_const(trial), state_t, truth, self.seeds[int(trial)])
 
 
-def make_config(name, seed=0, duration_s=None, **kw):
-    """Datasets shaped like BASELINE.json's configs, on synthesised trajectories.
+# The reference's own trajectory files for BASELINE.json's configs (data/euroc_V1_01_easy.txt, data/tum_corridor1_512_16_okvis.txt:
+# rows `t x y z qx qy qz qw`), kept as fixtures under tests/golden/ (V2GT_TRAJ_DIR overrides the directory).  The TUM file is
+# jittered (row spacing 0.0431 ... 0.0550 s), which the synthesised stand-ins of the same shape are not.
+TRAJ_FILES = {"tum_corridor1": "traj_tum_corridor1_512_16_okvis.txt", "euroc_V1_01": "traj_euroc_V1_01_easy.txt"}
+_traj_cache = {}
 
-    name: "C1" sim.launch defaults (400 Hz IMU, 100 Hz vicon, 100 Hz states, corridor1 shape)
-          "C2" EuRoC V1_01 shape: states at the trajectory timestamps (20 Hz), 200 Hz IMU, 100 Hz vicon
-          "C3" TUM corridor1 shape: states at the trajectory timestamps (20 Hz), 200 Hz IMU, 100 Hz vicon
-          "C5" one-hour sequence: states at the trajectory timestamps (20 Hz, ~72 k), 200 Hz IMU (~720 k), 100 Hz vicon
-    duration_s truncates the trajectory (smaller problems for tests).
-    """
-    if name == "C1":
-        shape = dict(TRAJ_SHAPES["tum_corridor1"])
-        sim_kw = dict(freq_imu=400.0, freq_cam=20.0, freq_vicon=100.0, state_freq=100)
-    elif name == "C2":
-        shape = dict(TRAJ_SHAPES["euroc_V1_01"])
-        sim_kw = dict(freq_imu=200.0, freq_cam=20.0, freq_vicon=100.0, state_freq=0)
-    elif name == "C3":
-        shape = dict(TRAJ_SHAPES["tum_corridor1"])
-        sim_kw = dict(freq_imu=200.0, freq_cam=20.0, freq_vicon=100.0, state_freq=0)
-    elif name == "C5":
-        shape = dict(TRAJ_SHAPES["one_hour"])
-        sim_kw = dict(freq_imu=200.0, freq_cam=20.0, freq_vicon=100.0, state_freq=0)
-    else:
-        raise ValueError(name)
+
+def trajectory_file(shape_name):
+    """Path of the reference's trajectory file for a shape, or None where it is not shipped (one_hour) / not found."""
+    import os
+
+    fn = TRAJ_FILES.get(shape_name)
+    if fn is None:
+        return None
+    for d in (os.environ.get("V2GT_TRAJ_DIR"), os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")):
+        if d and os.path.exists(os.path.join(d, fn)):
+            return os.path.join(d, fn)
+    return None
+
+
+def trajectory_rows(shape_name, duration_s=None, source=None):
+    """(rows [n][8], source) of a trajectory shape.  source: "file" = the reference's data file (error if absent), "synth" =
+    the synthesised stand-in of the same start time / row count / spacing, None = the file where there is one."""
+    path = trajectory_file(shape_name) if source in (None, "file") else None
+    if source == "file" and path is None:
+        raise FileNotFoundError(f"no trajectory file for {shape_name} (tests/golden/{TRAJ_FILES.get(shape_name)})")
+    if path is not None:
+        if path not in _traj_cache:
+            # the reference's loader (Simulator.cpp:281-308): space-separated, lines starting with '#' skipped, atof per field
+            _traj_cache[path] = np.loadtxt(path, comments="#", dtype=np.float64, ndmin=2)[:, :8].copy()
+        rows = _traj_cache[path]
+        if duration_s is not None:
+            rows = rows[: max(8, int(np.searchsorted(rows[:, 0], rows[0, 0] + duration_s, "right")))]
+        return np.ascontiguousarray(rows), "file:" + path.rsplit("/", 1)[-1]
+    shape = dict(TRAJ_SHAPES[shape_name])
     if duration_s is not None:
         shape["n_rows"] = max(8, min(shape["n_rows"], int(round(duration_s / shape["dt"])) + 1))
-    rows = make_trajectory(**shape)
+    return make_trajectory(**shape), "synthesised, %s shape" % shape_name
+
+
+CONFIG_SHAPES = {
+    # name: (trajectory shape, simulator rates).  state_freq 0: states at the trajectory timestamps (run_simulation.cpp:149-158)
+    "C1": ("tum_corridor1", dict(freq_imu=400.0, freq_cam=20.0, freq_vicon=100.0, state_freq=100)),
+    "C2": ("euroc_V1_01", dict(freq_imu=200.0, freq_cam=20.0, freq_vicon=100.0, state_freq=0)),
+    "C3": ("tum_corridor1", dict(freq_imu=200.0, freq_cam=20.0, freq_vicon=100.0, state_freq=0)),
+    "C5": ("one_hour", dict(freq_imu=200.0, freq_cam=20.0, freq_vicon=100.0, state_freq=0)),
+}
+
+
+def make_config(name, seed=0, duration_s=None, trajectory=None, **kw):
+    """Datasets of BASELINE.json's configs.
+
+    name: "C1" sim.launch defaults (data/tum_corridor1_512_16_okvis.txt, 400 Hz IMU, 100 Hz vicon, 100 Hz states)
+          "C2" EuRoC V1_01: states at the timestamps of data/euroc_V1_01_easy.txt (20 Hz), 200 Hz IMU, 100 Hz vicon
+          "C3" TUM corridor1: states at the (jittered) timestamps of data/tum_corridor1_512_16_okvis.txt, 200 Hz IMU, 100 Hz vicon
+          "C5" one-hour sequence (no reference file is that long: synthesised), 20 Hz states (~72 k), 200 Hz IMU (~720 k)
+    trajectory: "file" (the reference's data file), "synth" (synthesised stand-in of the same shape) or None (file where
+    there is one).  duration_s truncates the trajectory (smaller problems for tests).
+    """
+    if name not in CONFIG_SHAPES:
+        raise ValueError(name)
+    shape_name, sim_kw = CONFIG_SHAPES[name]
+    rows, src = trajectory_rows(shape_name, duration_s, trajectory)
+    sim_kw = dict(sim_kw)
     sim_kw.update(kw)
-    return simulate(traj_rows=rows, seed=seed, **sim_kw)
+    ds = simulate(traj_rows=rows, seed=seed, **sim_kw)
+    ds.truth["trajectory"] = src
+    return ds
