@@ -39,8 +39,8 @@ __host__ __device__ inline SegGeom seg_geom(int n, int P) {
 }
 
 // ---- per-warp shared memory (doubles): two staged normal-equation records, the broadcast buffers of the
-// factorisation (column of D [16] + row of X [16], double buffered; unused with ELIM_SHFL), two mbarriers, and (with
-// ELIM_ACC_SMEM) the persistent Schur sums of the segment
+// factorisation (two pivot columns of D [16][2] + two pivot rows of X [2][16], double buffered), two mbarriers, and
+// (with ELIM_ACC_SMEM) the persistent Schur sums of the segment
 #ifndef ELIM_WARPS_N
 #define ELIM_WARPS_N 4
 #endif
@@ -48,19 +48,13 @@ constexpr int ELIM_WARPS = ELIM_WARPS_N;
 #ifndef ELIM_MIN_CTAS
 #define ELIM_MIN_CTAS 3
 #endif
-#ifndef ELIM_SHFL
-#define ELIM_SHFL 0 // 1: pivot column / row broadcast by warp shuffles (measured slower: 681 vs 625 ms); 0: through shared memory
-#endif
 #ifndef ELIM_ACC_SMEM
 #define ELIM_ACC_SMEM 0 // 1: the persistent Schur sums live in shared memory (34 fewer doubles in registers)
-#endif
-#ifndef ELIM_LOCKSTEP
-#define ELIM_LOCKSTEP 0 // 1: all warps of the CTA (one CTA per SM) start every state together (named barrier), see elim_chain
 #endif
 #ifndef ELIM_BULK
 #define ELIM_BULK 1 // 1: record staged by one cp.async.bulk + mbarrier per state (0: cp.async 16-byte chunks per lane)
 #endif
-constexpr int SW_STAGE = 0, SW_CB = 2 * NE_STRIDE, SW_BAR = SW_CB + 64, SW_ACC = SW_BAR + 2;
+constexpr int SW_STAGE = 0, SW_CB = 2 * NE_STRIDE, SW_BAR = SW_CB + 128, SW_ACC = SW_BAR + 2;
 constexpr int SW_ACC_N = ELIM_ACC_SMEM ? (6 * 64 + 5 * 8) : 0;
 constexpr int SW_TOTAL = SW_ACC + SW_ACC_N;
 
@@ -197,13 +191,17 @@ __device__ __forceinline__ void sts2_if(const bool p, double *dst, const double 
                : "memory");
 }
 __device__ __forceinline__ double shfl_d(const double v, const int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double2 lds2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 
-// LDL^T of the 15x15 block held as the tiles d00 = D[gid][2tid+e], d10 = D[8+gid][2tid+e],
-// d11 = D[8+gid][8+2tid+e] together with the Gauss-Jordan inverse of its unit-lower factor; returns
-// L^-1 = D^-1/2 L'^-1 (L = Cholesky factor) in the same tile order.  Per pivot j every lane needs the pivot, the
-// entries of column j of D in its own row and in its two columns (D is symmetric), and row j of X in its two columns:
-// ELIM_SHFL fetches them with warp shuffles from the lanes that hold them (no shared memory, no barrier in the 15
-// dependent steps); otherwise the holders publish column and row through cb (64 doubles of shared memory).
+// Block LDL^T of the 15x15 block (padded to 16 by a unit pivot) with 2x2 pivot blocks, held as the tiles
+// d00 = D[gid][2tid+e], d10 = D[8+gid][2tid+e], d11 = D[8+gid][8+2tid+e], carried out together with the Gauss-Jordan
+// inverse X of its unit block-lower factor:  D = Lb B Lb^T, B = blockdiag(P_0 .. P_7), P_k = [a b; b c].
+// Returns L^-1 = C^-1 Lb^-1 in the same tile order, where P_k = C_k C_k^T is the 2x2 Cholesky factor of every pivot
+// block -- C^-1 Lb^-1 is lower triangular with Gram matrix D^-1, i.e. the inverse of THE Cholesky factor of D.
+// Eight dependent rounds instead of fifteen: per round the lanes holding columns 2k, 2k+1 of D and rows 2k, 2k+1 of X
+// publish them through cb (2 x 64 doubles of shared memory, double buffered), every lane forms the determinant, ONE
+// reciprocal (rcp_seed) and its two multipliers per row, and applies the rank-2 update.  The fixed cost of a round
+// (shared-memory round trip, reciprocal) is what a state's elimination mostly waits for; it is paid 8 times, not 15.
 __device__ __forceinline__ bool ldl_inverse(double (&d00)[2], double (&d10)[2], double (&d11)[2], double (&li00)[2],
                                             double (&li10)[2], double (&li11)[2], double *cb, const int gid, const int tid) {
   double x00[2], x10[2], x11[2];
@@ -212,102 +210,95 @@ __device__ __forceinline__ bool ldl_inverse(double (&d00)[2], double (&d10)[2], 
   x10[0] = x10[1] = 0.0;
   x11[0] = x00[0];
   x11[1] = x00[1];
-  double p0 = 1.0, p1 = 1.0;
+  // pivot block of the lane's own rows gid (tile 0) and 8 + gid (tile 1): a, b, det
+  double sa0 = 1.0, sb0 = 0.0, sd0 = 1.0, sa1 = 1.0, sb1 = 0.0, sd1 = 1.0;
 #pragma unroll
-  for (int j = 0; j < 15; j++) {
-    const int jj = j & 7, h = jj >> 1, e = jj & 1; // holders of column j: lanes with tid == h, register e
-    double piv, ca_g = 0.0, cb_g, ca0 = 0.0, ca1 = 0.0, cb0, cb1, xr0, xr1, xs0 = 0.0, xs1 = 0.0;
-#if ELIM_SHFL
-    if (j < 8) {
-      const double va = d00[e], vb = d10[e];
-      piv = shfl_d(va, 4 * jj + h);
-      ca_g = shfl_d(va, 4 * gid + h);         // D[gid][j]
-      cb_g = shfl_d(vb, 4 * gid + h);         // D[8+gid][j]
-      ca0 = shfl_d(va, 4 * (2 * tid) + h);    // D[2tid][j]   = D[j][2tid]
-      ca1 = shfl_d(va, 4 * (2 * tid + 1) + h);
-      cb0 = shfl_d(vb, 4 * (2 * tid) + h);    // D[8+2tid][j]
-      cb1 = shfl_d(vb, 4 * (2 * tid + 1) + h);
-      xr0 = shfl_d(x00[0], 4 * jj + tid);     // X[j][2tid], X[j][2tid+1]
-      xr1 = shfl_d(x00[1], 4 * jj + tid);
+  for (int k = 0; k < 8; k++) {
+    double *col = cb + 64 * (k & 1); // [16][2]: (D[r][p], D[r][q]) of the pivot columns p = 2k, q = 2k + 1
+    double *xb = col + 32;           // [2][16]: rows p, q of X
+    const int kk = k & 3;
+    const bool hc = (tid == kk);
+    if (k < 4) {
+      const bool hp = (gid == 2 * kk), hq = (gid == 2 * kk + 1);
+      sts2_if(hc, col + 2 * gid, d00[0], d00[1]);
+      sts2_if(hc, col + 2 * (8 + gid), d10[0], d10[1]);
+      sts2_if(hp, xb + 2 * tid, x00[0], x00[1]);
+      sts2_if(hq, xb + 16 + 2 * tid, x00[0], x00[1]);
     } else {
-      const double vb = d11[e];
-      piv = shfl_d(vb, 4 * jj + h);
-      cb_g = shfl_d(vb, 4 * gid + h);         // D[8+gid][j]
-      cb0 = shfl_d(vb, 4 * (2 * tid) + h);
-      cb1 = shfl_d(vb, 4 * (2 * tid + 1) + h);
-      xr0 = shfl_d(x10[0], 4 * jj + tid);     // X[j][2tid+e]
-      xr1 = shfl_d(x10[1], 4 * jj + tid);
-      xs0 = shfl_d(x11[0], 4 * jj + tid);     // X[j][8+2tid+e]
-      xs1 = shfl_d(x11[1], 4 * jj + tid);
-    }
-#else
-    double *buf = cb + 32 * (j & 1);
-    // the holders publish column j of D (rows 0..15) and row j of X (columns 0..15)
-    if (j < 8) {
-      const bool hc = (tid == h), hr = (gid == j);
-      sts_if(hc, buf + gid, d00[e]);
-      sts_if(hc, buf + 8 + gid, d10[e]);
-      sts2_if(hr, buf + 16 + 2 * tid, x00[0], x00[1]);
-    } else {
-      const bool hc = (tid == h), hr = (gid == jj);
-      sts_if(hc, buf + 8 + gid, d11[e]);
-      sts2_if(hr, buf + 16 + 2 * tid, x10[0], x10[1]);
-      sts2_if(hr, buf + 24 + 2 * tid, x11[0], x11[1]);
+      const bool hp = (gid == 2 * kk), hq = (gid == 2 * kk + 1);
+      sts2_if(hc, col + 2 * (8 + gid), d11[0], d11[1]);
+      sts2_if(hp, xb + 2 * tid, x10[0], x10[1]);
+      sts2_if(hp, xb + 8 + 2 * tid, x11[0], x11[1]);
+      sts2_if(hq, xb + 16 + 2 * tid, x10[0], x10[1]);
+      sts2_if(hq, xb + 24 + 2 * tid, x11[0], x11[1]);
     }
     __syncwarp();
-    piv = buf[j];
-    cb_g = buf[8 + gid];
-    cb0 = buf[8 + 2 * tid];
-    cb1 = buf[9 + 2 * tid];
-    xr0 = buf[16 + 2 * tid];
-    xr1 = buf[17 + 2 * tid];
-    if (j < 8) {
-      ca_g = buf[gid];
-      ca0 = buf[2 * tid];
-      ca1 = buf[2 * tid + 1];
-    } else {
-      xs0 = buf[24 + 2 * tid];
-      xs1 = buf[25 + 2 * tid];
-    }
-#endif
+    const int p = 2 * k;
+    const double2 cp = lds2(col + 2 * p), cq = lds2(col + 2 * p + 2); // (a, b), (b, c)
+    const double a = cp.x, b = cq.x, c = cq.y;
+    const double det = fma(a, c, -(b * b));
     double r0, pc;
-    rcp_seed(piv, r0, pc);
-    if (j < 8) {
-      p0 = (gid == j) ? piv : p0;
-      const double a0 = (gid > j) ? ca_g * r0 : 0.0, a1 = cb_g * r0;
-      const double mr0 = fma(a0, pc, a0), mr1 = fma(a1, pc, a1);
-      d00[0] = fma(-mr0, ca0, d00[0]);
-      d00[1] = fma(-mr0, ca1, d00[1]);
-      d10[0] = fma(-mr1, ca0, d10[0]);
-      d10[1] = fma(-mr1, ca1, d10[1]);
-      d11[0] = fma(-mr1, cb0, d11[0]);
-      d11[1] = fma(-mr1, cb1, d11[1]);
-      x00[0] = fma(-mr0, xr0, x00[0]);
-      x00[1] = fma(-mr0, xr1, x00[1]);
-      x10[0] = fma(-mr1, xr0, x10[0]);
-      x10[1] = fma(-mr1, xr1, x10[1]);
+    rcp_seed(det, r0, pc);
+    const double2 r1 = lds2(col + 2 * (8 + gid)); // (D[8+gid][p], D[8+gid][q])
+    // multipliers of a row (u, v) = (D[g][p], D[g][q]):  (m_p, m_q) = (u, v) P^-1 = (u c - v b, v a - u b) / det
+    const bool act1 = (k < 4) || (gid > 2 * kk + 1);
+    const double t1p = fma(r1.x, c, -(r1.y * b)) * r0, t1q = fma(r1.y, a, -(r1.x * b)) * r0;
+    const double m1p = act1 ? fma(t1p, pc, t1p) : 0.0, m1q = act1 ? fma(t1q, pc, t1q) : 0.0;
+    const double2 b0 = lds2(col + 2 * (8 + 2 * tid)), b1 = lds2(col + 2 * (9 + 2 * tid)); // columns 8+2tid+e: (D[.][p], D[.][q])
+    d11[0] = fma(-m1p, b0.x, fma(-m1q, b0.y, d11[0]));
+    d11[1] = fma(-m1p, b1.x, fma(-m1q, b1.y, d11[1]));
+    const double2 xp0 = lds2(xb + 2 * tid), xq0 = lds2(xb + 16 + 2 * tid); // X[p][2tid+e], X[q][2tid+e]
+    x10[0] = fma(-m1p, xp0.x, fma(-m1q, xq0.x, x10[0]));
+    x10[1] = fma(-m1p, xp0.y, fma(-m1q, xq0.y, x10[1]));
+    if (k < 4) {
+      const double2 r0w = lds2(col + 2 * gid); // (D[gid][p], D[gid][q])
+      const bool act0 = gid > 2 * kk + 1;
+      const double t0p = fma(r0w.x, c, -(r0w.y * b)) * r0, t0q = fma(r0w.y, a, -(r0w.x * b)) * r0;
+      const double m0p = act0 ? fma(t0p, pc, t0p) : 0.0, m0q = act0 ? fma(t0q, pc, t0q) : 0.0;
+      const double2 a0 = lds2(col + 2 * (2 * tid)), a1 = lds2(col + 2 * (2 * tid + 1)); // columns 2tid+e
+      d00[0] = fma(-m0p, a0.x, fma(-m0q, a0.y, d00[0]));
+      d00[1] = fma(-m0p, a1.x, fma(-m0q, a1.y, d00[1]));
+      d10[0] = fma(-m1p, a0.x, fma(-m1q, a0.y, d10[0]));
+      d10[1] = fma(-m1p, a1.x, fma(-m1q, a1.y, d10[1]));
+      x00[0] = fma(-m0p, xp0.x, fma(-m0q, xq0.x, x00[0]));
+      x00[1] = fma(-m0p, xp0.y, fma(-m0q, xq0.y, x00[1]));
+      const bool mine = (gid >> 1) == kk;
+      sa0 = mine ? a : sa0;
+      sb0 = mine ? b : sb0;
+      sd0 = mine ? det : sd0;
     } else {
-      p1 = (8 + gid == j) ? piv : p1;
-      const double a1 = (8 + gid > j) ? cb_g * r0 : 0.0;
-      const double mr1 = fma(a1, pc, a1);
-      d11[0] = fma(-mr1, cb0, d11[0]);
-      d11[1] = fma(-mr1, cb1, d11[1]);
-      x10[0] = fma(-mr1, xr0, x10[0]);
-      x10[1] = fma(-mr1, xr1, x10[1]);
-      x11[0] = fma(-mr1, xs0, x11[0]);
-      x11[1] = fma(-mr1, xs1, x11[1]);
+      const double2 xp1 = lds2(xb + 8 + 2 * tid), xq1 = lds2(xb + 24 + 2 * tid); // X[p][8+2tid+e], X[q][8+2tid+e]
+      x11[0] = fma(-m1p, xp1.x, fma(-m1q, xq1.x, x11[0]));
+      x11[1] = fma(-m1p, xp1.y, fma(-m1q, xq1.y, x11[1]));
+      const bool mine = (gid >> 1) == kk;
+      sa1 = mine ? a : sa1;
+      sb1 = mine ? b : sb1;
+      sd1 = mine ? det : sd1;
     }
   }
-  // every pivot is held by exactly one (gid, *) group: positive-definiteness check in one vote
-  const bool ok = __all_sync(0xffffffffu, (p0 > 0.0) && (p1 > 0.0));
-  const double s0 = fast_rsqrt(p0);
-  const double s1 = (gid < 7) ? fast_rsqrt(p1) : 0.0; // row 15 is padding
-  li00[0] = s0 * x00[0];
-  li00[1] = s0 * x00[1];
-  li10[0] = s1 * x10[0];
-  li10[1] = s1 * x10[1];
-  li11[0] = s1 * x11[0];
-  li11[1] = s1 * x11[1];
+  // positive definite <=> every leading pivot a > 0 and every block determinant > 0
+  const bool ok = __all_sync(0xffffffffu, (sa0 > 0.0) && (sd0 > 0.0) && (sa1 > 0.0) && (sd1 > 0.0));
+  // C_k^-1 = [1/sqrt(a) 0; -(b/a)/sqrt(s) 1/sqrt(s)], s = det / a: the even row of a block is scaled, the odd row first
+  // takes -(b/a) times the even row (held by the lanes of gid - 1)
+  const bool odd = gid & 1;
+  const int src = ((gid & ~1) << 2) | tid; // lane holding the even row of the block, same columns
+  double ra0, pa0, ra1, pa1;
+  rcp_seed(sa0, ra0, pa0);
+  rcp_seed(sa1, ra1, pa1);
+  ra0 = fma(ra0, pa0, ra0);
+  ra1 = fma(ra1, pa1, ra1);
+  const double f0 = sb0 * ra0, f1 = sb1 * ra1;
+  const double s0 = fast_rsqrt(odd ? sd0 * ra0 : sa0);
+  const double s1 = (gid < 7) ? fast_rsqrt(odd ? sd1 * ra1 : sa1) : 0.0; // row 15 is padding
+  const double e00 = shfl_d(x00[0], src), e01 = shfl_d(x00[1], src);
+  const double e10 = shfl_d(x10[0], src), e11 = shfl_d(x10[1], src);
+  const double e20 = shfl_d(x11[0], src), e21 = shfl_d(x11[1], src);
+  li00[0] = s0 * (odd ? fma(-f0, e00, x00[0]) : x00[0]);
+  li00[1] = s0 * (odd ? fma(-f0, e01, x00[1]) : x00[1]);
+  li10[0] = s1 * (odd ? fma(-f1, e10, x10[0]) : x10[0]);
+  li10[1] = s1 * (odd ? fma(-f1, e11, x10[1]) : x10[1]);
+  li11[0] = s1 * (odd ? fma(-f1, e20, x11[0]) : x11[0]);
+  li11[1] = s1 * (odd ? fma(-f1, e21, x11[1]) : x11[1]);
   return ok;
 }
 
@@ -459,17 +450,9 @@ __device__ __forceinline__ bool elim_node(const double *st, const double *__rest
 
 // Eliminate `count` consecutive states whose records start at ne0 (stride NE_STRIDE); factor records to fac0.
 // w: the warp's shared memory; the state's record is fetched one state ahead.
-// sync_threads > 0 (ELIM_LOCKSTEP): the warps of the CTA start every state together, for `sync_iters` states (a warp with
-// fewer states keeps arriving at the barrier).  Why: the factorisation is a chain of ~60 DEPENDENT FP64 operations per
-// state, the mma phase a stream of 90 DMMAs, and both use the one FP64 pipe of the SM sub-partition, whose arbitration
-// makes a dependent DFMA wait behind the DMMAs of every other warp (measured, tools/fp64_micro2.cu: 8.9 cycles per
-// dependent DFMA alone, 41 / 73 / 105 with one / two / three warps streaming DMMAs beside it).  Warps that run out of
-// phase spend two thirds of their time in the factorisation; warps in phase factorise on an idle pipe and then share
-// it at its full DMMA rate.
 template <bool HAS_F>
 __device__ __forceinline__ bool elim_chain(const double *__restrict__ ne0, const int count, const double *__restrict__ left_sep_ne,
-                                           const double lambda, double *__restrict__ fac0, ElimAcc &A, double *w, const int lane,
-                                           const int sync_threads = 0, const int sync_iters = 0) {
+                                           const double lambda, double *__restrict__ fac0, ElimAcc &A, double *w, const int lane) {
   double *stage = w + SW_STAGE;
   double *cb = w + SW_CB;
   bool ok = true;
@@ -484,18 +467,13 @@ __device__ __forceinline__ bool elim_chain(const double *__restrict__ ne0, const
   __syncwarp();
   if (count > 0 && lane == 0)
     bulk_load(stage, ne0, REC_BYTES, bar);
-  const int iters = sync_threads > 0 ? max(count, sync_iters) : count;
-  for (int k = 0; k < iters; k++) {
+  for (int k = 0; k < count; k++) {
     // the buffer of state k + 1 was read by state k - 1, whose lanes have all passed the __syncwarp of elim_node
     if (k + 1 < count && lane == 0)
       bulk_load(stage + NE_STRIDE * ((k + 1) & 1), ne0 + (long long)(k + 1) * NE_STRIDE, REC_BYTES, bar + ((k + 1) & 1));
-    if (k < count)
-      mbar_wait(bar + (k & 1), (unsigned)(k >> 1) & 1u);
-    if (sync_threads > 0)
-      asm volatile("bar.sync 1, %0;" ::"r"(sync_threads) : "memory");
-    if (k < count)
-      ok = elim_node<HAS_F>(stage + NE_STRIDE * (k & 1), (HAS_F && k == 0) ? left_sep_ne : nullptr, lambda, A, cb,
-                            fac0 + (long long)k * FAC_STRIDE, lane) && ok;
+    mbar_wait(bar + (k & 1), (unsigned)(k >> 1) & 1u);
+    ok = elim_node<HAS_F>(stage + NE_STRIDE * (k & 1), (HAS_F && k == 0) ? left_sep_ne : nullptr, lambda, A, cb,
+                          fac0 + (long long)k * FAC_STRIDE, lane) && ok;
   }
 #else
   if (count > 0)
@@ -527,32 +505,22 @@ __global__ void __launch_bounds__(ELIM_WARPS * 32, ELIM_MIN_CTAS) k_seg_eliminat
   const int j = blockIdx.x * ELIM_WARPS + wid + (d.chain ? d.c_j0 : 0);
   const int n = d.chain ? d.c_n : d.n_states[t];
   const SegGeom sg = seg_geom(n, d.P);
-  const bool live = j < (d.chain ? min(sg.nseg, d.c_j1) : sg.nseg);
-#if !ELIM_LOCKSTEP
-  if (!live)
+  if (j >= (d.chain ? min(sg.nseg, d.c_j1) : sg.nseg))
     return;
-  const int sync_threads = 0, sync_iters = 0;
-#else
-  // every warp of the CTA takes part in the per-state barrier; a full segment has stride - 1 interior states
-  const int sync_threads = ELIM_WARPS * 32, sync_iters = sg.stride - 1;
-#endif
   double *w = smem + (size_t)wid * SW_TOTAL;
   const TrialDev &tr = d.trials[t];
   const double lambda = lm.lambda;
   const int a0 = j * sg.stride;
-  const int b1 = live ? min(n, (j + 1) * sg.stride - 1) : a0; // exclusive end of the interior
+  const int b1 = min(n, (j + 1) * sg.stride - 1); // exclusive end of the interior
   const bool has_left = (j >= 1);
   const long long s0 = tr.st_off + a0 - (d.chain ? d.c_goff : 0);
   ElimAcc A;
   acc_zero(A, w + SW_ACC, lane);
   bool ok;
   if (has_left)
-    ok = elim_chain<true>(d.ne + s0 * NE_STRIDE, b1 - a0, d.ne + (s0 - 1) * NE_STRIDE, lambda, d.fac + s0 * FAC_STRIDE, A, w, lane,
-                          sync_threads, sync_iters);
+    ok = elim_chain<true>(d.ne + s0 * NE_STRIDE, b1 - a0, d.ne + (s0 - 1) * NE_STRIDE, lambda, d.fac + s0 * FAC_STRIDE, A, w, lane);
   else
-    ok = elim_chain<false>(d.ne + s0 * NE_STRIDE, b1 - a0, nullptr, lambda, d.fac + s0 * FAC_STRIDE, A, w, lane, sync_threads, sync_iters);
-  if (!live)
-    return;
+    ok = elim_chain<false>(d.ne + s0 * NE_STRIDE, b1 - a0, nullptr, lambda, d.fac + s0 * FAC_STRIDE, A, w, lane);
   // ---- segment outputs
   const int gid = lane >> 2, tid = lane & 3;
   double *so = d.seg + ((long long)t * d.P + j) * SEG_STRIDE;
