@@ -69,6 +69,9 @@ def parse():
                          "sequence chain-sharded over the GPUs with NCCL (configs[4]; second half of the metric: LM latency)")
     ap.add_argument("--segs-per-rank", type=int, default=0, help="chain workload: segments per GPU (0 = ~sqrt(states per GPU))")
     ap.add_argument("--chain-duration", type=float, default=0.0, help="chain workload: truncate the hour to this many seconds")
+    ap.add_argument("--waves-trials", type=int, default=1024,
+                    help="N = 1 only: solve this many trials (the whole configs[3] batch) on the one GPU in waves of --trials, staging "
+                         "of wave k+1 and read-back of wave k-1 overlapped with wave k's solve (0 = skip)")
     ap.add_argument("--no-chain", action="store_true", help="skip the chain-sharded leg (configs[4]) of the default line")
     ap.add_argument("--chain-graph-only", action="store_true", help="chain leg: skip the plain-launch pass (per-phase times)")
     ap.add_argument("--chain-steps", type=int, default=3)
@@ -578,6 +581,34 @@ def main():
             chain = {"error": repr(e)}
         barrier()
 
+    # ---------------- the WHOLE 1024-trial batch on one GPU, in waves (strong-scaling row: 1 GPU here, 8 GPUs = the N = 8 line)
+    waves = None
+    if world == 1 and args.waves_trials > T and args.duration <= 0:
+        try:
+            if bs is not None:
+                bs.close()
+                bs = None
+            extra = make_trials(args.waves_trials - T, seed0=T, duration=args.duration)
+            every = trials + extra
+            with api.WaveRunner(wave=T, device=device, **opts) as runner:
+                for _ in runner.run(p, every[:2 * T], read_back=False):  # allocations of the two handles (untimed)
+                    pass
+                n_ok = n_rows = 0
+                for first, off, t_, x_, g_, infs in runner.run(p, every):
+                    n_ok += sum(1 for inf in infs if inf.status == 0)
+                    n_rows += int(off[-1])
+                waves = {"trials": len(every), "trials_per_wave": T, "waves": (len(every) + T - 1) // T, "trials_ok": n_ok,
+                         "states_read_back": n_rows, "device_s": runner.device_ms * 1e-3, "wall_s": runner.wall_s,
+                         "value": len(every) / (runner.device_ms * 1e-3), "e2e": len(every) / runner.wall_s, "unit": UNIT,
+                         "e2e_over_value": (len(every) / runner.wall_s) / (len(every) / (runner.device_ms * 1e-3)),
+                         "upload_stall_s": runner.stall_s,
+                         "h2d_bytes": int(sum(ds.nbytes() for ds in every)),
+                         "note": "two resident batch handles; host threads stage + upload wave k+1 and read back wave k-1 while "
+                                 "wave k is solved (api.WaveRunner / WaveRunner of include/vicon2gt_b200.hpp)"}
+            del every, extra
+        except Exception as e:  # a widened row must never cost the headline line
+            waves = {"error": repr(e)}
+
     cpu = None
     if not args.no_cpu_baseline and rank == 0:
         cs_s = args.cpu_sample_s if args.duration <= 0 else min(args.cpu_sample_s, args.duration)
@@ -642,6 +673,7 @@ def main():
             "lm_iteration_latency": latency,
             "simulator": simulator,
             "chain": chain,
+            "waves_1024_on_one_gpu": waves,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))

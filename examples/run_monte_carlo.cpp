@@ -3,7 +3,9 @@
 // (SimBatch), handed to the solver device to device (BatchSolver::set_trial_sim), solved in ONE batch, and reported with
 // the per-run error statistics of run_simulation.cpp:198-297 computed on the device.
 //
-//   run_monte_carlo [--seeds N] [--duration S] [--ori_noise rad] [--pos_noise m] [--device N] [--out-dir DIR]
+//   run_monte_carlo [--seeds N] [--duration S] [--ori_noise rad] [--pos_noise m] [--device N] [--out-dir DIR] [--wave W]
+// --wave W: the runs are fed from HOST stores instead and solved W at a time by WaveRunner (a sweep larger than the GPU's
+// memory: staging of the next wave and read-back of the previous one overlap the solve).
 // Prints one line per run: seed, states, LM iterations, final cost, mean ATE (deg / m), time-offset error (ms).
 #include "v2gt_sim.h"
 #include "vicon2gt_b200.hpp"
@@ -16,7 +18,7 @@
 using namespace vicon2gt_b200;
 
 int main(int argc, char **argv) {
-  int seeds = 8, device = 0;
+  int seeds = 8, device = 0, wave = 0;
   double duration = 30.0, so = 0.0174, sp = 0.05;
   std::string out_dir;
   for (int i = 1; i < argc; i++) {
@@ -28,6 +30,7 @@ int main(int argc, char **argv) {
     else if (a == "--pos_noise") sp = std::atof(next());
     else if (a == "--device") device = std::atoi(next());
     else if (a == "--out-dir") out_dir = next();
+    else if (a == "--wave") wave = std::atoi(next());
   }
   if (seeds < 1)
     return EXIT_FAILURE;
@@ -54,6 +57,46 @@ int main(int argc, char **argv) {
     }
     sim.run();
     const auto t1 = std::chrono::steady_clock::now();
+    if (wave > 0) {
+      // ---- host stores per run (feed_imu / feed_pose loop of run_simulation.cpp:118-145), solved in waves
+      std::vector<Propagator> imus;
+      std::vector<Interpolator> vics((size_t)seeds);
+      std::vector<std::vector<double>> grids((size_t)seeds);
+      Mat3 R_q{}, R_p{};
+      for (int d = 0; d < 3; d++) {
+        R_q[4 * d] = so * so;
+        R_p[4 * d] = sp * sp;
+      }
+      v2gt_sim_params dp;
+      v2gt_sim_params_default(&dp);
+      for (int k = 0; k < seeds; k++) {
+        std::vector<double> it, iw, ia, vt, vq, vp;
+        sim.get(k, it, iw, ia, vt, vq, vp, grids[(size_t)k]);
+        imus.emplace_back(dp.sigma_w, dp.sigma_wb, dp.sigma_a, dp.sigma_ab);
+        for (size_t i = 0; i < it.size(); i++)
+          imus.back().feed_imu(it[i], {iw[3 * i], iw[3 * i + 1], iw[3 * i + 2]}, {ia[3 * i], ia[3 * i + 1], ia[3 * i + 2]});
+        for (size_t i = 0; i < vt.size(); i++)
+          vics[(size_t)k].feed_pose(vt[i], {vq[4 * i], vq[4 * i + 1], vq[4 * i + 2], vq[4 * i + 3]}, {vp[3 * i], vp[3 * i + 1], vp[3 * i + 2]},
+                                    R_q, R_p);
+      }
+      ViconGraphSolverParams params;
+      std::vector<WaveRunner::Trial> trials;
+      for (int k = 0; k < seeds; k++)
+        trials.push_back({&params, &imus[(size_t)k], &vics[(size_t)k], &grids[(size_t)k]});
+      std::vector<v2gt_trial_info> infos((size_t)seeds);
+      WaveRunner runner(wave, device);
+      const auto w0 = std::chrono::steady_clock::now();
+      runner.run(trials, [&](int first, BatchSolver &h) {
+        for (int i = 0; i < h.size(); i++)
+          infos[(size_t)(first + i)] = h.info(i);
+      });
+      const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count();
+      std::printf("[MC]: %d runs in waves of %d, %.3f s wall, %.3f s on the device\n", seeds, wave, secs, runner.device_ms() * 1e-3);
+      for (int k = 0; k < seeds; k++)
+        std::printf("run %3d: status %d, %d states, %d iterations, cost %.6e\n", k, infos[(size_t)k].status, infos[(size_t)k].n_states,
+                    infos[(size_t)k].iterations, infos[(size_t)k].final_error);
+      return EXIT_SUCCESS;
+    }
     // ---- solve them as one batch
     std::array<double, 18> R{}; // run_simulation.cpp:84-96
     for (int d = 0; d < 3; d++) {

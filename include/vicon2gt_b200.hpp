@@ -16,19 +16,24 @@
  *     508-524).  Here they throw vicon2gt_b200::SolverError carrying the V2GT_ERR_* code; construct the
  *     solver with exit_on_failure = true to get the reference's behaviour.
  * Everything numeric runs in libvicon2gt_b200.so (CUDA, sm_100a); there is no CPU path.
- * BatchSolver is the batch form (independent Monte-Carlo trials on one GPU, scripts/run_monte_carlo.sh shape).
+ * BatchSolver is the batch form (independent Monte-Carlo trials on one GPU, scripts/run_monte_carlo.sh shape);
+ * ChainSolver shards ONE long sequence over the GPUs of a node (NCCL inside the library).
  */
 #ifndef VICON2GT_B200_HPP
 #define VICON2GT_B200_HPP
 
 #include "vicon2gt_b200.h"
 
+#include <algorithm>
 #include <array>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
+#include <exception>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace vicon2gt_b200 {
@@ -257,6 +262,78 @@ private:
   v2gt_batch *h_ = nullptr;
 };
 
+/* A Monte-Carlo batch larger than one GPU's memory, solved in waves of `wave` trials (scripts/run_monte_carlo.sh runs its
+ * trials one roslaunch after the other).  Two resident batch handles: while wave k is being solved, one host thread stages
+ * and uploads wave k+1 into the other handle (pinned fill + H2D copies on that handle's stream run under wave k's kernels)
+ * and another hands wave k-1 to `on_wave(first_trial, solver)` (read the results there), so the GPU never waits for the
+ * host.  The stores and timestamp vectors of `trials` are borrowed until run() returns. */
+class WaveRunner {
+public:
+  struct Trial {
+    const v2gt_params *params;
+    const Propagator *imu;
+    const Interpolator *vicon;
+    const std::vector<double> *timestamp_cameras;
+  };
+  explicit WaveRunner(int wave, int device = 0) : wave_(wave), device_(device) {}
+  double device_ms() const { return device_ms_; } /* CUDA-event time of build + optimise, summed over the waves */
+
+  template <class F> void run(const std::vector<Trial> &trials, F on_wave) {
+    const int n = (int)trials.size(), n_waves = (n + wave_ - 1) / wave_;
+    device_ms_ = 0;
+    std::exception_ptr err;
+    auto stage = [&](int w) {
+      try {
+        const int a = w * wave_, cnt = std::min(wave_, n - a);
+        std::unique_ptr<BatchSolver> &h = h_[w % 2];
+        if (!h || h->size() != cnt)
+          h.reset(new BatchSolver(cnt, device_));
+        for (int i = 0; i < cnt; i++)
+          h->set_trial_view(i, *trials[a + i].params, *trials[a + i].imu, *trials[a + i].vicon, *trials[a + i].timestamp_cameras);
+        check(v2gt_batch_upload(h->handle()), "v2gt_batch_upload");
+      } catch (...) {
+        err = std::current_exception();
+      }
+    };
+    std::thread up(stage, 0), rb;
+    for (int w = 0; w < n_waves; w++) {
+      up.join();
+      if (err)
+        break;
+      if (w + 1 < n_waves) {
+        if (rb.joinable()) /* wave w-1 lives in the handle wave w+1 is about to overwrite */
+          rb.join();
+        up = std::thread(stage, w + 1);
+      }
+      BatchSolver &h = *h_[w % 2];
+      h.build_and_solve();
+      double ms[8];
+      check(v2gt_batch_get_timing(h.handle(), ms, nullptr), "v2gt_batch_get_timing");
+      device_ms_ += ms[0] + ms[7];
+      if (rb.joinable())
+        rb.join();
+      rb = std::thread([&, w]() {
+        try {
+          on_wave(w * wave_, *h_[w % 2]);
+        } catch (...) {
+          err = std::current_exception();
+        }
+      });
+    }
+    if (up.joinable())
+      up.join();
+    if (rb.joinable())
+      rb.join();
+    if (err)
+      std::rethrow_exception(err);
+  }
+
+private:
+  int wave_, device_;
+  double device_ms_ = 0;
+  std::unique_ptr<BatchSolver> h_[2];
+};
+
 /* Single-trajectory solver with the reference's method names (src/solver/ViconGraphSolver.h:71-110). */
 class ViconGraphSolver {
 public:
@@ -335,6 +412,108 @@ private:
   bool exit_on_failure_;
   std::unique_ptr<BatchSolver> batch_;
   v2gt_trial_info info_{};
+};
+
+/* One long sequence sharded over the GPUs of a node as contiguous chain segments (BASELINE config 5): the C++ face of the
+ * chain mode of the C ABI.  One process (or host thread) per GPU constructs a ChainSolver with its rank; the constructor
+ * does what ViconGraphSolver::build_and_solve does up to the optimiser for THIS rank's piece of the chain (timestamp
+ * cleaning of the whole sequence, src/solver/ViconGraphSolver.cpp:114-142; the rank's slice of the measurements; state
+ * initialisation and preintegration on its GPU).  Rank 0 then obtains an NCCL id (unique_id()), hands it to the other
+ * ranks by any means, every rank calls comm_init(id) and optimize(): the Levenberg-Marquardt loop runs inside the
+ * library, two ncclAllGather calls per damped solve on the solver's stream, one damped solve replayed as a CUDA graph.
+ * All ranks end with the same calibration; states() returns the rank's own states.  world == 1 needs no NCCL. */
+class ChainSolver {
+public:
+  using NcclId = std::array<uint8_t, V2GT_NCCL_ID_BYTES>;
+
+  ChainSolver(const ViconGraphSolverParams &params, const Propagator &imu, const Interpolator &vicon,
+              const std::vector<double> &timestamp_cameras, int rank, int world, int segs_per_rank = 16, int device = 0)
+      : batch_(1, device) {
+    v2gt_params p = params;
+    p.sigma_w = imu.sigma_w();
+    p.sigma_wb = imu.sigma_wb();
+    p.sigma_a = imu.sigma_a();
+    p.sigma_ab = imu.sigma_ab();
+    const std::vector<double> &it = imu.times(), &vt = vicon.times();
+    if (it.empty() || vt.size() < 2)
+      throw SolverError(V2GT_ERR_NO_VICON, "ChainSolver");
+    // ---- timestamp cleaning of the whole sequence (time-ordered stores)
+    const double first = vicon.get_time_min() + p.toff_imu_to_vicon + 2 * p.time_offset_window;
+    const double last = vicon.get_time_max() + p.toff_imu_to_vicon - 2 * p.time_offset_window;
+    std::vector<double> ts;
+    for (double t : timestamp_cameras)
+      if (t >= it.front() && t <= it.back() && t >= first && t <= last)
+        ts.push_back(t);
+    int32_t spr = 0;
+    check(v2gt_chain_fit_segments((int64_t)ts.size(), world, segs_per_rank, &spr), "v2gt_chain_fit_segments");
+    check(v2gt_chain_plan((int64_t)ts.size(), world, spr, rank, &plan_), "v2gt_chain_plan");
+    // ---- this rank's states (own + one halo state on each inner side) and the measurements around them
+    const std::vector<double> local(ts.begin() + plan_.g_off, ts.begin() + plan_.g_off + plan_.n_local);
+    const double margin = std::abs(p.toff_imu_to_vicon) + 2 * p.time_offset_window + p.interp_gap_init + 1.0;
+    const size_t v0 = lower_index(vt, local.front() - margin, 1), v1 = upper_index(vt, local.back() + margin, 1);
+    const size_t i0 = lower_index(it, local.front() - 0.05, 2), i1 = upper_index(it, local.back() + 0.05, 2);
+    check(v2gt_batch_set_trial(batch_.handle(), 0, &p, (int64_t)(i1 - i0), it.data() + i0, imu.gyro().data() + 3 * i0,
+                               imu.accel().data() + 3 * i0, (int64_t)(v1 - v0), vt.data() + v0, vicon.quats().data() + 4 * v0,
+                               vicon.positions().data() + 3 * v0, vicon.cov_q().data() + 9 * v0, vicon.cov_p().data() + 9 * v0, nullptr,
+                               (int64_t)local.size(), local.data()),
+          "v2gt_batch_set_trial");
+    check(v2gt_chain_configure(batch_.handle(), rank, world, plan_.n_total, plan_.g_off, plan_.p_total, plan_.j0, plan_.j1, plan_.own_lo,
+                               plan_.own_hi),
+          "v2gt_chain_configure");
+    check(v2gt_batch_upload(batch_.handle()), "v2gt_batch_upload");
+    build();
+  }
+  /* state initialisation + preintegration from the uploaded inputs (a fresh solve) */
+  void build() {
+    check(v2gt_batch_build(batch_.handle(), 1), "v2gt_batch_build");
+    const v2gt_trial_info inf = batch_.info(0);
+    if (inf.status != V2GT_OK || inf.n_states != plan_.n_local)
+      throw SolverError(inf.status ? inf.status : V2GT_ERR_INVALID_ARG, "chain build: local states lost in the rank's slice");
+  }
+  static NcclId unique_id() {
+    NcclId id;
+    check(v2gt_chain_nccl_unique_id(id.data()), "v2gt_chain_nccl_unique_id");
+    return id;
+  }
+  void comm_init(const NcclId &id) { check(v2gt_chain_comm_init(batch_.handle(), id.data()), "v2gt_chain_comm_init"); }
+  /* Levenberg-Marquardt over the whole chain (collective when world > 1); returns the replicated optimiser summary */
+  v2gt_trial_info optimize(int max_tries = 0, bool use_graph = true) {
+    check(v2gt_chain_optimize(batch_.handle(), max_tries, use_graph ? 1 : 0), "v2gt_chain_optimize");
+    return batch_.info(0);
+  }
+  const v2gt_chain_plan_t &plan() const { return plan_; }
+  /* the rank's OWN states: global index of the first one, times[n], states[n][16] */
+  int64_t states(std::vector<double> &times, std::vector<double> &states16) {
+    std::vector<double> t, x;
+    batch_.get_states(0, t, x);
+    times.assign(t.begin() + plan_.own_lo, t.begin() + plan_.own_hi);
+    states16.assign(x.begin() + 16 * (size_t)plan_.own_lo, x.begin() + 16 * (size_t)plan_.own_hi);
+    return plan_.g_off + plan_.own_lo;
+  }
+  void get_calibration(Vec4 &q_BtoI, Vec3 &p_BinI, double &toff, std::array<double, 2> &theta_xy) {
+    batch_.get_calibration(0, q_BtoI, p_BinI, toff, theta_xy);
+  }
+  /* [build, linearize, eliminate + pack, exchange A + reduced, backsub, cost, exchange B + decide, optimise total] ms */
+  std::array<double, 8> timing_ms() {
+    std::array<double, 8> ms{};
+    check(v2gt_batch_get_timing(batch_.handle(), ms.data(), nullptr), "v2gt_batch_get_timing");
+    return ms;
+  }
+  BatchSolver &batch() { return batch_; }
+
+private:
+  // first index whose time is >= t, moved `back` samples towards the start / one past the last index whose time is <= t,
+  // moved `fwd` samples towards the end (sorted times)
+  static size_t lower_index(const std::vector<double> &v, double t, size_t back) {
+    const size_t i = (size_t)(std::lower_bound(v.begin(), v.end(), t) - v.begin());
+    return i > back ? i - back : 0;
+  }
+  static size_t upper_index(const std::vector<double> &v, double t, size_t fwd) {
+    const size_t i = (size_t)(std::upper_bound(v.begin(), v.end(), t) - v.begin());
+    return std::min(v.size(), i + fwd);
+  }
+  BatchSolver batch_;
+  v2gt_chain_plan_t plan_{};
 };
 
 } // namespace vicon2gt_b200

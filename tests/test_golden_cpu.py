@@ -8,7 +8,7 @@ import pytest
 from conftest import default_params, load_golden
 
 
-@pytest.mark.parametrize("name", ["c2_8s", "c1_6s"])
+@pytest.mark.parametrize("name", ["c2_8s", "c1_12s"])
 def test_oracle_reproduces_golden(name):
     from oracle import binding as ob
     from vicon2gt_b200._cdefs import TrialInfo

@@ -316,7 +316,7 @@ def test_write_to_file_matches_oracle(ds_c2_small, tmp_path):
     assert len(io) == len(ig)
 
 
-@pytest.mark.parametrize("name", ["c2_8s", "c1_6s"])
+@pytest.mark.parametrize("name", ["c2_8s", "c1_12s"])
 def test_cuda_path_matches_golden_fixture(name):
     """CUDA path against the committed golden vectors (inputs + oracle outputs, tools/make_golden.py): bracket
     indices bit-exact, states / calibration within 1e-6, chi2 within 1e-8 relative -- no oracle call in this test."""
@@ -356,24 +356,18 @@ def test_cuda_path_matches_golden_fixture(name):
     rg = lin["Gamma"].reshape(9, 9) @ xg + 1e-5 * xg + np.einsum("nij,ni->j", B, x) - lin["g_gamma"]
     gn = np.sqrt(np.sum(lin["g"] ** 2) + np.sum(lin["g_gamma"] ** 2))
     assert np.sqrt(np.sum(r ** 2) + np.sum(rg ** 2)) / gn < 1e-12
-    # ... and agrees with the oracle's step as far as the conditioning allows: c2_8s has cond(H) ~ 2e9; c1_6s
-    # (3 s of data from the far initial guess) has cond(H) ~ 2e15, where two backward-stable solvers (the oracle,
-    # SuperLU, this one) differ by ~1e-4 in the step itself
+    # ... and agrees with the oracle's step as far as the conditioning of this ONE system allows (an intermediate check, not
+    # one of north_star's tolerances: those are the converged states / chi2 below).  c2_8s: cond(H) ~ 2e9; c1_12s is
+    # linearised at the far initial guess of the sim.launch shape, where two backward-stable solvers differ by ~1e-5
     sc = np.max(np.abs(g["solve_delta"][: 15 * n].reshape(n, 15)), axis=0)
-    assert np.max(np.abs(delta[: 15 * n] - g["solve_delta"][: 15 * n]).reshape(n, 15) / sc) < (1e-7 if name == "c2_8s" else 5e-3)
+    assert np.max(np.abs(delta[: 15 * n] - g["solve_delta"][: 15 * n]).reshape(n, 15) / sc) < (1e-7 if name == "c2_8s" else 5e-5)
     bs.build_and_solve()
     inf = bs.info(0)
     assert inf.status == 0
     _, x1 = bs.states(0)
     dq = np.abs(np.sum(x1[:, :4] * g["final_states"][:, :4], axis=1))
     assert (2 * np.arccos(np.clip(dq, 0, 1))).max() < 1e-6
-    # c1_6s: six seconds of data leave the accelerometer bias weakly observable (cond(H) ~ 2e15); its converged value
-    # moves by 0.5e-6 .. 2.5e-6 with the segment count of the elimination alone -- segments = 1, the oracle's own
-    # elimination order, included -- while chi2 stays within 4e-9 (profiles/r01d_fixture_roundoff_sensitivity.txt,
-    # tools/diag_fixture_sensitivity.py).  Everything else, and every state of the well-conditioned fixture, is held to 1e-6.
-    dx = np.abs(x1[:, 4:] - g["final_states"][:, 4:])
-    assert np.max(np.delete(dx, [6, 7, 8], axis=1)) < 1e-6
-    assert np.max(dx[:, 6:9]) < (1e-6 if name == "c2_8s" else 5e-6)
+    assert np.max(np.abs(x1[:, 4:] - g["final_states"][:, 4:])) < 1e-6
     gl = bs.globals10(0)
     assert np.max(np.abs(gl[4:] - g["final_globals"][4:])) < 1e-6
     assert abs(inf.final_error - g["final_error"]) / g["final_error"] < 1e-8

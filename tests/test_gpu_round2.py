@@ -180,3 +180,91 @@ def test_chain_in_library_driver_world_of_one(ds_c3_small, graph):
     ic2 = cs.optimize()
     assert ic2.final_error == ic.final_error and ic2.tries == ic.tries
     cs.close()
+
+
+def test_sixteen_full_size_monte_carlo_trials_in_one_batch_against_the_oracle():
+    """The first 16 trials of the benchmark's Monte-Carlo batch (seeds 0..15, 29.8 k states each, the reference's TUM
+    trajectory file) solved as ONE batch: every trial against the CPU oracle's solution of the same trial
+    (tests/golden/mc16_oracle.npz, tools/make_mc_golden.py): states / calibration 1e-6, chi2 1e-8 relative."""
+    import os
+
+    from conftest import ROOT
+    from vicon2gt_b200 import api, sim
+
+    path = os.path.join(ROOT, "tests", "golden", "mc16_oracle.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/mc16_oracle.npz missing (tools/make_mc_golden.py)")
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("make_ref_golden", os.path.join(ROOT, "tools", "make_ref_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    G = np.load(path)
+    n, stride = int(G["n_trials"]), int(G["stride"])
+    p = default_params()
+    dss = [sim.make_config("C1", seed=s, trajectory="file") for s in range(n)]
+    bs = api.BatchSolver(n)
+    for s, ds in enumerate(dss):
+        assert np.array_equal(mod.dataset_digest(ds), G[f"s{s}_digest"]), "simulator output changed: rerun tools/make_mc_golden.py"
+        bs.set_trial_dataset(s, p, ds)
+    bs.build_and_solve()
+    worst = [0.0, 0.0, 0.0]
+    for s in range(n):
+        inf = bs.info(s)
+        _, x = bs.states(s)
+        assert inf.status == 0 and inf.n_states == int(G[f"s{s}_n"])
+        dx = float(np.max(np.abs(x[::stride] - G[f"s{s}_x"])))
+        dg = float(np.max(np.abs(bs.globals10(s) - G[f"s{s}_g"])))
+        rel = abs(inf.final_error - float(G[f"s{s}_final_error"])) / float(G[f"s{s}_final_error"])
+        worst = [max(worst[0], dx), max(worst[1], dg), max(worst[2], rel)]
+        assert dx < 1e-6 and dg < 1e-6 and rel < 1e-8, (s, dx, dg, rel, inf.iterations, int(G[f"s{s}_iterations"]))
+    print("16 full-size trials vs oracle: max |dx| %.2e, max |d calibration| %.2e, max rel chi2 %.2e" % tuple(worst))
+    bs.close()
+
+
+def test_wave_runner_matches_one_batch(ds_c1_small, ds_c2_small, ds_c3_small):
+    """api.WaveRunner (two resident handles, staging / read-back threads overlapped with the solve): five trials in waves of
+    two give, trial by trial, what one five-trial batch gives (fixed segment count: the same arithmetic, bit for bit)."""
+    from vicon2gt_b200 import api
+
+    p = default_params(lm_max_iterations=5)
+    dss = [ds_c2_small, ds_c1_small, ds_c3_small, ds_c2_small, ds_c3_small]
+    with api.BatchSolver(len(dss), segments=6) as bs:
+        for k, ds in enumerate(dss):
+            bs.set_trial_dataset(k, p, ds)
+        bs.build_and_solve()
+        want = [(bs.info(k).final_error, bs.states(k)[1], bs.globals10(k)) for k in range(len(dss))]
+    seen = 0
+    with api.WaveRunner(wave=2, segments=6) as runner:
+        for first, off, t, x, g, infos in runner.run(p, dss):
+            for i, inf in enumerate(infos):
+                k = first + i
+                assert inf.status == 0 and inf.final_error == want[k][0]
+                assert np.array_equal(x[off[i]:off[i + 1]], want[k][1]) and np.array_equal(g[i], want[k][2])
+                seen += 1
+        assert runner.device_ms > 0 and runner.wall_s > 0
+    assert seen == len(dss)
+
+
+def test_cpp_wave_runner_example():
+    """examples/run_monte_carlo --wave: the C++ WaveRunner of include/vicon2gt_b200.hpp against the one-batch run of the
+    same example (same seeds: the printed costs agree)."""
+    import os
+    import re
+    import subprocess
+
+    from conftest import ROOT
+    from vicon2gt_b200 import build
+
+    build.build_examples()
+    exe = os.path.join(ROOT, "examples", "run_monte_carlo")
+    args = [exe, "--seeds", "5", "--duration", "10", "--ori_noise", "0.001", "--pos_noise", "0.01"]
+    a = subprocess.run(args, capture_output=True, text=True, timeout=300)
+    b = subprocess.run(args + ["--wave", "2"], capture_output=True, text=True, timeout=300)
+    assert a.returncode == 0 and b.returncode == 0, a.stderr + b.stderr
+    pat = re.compile(r"run\s+(\d+): status (\d+), (\d+) states, (\d+) iterations, cost (\S+?)[,\n]")
+    ga, gb = pat.findall(a.stdout), pat.findall(b.stdout + "\n")
+    assert len(ga) == 5 and len(gb) == 5
+    for x, y in zip(ga, gb):
+        assert x[:3] == y[:3] and x[1] == "0"
+        assert abs(float(x[4]) - float(y[4])) <= 2e-6 * float(x[4])

@@ -234,8 +234,11 @@ E2E_FULL = {
     "e2e_c2_full": ("C2", dict(seed=21, trajectory="file"), {}),
     "e2e_c3_full": ("C3", dict(seed=21, trajectory="file"), {}),
     "e2e_c1_full": ("C1", dict(seed=0, trajectory="file"), {}),
+    # BASELINE.json configs[4]: the synthesised one-hour sequence (72 k states; no reference data file is that long), the
+    # input of the chain-sharded solve.  About 15 min of CPU: generated on its own (--only e2e_c5_full) and merged.
+    "e2e_c5_full": ("C5", dict(seed=5), {}),
 }
-FULL_STRIDE = {"e2e_c2_full": 4, "e2e_c3_full": 4, "e2e_c1_full": 16}
+FULL_STRIDE = {"e2e_c2_full": 4, "e2e_c3_full": 4, "e2e_c1_full": 16, "e2e_c5_full": 32}
 
 
 def dataset_digest(ds):
@@ -286,10 +289,10 @@ def end_to_end(rb, out):
         rs.close()
 
 
-def end_to_end_full(rb, out):
+def end_to_end_full(rb, out, names=None):
     import hashlib
 
-    for name in E2E_FULL:
+    for name in (names or [n for n in E2E_FULL if n != "e2e_c5_full"]):
         ds, p = e2e_dataset(name)
         rs = rb.RefSolver(p, ds)
         rs.build_and_solve()
@@ -364,7 +367,23 @@ def generate(full=True):
 
 
 if __name__ == "__main__":
-    out = generate()
     path = os.path.join(ROOT, "tests", "golden", "ref_pin.npz")
+    if len(sys.argv) > 2 and sys.argv[1] == "--only":
+        # regenerate the named full-size cases only and merge them into the committed file
+        from oracle import ref_binding as rb
+        from vicon2gt_b200 import build
+
+        build.build_sim()
+        build.build_oracle()
+        rb.build()
+        out = dict(np.load(path))
+        end_to_end_full(rb, out, sys.argv[2:])
+        np.savez_compressed(path, **out)
+        print(path, os.path.getsize(path) // 1024, "KiB,", len(out), "arrays")
+        sys.exit(0)
+    out = generate()
+    if os.path.exists(path):  # keep the separately generated one-hour case
+        old = np.load(path)
+        out.update({k: old[k] for k in old.files if k.startswith("e2e_c5_full_")})
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path) // 1024, "KiB,", len(out), "arrays")

@@ -324,6 +324,113 @@ class BatchSolver:
         return ms, launches
 
 
+class WaveRunner:
+    """A Monte-Carlo batch larger than one GPU's memory, solved in waves (scripts/run_monte_carlo.sh runs its trials one
+    roslaunch after the other; here `wave` trials at a time).  Two resident batch handles: while wave k is being solved,
+    a host thread stages and uploads wave k+1 into the other handle (pinned fill + H2D copies on that handle's stream run
+    under wave k's kernels) and another reads wave k-1's results back, so the GPU never waits for the host.
+
+        runner = WaveRunner(wave=128)
+        for result in runner.run(params, datasets):      # datasets: any sequence of Dataset
+            first_trial, offsets, times, states, globals10, infos = result
+    """
+
+    def __init__(self, wave=128, device=0, **options):
+        self.wave = int(wave)
+        self.device = int(device)
+        self.options = options
+        self.handles = []
+        self.device_ms = 0.0     # CUDA-event time of build + optimise, summed over the waves of the last run
+        self.wall_s = 0.0        # first staging call -> last result read back
+        self.stall_s = 0.0       # time the solving thread spent waiting for an upload to finish (0 when fully hidden)
+
+    def close(self):
+        for h in self.handles:
+            h.close()
+        self.handles = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _handle(self, k, n):
+        while len(self.handles) <= k:
+            self.handles.append(None)
+        h = self.handles[k]
+        if h is None or h.n_trials != n:
+            if h is not None:
+                h.close()
+            h = self.handles[k] = BatchSolver(n, device=self.device, **self.options)
+        return h
+
+    def run(self, params, datasets, read_back=True):
+        import threading
+        import time
+
+        n_total = len(datasets)
+        starts = list(range(0, n_total, self.wave))
+        self.device_ms = self.stall_s = 0.0
+        t_begin = time.perf_counter()
+        errors = []
+
+        def stage(w):
+            try:
+                a = starts[w]
+                chunk = datasets[a:a + self.wave]
+                h = self._handle(w % 2, len(chunk))
+                for i, ds in enumerate(chunk):
+                    h.set_trial_dataset(i, params, ds, borrow=True)
+                h.upload()
+            except Exception as e:  # noqa: BLE001
+                errors.append(e)
+
+        def fetch(w, out):
+            try:
+                h = self.handles[w % 2]
+                infos = [h.info(i) for i in range(h.n_trials)]
+                out.append((starts[w],) + (h.all_states() if read_back else (None, None, None, None)) + (infos,))
+            except Exception as e:  # noqa: BLE001
+                errors.append(e)
+
+        results = [[] for _ in starts]
+        up = threading.Thread(target=stage, args=(0,))
+        up.start()
+        rb = None
+        for w in range(len(starts)):
+            t0 = time.perf_counter()
+            up.join()
+            self.stall_s += time.perf_counter() - t0 if w else 0.0
+            if errors:
+                raise errors[0]
+            if w + 1 < len(starts):
+                if rb is not None:  # wave w-1 lives in the handle wave w+1 is about to overwrite
+                    rb.join()
+                    rb = None
+                up = threading.Thread(target=stage, args=(w + 1,))
+                up.start()
+            h = self.handles[w % 2]
+            h.build_and_solve()
+            ms, _ = h.timing()
+            self.device_ms += float(ms[0] + ms[7])
+            if rb is not None:
+                rb.join()
+            rb = threading.Thread(target=fetch, args=(w, results[w]))
+            rb.start()
+            if w >= 1 and results[w - 1]:
+                yield results[w - 1][0]
+                results[w - 1] = None
+        if rb is not None:
+            rb.join()
+        if errors:
+            raise errors[0]
+        self.wall_s = time.perf_counter() - t_begin
+        for r in results:
+            if r:
+                yield r[0]
+
+
 class Propagator:
     """IMU store of the reference (src/meas/Propagator.h:41-55): holds the noise densities, appends samples."""
 

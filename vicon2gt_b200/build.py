@@ -132,18 +132,18 @@ def build_ref(force=False):
 
 
 def build_examples(force=False):
-    """g++ -> examples/run_simulation and examples/run_monte_carlo (host C++ over the C ABI: include/vicon2gt_b200.hpp); needs
+    """g++ -> examples/run_simulation, run_monte_carlo and run_chain (host C++ over the C ABI: include/vicon2gt_b200.hpp); needs
     the two libraries.  Returns the path of run_simulation."""
     gxx = _find("g++", ["/usr/bin/g++"])
     outs = []
-    for name in ("run_simulation", "run_monte_carlo"):
+    for name in ("run_simulation", "run_monte_carlo", "run_chain"):
         src = os.path.join(ROOT, "examples", name + ".cpp")
         out = os.path.join(ROOT, "examples", name)
         deps = [src, os.path.join(ROOT, "include", "vicon2gt_b200.hpp"), os.path.join(ROOT, "include", "vicon2gt_b200.h"), _LIBS["cuda"], _LIBS["sim"]]
         outs.append(out)
         if not force and not _newer(out, deps):
             continue
-        _run([gxx, "-O2", "-std=c++14", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", HOST, "-o", out, src,
+        _run([gxx, "-O2", "-std=c++14", "-Wall", "-pthread", "-I", os.path.join(ROOT, "include"), "-I", HOST, "-o", out, src,
               "-L", PKG_DIR, "-L", HOST, "-lvicon2gt_b200", "-lv2gt_sim",
               "-Wl,-rpath," + PKG_DIR, "-Wl,-rpath," + HOST, "-Wl,-rpath,$ORIGIN/../vicon2gt_b200", "-Wl,-rpath,$ORIGIN/../vicon2gt_b200/host",
               "-Wl,-rpath,/usr/local/cuda/lib64"])
