@@ -51,6 +51,9 @@ constexpr int ELIM_WARPS = ELIM_WARPS_N;
 #ifndef ELIM_ACC_SMEM
 #define ELIM_ACC_SMEM 0 // 1: the persistent Schur sums live in shared memory (34 fewer doubles in registers)
 #endif
+#ifndef ELIM_PIVOT2
+#define ELIM_PIVOT2 0 // 1: 2x2 block pivots (8 dependent rounds, 321 FP64 instructions) instead of 15 scalar pivots (259)
+#endif
 #ifndef ELIM_BULK
 #define ELIM_BULK 1 // 1: record staged by one cp.async.bulk + mbarrier per state (0: cp.async 16-byte chunks per lane)
 #endif
@@ -193,6 +196,97 @@ __device__ __forceinline__ void sts2_if(const bool p, double *dst, const double 
 __device__ __forceinline__ double shfl_d(const double v, const int src) { return __shfl_sync(0xffffffffu, v, src); }
 __device__ __forceinline__ double2 lds2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 
+// LDL^T of the 15x15 block held as the tiles d00 = D[gid][2tid+e], d10 = D[8+gid][2tid+e],
+// d11 = D[8+gid][8+2tid+e] together with the Gauss-Jordan inverse of its unit-lower factor; returns
+// L^-1 = D^-1/2 L'^-1 (L = Cholesky factor) in the same tile order.  Per pivot j every lane needs the pivot, the
+// entries of column j of D in its own row and in its two columns (D is symmetric), and row j of X in its two columns:
+// the holders publish column and row through cb (2 x 32 doubles of shared memory, double buffered) with predicated
+// stores.  Fifteen scalar pivots: 259 FP64 instructions per state block, against 321 for the 2x2 block-pivot form
+// below (ELIM_PIVOT2) -- under load every scalar FP64 instruction costs a warp about as much time as a DMMA (it queues
+// behind the other warps' DMMAs on the one FP64 pipe of the sub-partition), so the instruction count decides.
+#if !ELIM_PIVOT2
+__device__ __forceinline__ bool ldl_inverse(double (&d00)[2], double (&d10)[2], double (&d11)[2], double (&li00)[2],
+                                            double (&li10)[2], double (&li11)[2], double *cb, const int gid, const int tid) {
+  double x00[2], x10[2], x11[2];
+  x00[0] = (gid == 2 * tid) ? 1.0 : 0.0;
+  x00[1] = (gid == 2 * tid + 1) ? 1.0 : 0.0;
+  x10[0] = x10[1] = 0.0;
+  x11[0] = x00[0];
+  x11[1] = x00[1];
+  double p0 = 1.0, p1 = 1.0;
+#pragma unroll
+  for (int j = 0; j < 15; j++) {
+    const int jj = j & 7, h = jj >> 1, e = jj & 1; // holders of column j: lanes with tid == h, register e
+    double piv, ca_g = 0.0, cb_g, ca0 = 0.0, ca1 = 0.0, cb0, cb1, xr0, xr1, xs0 = 0.0, xs1 = 0.0;
+    double *buf = cb + 32 * (j & 1);
+    // the holders publish column j of D (rows 0..15) and row j of X (columns 0..15)
+    if (j < 8) {
+      const bool hc = (tid == h), hr = (gid == j);
+      sts_if(hc, buf + gid, d00[e]);
+      sts_if(hc, buf + 8 + gid, d10[e]);
+      sts2_if(hr, buf + 16 + 2 * tid, x00[0], x00[1]);
+    } else {
+      const bool hc = (tid == h), hr = (gid == jj);
+      sts_if(hc, buf + 8 + gid, d11[e]);
+      sts2_if(hr, buf + 16 + 2 * tid, x10[0], x10[1]);
+      sts2_if(hr, buf + 24 + 2 * tid, x11[0], x11[1]);
+    }
+    __syncwarp();
+    piv = buf[j];
+    cb_g = buf[8 + gid];
+    cb0 = buf[8 + 2 * tid];
+    cb1 = buf[9 + 2 * tid];
+    xr0 = buf[16 + 2 * tid];
+    xr1 = buf[17 + 2 * tid];
+    if (j < 8) {
+      ca_g = buf[gid];
+      ca0 = buf[2 * tid];
+      ca1 = buf[2 * tid + 1];
+    } else {
+      xs0 = buf[24 + 2 * tid];
+      xs1 = buf[25 + 2 * tid];
+    }
+    double r0, pc;
+    rcp_seed(piv, r0, pc);
+    if (j < 8) {
+      p0 = (gid == j) ? piv : p0;
+      const double a0 = (gid > j) ? ca_g * r0 : 0.0, a1 = cb_g * r0;
+      const double mr0 = fma(a0, pc, a0), mr1 = fma(a1, pc, a1);
+      d00[0] = fma(-mr0, ca0, d00[0]);
+      d00[1] = fma(-mr0, ca1, d00[1]);
+      d10[0] = fma(-mr1, ca0, d10[0]);
+      d10[1] = fma(-mr1, ca1, d10[1]);
+      d11[0] = fma(-mr1, cb0, d11[0]);
+      d11[1] = fma(-mr1, cb1, d11[1]);
+      x00[0] = fma(-mr0, xr0, x00[0]);
+      x00[1] = fma(-mr0, xr1, x00[1]);
+      x10[0] = fma(-mr1, xr0, x10[0]);
+      x10[1] = fma(-mr1, xr1, x10[1]);
+    } else {
+      p1 = (8 + gid == j) ? piv : p1;
+      const double a1 = (8 + gid > j) ? cb_g * r0 : 0.0;
+      const double mr1 = fma(a1, pc, a1);
+      d11[0] = fma(-mr1, cb0, d11[0]);
+      d11[1] = fma(-mr1, cb1, d11[1]);
+      x10[0] = fma(-mr1, xr0, x10[0]);
+      x10[1] = fma(-mr1, xr1, x10[1]);
+      x11[0] = fma(-mr1, xs0, x11[0]);
+      x11[1] = fma(-mr1, xs1, x11[1]);
+    }
+  }
+  // every pivot is held by exactly one (gid, *) group: positive-definiteness check in one vote
+  const bool ok = __all_sync(0xffffffffu, (p0 > 0.0) && (p1 > 0.0));
+  const double s0 = fast_rsqrt(p0);
+  const double s1 = (gid < 7) ? fast_rsqrt(p1) : 0.0; // row 15 is padding
+  li00[0] = s0 * x00[0];
+  li00[1] = s0 * x00[1];
+  li10[0] = s1 * x10[0];
+  li10[1] = s1 * x10[1];
+  li11[0] = s1 * x11[0];
+  li11[1] = s1 * x11[1];
+  return ok;
+}
+#else
 // Block LDL^T of the 15x15 block (padded to 16 by a unit pivot) with 2x2 pivot blocks, held as the tiles
 // d00 = D[gid][2tid+e], d10 = D[8+gid][2tid+e], d11 = D[8+gid][8+2tid+e], carried out together with the Gauss-Jordan
 // inverse X of its unit block-lower factor:  D = Lb B Lb^T, B = blockdiag(P_0 .. P_7), P_k = [a b; b c].
@@ -301,6 +395,7 @@ __device__ __forceinline__ bool ldl_inverse(double (&d00)[2], double (&d10)[2], 
   li11[1] = s1 * (odd ? fma(-f1, e21, x11[1]) : x11[1]);
   return ok;
 }
+#endif // ELIM_PIVOT2
 
 // Eliminate one state.  st: its staged normal-equation record (shared memory); Finit: for the first state of a
 // segment with a left separator, the record of that separator (global; F = O_sep^T), else nullptr.
