@@ -20,6 +20,12 @@ KEYS = [
     "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
     "smsp__inst_executed.sum", "smsp__cycles_active.avg", "sm__cycles_elapsed.max",
+    # the FP64 pipe of a sub-partition is shared by the scalar FP64 instructions and DMMA: "pipe_shared" is its busy fraction
+    # (calibrated on tools/fp64_micro2.cu: 99 % for a saturated DMMA stream), "fp64" the scalar part, "dmma" the mma part
+    "sm__pipe_shared_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active",
+    "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed", "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed",
+    "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed", "SM_C.TriageCompute.smsp__pipe_tensor_subpipe_dmma_cycles_active.avg",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
 ]
 STALL = re.compile(r"smsp__average_warps_issue_stalled_(\w+)_per_issue_active\.ratio")
 
@@ -49,7 +55,10 @@ def launches(path, out):
 
 
 def raw(rep, out, pattern=None):
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+    if rep.endswith(".csv"):  # raw page already exported on the GPU box (tools/gpu_r2_profiles.sh)
+        txt = open(rep, errors="replace").read()
+    else:
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
     hdr, units = rows[0], rows[1]
     with open(out, "w") as f:
