@@ -226,12 +226,17 @@ def test_chain_one_hour_sequence_against_the_reference_class(driver):
 
 
 @pytest.mark.gpu
-def test_chain_on_the_60s_dataset_what_holds_across_a_bracket_switch():
-    """The dataset on which the first round's 2-rank solve and the single-GPU solve ended 3.3e-5 apart in chi2.  The cost is
-    discontinuous in t_off (a state's vicon bracket switches when t - t_off crosses a pose stamp, Interpolator.cpp:175-237),
-    so two round-off-different LM paths may stop on different sides of a switch.  What must hold regardless: the estimates
-    agree to 1e-6, each reported chi2 is the cost of its OWN estimate, and a chi2 gap larger than 1e-8 comes with a state
-    whose bracket differs between the two estimates."""
+def test_chain_on_the_60s_dataset_what_holds_when_two_lm_paths_part():
+    """The dataset on which the first round's 2-rank solve and the single-GPU solve ended 3.3e-5 apart in chi2 (74 against
+    30 damped solves).  The vicon factor whitens with W(t_off) but differentiates as if W were constant
+    (MeasBased_ViconPoseTimeoffsetFactor.cpp:52-66 against :126-132; SURVEY 8a15: dW/dt_off is ~80 % of the true
+    derivative), so Levenberg-Marquardt stops where its MODEL gradient vanishes, on a point where the cost itself still has
+    a steep slope along the time offset (~1e6 per second here); and the cost jumps when t - t_off crosses a pose stamp
+    (Interpolator.cpp:175-237), so two round-off-different paths may take different accept / reject decisions and stop a
+    few 1e-8 s apart in t_off -- a chi2 gap of 1e-5 with estimates that agree to 1e-6.  What must hold regardless, and is
+    asserted: the estimates agree to 1e-6, each reported chi2 is the cost of its OWN estimate, and a chi2 gap larger than
+    1e-8 is carried by the difference in the time offset (moving t_off alone from one estimate to the other moves the
+    cost by the gap, same sign, same order)."""
     from vicon2gt_b200 import api, sim
     from vicon2gt_b200.chain import ChainSolver, LocalComm
 
@@ -258,12 +263,17 @@ def test_chain_on_the_60s_dataset_what_holds_across_a_bracket_switch():
     assert abs(single.cost(0) - ic.final_error) / ic.final_error < 1e-10
     single.set_estimate(0, x1, g1)
     assert abs(single.cost(0) - i1.final_error) / i1.final_error < 1e-10
-    rel = abs(ic.final_error - i1.final_error) / i1.final_error
+    gap = ic.final_error - i1.final_error
+    rel = abs(gap) / i1.final_error
+    ratio = float("nan")
     if rel >= 1e-8:
-        ba = single.eval_interp(0, t1 - g1[7], p.interp_gap_factor)
-        bb = single.eval_interp(0, t1 - gc[7], p.interp_gap_factor)
-        assert np.any(ba["idx0"] != bb["idx0"]) or np.any(ba["idx1"] != bb["idx1"]), rel
-    print("60 s dataset: rel chi2", rel, "d t_off", abs(gc[7] - g1[7]), "tries", ic.tries, i1.tries)
+        g_sw = g1.copy()
+        g_sw[7] = gc[7]
+        single.set_estimate(0, x1, g_sw)
+        ratio = (single.cost(0) - i1.final_error) / gap
+        single.set_estimate(0, x1, g1)
+        assert abs(gc[7] - g1[7]) > 1e-10 and 0.05 < ratio < 20.0, (rel, gc[7] - g1[7], ratio)
+    print("60 s dataset: rel chi2", rel, "d t_off", gc[7] - g1[7], "share of the gap carried by t_off alone", ratio, "tries", ic.tries, i1.tries)
     cs.close()
     single.close()
 
