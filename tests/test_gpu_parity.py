@@ -246,7 +246,8 @@ def test_batch_of_trials_matches_single(ds_c1_small, ds_c2_small, ds_c3_small):
         ts, xs = single.states(0)
         assert np.array_equal(tb, ts)
         assert np.max(np.abs(xb - xs)) < 1e-6  # same kernels, other segment geometry: round-off after 6 LM iterations
-        assert abs(bs.info(i).final_error - single.info(0).final_error) / single.info(0).final_error < 1e-9
+        # two segment geometries = two summation orders of the same elimination: chi2 to north_star's 1e-8
+        assert abs(bs.info(i).final_error - single.info(0).final_error) / single.info(0).final_error < 1e-8
         single.close()
     # trials 0 and 3 are the same problem: bitwise identical (deterministic reductions)
     assert np.array_equal(bs.states(0)[1], bs.states(3)[1])

@@ -51,6 +51,9 @@ constexpr int ELIM_WARPS = ELIM_WARPS_N;
 #ifndef ELIM_ACC_SMEM
 #define ELIM_ACC_SMEM 0 // 1: the persistent Schur sums live in shared memory (34 fewer doubles in registers)
 #endif
+#ifndef ELIM_BLOCKED
+#define ELIM_BLOCKED 1 // blocked factorisation: scalar pivots inside the two diagonal 8x8 tiles, everything else on DMMAs
+#endif
 #ifndef ELIM_PIVOT2
 #define ELIM_PIVOT2 0 // 1: 2x2 block pivots (8 dependent rounds, 321 FP64 instructions) instead of 15 scalar pivots (259)
 #endif
@@ -170,15 +173,14 @@ __device__ __forceinline__ void rcp_seed(const double x, double &r0, double &p) 
   p = fma(e, e, e);
 }
 __device__ __forceinline__ double fast_rsqrt(const double x) {
-  double r;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  // two Newton steps on r <- r (1.5 - 0.5 x r^2)
-  double h = 0.5 * x;
-  r = r * fma(-h * r, r, 1.5);
-  r = r * fma(-h * r, r, 1.5);
-  // one correction in the residual form for the last bits
-  const double e = fma(-x * r, r, 1.0);
-  return fma(0.5 * r, e, r);
+  // MUFU.RSQ64H seed r0 (relative error < 2^-20), e = 1 - x r0^2, then the third-order correction
+  // 1/sqrt(1 - e) = 1 + e/2 + 3 e^2/8 + O(e^3): five dependent-light FP64 instructions instead of eleven
+  double r0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
+  const double y = x * r0;
+  const double e = fma(-y, r0, 1.0);
+  const double t = fma(0.375, e, 0.5) * e;
+  return fma(r0, t, r0);
 }
 
 // predicated shared-memory stores (one STS under a predicate: no branch, and the lanes that do not hold the value
@@ -204,7 +206,89 @@ __device__ __forceinline__ double2 lds2(const double *p) { return *reinterpret_c
 // stores.  Fifteen scalar pivots: 259 FP64 instructions per state block, against 321 for the 2x2 block-pivot form
 // below (ELIM_PIVOT2) -- under load every scalar FP64 instruction costs a warp about as much time as a DMMA (it queues
 // behind the other warps' DMMAs on the one FP64 pipe of the sub-partition), so the instruction count decides.
-#if !ELIM_PIVOT2
+// Blocked form of the same factorisation (ELIM_BLOCKED): D = [A B^T; B C] in its 8x8 tiles,
+//   L00 = chol(A)                 eight scalar pivots on tile (0,0) alone, with the Gauss-Jordan inverse of that tile
+//   L10 = B L00^-T                2 DMMAs  (tile products T V^T come straight from the fragment registers: the A operand
+//   S   = C - L10 L10^T           2 DMMAs   of a k-step is register e of T, the B operand register e of V)
+//   L11 = chol(S)                 seven scalar pivots on tile (1,1) alone
+//   (L^-1)10 = -L11^-1 L10 L00^-1   4 DMMAs and two 8x8 tile transposes (warp shuffles)
+// i.e. the updates of the off-diagonal tile and of the trailing tile, which the scalar form carries through every one of
+// the first eight pivots, become eight DMMAs: 142 scalar FP64 instructions per state block instead of 259.  Under load a
+// scalar FP64 instruction costs a warp about as much time as a DMMA (both queue on the one FP64 pipe of the
+// sub-partition), so the instruction count is what decides.
+#if ELIM_BLOCKED
+// transpose of an 8x8 tile held as T[gid][2tid+e]: element (2tid+e, gid) sits on lane (2tid+e, gid >> 1), register gid & 1
+__device__ __forceinline__ void tile_transpose(const double (&t)[2], double (&o)[2], const int gid, const int tid) {
+#pragma unroll
+  for (int e = 0; e < 2; e++) {
+    const int src = 4 * (2 * tid + e) + (gid >> 1);
+    const double v0 = shfl_d(t[0], src), v1 = shfl_d(t[1], src);
+    o[e] = (gid & 1) ? v1 : v0;
+  }
+}
+__device__ __forceinline__ double neg_d(const double x) { return __hiloint2double(__double2hiint(x) ^ 0x80000000, __double2loint(x)); }
+// scalar pivots on ONE 8x8 tile d (symmetric, full) with the Gauss-Jordan inverse x of its unit-lower factor; n pivots;
+// returns the pivot of the lane's row in p
+__device__ __forceinline__ void tile_ldl(double (&d)[2], double (&x)[2], double &p, const int n, double *cb, const int gid, const int tid) {
+  x[0] = (gid == 2 * tid) ? 1.0 : 0.0;
+  x[1] = (gid == 2 * tid + 1) ? 1.0 : 0.0;
+  p = 1.0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    if (j < n) {
+      double *buf = cb + 32 * (j & 1);
+      const int h = j >> 1, e = j & 1;
+      sts_if(tid == h, buf + gid, d[e]);             // column j of the tile
+      sts2_if(gid == j, buf + 8 + 2 * tid, x[0], x[1]); // row j of X
+      __syncwarp();
+      const double piv = buf[j];
+      double r0, pc;
+      rcp_seed(piv, r0, pc);
+      p = (gid == j) ? piv : p;
+      const double a0 = (gid > j) ? buf[gid] * r0 : 0.0;
+      const double mr = fma(a0, pc, a0);
+      const double2 c = lds2(buf + 2 * tid), xr = lds2(buf + 8 + 2 * tid);
+      d[0] = fma(-mr, c.x, d[0]);
+      d[1] = fma(-mr, c.y, d[1]);
+      x[0] = fma(-mr, xr.x, x[0]);
+      x[1] = fma(-mr, xr.y, x[1]);
+    }
+  }
+}
+__device__ __forceinline__ bool ldl_inverse(double (&d00)[2], double (&d10)[2], double (&d11)[2], double (&li00)[2],
+                                            double (&li10)[2], double (&li11)[2], double *cb, const int gid, const int tid) {
+  double x00[2], x11[2], p0, p1;
+  tile_ldl(d00, x00, p0, 8, cb, gid, tid);
+  const double s0 = fast_rsqrt(p0);
+  li00[0] = s0 * x00[0];
+  li00[1] = s0 * x00[1];
+  // L10 = B L00^-T, S = C - L10 L10^T
+  double g[2] = {0.0, 0.0}, q[2] = {0.0, 0.0};
+  dmma(g[0], g[1], d10[0], li00[0]);
+  dmma(g[0], g[1], d10[1], li00[1]);
+  dmma(q[0], q[1], g[0], g[0]);
+  dmma(q[0], q[1], g[1], g[1]);
+  d11[0] -= q[0];
+  d11[1] -= q[1];
+  __syncwarp(); // the broadcast buffers of the first tile are free again
+  tile_ldl(d11, x11, p1, 7, cb, gid, tid);
+  const bool ok = __all_sync(0xffffffffu, (p0 > 0.0) && ((gid == 7) || (p1 > 0.0)));
+  const double s1 = (gid < 7) ? fast_rsqrt(p1) : 0.0; // row 15 is padding
+  li11[0] = s1 * x11[0];
+  li11[1] = s1 * x11[1];
+  // (L^-1)10 = -(L11^-1 L10) L00^-1
+  double gt[2], lt[2], u[2] = {0.0, 0.0}, nn[2] = {0.0, 0.0};
+  tile_transpose(g, gt, gid, tid);
+  tile_transpose(li00, lt, gid, tid);
+  dmma(u[0], u[1], li11[0], gt[0]);
+  dmma(u[0], u[1], li11[1], gt[1]);
+  dmma(nn[0], nn[1], u[0], lt[0]);
+  dmma(nn[0], nn[1], u[1], lt[1]);
+  li10[0] = neg_d(nn[0]);
+  li10[1] = neg_d(nn[1]);
+  return ok;
+}
+#elif !ELIM_PIVOT2
 __device__ __forceinline__ bool ldl_inverse(double (&d00)[2], double (&d10)[2], double (&d11)[2], double (&li00)[2],
                                             double (&li10)[2], double (&li11)[2], double *cb, const int gid, const int tid) {
   double x00[2], x10[2], x11[2];
