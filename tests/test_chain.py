@@ -163,15 +163,11 @@ def test_chain_sharded_solve_matches_single_gpu(ds_c3_small, world, spr):
     while k < min(len(tr1), len(trc)) and tr1[k, 3] > 1e-9 * tr1[k, 1] and trc[k, 3] > 1e-9 * trc[k, 1]:
         k += 1
     assert k >= 5 and np.array_equal(tr1[:k, 0], trc[:k, 0]) and np.array_equal(tr1[:k, 4], trc[:k, 4])
-    print("chain vs single: rel chi2", abs(ic.final_error - i1.final_error) / i1.final_error, "max |dx|", np.max(np.abs(xc - x1)),
-          "tries", ic.tries, i1.tries)
-    assert abs(ic.final_error - i1.final_error) / i1.final_error < 1e-8
-    dq = np.abs(np.sum(xc[:, :4] * x1[:, :4], axis=1))
-    assert (2 * np.arccos(np.clip(dq, 0, 1))).max() < 1e-6
-    assert np.max(np.abs(xc[:, 4:] - x1[:, 4:])) < 1e-6
-    q1, p1, toff1, th1 = single.calibration(0)
+    from conftest import assert_same_solution_or_toff_split
+
     qc, pc, toffc, thc = cs.calibration()
-    assert abs(toffc - toff1) < 1e-6 and np.max(np.abs(pc - p1)) < 1e-6 and np.max(np.abs(thc - th1)) < 1e-6
+    rel, share = assert_same_solution_or_toff_split(single, (i1, x1, single.globals10(0)), (ic, xc, np.concatenate([qc, pc, [toffc], thc])))
+    print("chain vs single: rel chi2", rel, "share of a gap carried by t_off", share, "max |dx|", np.max(np.abs(xc - x1)), "tries", ic.tries, i1.tries)
     cs.close()
     single.close()
 
@@ -195,8 +191,7 @@ def test_chain_sharded_solve_over_nccl_two_gpus():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
     res = json.loads(line)
-    assert res["ok"], res
-    assert res["same_basin"], res  # this dataset's LM path does not sit on a bracket-switch discontinuity
+    assert res["ok"], res  # estimates 1e-6, cost bookkeeping 1e-10, chi2 1e-8 or a gap carried by the time offset
 
 
 @pytest.mark.gpu
@@ -228,15 +223,12 @@ def test_chain_one_hour_sequence_against_the_reference_class(driver):
 @pytest.mark.gpu
 def test_chain_on_the_60s_dataset_what_holds_when_two_lm_paths_part():
     """The dataset on which the first round's 2-rank solve and the single-GPU solve ended 3.3e-5 apart in chi2 (74 against
-    30 damped solves).  The vicon factor whitens with W(t_off) but differentiates as if W were constant
-    (MeasBased_ViconPoseTimeoffsetFactor.cpp:52-66 against :126-132; SURVEY 8a15: dW/dt_off is ~80 % of the true
-    derivative), so Levenberg-Marquardt stops where its MODEL gradient vanishes, on a point where the cost itself still has
-    a steep slope along the time offset (~1e6 per second here); and the cost jumps when t - t_off crosses a pose stamp
-    (Interpolator.cpp:175-237), so two round-off-different paths may take different accept / reject decisions and stop a
-    few 1e-8 s apart in t_off -- a chi2 gap of 1e-5 with estimates that agree to 1e-6.  What must hold regardless, and is
-    asserted: the estimates agree to 1e-6, each reported chi2 is the cost of its OWN estimate, and a chi2 gap larger than
-    1e-8 is carried by the difference in the time offset (moving t_off alone from one estimate to the other moves the
-    cost by the gap, same sign, same order)."""
+    30 damped solves).  The cost is piecewise constant in the time offset -- the factor's query time `t_I - t_off` is one
+    fp64 subtraction at epoch scale, ulp 2.4e-7 s, and all states' query times step together -- with neighbouring
+    plateaus ~3e-5 apart (conftest.assert_same_solution_or_toff_split has the measurement); two round-off-different
+    solves 1e-8 s apart in t_off may sit on adjacent plateaus.  What must hold regardless, and is asserted: the estimates
+    agree to 1e-6, each reported chi2 is the cost of its OWN estimate, and a chi2 gap larger than 1e-8 is carried by the
+    time offset alone."""
     from vicon2gt_b200 import api, sim
     from vicon2gt_b200.chain import ChainSolver, LocalComm
 
@@ -254,26 +246,10 @@ def test_chain_on_the_60s_dataset_what_holds_when_two_lm_paths_part():
     qc, pc, toffc, thc = cs.calibration()
     gc = np.concatenate([qc, pc, [toffc], thc])
     assert ic.status == 0 and np.array_equal(tc, t1)
-    assert np.max(np.abs(xc[:, 4:] - x1[:, 4:])) < 1e-6 and np.max(np.abs(gc - g1)) < 1e-6
-    dq = np.abs(np.sum(xc[:, :4] * x1[:, :4], axis=1))
-    assert (2 * np.arccos(np.clip(dq, 0, 1))).max() < 1e-6
-    # the sharded cost bookkeeping (ownership of the factors at the rank boundary, sums over the exchange) reports the
-    # cost of the chain's own estimate: re-evaluated by the single-GPU cost function
-    single.set_estimate(0, xc, gc)
-    assert abs(single.cost(0) - ic.final_error) / ic.final_error < 1e-10
-    single.set_estimate(0, x1, g1)
-    assert abs(single.cost(0) - i1.final_error) / i1.final_error < 1e-10
-    gap = ic.final_error - i1.final_error
-    rel = abs(gap) / i1.final_error
-    ratio = float("nan")
-    if rel >= 1e-8:
-        g_sw = g1.copy()
-        g_sw[7] = gc[7]
-        single.set_estimate(0, x1, g_sw)
-        ratio = (single.cost(0) - i1.final_error) / gap
-        single.set_estimate(0, x1, g1)
-        assert abs(gc[7] - g1[7]) > 1e-10 and 0.05 < ratio < 20.0, (rel, gc[7] - g1[7], ratio)
-    print("60 s dataset: rel chi2", rel, "d t_off", gc[7] - g1[7], "share of the gap carried by t_off alone", ratio, "tries", ic.tries, i1.tries)
+    from conftest import assert_same_solution_or_toff_split
+
+    rel, share = assert_same_solution_or_toff_split(single, (i1, x1, g1), (ic, xc, gc))
+    print("60 s dataset: rel chi2", rel, "d t_off", gc[7] - g1[7], "share of the gap carried by t_off alone", share, "tries", ic.tries, i1.tries)
     cs.close()
     single.close()
 

@@ -163,17 +163,22 @@ def test_chain_in_library_driver_world_of_one(ds_c3_small, graph):
     from vicon2gt_b200 import api
     from vicon2gt_b200.chain import ChainSolver, NativeComm
 
+    from conftest import assert_same_solution_or_toff_split
+
     ds = ds_c3_small
     p = default_params()
-    i1, (t1, x1), g1, _ = _solve_single(ds, p)
+    single = api.BatchSolver(1)
+    single.set_trial_dataset(0, p, ds)
+    single.build_and_solve()
+    i1, (t1, x1), g1 = single.info(0), single.states(0), single.globals10(0)
     cs = ChainSolver(p, ds, NativeComm(None), segs_per_rank=6, use_graph=graph)
     ic = cs.optimize()
     tc, xc = cs.states()
+    qc, pc, toffc, thc = cs.calibration()
     assert ic.status == 0 and np.array_equal(tc, t1)
-    assert abs(ic.final_error - i1.final_error) / i1.final_error < 1e-8
-    assert np.max(np.abs(xc[:, 4:] - x1[:, 4:])) < 1e-6
-    dq = np.abs(np.sum(xc[:, :4] * x1[:, :4], axis=1))
-    assert (2 * np.arccos(np.clip(dq, 0, 1))).max() < 1e-6
+    rel, share = assert_same_solution_or_toff_split(single, (i1, x1, g1), (ic, xc, np.concatenate([qc, pc, [toffc], thc])))
+    print("chain (in-library, world 1) vs single: rel chi2", rel, "share of a gap carried by t_off", share, "tries", ic.tries, i1.tries)
+    single.close()
     assert cs.check_brackets()
     # a second solve from a fresh build replays the cached graph
     cs.rebuild()

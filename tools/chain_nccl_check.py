@@ -49,13 +49,23 @@ def main():
                "d_toff": abs(toffc - toff1), "d_p_BinI": float(np.max(np.abs(pc - p1))), "d_theta": float(np.max(np.abs(thc - th1))),
                "tries_chain": ic.tries, "tries_single": i1.tries, "status": ic.status,
                "rel_cost_bookkeeping": abs(cost_at_chain - ic.final_error) / ic.final_error}
-        # chi2: 1e-8 relative -- unless the two LM paths ended on different sides of one of the cost's jump discontinuities
-        # (the vicon bracket switches when t - t_off crosses a stamp): then a 1e-7 difference in t_off moves
-        # chi2 by 1e-5 although every estimate agrees to 1e-6; the sharded cost must then still be the cost of its point.
+        # chi2: 1e-8 relative -- unless the two LM paths parted (the factor differentiates as if its whitening W(t_off) were
+        # constant, so LM stops where the cost still slopes steeply along t_off, and the cost jumps where t - t_off crosses a
+        # pose stamp): then the gap must be carried by the difference in the time offset -- moving t_off
+        # alone from one estimate to the other moves the cost by the gap -- and the sharded cost must still be the cost of
+        # its own point.
         same_basin = out["rel_chi2"] < 1e-8
-        out["chi2_note"] = "" if same_basin else "LM paths separated by a bracket-switch discontinuity of the cost"
+        share = None
+        if not same_basin:
+            g_sw = np.concatenate([q1, p1, [toffc], th1])
+            single.set_estimate(0, x1, g_sw)
+            share = (single.cost(0) - i1.final_error) / (ic.final_error - i1.final_error)
+            single.set_estimate(0, x1, np.concatenate([q1, p1, [toff1], th1]))
+        out["toff_share_of_gap"] = share
+        out["chi2_note"] = "" if same_basin else "LM paths parted; the chi2 gap is carried by the time offset"
         ok = (out["times_equal"] and out["status"] == 0 and out["rel_cost_bookkeeping"] < 1e-10 and out["max_rot_rad"] < 1e-6
-              and out["max_dx"] < 1e-6 and out["d_toff"] < 1e-6 and out["d_p_BinI"] < 1e-6 and out["d_theta"] < 1e-6)
+              and out["max_dx"] < 1e-6 and out["d_toff"] < 1e-6 and out["d_p_BinI"] < 1e-6 and out["d_theta"] < 1e-6
+              and (same_basin or (share is not None and 0.05 < share < 20.0)))
         out["same_basin"] = bool(same_basin)
         out["ok"] = bool(ok)
         print(json.dumps(out))
