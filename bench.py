@@ -7,16 +7,21 @@ simulated trials of the `launch/sim.launch` shape (400 Hz IMU, 100 Hz vicon, 100
 (weak scaling: --trials trials per GPU).  One "step" = the full build-and-solve of the rank's batch
 (state initialisation, continuous preintegration, 30-iteration Levenberg-Marquardt).
 
-  value  trajectories/s with the inputs already resident in HBM (CUDA events around build + optimise)
-  e2e    the same through the public API with HOST buffers: staging + pinned H2D copy of every input array,
-         build + optimise, D2H read of states + calibration, wall clock around the call
+  value  trajectories/s with the inputs already resident in HBM (CUDA events around build + optimise, max over ranks)
+  e2e    the same through the public API with HOST buffers, pipelined (api.WaveRunner, two resident handles): per step
+         the staging + pinned H2D copy of every input array, build + optimise and the D2H read of all states +
+         calibrations, wall clock over all steps; e2e.serial = one blocking step at a time
   roofline  dominant kernel (k_seg_eliminate): algorithmic bytes / summed launch durations (CUDA events on the
          handle's stream, inside the timed steps) against MEASURED_PEAKS.json's HBM number; FP64 fraction
          against a DFMA peak measured in the same process
+  per_rank  every rank's device time, damped solves and eliminated state blocks per step
+  chain  BASELINE.json configs[4] on the same GPUs: one one-hour sequence chain-sharded over the ranks, the
+         Levenberg-Marquardt loop inside the library (2 ncclAllGather per damped solve, CUDA graph); ms per damped solve
+  waves_1024_on_one_gpu  (N = 1) the WHOLE 1024-trial batch on the one GPU in 8 double-buffered waves
   cpu_baseline  the oracle (CPU restatement of the reference; the reference itself cannot be built here:
          no Eigen / Boost / GTSAM / ROS) on a bounded sample of the same workload
 
-`--impl reference` times that CPU restatement on all host threads instead (kind "port").
+`--impl reference` times that CPU restatement on all host threads, on this arm's workload and `config` (kind "port").
 """
 import argparse
 import json

@@ -317,6 +317,10 @@ int v2gt_batch_set_trial_sim(v2gt_batch *b, int32_t trial, const v2gt_params *pa
  * build/optimise: [0] build(init+preint) [1] linearise+assemble [2] eliminate [3] reduced solve
  * [4] back-substitute+retract [5] cost evaluation [6] LM bookkeeping; launches[7] kernel launch counts. */
 int v2gt_batch_get_timing(v2gt_batch *b, double *ms, int64_t *launches);
+/* Options (before upload): "segments" (chain segments per trial, 0 = chosen per optimiser round), "target_warps" (segment
+ * warps an elimination launch aims for), "keep_cov" (1: keep the preintegrated covariances for v2gt_batch_get_preint_cov),
+ * "tries_per_sync" (damped solves between two host reads of the running-trial counter, default 8), "graph" (-1: replay a
+ * captured CUDA graph per damped solve for small problems, 0: never, 1: always). */
 int v2gt_batch_set_option(v2gt_batch *b, const char *name, double value);
 /* Measured FP64 FMA peak of `device` in TFLOP/s (dependent-chain-free DFMA loop, best of 4): the FP64
  * roofline denominator (MEASURED_PEAKS.json only carries HBM and bf16 tensor numbers). */
