@@ -197,6 +197,9 @@ __device__ __forceinline__ void sts2_if(const bool p, double *dst, const double 
 }
 __device__ __forceinline__ double shfl_d(const double v, const int src) { return __shfl_sync(0xffffffffu, v, src); }
 __device__ __forceinline__ double2 lds2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+// sign flip on the integer pipe: the FP64 pipe is the contended one, a DADD with a negated operand
+// costs a warp about as much as a DMMA there
+__device__ __forceinline__ double neg_d(const double x) { return __hiloint2double(__double2hiint(x) ^ 0x80000000, __double2loint(x)); }
 
 // LDL^T of the 15x15 block held as the tiles d00 = D[gid][2tid+e], d10 = D[8+gid][2tid+e],
 // d11 = D[8+gid][8+2tid+e] together with the Gauss-Jordan inverse of its unit-lower factor; returns
@@ -226,7 +229,6 @@ __device__ __forceinline__ void tile_transpose(const double (&t)[2], double (&o)
     o[e] = (gid & 1) ? v1 : v0;
   }
 }
-__device__ __forceinline__ double neg_d(const double x) { return __hiloint2double(__double2hiint(x) ^ 0x80000000, __double2loint(x)); }
 // scalar pivots on ONE 8x8 tile d (symmetric, full) with the Gauss-Jordan inverse x of its unit-lower factor; n pivots;
 // returns the pivot of the lane's row in p
 __device__ __forceinline__ void tile_ldl(double (&d)[2], double (&x)[2], double &p, const int n, double *cb, const int gid, const int tid) {
@@ -263,13 +265,11 @@ __device__ __forceinline__ bool ldl_inverse(double (&d00)[2], double (&d10)[2], 
   li00[0] = s0 * x00[0];
   li00[1] = s0 * x00[1];
   // L10 = B L00^-T, S = C - L10 L10^T
-  double g[2] = {0.0, 0.0}, q[2] = {0.0, 0.0};
+  double g[2] = {0.0, 0.0};
   dmma(g[0], g[1], d10[0], li00[0]);
   dmma(g[0], g[1], d10[1], li00[1]);
-  dmma(q[0], q[1], g[0], g[0]);
-  dmma(q[0], q[1], g[1], g[1]);
-  d11[0] -= q[0];
-  d11[1] -= q[1];
+  dmma(d11[0], d11[1], g[0], neg_d(g[0])); // accumulated straight onto C with one operand negated
+  dmma(d11[0], d11[1], g[1], neg_d(g[1]));
   __syncwarp(); // the broadcast buffers of the first tile are free again
   tile_ldl(d11, x11, p1, 7, cb, gid, tid);
   const bool ok = __all_sync(0xffffffffu, (p0 > 0.0) && ((gid == 7) || (p1 > 0.0)));
@@ -519,9 +519,9 @@ __device__ __forceinline__ bool elim_node(const double *st, const double *__rest
         v2 = __ldg(fi + 15 * (1 + gid));    // F[r][1+gid]
         v3 = (gid < 6) ? __ldg(fi + 15 * (9 + gid)) : 0.0;
       } else {
-        v1 = -A.cy[1][u][e];
-        v2 = -A.cy[2][u][e];
-        v3 = -A.cy[3][u][e];
+        v1 = neg_d(A.cy[1][u][e]);
+        v2 = neg_d(A.cy[2][u][e]);
+        v3 = neg_d(A.cy[3][u][e]);
       }
     } else {
       v1 = v2 = v3 = 0.0;
