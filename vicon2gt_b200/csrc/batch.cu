@@ -1012,7 +1012,7 @@ int v2gt_batch_build(v2gt_batch *b, int32_t init_states) {
   std::swap(b->d.st_t, b->d.st_t_tmp); // k_compact wrote the surviving times into st_t_tmp
   V2_TRY(launch_preintegrate(b->d, b->n_max, b->opt_keep_cov, b->stream));
   V2_CUDA_CHECK(cudaEventRecord(b->ev[1], b->stream));
-  b->launches[0] += 3;
+  b->launches[0] += 4;
   b->built = true;
   return V2GT_OK;
 }

@@ -2,7 +2,8 @@
 //   k_init_states   initial guess + validity of every state (3 vicon lookups per state)
 //   k_compact       erase invalid states (stream compaction per trial, order preserving)
 //   k_preintegrate  kernel (1): IMU bracket search + continuous preintegration (CpiV1) of every
-//                   interval + covariance -> information matrix
+//                   interval: means and bias Jacobians
+//   k_preint_cov    kernel (1'): the interval's covariance (RK4) -> information matrix
 #include "v2gt_interp.cuh"
 #include <stdio.h>
 
@@ -184,168 +185,133 @@ __global__ void __launch_bounds__(256) k_compact(DevPtrs d) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// kernel (1): continuous preintegration, one thread per interval; the 15x15 covariance lives in
-// shared memory as fifteen 3x3 blocks per thread, element-major ([entry][thread]) so that a warp
-// touches 32 consecutive words for every access.
-constexpr int PRE_NT = 32;           // threads (intervals) per CTA
-constexpr int PB = 15 * 9;           // doubles per covariance copy (15 blocks)
-// block ids of the symmetric 5x5 block matrix over [th bg v ba p]
-enum { B_TT = 0, B_TG, B_TV, B_TA, B_TP, B_GG, B_GV, B_GA, B_GP, B_VV, B_VA, B_VP, B_AA, B_AP, B_PP };
+// kernel (1): continuous preintegration (CpiV1) of every interval, in two launches over the same sample stream:
+//   k_preintegrate   one THREAD per interval: means and bias Jacobians (registers only)
+//   k_preint_cov     sixteen LANES per interval (two intervals per warp): the 15x15 covariance by RK4, one column
+//                    per lane in registers, and the information matrix P^-1 = L^-T L^-1 by shuffles
+// (one thread per interval for both needed four 15x15 copies per thread: 4.3 kB of shared / local memory per interval,
+//  three warps per SM, 13 kB of DRAM traffic per interval for 1.7 kB of results)
 
-struct SmemCov {
-  double *base; // points at [0][tid]
-  int st;       // element stride: PRE_NT for the shared-memory copies ([entry][thread]), 1 for thread-local ones
-  __device__ __forceinline__ double &at(int blk, int e) { return base[(blk * 9 + e) * st]; }
-  __device__ __forceinline__ void ld(int blk, double *o) const {
-#pragma unroll
-    for (int e = 0; e < 9; e++)
-      o[e] = base[(blk * 9 + e) * st];
-  }
-  __device__ __forceinline__ void ldT(int blk, double *o) const {
-#pragma unroll
-    for (int r = 0; r < 3; r++)
-#pragma unroll
-      for (int c = 0; c < 3; c++)
-        o[3 * r + c] = base[(blk * 9 + 3 * c + r) * st];
-  }
+// ---- sample selection of Propagator::propagate (Propagator.cpp:33-132) as a stream, the zero-dt filter of :118-126
+// applied on the fly.  step(s0, s1) is called for every consecutive pair of the selected samples, at ONE call site, so
+// that the lanes of a warp working on different intervals stay at the same instruction.  Returns the number of
+// selected samples.
+struct Smp {
+  double t, w[3], a[3];
 };
+__device__ __forceinline__ void smp_load(const double *is, long long idx, Smp &o) {
+  const double4 u0 = ldg4(is + 8 * idx);
+  const double4 u1 = ldg4(is + 8 * idx + 4);
+  o.t = u0.x; o.w[0] = u0.y; o.w[1] = u0.z; o.w[2] = u0.w;
+  o.a[0] = u1.x; o.a[1] = u1.y; o.a[2] = u1.z;
+}
+// Propagator.h:63-73
+__device__ __forceinline__ void smp_lerp(const double *is, long long i1, long long i2, double ts, Smp &o) {
+  Smp s1, s2;
+  smp_load(is, i1, s1);
+  smp_load(is, i2, s2);
+  const double lambda = (ts - s1.t) / (s2.t - s1.t);
+  o.t = ts;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    o.a[k] = (1 - lambda) * s1.a[k] + lambda * s2.a[k];
+    o.w[k] = (1 - lambda) * s1.w[k] + lambda * s2.w[k];
+  }
+}
 
-// K = F P + P F^T + G Qc G^T in block form; R is the rotation of this RK4 stage.
-//   A = -[w]x, C = -R^T [a]x, E = -R^T          (CpiV1.h:259-272)
-// emit(blk, K9) is called once per block.
-template <typename Emit>
-__device__ __forceinline__ void cov_derivative(const SmemCov &P, const double *A, const double *C, const double *E, double qw,
-                                               double qwb, double qa, double qab, Emit emit) {
-  double K[9], X[9], Y[9], T[9], U[9];
-  // ---- theta row
-  {
-    double Ptt[9], PtgT[9];
-    P.ld(B_TT, Ptt);
-    P.ldT(B_TG, PtgT);
-    mm3(A, Ptt, X);
-#pragma unroll
-    for (int e = 0; e < 9; e++)
-      X[e] -= PtgT[e];
-#pragma unroll
-    for (int r = 0; r < 3; r++)
-#pragma unroll
-      for (int c = 0; c < 3; c++)
-        K[3 * r + c] = X[3 * r + c] + X[3 * c + r] + ((r == c) ? qw : 0.0);
-    emit(B_TT, K);
-    // K_tv = A Ptv - Pgv + Ptt C^T + Pta E^T
-    double Ptv[9], Pgv[9], Pta[9];
-    P.ld(B_TV, Ptv);
-    P.ld(B_GV, Pgv);
-    P.ld(B_TA, Pta);
-    mm3(A, Ptv, X);
-    mm3_nt(Ptt, C, Y);
-    mm3_nt(Pta, E, T);
-#pragma unroll
-    for (int e = 0; e < 9; e++)
-      K[e] = X[e] - Pgv[e] + Y[e] + T[e];
-    emit(B_TV, K);
-    // K_ta = A Pta - Pga
-    double Pga[9];
-    P.ld(B_GA, Pga);
-    mm3(A, Pta, X);
-#pragma unroll
-    for (int e = 0; e < 9; e++)
-      K[e] = X[e] - Pga[e];
-    emit(B_TA, K);
-    // K_tp = A Ptp - Pgp + Ptv
-    double Ptp[9], Pgp[9];
-    P.ld(B_TP, Ptp);
-    P.ld(B_GP, Pgp);
-    mm3(A, Ptp, X);
-#pragma unroll
-    for (int e = 0; e < 9; e++)
-      K[e] = X[e] - Pgp[e] + Ptv[e];
-    emit(B_TP, K);
-    // K_vp = C Ptp + E Pap + Pvv
-    double Pap[9], Pvv[9];
-    P.ld(B_AP, Pap);
-    P.ld(B_VV, Pvv);
-    mm3(C, Ptp, X);
-    mm3(E, Pap, Y);
-#pragma unroll
-    for (int e = 0; e < 9; e++)
-      K[e] = X[e] + Y[e] + Pvv[e];
-    emit(B_VP, K);
-    // K_vv = Yv + Yv^T + qa I, Yv = C Ptv + E Pva^T
-    double PvaT[9];
-    P.ldT(B_VA, PvaT);
-    mm3(C, Ptv, X);
-    mm3(E, PvaT, Y);
-#pragma unroll
-    for (int e = 0; e < 9; e++)
-      U[e] = X[e] + Y[e];
-#pragma unroll
-    for (int r = 0; r < 3; r++)
-#pragma unroll
-      for (int c = 0; c < 3; c++)
-        K[3 * r + c] = U[3 * r + c] + U[3 * c + r] + ((r == c) ? qa : 0.0);
-    emit(B_VV, K);
-    // K_va = C Pta + E Paa
-    double Paa[9];
-    P.ld(B_AA, Paa);
-    mm3(C, Pta, X);
-    mm3(E, Paa, Y);
-#pragma unroll
-    for (int e = 0; e < 9; e++)
-      K[e] = X[e] + Y[e];
-    emit(B_VA, K);
+template <class Step>
+__device__ __forceinline__ int select_samples(const double *__restrict__ it, const double *__restrict__ is, long long M, int unsorted,
+                                              double time0, double time1, Step step) {
+  Smp pend = {}, fin = {}; // pend: last pushed sample (may still be dropped by the zero-dt filter); fin: last finalised one
+  int n_pushed = 0, n_final = 0;
+  bool more = (M >= 2);
+  // time-ordered store: start at the sample in front of time0 (every earlier iteration of the reference's scan from
+  // sample 0 matches none of its three cases); unordered store: the reference's scan itself (Propagator.cpp:46)
+  long long k = 0;
+  if (more) {
+    const long long lb = unsorted ? 0 : lower_bound_d(it, M, time0);
+    k = (lb >= 1) ? lb - 1 : 0;
   }
-  {
-    // K_tg = A Ptg - Pgg ; K_gv = Pgt C^T + Pga E^T
-    double Ptg[9], Pgg[9], Pga[9];
-    P.ld(B_TG, Ptg);
-    P.ld(B_GG, Pgg);
-    P.ld(B_GA, Pga);
-    mm3(A, Ptg, X);
-#pragma unroll
-    for (int e = 0; e < 9; e++)
-      K[e] = X[e] - Pgg[e];
-    emit(B_TG, K);
-    double Pgt[9];
-#pragma unroll
-    for (int r = 0; r < 3; r++)
-#pragma unroll
-      for (int c = 0; c < 3; c++)
-        Pgt[3 * r + c] = Ptg[3 * c + r];
-    mm3_nt(Pgt, C, X);
-    mm3_nt(Pga, E, Y);
-#pragma unroll
-    for (int e = 0; e < 9; e++)
-      K[e] = X[e] + Y[e];
-    emit(B_GV, K);
+  for (;;) {
+    // what this iteration of the scan pushes: kind 0 nothing, 1 the sample interpolated at time0 (CASE 1), 2 sample k
+    // (CASE 2 / 3), 3 the sample interpolated at time1 from k-1, k (CASE 3 with d0 beyond time1); `last`: CASE 3 was
+    // reached, a second sample interpolated at time1 follows unless the first one already sits there
+    int kind = 0;
+    bool last = false;
+    const long long kk = k;
+    if (more && k + 1 < M) {
+      const double t0 = __ldg(it + k), t1 = __ldg(it + k + 1);
+      if (t1 > time0 && t0 < time0) {
+        kind = 1;
+      } else if (t0 >= time0 && t1 <= time1) {
+        kind = 2;
+      } else if (t1 > time1) {
+        more = false;
+        if (!(t0 > time1 && k == 0)) {
+          kind = (t0 > time1) ? 3 : 2;
+          last = true;
+        }
+      }
+      k++;
+    } else {
+      more = false;
+    }
+#pragma unroll 1
+    for (int u = 0; u < 3; u++) {
+      // u = 0, 1: the pushes of this iteration; u = 2: the flush after the scan has ended
+      bool do_push = false, do_fin = false;
+      Smp s = {};
+      if (u == 0) {
+        do_push = (kind != 0);
+        if (kind == 1)
+          smp_lerp(is, kk, kk + 1, time0, s);
+        else if (kind == 2)
+          smp_load(is, kk, s);
+        else if (kind == 3)
+          smp_lerp(is, kk - 1, kk, time1, s);
+      } else if (u == 1) {
+        do_push = last && (pend.t != time1);
+        if (do_push)
+          smp_lerp(is, kk, kk + 1, time1, s);
+      } else {
+        do_fin = !more && n_pushed > 0;
+      }
+      if (do_push)
+        do_fin = (n_pushed > 0) && !(fabs(s.t - pend.t) < 1e-12); // the earlier entry of a zero-dt pair is erased
+      if (do_fin) {
+        if (n_final > 0)
+          step(fin, pend);
+        fin = pend;
+        n_final++;
+      }
+      if (do_push) {
+        pend = s;
+        n_pushed++;
+      }
+    }
+    if (!more)
+      break;
   }
-  {
-    // K_gg = qwb I ; K_ga = 0 ; K_gp = Pgv ; K_aa = qab I ; K_ap = Pva^T ; K_pp = Pvp + Pvp^T
+  return n_final;
+}
+
+// averaged, bias-corrected measurement of one step (CpiV1.h:70-76, imu_avg = true)
+__device__ __forceinline__ void step_rates(const Smp &s0, const Smp &s1, const double *bw, const double *ba, double *w, double *a) {
 #pragma unroll
-    for (int e = 0; e < 9; e++)
-      K[e] = (e % 4 == 0) ? qwb : 0.0;
-    emit(B_GG, K);
-#pragma unroll
-    for (int e = 0; e < 9; e++)
-      K[e] = 0.0;
-    emit(B_GA, K);
-    P.ld(B_GV, K);
-    emit(B_GP, K);
-#pragma unroll
-    for (int e = 0; e < 9; e++)
-      K[e] = (e % 4 == 0) ? qab : 0.0;
-    emit(B_AA, K);
-    P.ldT(B_VA, K);
-    emit(B_AP, K);
-    double Pvp[9];
-    P.ld(B_VP, Pvp);
-#pragma unroll
-    for (int r = 0; r < 3; r++)
-#pragma unroll
-      for (int c = 0; c < 3; c++)
-        K[3 * r + c] = Pvp[3 * r + c] + Pvp[3 * c + r];
-    emit(B_PP, K);
+  for (int k = 0; k < 3; k++) {
+    w[k] = 0.5 * ((s0.w[k] - bw[k]) + (s1.w[k] - bw[k]));
+    a[k] = .5 * ((s0.a[k] - ba[k]) + (s1.a[k] - ba[k]));
   }
+}
+// exp(-[w]x tau) as the reference forms it (CpiV1.h:108-118 with tau = dt, :252-258 with tau = dt / 2)
+__device__ __forceinline__ void step_rotation(const double *w_x, const double *w_x_2, double mag_w, bool small_w, double tau, double *Rd) {
+  double s, c;
+  sincos(mag_w * tau, &s, &c);
+  const double c1 = small_w ? tau : (s / mag_w);
+  const double c2 = small_w ? ((tau * tau) / 2) : ((1.0 - c) / (mag_w * mag_w));
+#pragma unroll
+  for (int e = 0; e < 9; e++)
+    Rd[e] = ((e % 4 == 0) ? 1.0 : 0.0) - c1 * w_x[e] + c2 * w_x_2[e];
 }
 
 // state of the running preintegration of one interval (registers)
@@ -356,29 +322,22 @@ struct CpiRegs {
   double Jq[9], Ja[9], Jb[9], Ha[9], Hb[9];
 };
 
-// One CpiV1::feed_IMU step (CpiV1.h:58-341) with imu_avg = true.
-__device__ inline void cpi_step(CpiRegs &c, double t0, double t1, const double *w0, const double *a0, const double *w1,
-                                const double *a1, const double *bw, const double *ba, double qw, double qwb, double qa,
-                                double qab, double *smem_thread) {
-  const double dt = t1 - t0;
+// One CpiV1::feed_IMU step (CpiV1.h:58-244, :337-341) with imu_avg = true: means and bias Jacobians.
+__device__ __forceinline__ void cpi_step(CpiRegs &c, const Smp &s0, const Smp &s1, const double *bw, const double *ba) {
+  const double dt = s1.t - s0.t;
   c.DT += dt;
   if (dt == 0)
     return;
   double w[3], a[3];
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-    w[k] = 0.5 * ((w0[k] - bw[k]) + (w1[k] - bw[k]));
-    a[k] = .5 * ((a0[k] - ba[k]) + (a1[k] - ba[k]));
-  }
+  step_rates(s0, s1, bw, ba, w, a);
   const double mag_w = norm3(w);
   const double w_dt = mag_w * dt;
   const bool small_w = (mag_w < 0.008726646);
   const double dt_2 = dt * dt;
   double sin_wt, cos_wt;
   sincos(w_dt, &sin_wt, &cos_wt);
-  double w_x[9], a_x[9], w_x_2[9];
+  double w_x[9], w_x_2[9];
   skew(w, w_x);
-  skew(a, a_x);
   mm3(w_x, w_x, w_x_2);
 
   // ---- means (CpiV1.h:108-148)
@@ -512,125 +471,22 @@ __device__ inline void cpi_step(CpiRegs &c, double t0, double t1, const double *
       }
     }
   }
-  // ---- covariance, RK4 (CpiV1.h:246-335) on the block form
-  {
-    double Rm[9];
-    {
-      double s_h, c_h;
-      sincos(mag_w * .5 * dt, &s_h, &c_h);
-      const double hdt = .5 * dt;
-      const double c1 = small_w ? hdt : (s_h / mag_w);
-      const double c2 = small_w ? ((hdt * hdt) / 2) : ((1.0 - c_h) / (mag_w * mag_w));
-      double Rh[9];
-#pragma unroll
-      for (int e = 0; e < 9; e++)
-        Rh[e] = ((e % 4 == 0) ? 1.0 : 0.0) - c1 * w_x[e] + c2 * w_x_2[e];
-      mm3(Rh, c.R, Rm);
-    }
-    // P and the RK4 accumulator live in shared memory; the two stage inputs are thread-local (L1-resident local
-    // memory), which keeps the shared-memory footprint at 2.1 kB per interval (3 CTAs per SM instead of 1)
-    double psa[PB], psb[PB];
-    SmemCov P0{smem_thread, PRE_NT}, Pacc{smem_thread + PB * PRE_NT, PRE_NT}, PsA{psa, 1}, PsB{psb, 1};
-    double A[9], C[9], E[9];
-#pragma unroll
-    for (int e = 0; e < 9; e++)
-      A[e] = -w_x[e];
-    auto stage_mats = [&](const double *Rk) {
-      double T[9];
-      mm3_tn(Rk, a_x, T);
-#pragma unroll
-      for (int r = 0; r < 3; r++)
-#pragma unroll
-        for (int cc = 0; cc < 3; cc++) {
-          C[3 * r + cc] = -T[3 * r + cc];
-          E[3 * r + cc] = -Rk[3 * cc + r];
-        }
-    };
-    const double h2 = dt / 2.0;
-    // k1 : input P0 -> Pacc = k1 ; PsA = P0 + k1*dt/2
-    stage_mats(c.R);
-    cov_derivative(P0, A, C, E, qw, qwb, qa, qab, [&](int blk, const double *K) {
-#pragma unroll
-      for (int e = 0; e < 9; e++) {
-        Pacc.at(blk, e) = K[e];
-        PsA.at(blk, e) = P0.base[(blk * 9 + e) * PRE_NT] + K[e] * dt / 2.0;
-      }
-    });
-    // k2 : input PsA -> Pacc += 2 k2 ; PsB = P0 + k2*dt/2
-    stage_mats(Rm);
-    cov_derivative(PsA, A, C, E, qw, qwb, qa, qab, [&](int blk, const double *K) {
-#pragma unroll
-      for (int e = 0; e < 9; e++) {
-        Pacc.at(blk, e) += 2.0 * K[e];
-        PsB.at(blk, e) = P0.base[(blk * 9 + e) * PRE_NT] + K[e] * dt / 2.0;
-      }
-    });
-    // k3 : input PsB -> Pacc += 2 k3 ; PsA = P0 + k3*dt
-    cov_derivative(PsB, A, C, E, qw, qwb, qa, qab, [&](int blk, const double *K) {
-#pragma unroll
-      for (int e = 0; e < 9; e++) {
-        Pacc.at(blk, e) += 2.0 * K[e];
-        PsA.at(blk, e) = P0.base[(blk * 9 + e) * PRE_NT] + K[e] * dt;
-      }
-    });
-    // k4 : input PsA -> P0 += dt/6 (Pacc + k4)
-    stage_mats(R1);
-    (void)h2;
-    cov_derivative(PsA, A, C, E, qw, qwb, qa, qab, [&](int blk, const double *K) {
-#pragma unroll
-      for (int e = 0; e < 9; e++)
-        Pacc.at(blk, e) += K[e];
-    });
-#pragma unroll 1
-    for (int i = 0; i < PB; i++)
-      P0.base[i * PRE_NT] += (dt / 6.0) * Pacc.base[i * PRE_NT];
-    // symmetrise the diagonal blocks (P = 1/2 (P + P^T), CpiV1.h:335)
-    const int diag[5] = {B_TT, B_GG, B_VV, B_AA, B_PP};
-#pragma unroll
-    for (int b = 0; b < 5; b++) {
-      const int blk = diag[b];
-#pragma unroll
-      for (int r = 0; r < 3; r++)
-#pragma unroll
-        for (int cc = r + 1; cc < 3; cc++) {
-          const double m = 0.5 * (P0.at(blk, 3 * r + cc) + P0.at(blk, 3 * cc + r));
-          P0.at(blk, 3 * r + cc) = m;
-          P0.at(blk, 3 * cc + r) = m;
-        }
-    }
-  }
 #pragma unroll
   for (int e = 0; e < 9; e++)
     c.R[e] = R1[e];
 }
 
-// (block row, block col) -> block id and transposition for the upper-stored 5x5 block matrix
-__device__ __forceinline__ double cov_entry(const SmemCov &P, int r, int c) {
-  const int br = r / 3, bc = c / 3, er = r % 3, ec = c % 3;
-  const int id[5][5] = {{B_TT, B_TG, B_TV, B_TA, B_TP},
-                        {B_TG, B_GG, B_GV, B_GA, B_GP},
-                        {B_TV, B_GV, B_VV, B_VA, B_VP},
-                        {B_TA, B_GA, B_VA, B_AA, B_AP},
-                        {B_TP, B_GP, B_VP, B_AP, B_PP}};
-  if (br <= bc)
-    return P.base[(id[br][bc] * 9 + 3 * er + ec) * PRE_NT];
-  return P.base[(id[br][bc] * 9 + 3 * ec + er) * PRE_NT];
-}
-
 __device__ inline void set_status(LmState *lm, int code) { atomicCAS(&lm->status, V2GT_OK, code); }
 
-// grid: (ceil(n_max / PRE_NT), T), PRE_NT threads, dynamic smem 2*PB*PRE_NT doubles.
-__global__ void __launch_bounds__(PRE_NT) k_preintegrate(DevPtrs d, int keep_cov) {
-  extern __shared__ double smem[];
+constexpr int PRE_NT = 128; // intervals (threads) per CTA of k_preintegrate
+
+// grid: (ceil(n_max / PRE_NT), T), PRE_NT threads.
+__global__ void __launch_bounds__(PRE_NT) k_preintegrate(DevPtrs d) {
   const int t = blockIdx.y;
   const TrialDev &tr = d.trials[t];
   const int n = d.n_states[t];
   const int i = blockIdx.x * PRE_NT + threadIdx.x;
-  if (d.lm[t].status != V2GT_OK || d.lm[t].frozen)
-    return;
-  const bool active = (i < n - 1);
-  double *sm = smem + threadIdx.x;
-  if (!active)
+  if (d.lm[t].status != V2GT_OK || d.lm[t].frozen || i >= n - 1)
     return;
   const long long s = tr.st_off + i;
   const int cur = d.lm[t].cur;
@@ -638,14 +494,7 @@ __global__ void __launch_bounds__(PRE_NT) k_preintegrate(DevPtrs d, int keep_cov
   const double bw[3] = {x0[4], x0[5], x0[6]};
   const double ba[3] = {x0[10], x0[11], x0[12]};
   const double time0 = d.st_t[s], time1 = d.st_t[s + 1];
-  const double qw = tr.prm.sigma_w * tr.prm.sigma_w, qwb = tr.prm.sigma_wb * tr.prm.sigma_wb;
-  const double qa = tr.prm.sigma_a * tr.prm.sigma_a, qab = tr.prm.sigma_ab * tr.prm.sigma_ab;
-  const double *it = d.imu_t + tr.imu_off;
-  const double *is = d.imu_s + 8 * tr.imu_off;
-  const long long M = tr.n_imu;
 
-  for (int k = 0; k < 2 * PB; k++)
-    sm[k * PRE_NT] = 0.0;
   CpiRegs c;
   c.DT = 0;
 #pragma unroll
@@ -658,87 +507,12 @@ __global__ void __launch_bounds__(PRE_NT) k_preintegrate(DevPtrs d, int keep_cov
   for (int e = 0; e < 9; e++) {
     c.Jq[e] = 0; c.Ja[e] = 0; c.Jb[e] = 0; c.Ha[e] = 0; c.Hb[e] = 0;
   }
-
-  // ---- sample selection (Propagator.cpp:33-132) as a stream; zero-dt filter of :118-126 applied on the fly
-  struct Smp {
-    double t, w[3], a[3];
-  };
-  auto load = [&](long long idx, Smp &o) {
-    const double4 u0 = ldg4(is + 8 * idx);
-    const double4 u1 = ldg4(is + 8 * idx + 4);
-    o.t = u0.x; o.w[0] = u0.y; o.w[1] = u0.z; o.w[2] = u0.w;
-    o.a[0] = u1.x; o.a[1] = u1.y; o.a[2] = u1.z;
-  };
-  auto lerp = [&](const Smp &s1, const Smp &s2, double ts, Smp &o) { // Propagator.h:63-73
-    const double lambda = (ts - s1.t) / (s2.t - s1.t);
-    o.t = ts;
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      o.a[k] = (1 - lambda) * s1.a[k] + lambda * s2.a[k];
-      o.w[k] = (1 - lambda) * s1.w[k] + lambda * s2.w[k];
-    }
-  };
-  Smp pend = {}, fin = {}; // pend: last pushed sample (may still be dropped by the zero-dt filter); fin: last finalised one
-  int n_pushed = 0, n_final = 0, n_steps = 0;
-  auto finalize = [&](const Smp &smp) {
-    if (n_final > 0) {
-      cpi_step(c, fin.t, smp.t, fin.w, fin.a, smp.w, smp.a, bw, ba, qw, qwb, qa, qab, sm);
-      n_steps++;
-    }
-    fin = smp;
-    n_final++;
-  };
-  auto push = [&](const Smp &smp) {
-    if (n_pushed > 0) {
-      if (fabs(smp.t - pend.t) < 1e-12) {
-        // the earlier entry of a zero-dt pair is erased
-      } else {
-        finalize(pend);
-      }
-    }
-    pend = smp;
-    n_pushed++;
-  };
-  if (M >= 2) {
-    // time-ordered store: start at the sample in front of time0 (every earlier iteration of the reference's scan from
-    // sample 0 matches none of its three cases); unordered store: the reference's scan itself (Propagator.cpp:46)
-    long long lb = tr.imu_unsorted ? 0 : lower_bound_d(it, M, time0);
-    long long ib = (lb >= 1) ? lb - 1 : 0;
-    Smp d0, d1, tmp;
-    load(ib, d1);
-    for (long long k = ib; k + 1 < M; k++) {
-      d0 = d1;
-      load(k + 1, d1);
-      if (d1.t > time0 && d0.t < time0) { // CASE 1
-        lerp(d0, d1, time0, tmp);
-        push(tmp);
-        continue;
-      }
-      if (d0.t >= time0 && d1.t <= time1) { // CASE 2
-        push(d0);
-        continue;
-      }
-      if (d1.t > time1) { // CASE 3
-        if (d0.t > time1 && k == 0) {
-          break;
-        } else if (d0.t > time1) {
-          Smp dm;
-          load(k - 1, dm);
-          lerp(dm, d0, time1, tmp);
-          push(tmp);
-        } else {
-          push(d0);
-        }
-        if (pend.t != time1) {
-          lerp(d0, d1, time1, tmp);
-          push(tmp);
-        }
-        break;
-      }
-    }
-  }
-  if (n_pushed > 0)
-    finalize(pend);
+  int n_steps = 0;
+  const int n_final = select_samples(d.imu_t + tr.imu_off, d.imu_s + 8 * tr.imu_off, tr.n_imu, tr.imu_unsorted, time0, time1,
+                                     [&](const Smp &s0, const Smp &s1) {
+                                       cpi_step(c, s0, s1, bw, ba);
+                                       n_steps++;
+                                     });
   if (n_final < 2 || c.DT != (time1 - time0)) { // ViconGraphSolver.cpp:508-512
     set_status(d.lm + t, V2GT_ERR_INVALID_PREINT);
     return;
@@ -766,58 +540,232 @@ __global__ void __launch_bounds__(PRE_NT) k_preintegrate(DevPtrs d, int keep_cov
   }
   pr[PRE_NSTEPS] = (double)n_steps;
   pr[63] = 0.0;
+}
 
-  // ---- information matrix P^-1 = L^-T L^-1 (Gaussian::Covariance, ImuFactorCPIv1.h:74)
-  SmemCov P0{sm, PRE_NT};
-  double *Lm = sm + PB * PRE_NT;      // packed lower L  (120), in the accumulator's shared-memory region
-  double Li[120];                     // packed lower L^-1, thread-local
-  if (keep_cov && d.cov) {
-    double *cv = d.cov + s * 225;
-    for (int r = 0; r < 15; r++)
-      for (int cc = 0; cc < 15; cc++)
-        cv[15 * r + cc] = cov_entry(P0, r, cc);
+// ---- covariance: P' = F P + P F^T + G Qc G^T (CpiV1.h:246-335) over the state order [th bg v ba p], with
+//   F = [A -I 0 0 0; 0; C 0 0 E 0; 0; 0 0 I 0 0],  A = -[w]x, C = -R^T [a]x, E = -R^T  (R the rotation of the RK4 stage),
+//   G Qc G^T = diag(qw, qwb, qa, qab, 0).
+// P is symmetric, so P F^T = (F P)^T: lane j of an interval's sixteen holds COLUMN j of P, forms column j of M = F P
+// from its own registers (rows th, v, p; the bias rows of F are zero), and gets row j of M -- one element from each
+// other lane -- through a small transposition buffer in shared memory.  Both triangles are carried and stay bitwise
+// symmetric (M_ij + M_ji is formed from the same two numbers on either side), which makes the reference's
+// P = (P + P^T) / 2 after every step the identity.
+constexpr int COV_WARPS = 4;            // warps per CTA, two intervals each
+constexpr int COV_TS = 11;              // doubles per column in the transposition buffer: 9 rows of M + a zero + pad (odd)
+constexpr int COV_TBUF = 16 * COV_TS;
+#ifndef COV_MIN_CTAS_N
+#define COV_MIN_CTAS_N 3
+#endif
+constexpr int COV_MIN_CTAS = COV_MIN_CTAS_N;
+
+// shared memory of one interval: two transposition buffers (alternating between the RK4 stages: one barrier per stage)
+// and the rotations of the step: slots 0 and 2 alternate as start / end of a step, slot 1 is the half step
+struct CovSmem {
+  double tb[2][COV_TBUF];
+  double R[3][9];
+};
+
+// sin and cos of a step's angle |w| tau: a few hundredths of a radian at IMU rates, where the Taylor polynomials are
+// exact to the last bit or two; the library routine for anything larger
+__device__ __forceinline__ void sincos_step(double x, double *s, double *c) {
+  if (fabs(x) < 0.25) {
+    const double x2 = x * x;
+    double ps = 1.0 / 1307674368000.0; // 1 / 15!
+    ps = fma(ps, x2, -1.0 / 6227020800.0);
+    ps = fma(ps, x2, 1.0 / 39916800.0);
+    ps = fma(ps, x2, -1.0 / 362880.0);
+    ps = fma(ps, x2, 1.0 / 5040.0);
+    ps = fma(ps, x2, -1.0 / 120.0);
+    ps = fma(ps, x2, 1.0 / 6.0);
+    *s = fma(-x * x2, ps, x);
+    double pc = -1.0 / 87178291200.0; // 1 / 14!
+    pc = fma(pc, x2, 1.0 / 479001600.0);
+    pc = fma(pc, x2, -1.0 / 3628800.0);
+    pc = fma(pc, x2, 1.0 / 40320.0);
+    pc = fma(pc, x2, -1.0 / 720.0);
+    pc = fma(pc, x2, 1.0 / 24.0);
+    pc = fma(pc, x2, -0.5);
+    *c = fma(x2, pc, 1.0);
+  } else {
+    sincos(x, s, c);
   }
+}
+
+// grid: (ceil(n_max / (2 COV_WARPS)), T), 32 COV_WARPS threads.  Runs after k_preintegrate, which has flagged the trials
+// with an invalid interval.
+__global__ void __launch_bounds__(32 * COV_WARPS, COV_MIN_CTAS) k_preint_cov(DevPtrs d, int keep_cov) {
+  __shared__ CovSmem sm_all[COV_WARPS * 2];
+  const int t = blockIdx.y;
+  const TrialDev &tr = d.trials[t];
+  const int n = d.n_states[t];
+  const int lane = threadIdx.x & 31, half = lane >> 4, j = lane & 15, wrp = threadIdx.x >> 5;
+  const int i = (blockIdx.x * COV_WARPS + wrp) * 2 + half;
+  if (d.lm[t].status != V2GT_OK || d.lm[t].frozen || i >= n - 1)
+    return;
+  const unsigned hm = 0xFFFFu << (16 * half); // the lanes of this interval: every barrier below is among them
+  CovSmem &sm = sm_all[wrp * 2 + half];
+  const long long s = tr.st_off + i;
+  const int cur = d.lm[t].cur;
+  const double *x0 = d.x + ((long long)cur * d.S + s) * X_STRIDE;
+  const double time0 = d.st_t[s], time1 = d.st_t[s + 1];
+  const int jb = j / 3; // block of this lane's column: 0 th, 1 bg, 2 v, 3 ba, 4 p, 5 = the idle sixteenth lane (a zero column)
+  const int jc = j - 3 * jb;
+  const double qd = (jb == 0)   ? tr.prm.sigma_w * tr.prm.sigma_w
+                    : (jb == 1) ? tr.prm.sigma_wb * tr.prm.sigma_wb
+                    : (jb == 2) ? tr.prm.sigma_a * tr.prm.sigma_a
+                    : (jb == 3) ? tr.prm.sigma_ab * tr.prm.sigma_ab
+                                : 0.0;
+  // where row j of M sits in a column of the buffer: th 0..2, v 3..5, p 6..8; the bias rows (and lane 15) read the zero
+  const int rs = (jb == 0) ? j : (jb == 2) ? j - 3 : (jb == 4) ? j - 6 : 9;
+  sm.tb[0][j * COV_TS + 9] = 0.0;
+  sm.tb[1][j * COV_TS + 9] = 0.0;
+  if (j < 9)
+    sm.R[0][j] = (j % 4 == 0) ? 1.0 : 0.0;
+  __syncwarp(hm);
+
+  double P[15], DT = 0;
+#pragma unroll
+  for (int e = 0; e < 15; e++)
+    P[e] = 0.0;
+  int r_start = 0; // slot of the rotation at the start of the step
+
+  const int n_final = select_samples(
+      d.imu_t + tr.imu_off, d.imu_s + 8 * tr.imu_off, tr.n_imu, tr.imu_unsorted, time0, time1, [&](const Smp &s0, const Smp &s1) {
+        const double dt = s1.t - s0.t;
+        DT += dt;
+        if (dt == 0)
+          return;
+        double w[3], a[3];
+        {
+          const double bw[3] = {__ldg(x0 + 4), __ldg(x0 + 5), __ldg(x0 + 6)};
+          const double ba[3] = {__ldg(x0 + 10), __ldg(x0 + 11), __ldg(x0 + 12)};
+          step_rates(s0, s1, bw, ba, w, a);
+        }
+        const double *R0 = sm.R[r_start], *Rh = sm.R[1], *R1 = sm.R[2 - r_start];
+        {
+          // the rotations of the step, R(tau) = exp(-[w]x tau) R_k = R_k - c1 [w]x R_k + c2 [w]x^2 R_k at tau = dt / 2 and
+          // dt (CpiV1.h:108-118, :252-258), one COLUMN per lane: [w]x r = w x r.  Lanes 0..2 store.
+          const double mag_w = norm3(w);
+          const bool small_w = (mag_w < 0.008726646);
+          const double hdt = .5 * dt;
+          double sf, cf, sh, ch;
+          sincos_step(mag_w * dt, &sf, &cf);
+          sincos_step(mag_w * hdt, &sh, &ch);
+          const double im = 1.0 / mag_w, im2 = 1.0 / (mag_w * mag_w);
+          const double c1f = small_w ? dt : sf * im, c2f = small_w ? (dt * dt) / 2 : (1.0 - cf) * im2;
+          const double c1h = small_w ? hdt : sh * im, c2h = small_w ? (hdt * hdt) / 2 : (1.0 - ch) * im2;
+          const double r[3] = {R0[jc], R0[3 + jc], R0[6 + jc]};
+          const double x1[3] = {w[1] * r[2] - w[2] * r[1], w[2] * r[0] - w[0] * r[2], w[0] * r[1] - w[1] * r[0]};
+          const double x2[3] = {w[1] * x1[2] - w[2] * x1[1], w[2] * x1[0] - w[0] * x1[2], w[0] * x1[1] - w[1] * x1[0]};
+          if (j < 3) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+              sm.R[1][3 * k + jc] = r[k] - c1h * x1[k] + c2h * x2[k];
+              sm.R[2 - r_start][3 * k + jc] = r[k] - c1f * x1[k] + c2f * x2[k];
+            }
+          }
+        }
+        double Pacc[15], Ps[12]; // Ps: stage input; its p rows are never read (no column of F meets them)
+        // one RK4 stage: K = F Pin + (F Pin)^T + Q, column j; emit(e, K_e) per element
+        auto stage = [&](const double *Rk, const double *Pin, double *buf, auto emit) {
+          double m[9];
+          // th rows: A pth - pg
+          m[0] = (w[2] * Pin[1] - w[1] * Pin[2]) - Pin[3];
+          m[1] = (w[0] * Pin[2] - w[2] * Pin[0]) - Pin[4];
+          m[2] = (w[1] * Pin[0] - w[0] * Pin[1]) - Pin[5];
+          // v rows: C pth + E pa = -R^T (a x pth + pa)
+          const double u0 = (a[1] * Pin[2] - a[2] * Pin[1]) + Pin[9];
+          const double u1 = (a[2] * Pin[0] - a[0] * Pin[2]) + Pin[10];
+          const double u2 = (a[0] * Pin[1] - a[1] * Pin[0]) + Pin[11];
+#pragma unroll
+          for (int r = 0; r < 3; r++)
+            m[3 + r] = -(Rk[r] * u0 + Rk[3 + r] * u1 + Rk[6 + r] * u2);
+          // p rows: pv
+#pragma unroll
+          for (int r = 0; r < 3; r++)
+            m[6 + r] = Pin[6 + r];
+#pragma unroll
+          for (int r = 0; r < 9; r++)
+            buf[j * COV_TS + r] = m[r];
+          __syncwarp(hm);
+#pragma unroll
+          for (int e = 0; e < 15; e++) {
+            const double mt = buf[e * COV_TS + rs]; // M[j][e]
+            const int blk = e / 3;
+            double K = (blk == 0) ? m[e] + mt : (blk == 2) ? m[e - 3] + mt : (blk == 4) ? m[e - 6] + mt : mt;
+            K += (e == j) ? qd : 0.0;
+            emit(e, K);
+          }
+        };
+        // k1 at R_k (CpiV1.h:274-281), k2 and k3 at the half-step rotation (:283-311), k4 at R_tau1 (:313-327); the
+        // barrier of stage 1 also orders the stores of the two new rotations before their first use
+        const double h2 = dt / 2.0, h6 = dt / 6.0;
+        stage(R0, P, sm.tb[0], [&](int e, double K) {
+          Pacc[e] = K;
+          if (e < 12)
+            Ps[e] = P[e] + K * h2;
+        });
+        stage(Rh, Ps, sm.tb[1], [&](int e, double K) {
+          Pacc[e] += 2.0 * K;
+          if (e < 12)
+            Ps[e] = P[e] + K * h2;
+        });
+        stage(Rh, Ps, sm.tb[0], [&](int e, double K) {
+          Pacc[e] += 2.0 * K;
+          if (e < 12)
+            Ps[e] = P[e] + K * dt;
+        });
+        stage(R1, Ps, sm.tb[1], [&](int e, double K) { P[e] += h6 * (Pacc[e] + K); });
+        r_start = 2 - r_start;
+      });
+  if (n_final < 2 || DT != (time1 - time0)) // flagged by k_preintegrate
+    return;
+
+  if (keep_cov && d.cov && j < 15) {
+    double *cv = d.cov + s * 225;
+#pragma unroll
+    for (int r = 0; r < 15; r++)
+      cv[15 * r + j] = P[r];
+  }
+  // ---- information matrix P^-1 (Gaussian::Covariance, ImuFactorCPIv1.h:74) by Gauss-Jordan sweeps in place, without
+  // pivoting (P is symmetric positive definite; the pivots are those of its Cholesky factorisation, squared): sweep k
+  // broadcasts column k through shared memory, every lane updates its own column
   bool bad = false;
-  for (int j = 0; j < 15; j++) {
-    double dd = cov_entry(P0, j, j);
-    for (int k = 0; k < j; k++) {
-      const double l = Lm[tri(j, k) * PRE_NT];
-      dd -= l * l;
+#pragma unroll
+  for (int k = 0; k < 15; k++) {
+    double *buf = sm.tb[k & 1];
+    if (j == k) {
+#pragma unroll
+      for (int r = 0; r < 15; r++)
+        buf[r] = P[r];
     }
-    if (!(dd > 0.0)) {
-      bad = true;
-      break;
+    __syncwarp(hm);
+    const double pk = buf[k];
+    if (!(pk > 0.0))
+      bad = true; // same value on the sixteen lanes
+    const double dinv = 1.0 / pk;
+    const double f = P[k] * dinv; // row k of the swept matrix
+#pragma unroll
+    for (int r = 0; r < 15; r++) {
+      if (r == k)
+        continue;
+      const double c = buf[r];
+      P[r] = (j == k) ? -c * dinv : P[r] - c * f;
     }
-    const double ljj = sqrt(dd);
-    Lm[tri(j, j) * PRE_NT] = ljj;
-    for (int r = j + 1; r < 15; r++) {
-      double sacc = cov_entry(P0, r, j);
-      for (int k = 0; k < j; k++)
-        sacc -= Lm[tri(r, k) * PRE_NT] * Lm[tri(j, k) * PRE_NT];
-      Lm[tri(r, j) * PRE_NT] = sacc / ljj;
-    }
+    P[k] = (j == k) ? dinv : f;
   }
   if (bad) {
-    set_status(d.lm + t, V2GT_ERR_NAN_COVARIANCE);
+    if (j == 0)
+      set_status(d.lm + t, V2GT_ERR_NAN_COVARIANCE);
     return;
-  }
-  for (int cc = 0; cc < 15; cc++) {
-    for (int r = cc; r < 15; r++) {
-      double sacc = (r == cc) ? 1.0 : 0.0;
-      for (int k = cc; k < r; k++)
-        sacc -= Lm[tri(r, k) * PRE_NT] * Li[tri(k, cc)];
-      Li[tri(r, cc)] = sacc / Lm[tri(r, r) * PRE_NT];
-    }
   }
   const SoaW inf = soa_w(d.info, s, INFO_STRIDE);
   bool nan_found = false;
+#pragma unroll
   for (int r = 0; r < 15; r++)
-    for (int cc = 0; cc <= r; cc++) {
-      double sacc = 0;
-      for (int k = r; k < 15; k++) // (Li^T Li)[r][cc] = sum_k Li[k][r] Li[k][cc], k >= max(r,cc) = r
-        sacc += Li[tri(k, r)] * Li[tri(k, cc)];
-      inf[tri(r, cc)] = sacc;
-      if (sacc != sacc)
+    if (r >= j) {
+      inf[tri(r, j)] = P[r];
+      if (P[r] != P[r])
         nan_found = true;
     }
   if (nan_found)
@@ -837,13 +785,10 @@ int launch_init_states(const DevPtrs &d, int n_max, int init_states, cudaStream_
 }
 
 int launch_preintegrate(const DevPtrs &d, int n_max, int keep_cov, cudaStream_t st) {
-  const size_t smem = sizeof(double) * 2 * PB * PRE_NT;
-  // function attributes are per device (context): set on every launch, a handle may live on any GPU of the process
-  V2_CUDA_CHECK(cudaFuncSetAttribute(k_preintegrate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((n_max + PRE_NT - 1) / PRE_NT, d.T);
-  if (grid.x == 0)
+  if (n_max <= 0)
     return V2GT_OK;
-  k_preintegrate<<<grid, PRE_NT, smem, st>>>(d, keep_cov);
+  k_preintegrate<<<dim3((n_max + PRE_NT - 1) / PRE_NT, d.T), PRE_NT, 0, st>>>(d);
+  k_preint_cov<<<dim3((n_max + 2 * COV_WARPS - 1) / (2 * COV_WARPS), d.T), 32 * COV_WARPS, 0, st>>>(d, keep_cov);
   V2_CUDA_CHECK(cudaGetLastError());
   return V2GT_OK;
 }
