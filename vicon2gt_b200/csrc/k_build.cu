@@ -205,6 +205,36 @@ __device__ __forceinline__ void smp_load(const double *is, long long idx, Smp &o
   o.t = u0.x; o.w[0] = u0.y; o.w[1] = u0.z; o.w[2] = u0.w;
   o.a[0] = u1.x; o.a[1] = u1.y; o.a[2] = u1.z;
 }
+// first raw sample of the scan for an interval starting at time0.  Time-ordered store: the sample in front of time0
+// (every earlier iteration of the reference's scan from sample 0 matches none of its three cases); unordered store:
+// the reference's scan itself (Propagator.cpp:46)
+__device__ __forceinline__ long long scan_start(const double *__restrict__ it, long long M, int unsorted, double time0) {
+  if (unsorted || M < 2)
+    return 0;
+  const long long lb = lower_bound_d(it, M, time0);
+  return (lb >= 1) ? lb - 1 : 0;
+}
+// the same by the sixteen lanes of an interval together: seventeen-way sections instead of halvings (five rounds of one
+// load for 10^5 samples instead of seventeen dependent ones)
+__device__ __forceinline__ long long scan_start16(const double *__restrict__ it, long long M, int unsorted, double time0, unsigned hm,
+                                                  int half, int j) {
+  if (unsorted || M < 2)
+    return 0;
+  long long lo = 0, hi = M; // the lower bound lies in [lo, hi]
+  while (lo < hi) {
+    const long long span = hi - lo;
+    const long long pj = lo + (span * (j + 1)) / 17; // < hi; non-decreasing in j
+    const bool below = __ldg(it + pj) < time0;
+    const int c = __popc((__ballot_sync(hm, below) >> (16 * half)) & 0xFFFFu); // lanes 0..c-1 are below (the store is sorted)
+    const long long p_lo = lo + (span * c) / 17, p_hi = lo + (span * (c + 1)) / 17;
+    if (c > 0)
+      lo = p_lo + 1;
+    if (c < 16)
+      hi = p_hi;
+  }
+  return (lo >= 1) ? lo - 1 : 0;
+}
+
 // Propagator.h:63-73
 __device__ __forceinline__ void smp_lerp(const double *is, long long i1, long long i2, double ts, Smp &o) {
   Smp s1, s2;
@@ -220,18 +250,12 @@ __device__ __forceinline__ void smp_lerp(const double *is, long long i1, long lo
 }
 
 template <class Step>
-__device__ __forceinline__ int select_samples(const double *__restrict__ it, const double *__restrict__ is, long long M, int unsorted,
+__device__ __forceinline__ int select_samples(const double *__restrict__ it, const double *__restrict__ is, long long M, long long k0,
                                               double time0, double time1, Step step) {
   Smp pend = {}, fin = {}; // pend: last pushed sample (may still be dropped by the zero-dt filter); fin: last finalised one
   int n_pushed = 0, n_final = 0;
   bool more = (M >= 2);
-  // time-ordered store: start at the sample in front of time0 (every earlier iteration of the reference's scan from
-  // sample 0 matches none of its three cases); unordered store: the reference's scan itself (Propagator.cpp:46)
-  long long k = 0;
-  if (more) {
-    const long long lb = unsorted ? 0 : lower_bound_d(it, M, time0);
-    k = (lb >= 1) ? lb - 1 : 0;
-  }
+  long long k = k0; // scan_start()
   for (;;) {
     // what this iteration of the scan pushes: kind 0 nothing, 1 the sample interpolated at time0 (CASE 1), 2 sample k
     // (CASE 2 / 3), 3 the sample interpolated at time1 from k-1, k (CASE 3 with d0 beyond time1); `last`: CASE 3 was
@@ -508,7 +532,8 @@ __global__ void __launch_bounds__(PRE_NT) k_preintegrate(DevPtrs d) {
     c.Jq[e] = 0; c.Ja[e] = 0; c.Jb[e] = 0; c.Ha[e] = 0; c.Hb[e] = 0;
   }
   int n_steps = 0;
-  const int n_final = select_samples(d.imu_t + tr.imu_off, d.imu_s + 8 * tr.imu_off, tr.n_imu, tr.imu_unsorted, time0, time1,
+  const long long k0 = scan_start(d.imu_t + tr.imu_off, tr.n_imu, tr.imu_unsorted, time0);
+  const int n_final = select_samples(d.imu_t + tr.imu_off, d.imu_s + 8 * tr.imu_off, tr.n_imu, k0, time0, time1,
                                      [&](const Smp &s0, const Smp &s1) {
                                        cpi_step(c, s0, s1, bw, ba);
                                        n_steps++;
@@ -551,7 +576,11 @@ __global__ void __launch_bounds__(PRE_NT) k_preintegrate(DevPtrs d) {
 // symmetric (M_ij + M_ji is formed from the same two numbers on either side), which makes the reference's
 // P = (P + P^T) / 2 after every step the identity.
 constexpr int COV_WARPS = 4;            // warps per CTA, two intervals each
-constexpr int COV_TS = 11;              // doubles per column in the transposition buffer: 9 rows of M + a zero + pad (odd)
+// doubles per column of the transposition buffer: slots 0..8 = the th, v, p rows of M in this column; slots 9..15 are
+// constants, one per lane whose row of M is zero (bg, ba, the idle lane): slot 9 + n of column e holds the process
+// noise q of that lane where e is its own column, zero elsewhere -- so the diagonal of Q arrives with the read of
+// M[j][e] instead of costing a compare per element; one pad (odd stride: conflict-free)
+constexpr int COV_TS = 17;
 constexpr int COV_TBUF = 16 * COV_TS;
 #ifndef COV_MIN_CTAS_N
 #define COV_MIN_CTAS_N 3
@@ -615,10 +644,14 @@ __global__ void __launch_bounds__(32 * COV_WARPS, COV_MIN_CTAS) k_preint_cov(Dev
                     : (jb == 2) ? tr.prm.sigma_a * tr.prm.sigma_a
                     : (jb == 3) ? tr.prm.sigma_ab * tr.prm.sigma_ab
                                 : 0.0;
-  // where row j of M sits in a column of the buffer: th 0..2, v 3..5, p 6..8; the bias rows (and lane 15) read the zero
-  const int rs = (jb == 0) ? j : (jb == 2) ? j - 3 : (jb == 4) ? j - 6 : 9;
-  sm.tb[0][j * COV_TS + 9] = 0.0;
-  sm.tb[1][j * COV_TS + 9] = 0.0;
+  // where row j of M sits in a column of the buffer: th 0..2, v 3..5, p 6..8; bg 9..11, ba 12..14, idle lane 15
+  const int rs = (jb == 0) ? j : (jb == 2) ? j - 3 : (jb == 4) ? j - 6 : (jb == 1) ? j + 6 : (jb == 3) ? j + 3 : 15;
+  const double qm = (rs < 9) ? qd : 0.0; // added to the stored M[j][j]; the zero-row lanes have q in their constant slot
+#pragma unroll
+  for (int r = 9; r < 16; r++) {
+    sm.tb[0][j * COV_TS + r] = (r == rs) ? qd : 0.0;
+    sm.tb[1][j * COV_TS + r] = (r == rs) ? qd : 0.0;
+  }
   if (j < 9)
     sm.R[0][j] = (j % 4 == 0) ? 1.0 : 0.0;
   __syncwarp(hm);
@@ -629,8 +662,9 @@ __global__ void __launch_bounds__(32 * COV_WARPS, COV_MIN_CTAS) k_preint_cov(Dev
     P[e] = 0.0;
   int r_start = 0; // slot of the rotation at the start of the step
 
+  const long long k0 = scan_start16(d.imu_t + tr.imu_off, tr.n_imu, tr.imu_unsorted, time0, hm, half, j);
   const int n_final = select_samples(
-      d.imu_t + tr.imu_off, d.imu_s + 8 * tr.imu_off, tr.n_imu, tr.imu_unsorted, time0, time1, [&](const Smp &s0, const Smp &s1) {
+      d.imu_t + tr.imu_off, d.imu_s + 8 * tr.imu_off, tr.n_imu, k0, time0, time1, [&](const Smp &s0, const Smp &s1) {
         const double dt = s1.t - s0.t;
         DT += dt;
         if (dt == 0)
@@ -687,13 +721,13 @@ __global__ void __launch_bounds__(32 * COV_WARPS, COV_MIN_CTAS) k_preint_cov(Dev
 #pragma unroll
           for (int r = 0; r < 9; r++)
             buf[j * COV_TS + r] = m[r];
+          buf[j * COV_TS + rs] += qm; // M[j][j] + q, read back by this lane alone
           __syncwarp(hm);
 #pragma unroll
           for (int e = 0; e < 15; e++) {
-            const double mt = buf[e * COV_TS + rs]; // M[j][e]
+            const double mt = buf[e * COV_TS + rs]; // M[j][e] (+ q on the diagonal)
             const int blk = e / 3;
-            double K = (blk == 0) ? m[e] + mt : (blk == 2) ? m[e - 3] + mt : (blk == 4) ? m[e - 6] + mt : mt;
-            K += (e == j) ? qd : 0.0;
+            const double K = (blk == 0) ? m[e] + mt : (blk == 2) ? m[e - 3] + mt : (blk == 4) ? m[e - 6] + mt : mt;
             emit(e, K);
           }
         };
@@ -744,15 +778,18 @@ __global__ void __launch_bounds__(32 * COV_WARPS, COV_MIN_CTAS) k_preint_cov(Dev
     if (!(pk > 0.0))
       bad = true; // same value on the sixteen lanes
     const double dinv = 1.0 / pk;
-    const double f = P[k] * dinv; // row k of the swept matrix
+    const double f = (j == k) ? dinv : P[k] * dinv; // row k of the swept matrix
+    // column k of the swept matrix is -c / p_kk: lane k restarts from zero (one predicated move per element; the
+    // compiler's own lowering of "if (j == k) P[r] = 0" is a zero and two predicated copies)
 #pragma unroll
-    for (int r = 0; r < 15; r++) {
-      if (r == k)
-        continue;
-      const double c = buf[r];
-      P[r] = (j == k) ? -c * dinv : P[r] - c * f;
-    }
-    P[k] = (j == k) ? dinv : f;
+    for (int r = 0; r < 15; r++)
+      if (r != k)
+        asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, %2;\n\t@p mov.f64 %0, 0d0000000000000000;\n\t}" : "+d"(P[r]) : "r"(j), "r"(k));
+#pragma unroll
+    for (int r = 0; r < 15; r++)
+      if (r != k)
+        P[r] = fma(-buf[r], f, P[r]);
+    P[k] = f;
   }
   if (bad) {
     if (j == 0)
