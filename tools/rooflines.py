@@ -18,7 +18,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ALG = {
     "k_init_states": ("raw state", 3 * 230 + 128, 3 * 1500, "latency", "three interpolations per state (t, t +- 0.25 s)"),
     "k_compact": ("raw state", 2 * 136, 0, "latency", "order-preserving compaction of times + state rows"),
-    "k_preintegrate": ("interval", 5 * 56 + 1456, 60e3, "fp64", "U1 x ~5 IMU steps + U1' epilogue (C1 shape: 60 kflop, 1.74 kB)"),
+    "k_preintegrate": ("interval", 5 * 56 + 128 + 512, 15e3, "latency", "U1 means and bias Jacobians x ~5 IMU steps, one thread per interval; writes the 64-double constants row"),
+    "k_preint_cov": ("interval", 5 * 56 + 128 + 960, 45e3, "fp64", "U1 covariance (RK4, ~5 IMU steps) + U1' information matrix, sixteen lanes per interval; writes the packed 120-double information matrix"),
     "k_factor_eval<1>": ("state", 1900 + 1216, 8e3, "hbm", "U3 without the whitening products: reads state / constants, writes the factor pieces"),
     "k_factor_eval<0>": ("state", 1900 + 128 + 384, 3e3, "hbm", "U5: trial point (retract) + both residuals"),
     "k_assemble": ("state", 960 + 456 + 704 + 512 + 3968 + 128, 17e3, "hbm", "J^T Lambda J from the 3x3 block structure; writes the 496-double record"),
