@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(256) k_compact(DevPtrs d) {
 // kernel (1): continuous preintegration (CpiV1) of every interval, in two launches over the same sample stream:
 //   k_preintegrate   one THREAD per interval: means and bias Jacobians (registers only)
 //   k_preint_cov     sixteen LANES per interval (two intervals per warp): the 15x15 covariance by RK4, one column
-//                    per lane in registers, and the information matrix P^-1 = L^-T L^-1 by shuffles
+//                    per lane in registers, and the information matrix P^-1 by Gauss-Jordan sweeps
 // (one thread per interval for both needed four 15x15 copies per thread: 4.3 kB of shared / local memory per interval,
 //  three warps per SM, 13 kB of DRAM traffic per interval for 1.7 kB of results)
 
