@@ -60,6 +60,9 @@ constexpr int ELIM_WARPS = ELIM_WARPS_N;
 #ifndef ELIM_BULK
 #define ELIM_BULK 1 // 1: record staged by one cp.async.bulk + mbarrier per state (0: cp.async 16-byte chunks per lane)
 #endif
+#ifndef ELIM_SERIAL
+#define ELIM_SERIAL 0 // K > 0: the DMMAs of W and of the Schur tiles are tied into K dependent chains (gaps on the FP64 pipe for the other warps' scalar instructions)
+#endif
 constexpr int SW_STAGE = 0, SW_CB = 2 * NE_STRIDE, SW_BAR = SW_CB + 128, SW_ACC = SW_BAR + 2;
 constexpr int SW_ACC_N = ELIM_ACC_SMEM ? (6 * 64 + 5 * 8) : 0;
 constexpr int SW_TOTAL = SW_ACC + SW_ACC_N;
@@ -69,6 +72,14 @@ constexpr int SW_TOTAL = SW_ACC + SW_ACC_N;
 __device__ __forceinline__ void dmma(double &c0, double &c1, const double a, const double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
+#if ELIM_SERIAL
+// a zero that the hardware has to wait for: (high word of prev) & zm with zm = 0 at run time only
+__device__ __forceinline__ double dep_zero(const double prev, const int zm) { return __hiloint2double(__double2hiint(prev) & zm, 0); }
+// the operand, unchanged, but not before prev exists
+__device__ __forceinline__ double dep_on(const double a, const double prev, const int zm) {
+  return __hiloint2double(__double2hiint(a) ^ (__double2hiint(prev) & zm), __double2loint(a));
+}
+#endif
 __device__ __forceinline__ void cp_async16(double *smem, const double *gmem) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
@@ -537,12 +548,31 @@ __device__ __forceinline__ bool elim_node(const double *st, const double *__rest
   const bool ok = ldl_inverse(d00, d10, d11, li00, li10, li11, cb, gid, tid);
   // ---- W^T = M^T L^-T  (row tile u of W from the kk-steps its triangle reaches)
   double w[4][5];
+#if ELIM_SERIAL
+  const int zm = (int)blockIdx.z; // 0 at run time, unknown to the compiler
+  double tok[ELIM_SERIAL];
+#pragma unroll
+  for (int q = 0; q < ELIM_SERIAL; q++)
+    tok[q] = li11[0];
+  int nch = 0;
+#endif
 #pragma unroll
   for (int t = 0; t < 5; t++) {
     if (!HAS_F && t == 2) {
       w[0][t] = w[1][t] = w[2][t] = w[3][t] = 0.0;
       continue;
     }
+#if ELIM_SERIAL
+    double a0 = dep_zero(tok[t % ELIM_SERIAL], zm), a1 = 0.0, b0 = 0.0, b1 = 0.0;
+    dmma(a0, a1, m[0][t], li00[0]);
+    dmma(a0, a1, m[1][t], li00[1]);
+    b0 = dep_zero(a0, zm);
+    dmma(b0, b1, m[0][t], li10[0]);
+    dmma(b0, b1, m[1][t], li10[1]);
+    dmma(b0, b1, m[2][t], li11[0]);
+    dmma(b0, b1, m[3][t], li11[1]);
+    tok[t % ELIM_SERIAL] = b0;
+#else
     double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
     dmma(a0, a1, m[0][t], li00[0]);
     dmma(b0, b1, m[0][t], li10[0]);
@@ -550,6 +580,7 @@ __device__ __forceinline__ bool elim_node(const double *st, const double *__rest
     dmma(b0, b1, m[1][t], li10[1]);
     dmma(b0, b1, m[2][t], li11[0]);
     dmma(b0, b1, m[3][t], li11[1]);
+#endif
     w[0][t] = a0;
     w[1][t] = a1;
     w[2][t] = b0;
@@ -580,9 +611,16 @@ __device__ __forceinline__ bool elim_node(const double *st, const double *__rest
     for (int u = 0; u < 2; u++) {
       double c0 = 0.0, c1 = 0.0;
       if (!(t == 0 && u == 1) && (HAS_F || t != 2)) {
+#if ELIM_SERIAL
+        c0 = dep_zero(tok[nch % ELIM_SERIAL], zm);
+#endif
 #pragma unroll
         for (int kk = 0; kk < 4; kk++)
           dmma(c0, c1, w[kk][t], w[kk][u]);
+#if ELIM_SERIAL
+        tok[nch % ELIM_SERIAL] = c0;
+        nch++;
+#endif
       }
       A.cy[t][u][0] = c0;
       A.cy[t][u][1] = c1;
@@ -616,9 +654,18 @@ __device__ __forceinline__ bool elim_node(const double *st, const double *__rest
           const double2 o = *q;
           *q = make_double2(o.x + c0, o.y + c1);
 #else
+#if ELIM_SERIAL
+          dmma(A.pt[i][0], A.pt[i][1], dep_on(w[0][ta], tok[nch % ELIM_SERIAL], zm), w[0][tb]);
+#pragma unroll
+          for (int kk = 1; kk < 4; kk++)
+            dmma(A.pt[i][0], A.pt[i][1], w[kk][ta], w[kk][tb]);
+          tok[nch % ELIM_SERIAL] = A.pt[i][0];
+          nch++;
+#else
 #pragma unroll
           for (int kk = 0; kk < 4; kk++)
             dmma(A.pt[i][0], A.pt[i][1], w[kk][ta], w[kk][tb]);
+#endif
 #endif
         }
         i++;
